@@ -1,0 +1,206 @@
+"""ctypes loader for the CPU oracle (oracle/sll_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Never imported by selalib_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    src = os.path.join(_HERE, "sll_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_sim6d_run.restype = C.c_int
+        _LIB.orc_sim4d_run.restype = C.c_int
+        _LIB.orc_sim2d_run.restype = C.c_int
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def spline_interpolate_array_disp(data, xmin, xmax, alpha, fast=-1):
+    data = _f(data); out = np.empty_like(data)
+    lib().orc_cubic_spline_interpolate_array_disp(C.c_int(data.size), C.c_double(xmin), C.c_double(xmax),
+                                                  C.c_int(fast), _p(data), C.c_double(alpha), _p(out))
+    return out
+
+
+def spline_interpolate_array_disp_inplace(data, xmin, xmax, alpha, fast=-1):
+    data = _f(data).copy()
+    lib().orc_cubic_spline_interpolate_array_disp_inplace(C.c_int(data.size), C.c_double(xmin), C.c_double(xmax),
+                                                          C.c_int(fast), _p(data), C.c_double(alpha))
+    return data
+
+
+def spline_coeffs(data, fast=-1):
+    data = _f(data); c = np.empty(data.size + 3)
+    lib().orc_spline_compute_interpolant_periodic(_p(data), C.c_int(data.size), C.c_int(fast), _p(c))
+    return c
+
+
+def periodic_interp(u, alpha, kind="spline", order=4):
+    u = _f(u); out = np.empty_like(u)
+    fn = lib().orc_periodic_interp_spline if kind == "spline" else lib().orc_periodic_interp_lagrange
+    fn(C.c_int(u.size), C.c_int(order), _p(u), C.c_double(alpha), _p(out))
+    return out
+
+
+def advect_1d_periodic_constant(kind, num_cells, xmin, xmax, order, A, dt, inp):
+    inp = _f(inp); out = np.empty_like(inp)
+    lib().orc_advect_1d_periodic_constant(C.c_int(0 if kind == "spline" else 1), C.c_int(num_cells),
+                                          C.c_double(xmin), C.c_double(xmax), C.c_int(order), C.c_double(A),
+                                          C.c_double(dt), _p(inp), _p(out), C.c_int(inp.size))
+    return out
+
+
+def lagr_coeff(s, p):
+    pp = np.zeros(11)
+    rc = lib().orc_lagr_coeff(C.c_int(s), C.c_double(p), _p(pp))
+    assert rc == 0
+    return pp[:s]
+
+
+def lagrange(variant, fi, p, s):
+    fi = _f(fi); fp = np.full_like(fi, np.nan)
+    fn = getattr(lib(), "orc_lagrange_" + variant)
+    fn.restype = C.c_int
+    rc = fn(_p(fi), _p(fp), C.c_int(fi.size), C.c_double(p), C.c_int(s))
+    if rc != 0:
+        raise ValueError("Lagrange stencil not implemented")
+    return fp
+
+
+def lagrange_centered_barycentric(fi, xmin, xmax, d, periodic_last, alpha):
+    fi = _f(fi); out = np.empty_like(fi)
+    lib().orc_lagrange_centered_barycentric(_p(fi), _p(out), C.c_int(fi.size if periodic_last else fi.size + 1),
+                                            C.c_double(xmin), C.c_double(xmax), C.c_int(d),
+                                            C.c_int(periodic_last), C.c_double(alpha))
+    return out
+
+
+def poisson_1d(rhs, xmin, xmax):
+    rhs = _f(rhs); field = np.empty_like(rhs)
+    lib().orc_poisson_1d_periodic_solve(C.c_int(rhs.size - 1), C.c_double(xmin), C.c_double(xmax), _p(rhs), _p(field))
+    return field
+
+
+def poisson_2d(rho, nc_x, nc_y, x_min, x_max, y_min, y_max, want_phi=False):
+    """rho: Fortran-ordered (ld1, ld2) array."""
+    rho = np.asfortranarray(rho, dtype=np.float64)
+    ld1, ld2 = rho.shape
+    ex = np.zeros_like(rho, order="F"); ey = np.zeros_like(rho, order="F"); phi = np.zeros_like(rho, order="F")
+    lib().orc_poisson_2d_periodic_solve_e(C.c_int(nc_x), C.c_int(nc_y), C.c_double(x_min), C.c_double(x_max),
+                                          C.c_double(y_min), C.c_double(y_max), _p(rho), C.c_int(ld1), C.c_int(ld2),
+                                          _p(ex), _p(ey), _p(phi) if want_phi else None)
+    return (ex, ey, phi) if want_phi else (ex, ey)
+
+
+def poisson_3d(rho, Lx, Ly, Lz):
+    rho = np.asfortranarray(rho, dtype=np.float64)
+    nx, ny, nz = rho.shape
+    outs = [np.zeros_like(rho, order="F") for _ in range(4)]
+    lib().orc_poisson_3d_periodic_solve(C.c_int(nx), C.c_int(ny), C.c_int(nz), C.c_double(Lx), C.c_double(Ly),
+                                        C.c_double(Lz), _p(rho), *[_p(o) for o in outs])
+    return outs  # phi, ex, ey, ez
+
+
+def reduction_34(f, delta3, delta4):
+    f = np.asfortranarray(f, dtype=np.float64)
+    n1, n2, n3, n4 = f.shape
+    out = np.zeros((n1, n2), order="F")
+    lib().orc_reduction_4d_to_2d_direction34(_p(f), C.c_int(n1), C.c_int(n2), C.c_int(n3), C.c_int(n4),
+                                             C.c_double(delta3), C.c_double(delta4), _p(out))
+    return out
+
+
+def charge_density_6d(f, volume_v):
+    f = np.asfortranarray(f, dtype=np.float64)
+    n = (C.c_int * 6)(*f.shape)
+    rho = np.zeros(f.shape[:3], order="F")
+    lib().orc_charge_density_6d(_p(f), n, C.c_double(volume_v), _p(rho))
+    return rho
+
+
+METHODS = {"spline": 0, "fft_spline": 1, "fft_lagrange": 2, "lagrange_fixed": 3, "lagrange_centered": 4}
+
+
+def advect_axis(f, axis, method, order, disp, dsel):
+    """Advect the Fortran-ordered array `f` in place along `axis`.
+
+    The displacement (in cells, out(i) = f(i + disp)) of line (o, in) is
+    disp[((o // odiv) % omod) * ostr + ((in // idiv) % imod) * istr], dsel = those six ints.
+    """
+    assert f.flags.f_contiguous
+    shape = f.shape
+    inner = int(np.prod(shape[:axis], dtype=np.int64))
+    outer = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    disp = _f(disp)
+    L = C.c_long
+    lib().orc_advect_axis(_p(f), L(outer), C.c_int(shape[axis]), L(inner), C.c_int(METHODS[method]), C.c_int(order),
+                          _p(disp), *[L(int(v)) for v in dsel])
+    return f
+
+
+def sim6d(n, v_max, xmax, stencil_x, stencil_v, delta_t, nsteps, alpha, kx, vth=(1.0, 1.0, 1.0),
+          time_in_phase=True, want_f=False):
+    nn = (C.c_int * 6)(*n)
+    rows = np.zeros((nsteps + 1, 14))
+    f = np.zeros(tuple(n), order="F") if want_f else None
+    rc = lib().orc_sim6d_run(nn, C.c_double(v_max), (C.c_double * 3)(*xmax), C.c_int(stencil_x), C.c_int(stencil_v),
+                             C.c_double(delta_t), C.c_int(nsteps), C.c_double(alpha), (C.c_double * 3)(*kx),
+                             (C.c_double * 3)(*vth), C.c_int(1 if time_in_phase else 0), _p(rows),
+                             _p(f) if want_f else None)
+    assert rc == 0
+    return (rows, f) if want_f else rows
+
+
+def sim4d(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split=0, method=0, order=4, want_f=False):
+    rows = np.zeros((nsteps + 1, 6))
+    f = np.zeros(tuple(c + 1 for c in nc), order="F") if want_f else None
+    rc = lib().orc_sim4d_run((C.c_int * 4)(*nc), (C.c_double * 4)(*xmin), (C.c_double * 4)(*xmax), C.c_double(kx1),
+                             C.c_double(kx2), C.c_double(eps), C.c_double(dt), C.c_int(nsteps), C.c_int(split),
+                             C.c_int(method), C.c_int(order), _p(rows), _p(f) if want_f else None)
+    assert rc == 0
+    return (rows, f) if want_f else rows
+
+
+def sim2d(nc_x1, nc_x2, x1_min, x1_max, x2_min, x2_max, init, kmode, eps, dt, nsteps, method=0, order=4,
+          want_f=False):
+    rows = np.zeros((nsteps, 8))
+    f = np.zeros((nc_x1 + 1, nc_x2 + 1), order="F") if want_f else None
+    E = np.zeros(nc_x1 + 1)
+    rc = lib().orc_sim2d_run(C.c_int(nc_x1), C.c_int(nc_x2), C.c_double(x1_min), C.c_double(x1_max),
+                             C.c_double(x2_min), C.c_double(x2_max), C.c_int(init), C.c_double(kmode), C.c_double(eps),
+                             C.c_double(dt), C.c_int(nsteps), C.c_int(method), C.c_int(order), _p(rows),
+                             _p(f) if want_f else None, _p(E))
+    assert rc == 0
+    return (rows, f, E) if want_f else rows

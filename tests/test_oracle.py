@@ -1,0 +1,198 @@
+"""Pins the CPU oracle (oracle/sll_oracle.c) against the reference's own golden vector and
+the analytic known-answer thresholds of its unit tests (G1, G2)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RNG = np.random.default_rng(20261017)
+
+
+def test_g1_golden_6d():
+    """simulations/parallel/bsl_vp_3d3v_cart_dd: CTest bsl_vp_3d3v_cart_dd_slim, tolerance 5e-7
+    (sll_m_sim_6d_utilities.F90:648-687).  The file prints 12 significant digits."""
+    gold = np.loadtxt(os.path.join(GOLD, "reffile_bsl_vp_3d3v_cart_dd.dat"))
+    rows = orc.sim6d([16] * 6, 6.0, [12.5663706144] * 3, 3, 3, 0.01, 2, 0.01, [0.499999999998376] * 3)
+    assert rows.shape == gold.shape == (3, 14)
+    assert np.abs(rows - gold).max() < 5e-7          # the reference's own tolerance
+    # and to the printed precision of the golden file (12 significant digits)
+    rel = np.abs(rows - gold) / np.maximum(np.abs(gold), 1e-300)
+    assert rel[:, [1, 2, 3, 4, 5, 6, 7, 11, 12, 13]].max() < 2e-11
+    assert np.abs(rows[:, 8:11] - gold[:, 8:11]).max() < 1e-14   # odd moments ~ -2.7e-8
+
+
+def test_poisson_1d_kat():
+    """test_poisson_1d_periodic.F90:47-76: rho = m^2 sin(m x), m=4, N=128 -> E = -m cos(m x), 1e-14"""
+    nc, m = 128, 4
+    x = np.arange(nc + 1) * 2 * np.pi / nc
+    E = orc.poisson_1d(m * m * np.sin(m * x), 0.0, 2 * np.pi)
+    assert np.abs(E + m * np.cos(m * x)).max() <= 1e-13
+
+
+def test_poisson_2d_kat():
+    """test_poisson_2d_periodic.F90:74-115: mode-2 product solution on 128^2, errors <= 1e-13"""
+    nc, mode = 128, 2
+    x = np.arange(nc + 1) * 2 * np.pi / nc
+    X1, X2 = np.meshgrid(x, x, indexing="ij")
+    phi_exact = mode * np.sin(mode * X1) * np.cos(mode * X2)
+    ex_exact = mode ** 2 * np.cos(mode * X1) * np.cos(mode * X2)
+    ey_exact = -mode ** 2 * np.sin(mode * X1) * np.sin(mode * X2)
+    rho = -2.0 * mode ** 3 * np.sin(mode * X1) * np.cos(mode * X2)
+    ex, ey, phi = orc.poisson_2d(rho, nc, nc, 0, 2 * np.pi, 0, 2 * np.pi, want_phi=True)
+    assert np.abs(phi_exact + phi).max() <= 1e-13
+    assert np.abs(ex_exact - ex).max() <= 1e-13
+    assert np.abs(ey_exact - ey).max() <= 1e-13
+
+
+def test_poisson_2d_matches_numpy_fftw_semantics():
+    """c2r must drop Im at the DC/Nyquist planes of the halved dimension like FFTW (numpy irfft2 does)."""
+    n1, n2 = 16, 12
+    rho = RNG.standard_normal((n1, n2))
+    ex, ey = orc.poisson_2d(rho, n1, n2, 0.0, 3.0, 0.0, 5.0)
+    rh = np.fft.rfft2(rho.T).T          # (n1/2+1, n2), halved dim first as in FFTW/Fortran
+    kx = 2 * np.pi / 3.0 * np.arange(n1 // 2 + 1)[:, None] * np.ones((1, n2))
+    j = np.arange(n2); j = np.where(j < n2 // 2, j, j - n2)
+    ky = np.ones((n1 // 2 + 1, 1)) * (2 * np.pi / 5.0 * j)[None, :]
+    kx[0, 0] = 1.0
+    k2 = kx ** 2 + ky ** 2
+    ex_np = np.fft.irfft2((-1j * kx / k2 * rh).T, s=(n2, n1)).T
+    ey_np = np.fft.irfft2((-1j * ky / k2 * rh).T, s=(n2, n1)).T
+    assert np.abs(ex - ex_np).max() < 1e-13 and np.abs(ey - ey_np).max() < 1e-13
+
+
+def test_poisson_3d_kat():
+    n, L = 32, 4 * np.pi
+    x = np.arange(n) * L / n
+    X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+    k = 0.5
+    phi_exact = np.cos(k * X) * np.cos(2 * k * Y) * np.sin(k * Z)
+    rho = (k * k + 4 * k * k + k * k) * phi_exact
+    phi, ex, ey, ez = orc.poisson_3d(rho, L, L, L)
+    assert np.abs(phi - phi_exact).max() < 1e-13
+    assert np.abs(ex - k * np.sin(k * X) * np.cos(2 * k * Y) * np.sin(k * Z)).max() < 1e-13
+    assert np.abs(ey - 2 * k * np.cos(k * X) * np.sin(2 * k * Y) * np.sin(k * Z)).max() < 1e-13
+    assert np.abs(ez + k * np.cos(k * X) * np.cos(2 * k * Y) * np.cos(k * Z)).max() < 1e-13
+
+
+@pytest.mark.parametrize("variant,npts,order,tol", [
+    ("fixed_no_bc", 100, 5, 1e-8), ("fixed_periodic", 100, 3, 8e-6), ("fixed_periodicl", 101, 5, 7e-9),
+    ("centered_periodicl", 101, 4, 3e-7), ("centered_periodicl", 101, 6, 2e-10)])
+def test_lagrange_fast_kat(variant, npts, order, tol):
+    """test_lagrange_interpolation_1d_fast.F90:41-45, f = cos(2 pi x / 100), alpha = 0.2"""
+    xi = np.arange(npts, dtype=float)
+    f = lambda x: np.cos(2 * np.pi * x / 100)
+    fp = orc.lagrange(variant, f(xi), 0.2, order)
+    assert np.abs(f(xi + 0.2) - fp).max() <= tol
+
+
+def test_lagrange_fixed_all_stencils_and_halo():
+    n = 64
+    fi = RNG.standard_normal(n)
+    for s in (3, 5, 7, 9, 11):
+        h = (s - 1) // 2
+        p = 0.37
+        pp = orc.lagr_coeff(s, p)
+        assert abs(pp.sum() - 1.0) < 1e-13
+        # reproduces polynomials of degree s-1 exactly
+        k = np.arange(-h, h + 1, dtype=float)
+        for deg in range(s):
+            assert abs((pp * k ** deg).sum() - p ** deg) < 1e-10
+        per = orc.lagrange("fixed_periodic", fi, p, s)
+        ext = np.concatenate([fi[-h:], fi, fi[:h]])
+        halo = orc.lagrange("fixed_haloc_cells", ext, p, s)
+        assert np.abs(halo[h:-h] - per).max() < 1e-14      # same stencil (fma contraction may differ)
+        assert np.isnan(halo[:h]).all() and np.isnan(halo[-h:]).all()   # halo cells untouched
+    with pytest.raises(ValueError):
+        orc.lagrange("fixed_periodic", fi, 0.1, 13)
+
+
+def test_lagrange_centered_even_and_barycentric():
+    n = 100
+    x = np.arange(n + 1, dtype=float)
+    f = lambda t: np.cos(2 * np.pi * t / n)
+    for s, tol in ((4, 3e-7), (6, 2e-10), (8, 1e-12)):
+        for p in (0.2, -1.7, 3.4):
+            fp = orc.lagrange("centered_periodicl", f(x), p, s)
+            assert np.abs(fp - f(x + p)).max() < tol * 5
+            bary = orc.lagrange_centered_barycentric(f(x), 0.0, float(n), s // 2, 1, p)
+            assert np.abs(bary - fp).max() < 1e-13
+    # fourier1dperlagodd (periodic advector sll_p_lagrange) == direct centred stencil
+    u = RNG.standard_normal(64)
+    for order in (4, 6, 8):
+        for a in (0.3, -2.6, 5.25):
+            fft = orc.periodic_interp(u, a, "lagrange", order)
+            direct = orc.lagrange("centered_periodicl", np.append(u, u[0]), -a, order)[:-1]
+            assert np.abs(fft - direct).max() < 5e-14
+
+
+def test_cubic_spline_kat_and_variants():
+    """test_cubic_spline_interpolator_1d.F90: f = 2(sin x + 2.5 + cos x), n=64, alpha=-1.2 dx, err<1e-6;
+    fast and LU algorithms; periodic advector constant preservation (test_advection_1d_periodic.F90)."""
+    n = 64
+    xmin, xmax = 0.0, 2 * np.pi
+    dx = (xmax - xmin) / n
+    x = xmin + dx * np.arange(n + 1)
+    f = lambda t: 2.0 * (np.sin(t) + 2.5 + np.cos(t))
+    alpha = -1.2 * dx
+    for fast in (1, 0):
+        out = orc.spline_interpolate_array_disp(f(x), xmin, xmax, alpha, fast)
+        assert np.abs(out - f(x + alpha)).max() < 1e-6
+        out2 = orc.spline_interpolate_array_disp_inplace(f(x), xmin, xmax, alpha, fast)
+        assert np.abs(out2 - out).max() < 2e-14
+    data = RNG.standard_normal(n); data = np.append(data, data[0])
+    cf = orc.spline_coeffs(data, 1); cl = orc.spline_coeffs(data, 0)
+    assert np.abs(cf - cl).max() < 1e-14
+    # interpolation property (c[j-1] + 4 c[j] + c[j+1]) / 6 = f_j
+    assert np.abs((cf[0:n] + 4 * cf[1:n + 1] + cf[2:n + 2]) / 6 - data[:n]).max() < 1e-14
+    # small-N LU fallback (num_points < 27)
+    d8 = RNG.standard_normal(8); d8 = np.append(d8, d8[0])
+    c8 = orc.spline_coeffs(d8)
+    assert np.abs((c8[0:8] + 4 * c8[1:9] + c8[2:10]) / 6 - d8[:8]).max() < 1e-14
+    # periodic advector (FFT, order 4) == direct spline; sign: out(x) = in(x - A dt)
+    A, dt = 0.73, 0.1
+    adv = orc.advect_1d_periodic_constant("spline", n, xmin, xmax, 4, A, dt, data)
+    ref = orc.spline_interpolate_array_disp(data, xmin, xmax, -A * dt)
+    assert np.abs(adv - ref).max() < 1e-13
+    assert adv[-1] == adv[0]
+    ones = np.ones(n + 1)
+    assert np.abs(orc.advect_1d_periodic_constant("spline", n, xmin, xmax, 4, 0.3, 0.1, ones) - 1.0).max() < 1e-15
+    assert np.array_equal(orc.spline_interpolate_array_disp(ones, xmin, xmax, 0.123), ones) or \
+        np.abs(orc.spline_interpolate_array_disp(ones, xmin, xmax, 0.123) - 1).max() < 1e-15
+
+
+def test_reductions():
+    f = RNG.standard_normal((5, 4, 9, 7))
+    out = orc.reduction_34(f, 0.3, 0.7)
+    w3 = np.ones(9); w3[[0, -1]] = 0.5
+    w4 = np.ones(7); w4[[0, -1]] = 0.5
+    ref = np.einsum("ijkl,k,l->ij", f, w3, w4) * 0.3 * 0.7
+    assert np.abs(out - ref).max() < 1e-13
+    f6 = RNG.standard_normal((4, 3, 2, 3, 2, 2))
+    rho = orc.charge_density_6d(f6, 0.25)
+    assert np.abs(rho + f6.sum(axis=(3, 4, 5)) * 0.25).max() < 1e-13
+
+
+def test_sim2d_landau_damping_rate():
+    """Physics sanity (G4, eyeball only in the reference): 1D Landau damping k=0.5, gamma=-0.1533
+    (vpsim2d_cartesian.gnu:10)."""
+    rows = orc.sim2d(32, 64, 0.0, 4 * np.pi, -6.0, 6.0, 0, 0.5, 1e-3, 0.1, 200)
+    t, epot = rows[:, 0], rows[:, 6]
+    # local maxima of sqrt(epot) decay like exp(gamma t)
+    s = np.sqrt(epot)
+    pk = [i for i in range(1, len(s) - 1) if s[i] > s[i - 1] and s[i] > s[i + 1] and t[i] < 18]
+    g = np.polyfit(t[pk], np.log(s[pk]), 1)[0]
+    assert abs(g + 0.1533) < 0.01
+    assert abs(rows[:, 1] / rows[0, 1] - 1).max() < 1e-9   # mass conserved
+
+
+def test_sim4d_runs_and_conserves_mass():
+    nc = [16, 16, 16, 16]
+    rows = orc.sim4d(nc, [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1, 3)
+    assert np.isfinite(rows).all()
+    assert abs(rows[:, 3] / rows[0, 3] - 1).max() < 1e-6
+    # FFT periodic advector (the sims' default SLL_SPLINES) agrees with the direct spline
+    rows_fft = orc.sim4d(nc, [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1, 3, method=1)
+    assert np.abs(rows_fft - rows).max() / np.abs(rows).max() < 1e-12
