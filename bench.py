@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the split semi-Lagrangian advection path.
+
+Metric (BASELINE.json): 4D phase-space point-updates/s per advection pass, on the 2D2V Landau-damping
+128^4 fp64 configuration (cubic-spline BSL, Strang VTV, FFT Poisson between the splitting stages).
+One "step" = one Strang time step = 6 advection passes over all of f (V/2: x3,x4; T: x1,x2; V/2: x3,x4)
+plus 2 charge-density reductions and 2 Poisson solves; value = 6 * N^4 * steps / time.
+Strong scaling: the same 128^4 problem on N GPUs (x <-> v remaps over NCCL).
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU restatement of the reference path)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "4D phase-space point-updates/s per advection pass"
+UNIT = "point-updates/s"
+NSIDE = int(os.environ.get("SLLB_BENCH_N", "128"))
+PASSES_PER_STEP = 6
+XMIN = [0.0, 0.0, -6.0, -6.0]
+XMAX = [4 * np.pi, 4 * np.pi, 6.0, 6.0]
+WORKLOAD = (f"2D2V Landau damping {NSIDE}^4 fp64, periodic cubic-spline BSL on all four axes, Strang VTV, "
+            "trapezoid rho + 2D FFT Poisson (sim_bsl_vp_2d2v_cart_poisson_serial semantics), dt=0.1, eps=1e-3, k=(0.5,0.5)")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi sampler running while the GPU sections execute (the recipe's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        # median over the samples taken under load (upper half by power draw)
+        if sm:
+            order = np.argsort(power)
+            hot = [sm[i] for i in order[len(order) // 2:]]
+            med = statistics.median(hot)
+        else:
+            med = None
+        return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm), "window": "warm-up + timed steps + per-kernel timing + e2e"}
+
+
+def cpu_sample_step(orc, f, n, frac, method="spline"):
+    """One Strang step's 6 advection passes (+ 2 Poisson solves) of the CPU restatement over 1/frac of the
+    lines of the n^4 field, full-length lines.  Returns point-updates done."""
+    v = XMIN[2] + (XMAX[2] - XMIN[2]) / n * np.arange(n)
+    dx = (XMAX[0] - XMIN[0]) / n
+    dv = (XMAX[2] - XMIN[2]) / n
+    dt = 0.1
+    E = 1e-3 * np.sin(np.arange(n * n) * 0.01)
+    rho = np.zeros((n, n), order="F")
+    done = 0
+
+    def vstage(step):
+        nonlocal done
+        orc.poisson_2d(rho, n, n, XMIN[0], XMAX[0], XMIN[1], XMAX[1])
+        done += orc.advect_axis_sub(f, 2, method, 4, E * (-step * dt / dv), (1, 1, 0, 1, n * n, 1), frac)
+        done += orc.advect_axis_sub(f, 3, method, 4, E * (-step * dt / dv), (1, 1, 0, 1, n * n, 1), frac)
+
+    vstage(0.5)
+    done += orc.advect_axis_sub(f, 0, method, 4, v * (-dt / dx), (n, n, 1, 1, 1, 0), frac)
+    done += orc.advect_axis_sub(f, 1, method, 4, v * (-dt / dx), (n, n, 1, 1, 1, 0), frac)
+    vstage(0.5)
+    return done
+
+
+def cpu_field(n):
+    rng = np.random.default_rng(20261017)
+    f = np.empty((n, n, n, n), order="F")
+    flat = f.reshape(-1, order="F")
+    chunk = 1 << 24
+    for i in range(0, flat.size, chunk):
+        flat[i:i + chunk] = rng.random(min(chunk, flat.size - i))
+    return f
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference path (the reference itself is Fortran and cannot be built
+    in this image), all host threads, on bounded samples of the same workload."""
+    if rank != 0:
+        return
+    from oracle import orc
+    cores = orc.num_threads()
+    n = NSIDE
+    f = cpu_field(n)
+    # size the per-step sample so that the whole run ends within a few minutes whatever K is
+    t0 = time.perf_counter()
+    d0 = cpu_sample_step(orc, f, n, 64)
+    thr = d0 / (time.perf_counter() - t0)
+    budget_s = float(os.environ.get("SLLB_REF_BUDGET_S", "90"))
+    full = PASSES_PER_STEP * float(n) ** 4
+    frac = env_int("SLLB_REF_FRAC", 0) or int(min(4096, max(4, np.ceil((args.steps + args.warmup) * full / (thr * budget_s)))))
+    for _ in range(args.warmup):
+        cpu_sample_step(orc, f, n, frac)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        done += cpu_sample_step(orc, f, n, frac)
+    dtm = time.perf_counter() - t0
+    value = done / dtm
+    sample = (f"per step: the 6 advection passes of one Strang step over 1/{frac} of the lines (full {n}-point lines, all four "
+              f"axes) of the {n}^4 field + 2 Poisson solves; direct cubic-spline algorithm (sll_m_cubic_splines fast path), "
+              "line copy-in/out, OpenMP static over lines; rho reduction excluded")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dtm / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "arm": "C restatement of the reference CPU path (oracle port), host cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+
+    import torch
+    import selalib_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; selalib_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    sb.init(local_rank)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.tensor(list(sb.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = sb.Comm(bytes(idt.cpu().tolist()), world, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = NSIDE
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    S = sb.Sim4d([n] * 4, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, split=0, method=sb.METHOD_SPLINE, order=4, comm=comm)
+    npts = float(n) ** 4
+
+    # ---- kernel-resident timing: inputs already in HBM -------------------------------------------
+    S.run(args.warmup, diagnostics=False)
+    barrier()
+    sb.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    S.run(args.steps, diagnostics=False)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sb.launch_count()
+    phase = S.phase_ms().tolist()
+    value = PASSES_PER_STEP * npts * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing for the roofline (CUDA events on the launch stream, local field) ------
+    F = S.field()
+    ext = F.extents
+    local_pts = float(np.prod(ext))
+    reps = 20
+    dispv = torch.linspace(-2.3, 2.3, max(ext), dtype=torch.float64, device="cuda")
+    Ef = (1e-2 * torch.sin(torch.arange(ext[0] * ext[1], dtype=torch.float64, device="cuda"))).contiguous()
+    kernel_ms = {}
+    axes = [0, 1] + ([2, 3] if world == 1 else [])
+    for axis in axes:
+        if axis < 2:
+            dsel = (ext[1] if axis == 0 else 1, ext[axis + 2], 1, 1, 1, 0)
+            call = lambda a=axis, d=dsel: F.advect_axis(a, sb.METHOD_SPLINE, 4, dispv.data_ptr(), 1.0, d, on_device=True)
+        else:
+            dsel = (1, 1, 0, 1, ext[0] * ext[1], 1)
+            call = lambda a=axis, d=dsel: F.advect_axis(a, sb.METHOD_SPLINE, 4, Ef.data_ptr(), 1.0, d, on_device=True)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            call()
+        a1.record()
+        torch.cuda.synchronize()
+        kernel_ms[axis] = a0.elapsed_time(a1) / reps
+    strided = [kernel_ms[a] for a in axes if a != 0]
+    t_dom = sum(strided) / len(strided)
+    peak, peak_src = measured_peak()
+    achieved = 16.0 * local_pts / (t_dom * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("k_advect_strided_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_advect_strided<32,spline> (x2/x3/x4 passes: 3 of 4 axes, 5 of 6 passes per step)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * local_pts,
+                "ms_per_launch": t_dom, "ms_per_launch_by_axis": {f"x{a + 1}": kernel_ms[a] for a in axes},
+                "gbs_by_axis": {f"x{a + 1}": 16.0 * local_pts / (kernel_ms[a] * 1e-3) / 1e9 for a in axes},
+                "timing": f"CUDA events on the launch stream, {reps} launches after 3 warm-ups, field {ext} "
+                          f"({local_pts * 8 / 1e9:.2f} GB > L2)"}
+
+    # ---- end to end through the C ABI with HOST buffers ------------------------------------------
+    host = torch.empty(int(local_pts), dtype=torch.float64).pin_memory()
+    lib = sb.lib()
+    hp = C.cast(C.c_void_p(host.data_ptr()), C.POINTER(C.c_double))
+    assert lib.sllb_field_download(F.h, hp, None) == 0
+    row = np.zeros(6)
+    e2e_steps = max(1, min(args.steps, env_int("SLLB_E2E_STEPS", 10)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        assert lib.sllb_field_upload(F.h, hp, None) == 0          # H2D of the step's input state (pinned)
+        r = S.run(1, diagnostics=True)                             # one Strang step + diagnostics row (D2H)
+        assert lib.sllb_field_download(F.h, hp, None) == 0         # D2H of the step's result
+        row = r[0]
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = PASSES_PER_STEP * npts * e2e_steps / e2e_s
+    # resident mode (how the simulation is meant to run: f never leaves HBM, only the diagnostics row does)
+    barrier()
+    t0 = time.perf_counter()
+    S.run(e2e_steps, diagnostics=True)
+    barrier()
+    res_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(local_pts * 8), "d2h_bytes_per_step": int(local_pts * 8 + 48),
+           "steps": e2e_steps, "what": "per step: sllb_field_upload (pinned host f -> HBM) + sllb_sim4d_run(1 step, diagnostics) + "
+                                       "sllb_field_download (HBM -> pinned host f); per-rank local box",
+           "resident_value": PASSES_PER_STEP * npts * e2e_steps / res_s,
+           "resident_what": "sllb_sim4d_run with f resident in HBM, one 6-double diagnostics row to the host per step"}
+    clocks = sampler.stop() if sampler else None
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not os.environ.get("SLLB_SKIP_CPU"):
+        from oracle import orc
+        frac = env_int("SLLB_REF_FRAC", 4)
+        fc = cpu_field(n)
+        cpu_sample_step(orc, fc, n, frac * 8)
+        t0 = time.perf_counter()
+        done = cpu_sample_step(orc, fc, n, frac)
+        t_direct = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        done_fft = cpu_sample_step(orc, fc, n, frac * 4, method="fft_spline")
+        t_fft = time.perf_counter() - t0
+        cpu_baseline = {"value": done / t_direct, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                        "sample": f"6 advection passes of one Strang step over 1/{frac} of the lines of the {n}^4 field (full-length "
+                                  "lines, all four axes) + 2 Poisson solves; C restatement of the reference CPU path, direct "
+                                  "cubic-spline algorithm, OpenMP over lines",
+                        "reference_algorithm_value": done_fft / t_fft,
+                        "reference_algorithm": f"same passes over 1/{frac * 4} of the lines with the FFT-diagonalised periodic spline "
+                                               "(sll_s_periodic_interp, the sims' default SLL_SPLINES advector)"}
+        del fc
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP, "points": int(npts),
+                           "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
+                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap (pack + NCCL send/recv group + unpack)",
+                           "staging": "TMA bulk (cp.async.bulk) for strided axes, cp.async transpose for x1"},
+                "phase_ms_per_step": {"advect": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
+                                      "remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "check": {"mass": float(row[3]), "field_energy": float(row[1])}}
+        print(json.dumps(line), flush=True)
+    S.destroy()
+    if comm is not None:
+        comm.destroy()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = env_int("RANK", 0)
+    world = env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,269 @@
+/*
+ * sll_b200.h -- C ABI of the B200-native split semi-Lagrangian advection path.
+ *
+ * Drop-in boundary for SeLaLib's sim_bsl_vp_* simulations.
+ * Every entry point is extern "C", takes plain pointers and sizes, and returns an
+ * int status (0 = ok, non-zero = error; text via sllb_last_error()).  A Fortran
+ * caller binds these with iso_c_binding (see fortran/ and INTEGRATION.md) and turns a
+ * non-zero status into SLL_ERROR, which is how the reference reports failures
+ * (src/low_level_utilities/errors/sll_errors.h:4).
+ *
+ * Conventions
+ *  - all arrays are column-major (Fortran order), fp64, indices int32 like sll_int32;
+ *  - line-granular calls (sllb_adv1d_*, sllb_interp1d_*) take HOST pointers and mirror
+ *    the reference objects call by call (parity / drop-in; each call copies the line to
+ *    the GPU and back);
+ *  - batched calls operate on a device-resident field (sllb_field_t) that stores the
+ *    periodic cells only (N per axis).  Upload/download add or strip the duplicated
+ *    periodic end point the 1D1V/2D2V simulations carry (N+1);
+ *  - one handle per host thread (same rule as the reference: objects own scratch);
+ *  - there is no CPU fallback: every compute entry point fails with SLLB_ERR_NO_DEVICE
+ *    when no CUDA device is usable.
+ * Paths cited below are relative to the reference tree.
+ */
+#ifndef SLL_B200_H
+#define SLL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------- */
+#define SLLB_OK 0
+#define SLLB_ERR_INVALID 1     /* bad argument */
+#define SLLB_ERR_UNSUPPORTED 2 /* method/stencil not implemented (reference: SLL_ERROR 'not implemented') */
+#define SLLB_ERR_CUDA 3        /* CUDA / cuFFT / NCCL runtime failure */
+#define SLLB_ERR_NO_DEVICE 4   /* no usable CUDA device */
+
+const char *sllb_last_error(void);
+int sllb_version(void);
+/* Select the device this thread's handles live on (default 0).  */
+int sllb_init(int device);
+int sllb_device_count(int *count);
+int sllb_synchronize(void);
+/* number of kernels this library launched since the last reset (bench bookkeeping) */
+int64_t sllb_launch_count(void);
+void sllb_launch_count_reset(void);
+
+/* ---- interpolation / advection methods ---------------------------------- */
+/* advector kinds: sll_t_advector_1d_periodic with sll_p_spline / sll_p_lagrange
+ * (src/semi_lagrangian/advection/sll_m_advection_1d_periodic.F90:41-54,
+ *  src/interpolation/periodic_interpolation/sll_m_periodic_interp.F90:38-41) */
+#define SLLB_ADV_PERIODIC_SPLINE 0
+#define SLLB_ADV_PERIODIC_LAGRANGE 1
+
+/* interpolator kinds (sll_c_interpolator_1d implementations) */
+#define SLLB_INTERP_CUBIC_SPLINE 0      /* sll_t_cubic_spline_interpolator_1d */
+#define SLLB_INTERP_LAGRANGE_CENTERED 1 /* sll_t_lagrange_interpolator_1d, sll_p_lagrange_centered */
+#define SLLB_INTERP_LAGRANGE_FIXED 2    /* sll_t_lagrange_interpolator_1d, sll_p_lagrange_fixed */
+#define SLLB_INTERP_PERIODIC_SPLINE 3   /* sll_t_periodic_interpolator_1d, sll_p_spline */
+#define SLLB_INTERP_PERIODIC_LAGRANGE 4 /* sll_t_periodic_interpolator_1d, sll_p_lagrange */
+
+#define SLLB_BC_PERIODIC 0 /* sll_p_periodic; other boundary types -> SLLB_ERR_UNSUPPORTED */
+
+/* batched per-axis methods */
+#define SLLB_METHOD_SPLINE 0            /* periodic cubic spline (order 4) */
+#define SLLB_METHOD_LAGRANGE_FIXED 1    /* odd stencil 3,5,7,9,11 centred on the grid point */
+#define SLLB_METHOD_LAGRANGE_CENTERED 2 /* even stencil 4,6,8 centred on the foot cell */
+
+/* ---- a1/a2: sll_c_advector_1d%advect_1d_constant -------------------------
+ * replaces sll_f_new_periodic_1d_advector / periodic_advect_1d_constant
+ * (sll_m_advection_1d_periodic.F90:57-130) and the abstract interface
+ * (sll_m_advection_1d_base.F90:53-68).  out(x_i) = in(x_i - A*dt); `in` may alias
+ * `out`; n = num_cells or num_cells+1 (the duplicate is filled when n > num_cells).
+ * kind PERIODIC_SPLINE supports order 4; PERIODIC_LAGRANGE supports order 4,6,8. */
+typedef struct sllb_adv1d *sllb_adv1d_t;
+int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int order, sllb_adv1d_t *h);
+int sllb_adv1d_advect_constant(sllb_adv1d_t h, double A, double dt, const double *in, double *out, int n);
+int sllb_adv1d_delete(sllb_adv1d_t h);
+
+/* ---- a5/a8: sll_c_interpolator_1d%interpolate_array_disp[_inplace] --------
+ * replaces spline_interpolate1d_disp[_inplace]
+ * (src/interpolation/interpolators/sll_m_cubic_spline_interpolator_1d.F90:112-180),
+ * interpolate_array_disp_li1d (sll_m_lagrange_interpolator_1d.F90:169-199) and
+ * per_interpolate1d_disp (sll_m_periodic_interpolator_1d.F90).
+ * out(i) = f(x_i + alpha).  num_points counts the duplicated periodic point when
+ * periodic_last = 1 (always for the spline interpolators).  d_or_order: Lagrange d
+ * (stencil 2d centred / 2d+1 fixed) or the periodic interpolator's order.
+ * fast_algorithm is accepted for API parity; both reference algorithms agree to 1e-15
+ * and the device solve is exact to 3.6e-16 (27-term series as in the reference). */
+typedef struct sllb_interp1d *sllb_interp1d_t;
+int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int bc, int d_or_order,
+                         int periodic_last, int fast_algorithm, sllb_interp1d_t *h);
+int sllb_interp1d_array_disp(sllb_interp1d_t h, int n, const double *data, double alpha, double *out);
+int sllb_interp1d_array_disp_inplace(sllb_interp1d_t h, int n, double *data, double alpha);
+int sllb_interp1d_delete(sllb_interp1d_t h);
+
+/* ---- device-resident distribution function ------------------------------ */
+typedef struct sllb_field *sllb_field_t;
+/* extents[d] = number of periodic cells along axis d (1 <= ndim <= 6) */
+int sllb_field_create(int ndim, const int *extents, sllb_field_t *F);
+int sllb_field_destroy(sllb_field_t F);
+/* dup_last[d] = 1: the host array has extents[d]+1 points along d (last = first).
+ * dup_last may be NULL (= all 0).  On download the duplicate is filled from index 1. */
+int sllb_field_upload(sllb_field_t F, const double *host, const int *dup_last);
+int sllb_field_download(sllb_field_t F, double *host, const int *dup_last);
+int sllb_field_device_ptr(sllb_field_t F, double **dptr);
+int sllb_field_extents(sllb_field_t F, int *ndim, int *extents);
+
+/* Displacement of line (o, in) of an axis pass, in cells, out(i) = f(i + disp):
+ *   disp = scale * values[ ((o / odiv) % omod) * ostr + ((in / idiv) % imod) * istr ]
+ * where `in` is the flattened index of the axes faster than the advected one and `o` of
+ * the slower ones.  Covers a16's formulas: alpha = v*step (one velocity index) and
+ * alpha = E(i1,i2[,i3])*step (the field, fused into the kernel = K5).
+ * values_on_device: 0 = host array of `nvalues` doubles (copied), 1 = device pointer. */
+typedef struct {
+    const double *values;
+    int64_t nvalues;
+    int values_on_device;
+    double scale;
+    int64_t odiv, omod, ostr, idiv, imod, istr;
+} sllb_disp_t;
+
+/* a2/a5/a10/a11 batched: one 1D advection applied to every line of F along `axis`,
+ * in place.  Replaces the per-line loops of
+ * sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:1037-1064,1143-1166,
+ * sll_m_sim_bsl_vp_1d1v_cart.F90:1570-1585,1656-1686 and
+ * sll_s_advection_6d_lagrange_dd_slim_advect_eta1..6
+ * (sll_m_advection_6d_lagrange_dd_slim.F90:806-2001). order: 4 for SPLINE, stencil
+ * width for Lagrange. */
+int sllb_advect_axis(sllb_field_t F, int axis, int method, int order, const sllb_disp_t *disp);
+/* convenience: disp = (vmin + i_vaxis*dv) * scale, the x-advection of a16 */
+int sllb_advect_axis_affine(sllb_field_t F, int axis, int method, int order, int v_axis, double vmin,
+                            double dv, double scale);
+/* convenience: disp = field[x] * scale with field a DEVICE array over the first
+ * `nfield_axes` axes of F (v-advection; K5) */
+int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, const double *d_field,
+                           int nfield_axes, double scale);
+/* tuning knob: 0 = auto, 1 = TMA bulk staging, 2 = cp.async staging (strided kernels) */
+int sllb_set_staging(int mode);
+
+/* ---- a14: velocity reduction -> charge density ----------------------------
+ * rho[x] = scale * sum over the last (ndim - nx_axes) axes of F.  With periodic cells
+ * only, the trapezoid rule over the duplicated end points
+ * (src/parallelization/reduction/sll_m_reduction.F90:187-272) IS the plain sum;
+ * 6D: scale = -dV_v (sll_m_sim_6d_utilities.F90:203-245). d_rho: DEVICE, prod(extents[0:nx_axes]). */
+int sllb_reduce_velocity(sllb_field_t F, int nx_axes, double scale, double *d_rho);
+/* same, result copied to a HOST array */
+int sllb_reduce_velocity_host(sllb_field_t F, int nx_axes, double scale, double *h_rho);
+/* K8: weighted moments over the whole field (diagnostics), HOST out[3 + 2*nv]:
+ *   [sum f, sum |f|, sum f^2, sum f*w1_a[i_a] (a = 1..nv), sum f*w2_a[i_a] (a = 1..nv)]
+ * for the trailing `nv` axes; w1 / w2 are HOST arrays holding the per-axis weights of those axes
+ * back to back (first and second velocity moments: v and v^2, with whatever end-point rule the
+ * caller's quadrature uses). */
+int sllb_moments(sllb_field_t F, int nv, const double *w1, const double *w2, double *out);
+
+/* ---- a15: periodic Poisson solvers (cuFFT) -------------------------------- */
+typedef struct sllb_poisson *sllb_poisson_t;
+/* sll_t_poisson_1d_periodic (sll_m_poisson_1d_periodic.F90:102-173) */
+int sllb_poisson1d_create(int nc, double xmin, double xmax, sllb_poisson_t *P);
+/* sll_t_poisson_2d_periodic_fft (sll_m_poisson_2d_periodic.F90:250-383) */
+int sllb_poisson2d_create(int nc_x, int nc_y, double x_min, double x_max, double y_min, double y_max,
+                          sllb_poisson_t *P);
+/* sll_t_poisson_3d_periodic_par (sll_m_poisson_3d_periodic_par.F90:297-470,981-1158), replicated */
+int sllb_poisson3d_create(int nx, int ny, int nz, double Lx, double Ly, double Lz, sllb_poisson_t *P);
+int sllb_poisson_destroy(sllb_poisson_t P);
+/* DEVICE arrays of the periodic cells only (nc_x*nc_y..., no duplicates).  Any of the
+ * outputs may be NULL.  1D: e2,e3 ignored. 2D: e3 ignored.  E = -grad phi, -lap phi = rho. */
+int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, double *d_e1, double *d_e2,
+                       double *d_e3);
+/* HOST arrays with leading dimensions ld (= nc or nc+1, duplicates filled like
+ * sll_m_poisson_2d_periodic.F90:370-374 / sll_m_poisson_1d_periodic.F90:170) */
+int sllb_poisson_solve_host(sllb_poisson_t P, const double *rho, const int *ld, double *phi, double *e1,
+                            double *e2, double *e3);
+
+/* ---- a13: layouts and remap (x <-> v transposes), multi-GPU ----------------
+ * Layout = box per rank of a global 4D array (sll_t_layout_4d,
+ * src/parallelization/remap/sll_m_remapper.F90:1345-1487); process meshes are powers of two
+ * from sll_s_factorize_in_two_powers_of_two (:6452-6476); rank = i+P1*(j+P2*(k+P3*l)) (:1056-1066).
+ * Host-only helpers (no device needed): */
+int sllb_factorize_in_two_powers_of_two(int num_procs, int *f1, int *f2);
+/* boxes[rank][axis][0/1] = inclusive 0-based min/max, sll split rule (:1860-1939) */
+int sllb_layout4d_boxes(const int global[4], const int procs[4], int nranks, int *boxes /* nranks*8 */);
+/* send/recv plan between two layouts for `rank`: for every peer the intersection box
+ * (global 0-based, inclusive) or an empty box (min>max). out: nranks*8 ints each. */
+int sllb_remap4d_plan(const int global[4], const int procs_from[4], const int procs_to[4], int nranks, int rank,
+                      int *send_boxes, int *recv_boxes);
+
+/* communicator: one process per GPU; id = 128-byte ncclUniqueId from rank 0 */
+typedef struct sllb_comm *sllb_comm_t;
+int sllb_comm_unique_id(void *id128);
+int sllb_comm_create(const void *id128, int nranks, int rank, sllb_comm_t *c);
+int sllb_comm_destroy(sllb_comm_t c);
+int sllb_comm_allreduce_sum(sllb_comm_t c, double *d_buf, int64_t count);
+int sllb_comm_allgather(sllb_comm_t c, const double *d_send, double *d_recv, int64_t count_per_rank);
+
+/* distributed 4D field: two layouts (x-sequential: axes 0,1 whole, axes 2,3 split;
+ * v-sequential: axes 2,3 whole, axes 0,1 split) and the remap between them
+ * (apply_remap_4D_double, sll_m_remapper.F90:3308-3456) = pack kernel + NCCL
+ * send/recv group (all-to-all) + unpack kernel. */
+typedef struct sllb_dist4d *sllb_dist4d_t;
+int sllb_dist4d_create(sllb_comm_t c, const int global[4], sllb_dist4d_t *D);
+int sllb_dist4d_destroy(sllb_dist4d_t D);
+/* local fields (owned by D); which = 0: x-sequential layout, 1: v-sequential layout */
+int sllb_dist4d_field(sllb_dist4d_t D, int which, sllb_field_t *F);
+int sllb_dist4d_box(sllb_dist4d_t D, int which, int box[8]);
+/* direction 0: x-seq -> v-seq, 1: v-seq -> x-seq */
+int sllb_dist4d_remap(sllb_dist4d_t D, int direction);
+
+/* ---- a12: 6D slim domain decomposition + halo exchange ----------------------
+ * sll_f_set_process_grid (src/parallelization/decomposition/sll_m_decomposition.F90:2473-2543) */
+int sllb_set_process_grid(int nranks, int grid[6]);
+
+/* ---- simulations (time loops of SURVEY.md section 3) --------------------- */
+/* 2D2V sim_bsl_vp_2d2v_cart_poisson_serial on 1..P GPUs.
+ * split: 0 Strang VTV, 1 Strang TVT, 2 Lie TV. method/order as SLLB_METHOD_*. */
+typedef struct sllb_sim4d *sllb_sim4d_t;
+typedef struct {
+    int nc[4];
+    double xmin[4], xmax[4];
+    double kx1, kx2, eps; /* sll_f_landau_mode_initializer_4d */
+    double dt;
+    int split;
+    int method, order;
+} sllb_sim4d_params_t;
+int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm /* NULL = single GPU */, sllb_sim4d_t *S);
+int sllb_sim4d_destroy(sllb_sim4d_t S);
+/* advance nsteps; rows (HOST, may be NULL): nsteps x 6 = time, nrj, ekin, int f, int|f|, int f^2
+ * (thdiag columns 1,2,3,8,9,10 of sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:1262-1275) */
+int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows);
+/* row for the current state (time 0 row before any step) */
+int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6);
+int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F); /* local x-sequential field */
+/* per-phase device time of the last run() in ms: [advect, reduce+poisson, remap, diag] */
+int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]);
+
+/* 1D1V sim_bsl_vp_1d1v_cart (single GPU). init 0 Landau, 1 two-stream. rows: nsteps x 8
+ * (time, mass, l1, momentum, l2, ekin, epot, etot; sll_m_sim_bsl_vp_1d1v_cart.F90:1783) */
+typedef struct sllb_sim2d *sllb_sim2d_t;
+int sllb_sim2d_create(int nc_x1, int nc_x2, double x1_min, double x1_max, double x2_min, double x2_max,
+                      int init, double kmode, double eps, double dt, int method, int order, sllb_sim2d_t *S);
+int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows);
+int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F);
+int sllb_sim2d_destroy(sllb_sim2d_t S);
+
+/* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (Lagrange fixed stencils), single GPU in this
+ * round (velocity-split multi-GPU = next). rows: (nsteps+1) x 14 as the reference's
+ * <prefix>.dat (sll_m_sim_6d_utilities.F90:357-364,632-633). */
+typedef struct sllb_sim6d *sllb_sim6d_t;
+typedef struct {
+    int n[6];
+    double v_max, x_max[3];
+    int stencil_x, stencil_v;
+    double delta_t;
+    double alpha, kx[3], v_thermal[3]; /* landau_prod */
+    int time_in_phase;
+} sllb_sim6d_params_t;
+int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *S);
+int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows);
+int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F);
+int sllb_sim6d_advect_x(sllb_sim6d_t S);
+int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt);
+int sllb_sim6d_destroy(sllb_sim6d_t S);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLL_B200_H */

@@ -46,10 +46,33 @@ int orc_num_threads(void) {
 /* Semantics of FFTPACK zfftf/zfftb (external/fftpack) and FFTW c2c: a DFT is  */
 /* unique, so any exact algorithm agrees to rounding.                          */
 /* ------------------------------------------------------------------------- */
+/* forward twiddles exp(-2 pi i k / n), k < n/2, cached per n (FFTPACK's wsave plays this role) */
+#define TW_SLOTS 8
+static struct { int n; cplx *w; } tw_cache[TW_SLOTS];
+static const cplx *twiddles(int n) {
+    for (int i = 0; i < TW_SLOTS; ++i) if (tw_cache[i].n == n) return tw_cache[i].w;
+    const cplx *res = NULL;
+#pragma omp critical(orc_tw)
+    {
+        int slot = -1;
+        for (int i = 0; i < TW_SLOTS; ++i) { if (tw_cache[i].n == n) { res = tw_cache[i].w; break; } if (tw_cache[i].n == 0 && slot < 0) slot = i; }
+        if (!res && slot >= 0) {
+            cplx *w = (cplx *)malloc(sizeof(cplx) * (n / 2 + 1));
+            for (int k = 0; k < n / 2; ++k) { double a = -ORC_TWOPI * k / n; w[k] = cos(a) + I * sin(a); }
+            tw_cache[slot].w = w;
+#pragma omp flush
+            tw_cache[slot].n = n;
+            res = w;
+        }
+    }
+    return res;
+}
+
 static void fft_inplace(cplx *x, int n, int sign) {
     if (n <= 1) return;
     if ((n & (n - 1)) == 0) {
         /* iterative radix-2 */
+        const cplx *tw = twiddles(n);
         for (int i = 1, j = 0; i < n; ++i) {
             int bit = n >> 1;
             for (; j & bit; bit >>= 1) j ^= bit;
@@ -57,14 +80,15 @@ static void fft_inplace(cplx *x, int n, int sign) {
             if (i < j) { cplx t = x[i]; x[i] = x[j]; x[j] = t; }
         }
         for (int len = 2; len <= n; len <<= 1) {
-            double ang = sign * ORC_TWOPI / len;
-            int half = len >> 1;
-            for (int k = 0; k < half; ++k) {
-                cplx w = cos(ang * k) + I * sin(ang * k);
-                for (int i = k; i < n; i += len) {
-                    cplx u = x[i], v = x[i + half] * w;
-                    x[i] = u + v;
-                    x[i + half] = u - v;
+            int half = len >> 1, step = n / len;
+            for (int i = 0; i < n; i += len) {
+                for (int k = 0; k < half; ++k) {
+                    cplx w;
+                    if (tw) { w = tw[k * step]; if (sign > 0) w = conj(w); }
+                    else { double ang = sign * ORC_TWOPI * k / len; w = cos(ang) + I * sin(ang); }
+                    cplx u = x[i + k], v = x[i + k + half] * w;
+                    x[i + k] = u + v;
+                    x[i + k + half] = u - v;
                 }
             }
         }
@@ -811,16 +835,19 @@ static void advect_line(int method, int order, int n, const double *in, double *
  * displacement of line (o, in) = disp[ (o / odiv) % omod * ostr + (in / idiv) % imod * istr ].
  * This covers: x-advection (disp depends on one velocity index) and v-advection
  * (disp depends on the (x1,x2[,x3]) position = low part of the inner index). */
-void orc_advect_axis(double *f, long outer, int n, long inner, int method, int order,
-                     const double *disp, long odiv, long omod, long ostr, long idiv, long imodn, long istr) {
+/* outer_count / inner_count restrict the pass to the first lines of each index range (a bounded sample of
+ * a pass with full-length lines, used by the timed CPU baseline); the full pass has counts = extents. */
+void orc_advect_axis_sub(double *f, long outer, int n, long inner, long outer_count, long inner_count, int method,
+                         int order, const double *disp, long odiv, long omod, long ostr, long idiv, long imodn,
+                         long istr) {
 #pragma omp parallel
     {
         double *lin = (double *)malloc(sizeof(double) * (4 * (size_t)n + 16));
         double *lout = lin + n;
         double *scratch = (double *)malloc(sizeof(double) * (4 * (size_t)n + 32));
 #pragma omp for schedule(static) collapse(2)
-        for (long o = 0; o < outer; ++o)
-            for (long in = 0; in < inner; ++in) {
+        for (long o = 0; o < outer_count; ++o)
+            for (long in = 0; in < inner_count; ++in) {
                 double *base = f + o * (long)n * inner + in;
                 double dc = disp[((o / odiv) % omod) * ostr + ((in / idiv) % imodn) * istr];
                 for (int i = 0; i < n; ++i) lin[i] = base[(long)i * inner];
@@ -829,6 +856,10 @@ void orc_advect_axis(double *f, long outer, int n, long inner, int method, int o
             }
         free(lin); free(scratch);
     }
+}
+void orc_advect_axis(double *f, long outer, int n, long inner, int method, int order,
+                     const double *disp, long odiv, long omod, long ostr, long idiv, long imodn, long istr) {
+    orc_advect_axis_sub(f, outer, n, inner, outer, inner, method, order, disp, odiv, omod, ostr, idiv, imodn, istr);
 }
 
 /* ------------------------------------------------------------------------- */

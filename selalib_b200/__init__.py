@@ -1,0 +1,16 @@
+"""selalib_b200 -- B200-native split semi-Lagrangian advection path of SeLaLib.
+
+The product is the C-ABI shared library ``selalib_b200/lib/libsllb200.so`` (CUDA, sm_100a;
+headers in ``include/``).  This package is a thin ctypes binding used by the tests and by
+bench.py; it never computes anything itself and there is no CPU fallback: importing
+:mod:`selalib_b200.capi` raises if the library has not been built.
+"""
+from .capi import (  # noqa: F401
+    SllbError, lib, last_error, init, device_count, synchronize, launch_count, launch_count_reset, set_staging,
+    Advector1dPeriodic, Interpolator1d, Field, Poisson, Comm, Dist4d, Sim4d, Sim2d, Sim6d,
+    factorize_in_two_powers_of_two, layout4d_boxes, remap4d_plan, set_process_grid,
+    METHOD_SPLINE, METHOD_LAGRANGE_FIXED, METHOD_LAGRANGE_CENTERED,
+    ADV_PERIODIC_SPLINE, ADV_PERIODIC_LAGRANGE,
+    INTERP_CUBIC_SPLINE, INTERP_LAGRANGE_CENTERED, INTERP_LAGRANGE_FIXED, INTERP_PERIODIC_SPLINE,
+    INTERP_PERIODIC_LAGRANGE,
+)

@@ -1,0 +1,431 @@
+"""ctypes binding of include/sll_b200.h (test / bench harness side of the C ABI)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "lib", "libsllb200.so")
+
+METHOD_SPLINE, METHOD_LAGRANGE_FIXED, METHOD_LAGRANGE_CENTERED = 0, 1, 2
+ADV_PERIODIC_SPLINE, ADV_PERIODIC_LAGRANGE = 0, 1
+(INTERP_CUBIC_SPLINE, INTERP_LAGRANGE_CENTERED, INTERP_LAGRANGE_FIXED, INTERP_PERIODIC_SPLINE,
+ INTERP_PERIODIC_LAGRANGE) = range(5)
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 1, 2, 3, 4
+
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int)
+vp = C.c_void_p
+
+
+class SllbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sllb error {code}: {msg}")
+        self.code = code
+
+
+class DispT(C.Structure):
+    _fields_ = [("values", dp), ("nvalues", C.c_int64), ("values_on_device", C.c_int), ("scale", C.c_double),
+                ("odiv", C.c_int64), ("omod", C.c_int64), ("ostr", C.c_int64),
+                ("idiv", C.c_int64), ("imod", C.c_int64), ("istr", C.c_int64)]
+
+
+class Sim4dParams(C.Structure):
+    _fields_ = [("nc", C.c_int * 4), ("xmin", C.c_double * 4), ("xmax", C.c_double * 4),
+                ("kx1", C.c_double), ("kx2", C.c_double), ("eps", C.c_double), ("dt", C.c_double),
+                ("split", C.c_int), ("method", C.c_int), ("order", C.c_int)]
+
+
+class Sim6dParams(C.Structure):
+    _fields_ = [("n", C.c_int * 6), ("v_max", C.c_double), ("x_max", C.c_double * 3),
+                ("stencil_x", C.c_int), ("stencil_v", C.c_int), ("delta_t", C.c_double),
+                ("alpha", C.c_double), ("kx", C.c_double * 3), ("v_thermal", C.c_double * 3),
+                ("time_in_phase", C.c_int)]
+
+
+_LIB = None
+
+
+def lib():
+    """Load the CUDA library; fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(selalib_b200 has no CPU fallback)")
+        _LIB = C.CDLL(_SO, mode=C.RTLD_GLOBAL)
+        _LIB.sllb_last_error.restype = C.c_char_p
+        _LIB.sllb_launch_count.restype = C.c_int64
+    return _LIB
+
+
+def last_error():
+    return lib().sllb_last_error().decode()
+
+
+def _ck(rc):
+    if rc != 0:
+        raise SllbError(rc, last_error())
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def _ints(v):
+    return (C.c_int * len(v))(*[int(x) for x in v])
+
+
+def init(device=0):
+    _ck(lib().sllb_init(C.c_int(device)))
+
+
+def device_count():
+    n = C.c_int(0)
+    _ck(lib().sllb_device_count(C.byref(n)))
+    return n.value
+
+
+def synchronize():
+    _ck(lib().sllb_synchronize())
+
+
+def launch_count():
+    return int(lib().sllb_launch_count())
+
+
+def launch_count_reset():
+    lib().sllb_launch_count_reset()
+
+
+def set_staging(mode):
+    _ck(lib().sllb_set_staging(C.c_int(mode)))
+
+
+# ---------------------------------------------------------------------------------------------
+# line-granular drop-in objects (mirror sll_t_advector_1d_periodic / sll_c_interpolator_1d)
+# ---------------------------------------------------------------------------------------------
+class Advector1dPeriodic:
+    """sll_t_advector_1d_periodic (sll_m_advection_1d_periodic.F90:41-130)."""
+
+    def __init__(self, num_cells, xmin, xmax, kind=ADV_PERIODIC_SPLINE, order=4):
+        self.h = vp()
+        _ck(lib().sllb_adv1d_create(C.c_int(kind), C.c_int(num_cells), C.c_double(xmin), C.c_double(xmax),
+                                    C.c_int(order), C.byref(self.h)))
+
+    def advect_1d_constant(self, A, dt, inp, out=None):
+        inp = np.ascontiguousarray(inp, dtype=np.float64)
+        if out is None:
+            out = np.empty_like(inp)
+        _ck(lib().sllb_adv1d_advect_constant(self.h, C.c_double(A), C.c_double(dt), _p(inp), _p(out), C.c_int(inp.size)))
+        return out
+
+    def delete(self):
+        if self.h:
+            lib().sllb_adv1d_delete(self.h)
+            self.h = vp()
+
+    __del__ = delete
+
+
+class Interpolator1d:
+    """sll_c_interpolator_1d implementations (interpolate_array_disp[_inplace])."""
+
+    def __init__(self, kind, num_points, xmin, xmax, d_or_order=4, periodic_last=1, fast_algorithm=1, bc=0):
+        self.h = vp()
+        _ck(lib().sllb_interp1d_create(C.c_int(kind), C.c_int(num_points), C.c_double(xmin), C.c_double(xmax),
+                                       C.c_int(bc), C.c_int(d_or_order), C.c_int(periodic_last),
+                                       C.c_int(fast_algorithm), C.byref(self.h)))
+
+    def interpolate_array_disp(self, num_pts, data, alpha):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        out = np.empty(num_pts)
+        _ck(lib().sllb_interp1d_array_disp(self.h, C.c_int(num_pts), _p(data), C.c_double(alpha), _p(out)))
+        return out
+
+    def interpolate_array_disp_inplace(self, num_pts, data, alpha):
+        assert data.dtype == np.float64 and data.flags.c_contiguous
+        _ck(lib().sllb_interp1d_array_disp_inplace(self.h, C.c_int(num_pts), _p(data), C.c_double(alpha)))
+        return data
+
+    def delete(self):
+        if self.h:
+            lib().sllb_interp1d_delete(self.h)
+            self.h = vp()
+
+    __del__ = delete
+
+
+# ---------------------------------------------------------------------------------------------
+# batched device-resident API
+# ---------------------------------------------------------------------------------------------
+class Field:
+    def __init__(self, extents=None, handle=None):
+        self.owns = handle is None
+        if handle is None:
+            self.h = vp()
+            _ck(lib().sllb_field_create(C.c_int(len(extents)), _ints(extents), C.byref(self.h)))
+        else:
+            self.h = handle
+        nd = C.c_int(0)
+        ext = (C.c_int * 6)()
+        _ck(lib().sllb_field_extents(self.h, C.byref(nd), ext))
+        self.extents = tuple(ext[i] for i in range(nd.value))
+
+    def upload(self, host, dup_last=None):
+        host = np.asfortranarray(host, dtype=np.float64)
+        dup = _ints(dup_last) if dup_last is not None else None
+        exp = tuple(e + (dup_last[i] if dup_last is not None else 0) for i, e in enumerate(self.extents))
+        assert host.shape == exp, (host.shape, exp)
+        _ck(lib().sllb_field_upload(self.h, _p(host), dup))
+        return self
+
+    def download(self, dup_last=None):
+        exp = tuple(e + (dup_last[i] if dup_last is not None else 0) for i, e in enumerate(self.extents))
+        out = np.empty(exp, order="F")
+        _ck(lib().sllb_field_download(self.h, _p(out), _ints(dup_last) if dup_last is not None else None))
+        return out
+
+    def device_ptr(self):
+        p = dp()
+        _ck(lib().sllb_field_device_ptr(self.h, C.byref(p)))
+        return C.cast(p, vp).value
+
+    def advect_axis(self, axis, method, order, values, scale=1.0, dsel=(1, 1, 0, 1, 1, 0), on_device=False):
+        d = DispT()
+        if on_device:
+            d.values = C.cast(vp(values), dp); d.nvalues = 0; d.values_on_device = 1
+        else:
+            values = np.ascontiguousarray(values, dtype=np.float64)
+            self._keep = values
+            d.values = _p(values); d.nvalues = values.size; d.values_on_device = 0
+        d.scale = scale
+        d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
+        _ck(lib().sllb_advect_axis(self.h, C.c_int(axis), C.c_int(method), C.c_int(order), C.byref(d)))
+
+    def advect_axis_affine(self, axis, method, order, v_axis, vmin, dv, scale):
+        _ck(lib().sllb_advect_axis_affine(self.h, C.c_int(axis), C.c_int(method), C.c_int(order), C.c_int(v_axis),
+                                          C.c_double(vmin), C.c_double(dv), C.c_double(scale)))
+
+    def advect_axis_field(self, axis, method, order, d_field_ptr, nfield_axes, scale):
+        _ck(lib().sllb_advect_axis_field(self.h, C.c_int(axis), C.c_int(method), C.c_int(order),
+                                         C.cast(vp(d_field_ptr), dp), C.c_int(nfield_axes), C.c_double(scale)))
+
+    def reduce_velocity(self, nx_axes, scale):
+        out = np.empty(self.extents[:nx_axes], order="F")
+        _ck(lib().sllb_reduce_velocity_host(self.h, C.c_int(nx_axes), C.c_double(scale), _p(out)))
+        return out
+
+    def moments(self, nv, w1, w2):
+        out = np.zeros(3 + 2 * nv)
+        w1 = np.ascontiguousarray(w1, dtype=np.float64); w2 = np.ascontiguousarray(w2, dtype=np.float64)
+        _ck(lib().sllb_moments(self.h, C.c_int(nv), _p(w1), _p(w2), _p(out)))
+        return out
+
+    def destroy(self):
+        if self.owns and self.h:
+            lib().sllb_field_destroy(self.h)
+            self.h = vp()
+
+    __del__ = destroy
+
+
+class Poisson:
+    def __init__(self, n, xmin, xmax):
+        self.h = vp()
+        self.n = tuple(int(v) for v in n)
+        if len(n) == 1:
+            _ck(lib().sllb_poisson1d_create(C.c_int(n[0]), C.c_double(xmin[0]), C.c_double(xmax[0]), C.byref(self.h)))
+        elif len(n) == 2:
+            _ck(lib().sllb_poisson2d_create(C.c_int(n[0]), C.c_int(n[1]), C.c_double(xmin[0]), C.c_double(xmax[0]),
+                                            C.c_double(xmin[1]), C.c_double(xmax[1]), C.byref(self.h)))
+        else:
+            _ck(lib().sllb_poisson3d_create(C.c_int(n[0]), C.c_int(n[1]), C.c_int(n[2]), C.c_double(xmax[0] - xmin[0]),
+                                            C.c_double(xmax[1] - xmin[1]), C.c_double(xmax[2] - xmin[2]), C.byref(self.h)))
+
+    def solve(self, rho, want_phi=True):
+        """rho: Fortran-ordered host array with nc or nc+1 points per axis. Returns (phi, e1[, e2[, e3]])."""
+        rho = np.asfortranarray(rho, dtype=np.float64)
+        dim = len(self.n)
+        ld = _ints(rho.shape)
+        outs = [np.zeros_like(rho, order="F") for _ in range(4)]
+        ptrs = [_p(o) for o in outs]
+        if not want_phi or dim == 1:
+            ptrs[0] = None
+        for k in range(dim + 1, 4):
+            ptrs[k] = None
+        _ck(lib().sllb_poisson_solve_host(self.h, _p(rho), ld, *ptrs))
+        return tuple(outs[: dim + 1])
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_poisson_destroy(self.h)
+            self.h = vp()
+
+    __del__ = destroy
+
+
+# ---------------------------------------------------------------------------------------------
+# layouts / remap plans (host logic, no device needed)
+# ---------------------------------------------------------------------------------------------
+def factorize_in_two_powers_of_two(n):
+    a, b = C.c_int(0), C.c_int(0)
+    _ck(lib().sllb_factorize_in_two_powers_of_two(C.c_int(n), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def layout4d_boxes(global_ext, procs, nranks):
+    out = (C.c_int * (8 * nranks))()
+    _ck(lib().sllb_layout4d_boxes(_ints(global_ext), _ints(procs), C.c_int(nranks), out))
+    return np.array(out[:]).reshape(nranks, 4, 2)
+
+
+def remap4d_plan(global_ext, procs_from, procs_to, nranks, rank):
+    s = (C.c_int * (8 * nranks))(); r = (C.c_int * (8 * nranks))()
+    _ck(lib().sllb_remap4d_plan(_ints(global_ext), _ints(procs_from), _ints(procs_to), C.c_int(nranks), C.c_int(rank), s, r))
+    return np.array(s[:]).reshape(nranks, 4, 2), np.array(r[:]).reshape(nranks, 4, 2)
+
+
+def set_process_grid(nranks):
+    g = (C.c_int * 6)()
+    _ck(lib().sllb_set_process_grid(C.c_int(nranks), g))
+    return tuple(g[:])
+
+
+class Comm:
+    """NCCL communicator, one process per GPU.  The 128-byte id travels over torch.distributed."""
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        _ck(lib().sllb_comm_unique_id(buf))
+        return bytes(buf)
+
+    def __init__(self, id_bytes, nranks, rank):
+        self.h = vp()
+        self.nranks, self.rank = nranks, rank
+        buf = (C.c_ubyte * 128)(*id_bytes)
+        _ck(lib().sllb_comm_create(buf, C.c_int(nranks), C.c_int(rank), C.byref(self.h)))
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_comm_destroy(self.h)
+            self.h = vp()
+
+
+class Dist4d:
+    def __init__(self, comm, global_ext):
+        self.h = vp()
+        _ck(lib().sllb_dist4d_create(comm.h if comm is not None else None, _ints(global_ext), C.byref(self.h)))
+
+    def field(self, which):
+        f = vp()
+        _ck(lib().sllb_dist4d_field(self.h, C.c_int(which), C.byref(f)))
+        return Field(handle=f)
+
+    def box(self, which):
+        b = (C.c_int * 8)()
+        _ck(lib().sllb_dist4d_box(self.h, C.c_int(which), b))
+        return np.array(b[:]).reshape(4, 2)
+
+    def remap(self, direction):
+        _ck(lib().sllb_dist4d_remap(self.h, C.c_int(direction)))
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_dist4d_destroy(self.h)
+            self.h = vp()
+
+
+# ---------------------------------------------------------------------------------------------
+# simulations
+# ---------------------------------------------------------------------------------------------
+class Sim4d:
+    def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None):
+        p = Sim4dParams()
+        p.nc[:] = nc; p.xmin[:] = xmin; p.xmax[:] = xmax
+        p.kx1, p.kx2, p.eps, p.dt = kx1, kx2, eps, dt
+        p.split, p.method, p.order = split, method, order
+        self.h = vp()
+        _ck(lib().sllb_sim4d_create(C.byref(p), comm.h if comm is not None else None, C.byref(self.h)))
+
+    def run(self, nsteps, diagnostics=True):
+        rows = np.zeros((nsteps, 6))
+        _ck(lib().sllb_sim4d_run(self.h, C.c_int(nsteps), C.c_int(1 if diagnostics else 0), _p(rows) if diagnostics else None))
+        return rows
+
+    def diagnostics(self):
+        row = np.zeros(6)
+        _ck(lib().sllb_sim4d_diagnostics(self.h, _p(row)))
+        return row
+
+    def field(self):
+        f = vp()
+        _ck(lib().sllb_sim4d_field(self.h, C.byref(f)))
+        return Field(handle=f)
+
+    def phase_ms(self):
+        out = np.zeros(4)
+        _ck(lib().sllb_sim4d_phase_ms(self.h, _p(out)))
+        return out
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_sim4d_destroy(self.h)
+            self.h = vp()
+
+
+class Sim2d:
+    def __init__(self, nc_x1, nc_x2, x1_min, x1_max, x2_min, x2_max, init, kmode, eps, dt, method=METHOD_SPLINE, order=4):
+        self.h = vp()
+        _ck(lib().sllb_sim2d_create(C.c_int(nc_x1), C.c_int(nc_x2), C.c_double(x1_min), C.c_double(x1_max),
+                                    C.c_double(x2_min), C.c_double(x2_max), C.c_int(init), C.c_double(kmode),
+                                    C.c_double(eps), C.c_double(dt), C.c_int(method), C.c_int(order), C.byref(self.h)))
+
+    def run(self, nsteps):
+        rows = np.zeros((nsteps, 8))
+        _ck(lib().sllb_sim2d_run(self.h, C.c_int(nsteps), _p(rows)))
+        return rows
+
+    def field(self):
+        f = vp()
+        _ck(lib().sllb_sim2d_field(self.h, C.byref(f)))
+        return Field(handle=f)
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_sim2d_destroy(self.h)
+            self.h = vp()
+
+
+class Sim6d:
+    def __init__(self, n, v_max, x_max, stencil_x, stencil_v, delta_t, alpha, kx, v_thermal=(1.0, 1.0, 1.0),
+                 time_in_phase=True):
+        p = Sim6dParams()
+        p.n[:] = n; p.v_max = v_max; p.x_max[:] = x_max
+        p.stencil_x, p.stencil_v, p.delta_t = stencil_x, stencil_v, delta_t
+        p.alpha = alpha; p.kx[:] = kx; p.v_thermal[:] = v_thermal
+        p.time_in_phase = 1 if time_in_phase else 0
+        self.h = vp()
+        _ck(lib().sllb_sim6d_create(C.byref(p), C.byref(self.h)))
+
+    def run(self, nsteps, first=True):
+        rows = np.zeros((nsteps + (1 if first else 0), 14))
+        _ck(lib().sllb_sim6d_run(self.h, C.c_int(nsteps), _p(rows)))
+        return rows
+
+    def field(self):
+        f = vp()
+        _ck(lib().sllb_sim6d_field(self.h, C.byref(f)))
+        return Field(handle=f)
+
+    def advect_x(self):
+        _ck(lib().sllb_sim6d_advect_x(self.h))
+
+    def advect_v(self, dt):
+        _ck(lib().sllb_sim6d_advect_v(self.h, C.c_double(dt)))
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_sim6d_destroy(self.h)
+            self.h = vp()

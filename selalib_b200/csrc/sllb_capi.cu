@@ -1,0 +1,558 @@
+// sllb_capi.cu -- C ABI (include/sll_b200.h): handles, device-resident fields, batched axis
+// advection, velocity reduction, moments and the cuFFT Poisson solvers.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sllb_internal.h"
+
+namespace sllb {
+
+static thread_local std::string t_error;
+int g_staging = STAGING_AUTO;
+static int g_device = 0;
+static bool g_device_ok = false;
+
+void set_error(const std::string &msg) { t_error = msg; }
+int fail(int code, const std::string &msg) {
+    t_error = msg;
+    return code;
+}
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return SLLB_OK;
+    if (e == cudaErrorInvalidValue && what && strstr(what, "launch_advect"))
+        return fail(SLLB_ERR_UNSUPPORTED, std::string("advection method / stencil / size not implemented: ") + what);
+    return fail(SLLB_ERR_CUDA, std::string(what ? what : "cuda") + ": " + cudaGetErrorString(e));
+}
+int check_cufft(cufftResult r, const char *what) {
+    if (r == CUFFT_SUCCESS) return SLLB_OK;
+    return fail(SLLB_ERR_CUDA, std::string(what ? what : "cufft") + ": cufft error " + std::to_string((int)r));
+}
+int require_device() {
+    if (g_device_ok) return SLLB_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(SLLB_ERR_NO_DEVICE, "no usable CUDA device (there is no CPU fallback)");
+    }
+    if (g_device >= n) return fail(SLLB_ERR_NO_DEVICE, "requested device index out of range");
+    e = cudaSetDevice(g_device);
+    if (e != cudaSuccess) return fail(SLLB_ERR_NO_DEVICE, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    g_device_ok = true;
+    return SLLB_OK;
+}
+
+int DevBuf::ensure(size_t count) {
+    if (count <= n && p) return SLLB_OK;
+    release();
+    SLLB_CUDA(cudaMalloc(&p, count * sizeof(double)));
+    n = count;
+    return SLLB_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+}
+
+// generic <=6D copy with periodic wrap of the source index: dst[i] = src[i mod ext_src]
+__global__ void __launch_bounds__(256) k_copy_wrap(const double *__restrict__ src, Ext6 es, double *__restrict__ dst,
+                                                   Ext6 ed, long long ntot) {
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < ntot; t += (long long)gridDim.x * 256) {
+        long long r = t, sidx = 0, sstride = 1;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) {
+            int i = (int)(r % ed.e[d]);
+            r /= ed.e[d];
+            if (i >= es.e[d]) i -= es.e[d];
+            sidx += (long long)i * sstride;
+            sstride *= es.e[d];
+        }
+        dst[t] = src[sidx];
+    }
+}
+
+int field_alloc(int ndim, const int *ext, sllb_field **F) {
+    if (ndim < 1 || ndim > 6 || !ext || !F) return fail(SLLB_ERR_INVALID, "field_create: bad arguments");
+    SLLB_TRY(require_device());
+    sllb_field *f = new sllb_field();
+    f->ndim = ndim;
+    f->total = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (ext[d] < 1) { delete f; return fail(SLLB_ERR_INVALID, "field_create: extent < 1"); }
+        f->ext[d] = ext[d];
+        f->total *= ext[d];
+    }
+    cudaError_t e = cudaMalloc(&f->d, (size_t)f->total * sizeof(double));
+    if (e != cudaSuccess) { delete f; return check_cuda(e, "cudaMalloc(field)"); }
+    *F = f;
+    return SLLB_OK;
+}
+int field_wrap(int ndim, const int *ext, double *d, sllb_field **F) {
+    sllb_field *f = new sllb_field();
+    f->ndim = ndim;
+    f->total = 1;
+    for (int k = 0; k < ndim; ++k) { f->ext[k] = ext[k]; f->total *= ext[k]; }
+    f->d = d;
+    f->owns = false;
+    *F = f;
+    return SLLB_OK;
+}
+
+int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd) {
+    if (!F || axis < 0 || axis >= F->ndim) return fail(SLLB_ERR_INVALID, "advect_axis: bad field/axis");
+    long long inner = 1, outer = 1;
+    for (int d = 0; d < axis; ++d) inner *= F->ext[d];
+    for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
+    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, 0);
+    if (e == cudaErrorInvalidValue) {
+        cudaGetLastError();
+        return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: method/order/line length not implemented (spline: order 4; "
+                                          "Lagrange fixed: 3,5,7,9,11; centred: 4,6,8; 8 <= n, line must fit shared memory)");
+    }
+    return check_cuda(e, "advect kernel launch");
+}
+
+int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out) {
+    if (!F || nv < 0 || nv >= F->ndim || !out) return fail(SLLB_ERR_INVALID, "moments: bad arguments");
+    long long nx = 1, nvt = 1;
+    for (int d = 0; d < F->ndim - nv; ++d) nx *= F->ext[d];
+    for (int d = F->ndim - nv; d < F->ndim; ++d) nvt *= F->ext[d];
+    SLLB_TRY(F->rows.ensure((size_t)nvt * 3));
+    SLLB_CUDA(launch_row_sums(F->d, nx, nvt, F->rows.p, 0));
+    std::vector<double> h((size_t)nvt * 3);
+    SLLB_CUDA(cudaMemcpy(h.data(), F->rows.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3 + 2 * nv; ++k) out[k] = 0.0;
+    int idx[6] = {0, 0, 0, 0, 0, 0};
+    const int *ve = F->ext + (F->ndim - nv);
+    std::vector<long long> woff(nv + 1, 0);
+    for (int a = 0; a < nv; ++a) woff[a + 1] = woff[a] + ve[a];
+    for (long long v = 0; v < nvt; ++v) {
+        const double s0 = h[3 * v], s1 = h[3 * v + 1], s2 = h[3 * v + 2];
+        out[0] += s0; out[1] += s1; out[2] += s2;
+        for (int a = 0; a < nv; ++a) {
+            if (w1) out[3 + a] += s0 * w1[woff[a] + idx[a]];
+            if (w2) out[3 + nv + a] += s0 * w2[woff[a] + idx[a]];
+        }
+        for (int a = 0; a < nv; ++a) { // increment mixed-radix index, first velocity axis fastest
+            if (++idx[a] < ve[a]) break;
+            idx[a] = 0;
+        }
+    }
+    return SLLB_OK;
+}
+
+} // namespace sllb
+
+using namespace sllb;
+
+extern "C" {
+
+const char *sllb_last_error(void) { return t_error.c_str(); }
+int sllb_version(void) { return 100; }
+int sllb_init(int device) {
+    g_device = device;
+    g_device_ok = false;
+    return require_device();
+}
+int sllb_device_count(int *count) {
+    if (!count) return fail(SLLB_ERR_INVALID, "device_count: null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return SLLB_OK;
+}
+int sllb_synchronize(void) {
+    SLLB_TRY(require_device());
+    SLLB_CUDA(cudaDeviceSynchronize());
+    return SLLB_OK;
+}
+int64_t sllb_launch_count(void) { return launch_count(); }
+void sllb_launch_count_reset(void) { launch_count_reset(); }
+int sllb_set_staging(int mode) {
+    if (mode < 0 || mode > 2) return fail(SLLB_ERR_INVALID, "set_staging: mode must be 0,1,2");
+    g_staging = mode;
+    return SLLB_OK;
+}
+
+/* ---------------- fields ---------------- */
+int sllb_field_create(int ndim, const int *extents, sllb_field_t *F) { return field_alloc(ndim, extents, F); }
+int sllb_field_destroy(sllb_field_t F) {
+    if (!F) return SLLB_OK;
+    if (F->owns && F->d) cudaFree(F->d);
+    delete F;
+    return SLLB_OK;
+}
+int sllb_field_device_ptr(sllb_field_t F, double **dptr) {
+    if (!F || !dptr) return fail(SLLB_ERR_INVALID, "field_device_ptr: null");
+    *dptr = F->d;
+    return SLLB_OK;
+}
+int sllb_field_extents(sllb_field_t F, int *ndim, int *extents) {
+    if (!F) return fail(SLLB_ERR_INVALID, "field_extents: null");
+    if (ndim) *ndim = F->ndim;
+    if (extents) for (int d = 0; d < F->ndim; ++d) extents[d] = F->ext[d];
+    return SLLB_OK;
+}
+static bool any_dup(const sllb_field *F, const int *dup) {
+    if (!dup) return false;
+    for (int d = 0; d < F->ndim; ++d) if (dup[d]) return true;
+    return false;
+}
+int sllb_field_upload(sllb_field_t F, const double *host, const int *dup_last) {
+    if (!F || !host) return fail(SLLB_ERR_INVALID, "field_upload: null");
+    SLLB_TRY(require_device());
+    if (!any_dup(F, dup_last)) {
+        SLLB_CUDA(cudaMemcpy(F->d, host, (size_t)F->total * sizeof(double), cudaMemcpyHostToDevice));
+        return SLLB_OK;
+    }
+    Ext6 es, ed;
+    long long ntot_src = 1;
+    for (int d = 0; d < 6; ++d) {
+        ed.e[d] = F->ext[d];
+        es.e[d] = F->ext[d] + ((d < F->ndim && dup_last[d]) ? 1 : 0);
+        ntot_src *= es.e[d];
+    }
+    SLLB_TRY(F->stage.ensure((size_t)ntot_src));
+    SLLB_CUDA(cudaMemcpy(F->stage.p, host, (size_t)ntot_src * sizeof(double), cudaMemcpyHostToDevice));
+    k_copy_wrap<<<148 * 8, 256>>>(F->stage.p, es, F->d, ed, F->total);
+    SLLB_CUDA(cudaGetLastError());
+    SLLB_CUDA(cudaDeviceSynchronize());
+    F->stage.release();
+    return SLLB_OK;
+}
+int sllb_field_download(sllb_field_t F, double *host, const int *dup_last) {
+    if (!F || !host) return fail(SLLB_ERR_INVALID, "field_download: null");
+    SLLB_TRY(require_device());
+    if (!any_dup(F, dup_last)) {
+        SLLB_CUDA(cudaMemcpy(host, F->d, (size_t)F->total * sizeof(double), cudaMemcpyDeviceToHost));
+        return SLLB_OK;
+    }
+    Ext6 es, ed;
+    long long ntot_dst = 1;
+    for (int d = 0; d < 6; ++d) {
+        es.e[d] = F->ext[d];
+        ed.e[d] = F->ext[d] + ((d < F->ndim && dup_last[d]) ? 1 : 0);
+        ntot_dst *= ed.e[d];
+    }
+    SLLB_TRY(F->stage.ensure((size_t)ntot_dst));
+    k_copy_wrap<<<148 * 8, 256>>>(F->d, es, F->stage.p, ed, ntot_dst);
+    SLLB_CUDA(cudaGetLastError());
+    SLLB_CUDA(cudaMemcpy(host, F->stage.p, (size_t)ntot_dst * sizeof(double), cudaMemcpyDeviceToHost));
+    F->stage.release();
+    return SLLB_OK;
+}
+
+/* ---------------- batched advection ---------------- */
+int sllb_advect_axis(sllb_field_t F, int axis, int method, int order, const sllb_disp_t *disp) {
+    if (!F || !disp || !disp->values) return fail(SLLB_ERR_INVALID, "advect_axis: null argument");
+    SLLB_TRY(require_device());
+    DispDesc dd;
+    if (disp->values_on_device) dd.v = disp->values;
+    else {
+        if (disp->nvalues < 1) return fail(SLLB_ERR_INVALID, "advect_axis: nvalues < 1");
+        SLLB_TRY(F->disp_scratch.ensure((size_t)disp->nvalues));
+        SLLB_CUDA(cudaMemcpyAsync(F->disp_scratch.p, disp->values, (size_t)disp->nvalues * sizeof(double),
+                                  cudaMemcpyHostToDevice, 0));
+        dd.v = F->disp_scratch.p;
+    }
+    dd.scale = disp->scale;
+    dd.odiv = disp->odiv > 0 ? disp->odiv : 1; dd.omod = disp->omod > 0 ? disp->omod : 1; dd.ostr = disp->ostr;
+    dd.idiv = disp->idiv > 0 ? disp->idiv : 1; dd.imod = disp->imod > 0 ? disp->imod : 1; dd.istr = disp->istr;
+    return advect_axis_dev(F, axis, method, order, dd);
+}
+int sllb_advect_axis_affine(sllb_field_t F, int axis, int method, int order, int v_axis, double vmin, double dv,
+                            double scale) {
+    if (!F || v_axis < 0 || v_axis >= F->ndim || v_axis == axis)
+        return fail(SLLB_ERR_INVALID, "advect_axis_affine: bad v_axis");
+    SLLB_TRY(require_device());
+    const int nvv = F->ext[v_axis];
+    SLLB_TRY(F->disp_scratch.ensure((size_t)nvv));
+    SLLB_CUDA(launch_affine(F->disp_scratch.p, nvv, vmin, dv, 0));
+    DispDesc dd;
+    dd.v = F->disp_scratch.p; dd.scale = scale;
+    dd.odiv = dd.omod = dd.idiv = dd.imod = 1; dd.ostr = dd.istr = 0;
+    long long stride = 1;
+    if (v_axis > axis) {
+        for (int d = axis + 1; d < v_axis; ++d) stride *= F->ext[d];
+        dd.odiv = stride; dd.omod = nvv; dd.ostr = 1;
+    } else {
+        for (int d = 0; d < v_axis; ++d) stride *= F->ext[d];
+        dd.idiv = stride; dd.imod = nvv; dd.istr = 1;
+    }
+    return advect_axis_dev(F, axis, method, order, dd);
+}
+int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, const double *d_field, int nfield_axes,
+                           double scale) {
+    if (!F || !d_field || nfield_axes < 1 || nfield_axes > axis)
+        return fail(SLLB_ERR_INVALID, "advect_axis_field: field axes must be faster than the advected axis");
+    SLLB_TRY(require_device());
+    long long nf = 1;
+    for (int d = 0; d < nfield_axes; ++d) nf *= F->ext[d];
+    DispDesc dd;
+    dd.v = d_field; dd.scale = scale;
+    dd.odiv = dd.omod = 1; dd.ostr = 0;
+    dd.idiv = 1; dd.imod = nf; dd.istr = 1;
+    return advect_axis_dev(F, axis, method, order, dd);
+}
+
+/* ---------------- reductions ---------------- */
+int sllb_reduce_velocity(sllb_field_t F, int nx_axes, double scale, double *d_rho) {
+    if (!F || !d_rho || nx_axes < 1 || nx_axes >= F->ndim) return fail(SLLB_ERR_INVALID, "reduce_velocity: bad arguments");
+    SLLB_TRY(require_device());
+    long long nx = 1, nv = 1;
+    for (int d = 0; d < nx_axes; ++d) nx *= F->ext[d];
+    for (int d = nx_axes; d < F->ndim; ++d) nv *= F->ext[d];
+    SLLB_TRY(F->red_scratch.ensure(reduce_scratch_doubles(nx, nv)));
+    SLLB_CUDA(launch_reduce_velocity(F->d, nx, nv, scale, d_rho, F->red_scratch.p, 0));
+    return SLLB_OK;
+}
+int sllb_reduce_velocity_host(sllb_field_t F, int nx_axes, double scale, double *h_rho) {
+    if (!F || !h_rho || nx_axes < 1 || nx_axes >= F->ndim) return fail(SLLB_ERR_INVALID, "reduce_velocity: bad arguments");
+    long long nx = 1;
+    for (int d = 0; d < nx_axes; ++d) nx *= F->ext[d];
+    DevBuf tmp;
+    SLLB_TRY(require_device());
+    SLLB_TRY(tmp.ensure((size_t)nx));
+    SLLB_TRY(sllb_reduce_velocity(F, nx_axes, scale, tmp.p));
+    SLLB_CUDA(cudaMemcpy(h_rho, tmp.p, (size_t)nx * sizeof(double), cudaMemcpyDeviceToHost));
+    return SLLB_OK;
+}
+int sllb_moments(sllb_field_t F, int nv, const double *w1, const double *w2, double *out) {
+    SLLB_TRY(require_device());
+    return moments_local(F, nv, w1, w2, out);
+}
+
+/* ---------------- Poisson ---------------- */
+static int poisson_common(sllb_poisson *p) {
+    p->nreal = (long long)p->n[0] * p->n[1] * p->n[2];
+    p->ncplx = (long long)(p->n[0] / 2 + 1) * p->n[1] * p->n[2];
+    SLLB_CUDA(cudaMalloc(&p->rho_hat, (size_t)p->ncplx * sizeof(cufftDoubleComplex)));
+    for (int k = 0; k < 4; ++k) SLLB_CUDA(cudaMalloc(&p->spec[k], (size_t)p->ncplx * sizeof(cufftDoubleComplex)));
+    if (p->dim == 1) {
+        SLLB_CUFFT(cufftPlan1d(&p->fwd, p->n[0], CUFFT_D2Z, 1));
+        SLLB_CUFFT(cufftPlan1d(&p->bwd, p->n[0], CUFFT_Z2D, 1));
+    } else if (p->dim == 2) {
+        SLLB_CUFFT(cufftPlan2d(&p->fwd, p->n[1], p->n[0], CUFFT_D2Z));
+        SLLB_CUFFT(cufftPlan2d(&p->bwd, p->n[1], p->n[0], CUFFT_Z2D));
+    } else {
+        SLLB_CUFFT(cufftPlan3d(&p->fwd, p->n[2], p->n[1], p->n[0], CUFFT_D2Z));
+        SLLB_CUFFT(cufftPlan3d(&p->bwd, p->n[2], p->n[1], p->n[0], CUFFT_Z2D));
+    }
+    p->plans = true;
+    SLLB_CUFFT(cufftSetStream(p->fwd, 0));
+    SLLB_CUFFT(cufftSetStream(p->bwd, 0));
+    return SLLB_OK;
+}
+int sllb_poisson1d_create(int nc, double xmin, double xmax, sllb_poisson_t *P) {
+    if (!P || nc < 4 || !(xmax > xmin)) return fail(SLLB_ERR_INVALID, "poisson1d_create: bad arguments");
+    SLLB_TRY(require_device());
+    sllb_poisson *p = new sllb_poisson();
+    p->dim = 1; p->n[0] = nc; p->L[0] = xmax - xmin; p->xmin[0] = xmin;
+    int rc = poisson_common(p);
+    if (rc) { sllb_poisson_destroy(p); return rc; }
+    *P = p;
+    return SLLB_OK;
+}
+int sllb_poisson2d_create(int nc_x, int nc_y, double x_min, double x_max, double y_min, double y_max,
+                          sllb_poisson_t *P) {
+    if (!P || nc_x < 4 || nc_y < 4 || !(x_max > x_min) || !(y_max > y_min))
+        return fail(SLLB_ERR_INVALID, "poisson2d_create: bad arguments");
+    SLLB_TRY(require_device());
+    sllb_poisson *p = new sllb_poisson();
+    p->dim = 2; p->n[0] = nc_x; p->n[1] = nc_y; p->L[0] = x_max - x_min; p->L[1] = y_max - y_min;
+    int rc = poisson_common(p);
+    if (rc) { sllb_poisson_destroy(p); return rc; }
+    *P = p;
+    return SLLB_OK;
+}
+int sllb_poisson3d_create(int nx, int ny, int nz, double Lx, double Ly, double Lz, sllb_poisson_t *P) {
+    if (!P || nx < 4 || ny < 4 || nz < 4 || !(Lx > 0) || !(Ly > 0) || !(Lz > 0))
+        return fail(SLLB_ERR_INVALID, "poisson3d_create: bad arguments");
+    SLLB_TRY(require_device());
+    sllb_poisson *p = new sllb_poisson();
+    p->dim = 3; p->n[0] = nx; p->n[1] = ny; p->n[2] = nz; p->L[0] = Lx; p->L[1] = Ly; p->L[2] = Lz;
+    int rc = poisson_common(p);
+    if (rc) { sllb_poisson_destroy(p); return rc; }
+    *P = p;
+    return SLLB_OK;
+}
+int sllb_poisson_destroy(sllb_poisson_t P) {
+    if (!P) return SLLB_OK;
+    if (P->plans) { cufftDestroy(P->fwd); cufftDestroy(P->bwd); }
+    if (P->rho_hat) cudaFree(P->rho_hat);
+    for (int k = 0; k < 4; ++k) if (P->spec[k]) cudaFree(P->spec[k]);
+    delete P;
+    return SLLB_OK;
+}
+int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, double *d_e1, double *d_e2, double *d_e3) {
+    if (!P || !d_rho) return fail(SLLB_ERR_INVALID, "poisson_solve: null");
+    SLLB_TRY(require_device());
+    SLLB_CUFFT(cufftExecD2Z(P->fwd, const_cast<double *>(d_rho), P->rho_hat));
+    cufftDoubleComplex *ph = d_phi ? P->spec[0] : nullptr, *e1 = d_e1 ? P->spec[1] : nullptr;
+    cufftDoubleComplex *e2 = d_e2 ? P->spec[2] : nullptr, *e3 = d_e3 ? P->spec[3] : nullptr;
+    if (P->dim == 1) {
+        if (d_phi) return fail(SLLB_ERR_UNSUPPORTED, "poisson1d: potential output not implemented (the reference returns E only)");
+        if (e1) SLLB_CUDA(launch_poisson1d_mult(P->rho_hat, P->n[0], P->L[0], e1, 0));
+        e2 = e3 = nullptr;
+    } else if (P->dim == 2) {
+        SLLB_CUDA(launch_poisson2d_mult(P->rho_hat, P->n[0], P->n[1], P->L[0], P->L[1], ph, e1, e2, 0));
+        e3 = nullptr;
+    } else {
+        SLLB_CUDA(launch_poisson3d_mult(P->rho_hat, P->n[0], P->n[1], P->n[2], P->L[0], P->L[1], P->L[2], ph, e1, e2, e3, 0));
+    }
+    if (ph) SLLB_CUFFT(cufftExecZ2D(P->bwd, ph, d_phi));
+    if (e1) SLLB_CUFFT(cufftExecZ2D(P->bwd, e1, d_e1));
+    if (e2) SLLB_CUFFT(cufftExecZ2D(P->bwd, e2, d_e2));
+    if (e3) SLLB_CUFFT(cufftExecZ2D(P->bwd, e3, d_e3));
+    return SLLB_OK;
+}
+int sllb_poisson_solve_host(sllb_poisson_t P, const double *rho, const int *ld, double *phi, double *e1, double *e2,
+                            double *e3) {
+    if (!P || !rho || !ld) return fail(SLLB_ERR_INVALID, "poisson_solve_host: null");
+    SLLB_TRY(require_device());
+    int l[3] = {1, 1, 1};
+    for (int d = 0; d < P->dim; ++d) {
+        l[d] = ld[d];
+        if (l[d] != P->n[d] && l[d] != P->n[d] + 1) return fail(SLLB_ERR_INVALID, "poisson_solve_host: ld must be nc or nc+1");
+    }
+    std::vector<double> h((size_t)P->nreal);
+    for (int k = 0; k < P->n[2]; ++k) for (int j = 0; j < P->n[1]; ++j) for (int i = 0; i < P->n[0]; ++i)
+        h[i + (size_t)P->n[0] * (j + (size_t)P->n[1] * k)] = rho[i + (size_t)l[0] * (j + (size_t)l[1] * k)];
+    SLLB_TRY(P->rho_in.ensure((size_t)P->nreal));
+    SLLB_CUDA(cudaMemcpy(P->rho_in.p, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    double *outs[4] = {phi, e1, P->dim >= 2 ? e2 : nullptr, P->dim >= 3 ? e3 : nullptr};
+    double *douts[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 4; ++k) if (outs[k]) { SLLB_TRY(P->out[k].ensure((size_t)P->nreal)); douts[k] = P->out[k].p; }
+    SLLB_TRY(sllb_poisson_solve(P, P->rho_in.p, douts[0], douts[1], douts[2], douts[3]));
+    for (int q = 0; q < 4; ++q) {
+        if (!outs[q]) continue;
+        SLLB_CUDA(cudaMemcpy(h.data(), douts[q], h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < l[2]; ++k) for (int j = 0; j < l[1]; ++j) for (int i = 0; i < l[0]; ++i)
+            outs[q][i + (size_t)l[0] * (j + (size_t)l[1] * k)] =
+                h[(i % P->n[0]) + (size_t)P->n[0] * ((j % P->n[1]) + (size_t)P->n[1] * (k % P->n[2]))];
+    }
+    return SLLB_OK;
+}
+
+/* ---------------- line-granular drop-in handles ---------------- */
+} // extern "C"
+
+struct sllb_adv1d {
+    int kind, num_cells, order;
+    double xmin, xmax;
+    int method, stencil;
+    sllb_field *line = nullptr;
+};
+struct sllb_interp1d {
+    int kind, num_points, num_cells, periodic_last;
+    double xmin, xmax, delta;
+    int method, stencil;
+    sllb_field *line = nullptr;
+};
+
+static int line_shift(sllb_field *line, int method, int stencil, double disp_cells, const double *in, double *out, int n) {
+    const int N = line->ext[0];
+    SLLB_CUDA(cudaMemcpy(line->d, in, (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+    sllb_disp_t d;
+    memset(&d, 0, sizeof(d));
+    d.values = &disp_cells; d.nvalues = 1; d.values_on_device = 0; d.scale = 1.0;
+    d.odiv = d.omod = d.idiv = d.imod = 1;
+    SLLB_TRY(sllb_advect_axis(line, 0, method, stencil, &d));
+    SLLB_CUDA(cudaMemcpy(out, line->d, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n > N) out[N] = out[0];
+    return SLLB_OK;
+}
+
+extern "C" {
+
+int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int order, sllb_adv1d_t *h) {
+    if (!h || num_cells < 8 || !(xmax > xmin)) return fail(SLLB_ERR_INVALID, "adv1d_create: bad arguments");
+    int method, stencil;
+    if (kind == SLLB_ADV_PERIODIC_SPLINE) {
+        if (order != 4) return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_spline implemented for order 4 (cubic) only");
+        method = SLLB_METHOD_SPLINE; stencil = 4;
+    } else if (kind == SLLB_ADV_PERIODIC_LAGRANGE) {
+        if (order != 4 && order != 6 && order != 8)
+            return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_lagrange implemented for order 4, 6, 8");
+        method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = order;
+    } else return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: advector kind not implemented");
+    SLLB_TRY(require_device());
+    sllb_adv1d *a = new sllb_adv1d();
+    a->kind = kind; a->num_cells = num_cells; a->order = order; a->xmin = xmin; a->xmax = xmax;
+    a->method = method; a->stencil = stencil;
+    int rc = field_alloc(1, &num_cells, &a->line);
+    if (rc) { delete a; return rc; }
+    *h = a;
+    return SLLB_OK;
+}
+int sllb_adv1d_advect_constant(sllb_adv1d_t h, double A, double dt, const double *in, double *out, int n) {
+    if (!h || !in || !out) return fail(SLLB_ERR_INVALID, "advect_constant: null");
+    if (n != h->num_cells && n != h->num_cells + 1) return fail(SLLB_ERR_INVALID, "advect_constant: n must be num_cells or num_cells+1");
+    SLLB_TRY(require_device());
+    /* shift = A*dt/(xmax-xmin)*num_cells (sll_m_advection_1d_periodic.F90:117); out(j) = interp(j - shift) */
+    const double shift = A * dt / (h->xmax - h->xmin) * (double)h->num_cells;
+    return line_shift(h->line, h->method, h->stencil, -shift, in, out, n);
+}
+int sllb_adv1d_delete(sllb_adv1d_t h) {
+    if (!h) return SLLB_OK;
+    sllb_field_destroy(h->line);
+    delete h;
+    return SLLB_OK;
+}
+
+int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int bc, int d_or_order, int periodic_last,
+                         int fast_algorithm, sllb_interp1d_t *h) {
+    (void)fast_algorithm;
+    if (!h || !(xmax > xmin)) return fail(SLLB_ERR_INVALID, "interp1d_create: bad arguments");
+    if (bc != SLLB_BC_PERIODIC) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: only sll_p_periodic is implemented");
+    int method, stencil, ncell;
+    switch (kind) {
+    case SLLB_INTERP_CUBIC_SPLINE: method = SLLB_METHOD_SPLINE; stencil = 4; periodic_last = 1; break;
+    case SLLB_INTERP_PERIODIC_SPLINE:
+        if (d_or_order != 4) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: periodic spline implemented for order 4 only");
+        method = SLLB_METHOD_SPLINE; stencil = 4; periodic_last = 1; break;
+    case SLLB_INTERP_PERIODIC_LAGRANGE: method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = d_or_order; periodic_last = 1; break;
+    case SLLB_INTERP_LAGRANGE_CENTERED: method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = 2 * d_or_order; break;
+    case SLLB_INTERP_LAGRANGE_FIXED: method = SLLB_METHOD_LAGRANGE_FIXED; stencil = 2 * d_or_order + 1; break;
+    default: return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: interpolator kind not implemented");
+    }
+    if (method == SLLB_METHOD_LAGRANGE_CENTERED && stencil != 4 && stencil != 6 && stencil != 8)
+        return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: centred Lagrange implemented for stencils 4, 6, 8");
+    if (method == SLLB_METHOD_LAGRANGE_FIXED && (stencil < 3 || stencil > 11))
+        return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: fixed Lagrange implemented for stencils 3..11");
+    /* both interpolators define the cell size from num_points-1 cells
+     * (sll_m_cubic_splines.F90:262, sll_m_lagrange_interpolation_1d.F90:58-60) */
+    ncell = num_points - 1;
+    if (ncell < 8) return fail(SLLB_ERR_INVALID, "interp1d_create: too few points");
+    SLLB_TRY(require_device());
+    sllb_interp1d *p = new sllb_interp1d();
+    p->kind = kind; p->num_points = num_points; p->num_cells = ncell; p->periodic_last = periodic_last ? 1 : 0;
+    p->xmin = xmin; p->xmax = xmax; p->delta = (xmax - xmin) / (double)ncell;
+    p->method = method; p->stencil = stencil;
+    int rc = field_alloc(1, &ncell, &p->line);
+    if (rc) { delete p; return rc; }
+    *h = p;
+    return SLLB_OK;
+}
+int sllb_interp1d_array_disp(sllb_interp1d_t h, int n, const double *data, double alpha, double *out) {
+    if (!h || !data || !out) return fail(SLLB_ERR_INVALID, "interpolate_array_disp: null");
+    if (n != h->num_cells && n != h->num_cells + 1) return fail(SLLB_ERR_INVALID, "interpolate_array_disp: bad num_pts");
+    SLLB_TRY(require_device());
+    return line_shift(h->line, h->method, h->stencil, alpha / h->delta, data, out, n);
+}
+int sllb_interp1d_array_disp_inplace(sllb_interp1d_t h, int n, double *data, double alpha) {
+    return sllb_interp1d_array_disp(h, n, data, alpha, data);
+}
+int sllb_interp1d_delete(sllb_interp1d_t h) {
+    if (!h) return SLLB_OK;
+    sllb_field_destroy(h->line);
+    delete h;
+    return SLLB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,79 @@
+// Internal structures shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sll_b200.h"
+#include "sllb_kernels.cuh"
+
+namespace sllb {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int check_cuda(cudaError_t e, const char *what);
+int check_cufft(cufftResult r, const char *what);
+int require_device();
+extern int g_staging;
+
+#define SLLB_CUDA(call)                                  \
+    do {                                                 \
+        int _rc = sllb::check_cuda((call), #call);       \
+        if (_rc) return _rc;                             \
+    } while (0)
+#define SLLB_CUFFT(call)                                 \
+    do {                                                 \
+        int _rc = sllb::check_cufft((call), #call);      \
+        if (_rc) return _rc;                             \
+    } while (0)
+#define SLLB_TRY(call)                                   \
+    do {                                                 \
+        int _rc = (call);                                \
+        if (_rc) return _rc;                             \
+    } while (0)
+
+struct Ext6 { int e[6]; };
+
+// simple owning device buffer
+struct DevBuf {
+    double *p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count);
+    void release();
+    ~DevBuf() { release(); }
+};
+
+} // namespace sllb
+
+struct sllb_field {
+    int ndim = 0;
+    int ext[6] = {1, 1, 1, 1, 1, 1};
+    long long total = 0;
+    double *d = nullptr;
+    bool owns = true;
+    sllb::DevBuf disp_scratch;   // uploaded displacement values
+    sllb::DevBuf red_scratch;    // reduction partials
+    sllb::DevBuf stage;          // upload/download staging with duplicates
+    sllb::DevBuf rows;           // diagnostics row sums
+};
+
+struct sllb_poisson {
+    int dim = 0;
+    int n[3] = {1, 1, 1};
+    double L[3] = {1, 1, 1};
+    double xmin[3] = {0, 0, 0};
+    cufftHandle fwd = 0, bwd = 0;
+    bool plans = false;
+    cufftDoubleComplex *rho_hat = nullptr, *spec[4] = {nullptr, nullptr, nullptr, nullptr};
+    sllb::DevBuf rho_in, out[4];
+    long long nreal = 0, ncplx = 0;
+};
+
+namespace sllb {
+// internal (device-pointer) entry points used by the simulations
+int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd);
+int field_alloc(int ndim, const int *ext, sllb_field **F);
+int field_wrap(int ndim, const int *ext, double *d, sllb_field **F);
+int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out);
+} // namespace sllb

@@ -1,0 +1,767 @@
+// sllb_kernels.cu -- hand-written sm_100a kernels of the split semi-Lagrangian advection path.
+//
+// K1  periodic cubic-spline shift     (replaces compute_spline_1D_periodic_aux + eval_disp,
+//                                      sll_m_cubic_splines.F90:531-581,2616-2711, per line)
+// K2  Lagrange fixed/centred shift    (sll_m_lagrange_interpolation_1d_fast.F90:609-837)
+// K3  velocity reduction              (sll_m_reduction.F90:187-272, sll_m_sim_6d_utilities.F90:203-245)
+// K4  spectral Poisson multipliers    (sll_m_poisson_{1d,2d}_periodic.F90, sll_m_poisson_3d_periodic_par.F90)
+// K6  pack / unpack for remaps        (apply_remap_4D_double, sll_m_remapper.F90:3386-3395,3444-3453)
+// K8  diagnostics row sums
+//
+// Every advection kernel stages whole lines of f in shared memory (TMA bulk copies completing on an
+// mbarrier, or cp.async when the tile is not 16-byte tileable), solves / evaluates in the block and
+// writes each point once: 16 B of HBM traffic per point per pass.  All arithmetic is fp64.
+#include "sllb_kernels.cuh"
+#include <cstdio>
+
+namespace sllb {
+
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
+void launch_count_reset() { g_launches = 0; }
+#define COUNT_LAUNCH() (++g_launches)
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1D bulk TMA (cp.async.bulk) + cp.async
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// streaming store: written once, not re-read by this pass
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+
+__device__ __forceinline__ double disp_of(const DispDesc &d, long long o, long long in) {
+    return d.scale * d.v[((o / d.odiv) % d.omod) * d.ostr + ((in / d.idiv) % d.imod) * d.istr];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Periodic cubic spline on one line held in shared memory (elements at sc[k*PITCH]).
+//
+// Reference recurrences (sll_m_cubic_splines.F90:560-580), a = sqrt((2+sqrt3)/6), b = sqrt((2-sqrt3)/6):
+//     d(i) = (f(i) - b d(i-1))/a,   c(i) = (d(i) - b c(i+1))/a,   wrap terms = 27-term series in -b/a.
+// Scaled by 1/a they become e(i) = f(i) - q e(i-1), g(i) = e(i) - q g(i+1) with q = b/a = 2 - sqrt3 and
+// c = g/a^2; the factor 1/a^2 = 6(2-sqrt3) and the 1/6 of the B-spline evaluation are folded into the four
+// per-line weights, so the whole pass costs 6 FMA per point.
+// ------------------------------------------------------------------------------------------------
+#define SLLB_NUM_TERMS 27
+__constant__ double c_pw[SLLB_NUM_TERMS]; // (-q)^(i+1)
+
+template <int PITCH, bool TO_GLOBAL>
+__device__ __forceinline__ void spline_line(double *sc, const int N, const double disp, double *gbase,
+                                            const long long gstride) {
+    const double q = 0.26794919243112270647; // 2 - sqrt(3)
+    const double r2 = 1.60769515458673623883; // 6 (2 - sqrt 3) = 1/a^2
+    const double fl = floor(disp);
+    const int dcell = (int)fl;
+    const double dx = disp - fl, cdx = 1.0 - dx;
+    const double s6 = r2 * (1.0 / 6.0);
+    const double w0 = cdx * cdx * cdx * s6;
+    const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+    const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+    const double w3 = dx * dx * dx * s6;
+
+    // forward sweep: e_1 = f_1 + sum_{i=0..26} (-q)^{i+1} f_{N-i}
+    double e = sc[0];
+    {
+        int idx = N - 1;
+#pragma unroll
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            e = fma(c_pw[i], sc[idx * PITCH], e);
+            idx = (idx == 0) ? N - 1 : idx - 1;
+        }
+    }
+    sc[0] = e;
+#pragma unroll 8
+    for (int k = 1; k < N; ++k) {
+        e = fma(-q, e, sc[k * PITCH]);
+        sc[k * PITCH] = e;
+    }
+    // backward sweep: g_N = e_N + sum_{i=1..27} (-q)^i e_i
+    double g = e;
+    {
+        int idx = 0;
+#pragma unroll
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            g = fma(c_pw[i], sc[idx * PITCH], g);
+            idx = (idx == N - 1) ? 0 : idx + 1;
+        }
+    }
+    const double gt0 = g;                                   // g[N-1]
+    const double gt1 = fma(-q, gt0, sc[(N - 2) * PITCH]);   // g[N-2]
+    const double gt2 = fma(-q, gt1, sc[(N - 3) * PITCH]);   // g[N-3]
+    double a3 = gt0, a2 = gt1, a1 = gt2;
+    // output index of cell kc is (kc - dcell) mod N; cells are emitted kc = N-3, N-4, ..., 1
+    int iout = ((N - 3 - dcell) % N + N) % N;
+#pragma unroll 8
+    for (int k = N - 4; k >= 0; --k) {
+        const double a0 = fma(-q, a1, sc[k * PITCH]);
+        const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
+        if (TO_GLOBAL) st_stream(gbase + (long long)iout * gstride, val);
+        else sc[(k + 1) * PITCH] = val; // slot k+1 already consumed
+        iout = (iout == 0) ? N - 1 : iout - 1;
+        a3 = a2; a2 = a1; a1 = a0;
+    }
+    // now a1 = g[0], a2 = g[1], a3 = g[2]
+    const double v0 = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * gt0)));   // cell 0
+    const double vm1 = fma(w3, a2, fma(w2, a1, fma(w1, gt0, w0 * gt1))); // cell N-1
+    const double vm2 = fma(w3, a1, fma(w2, gt0, fma(w1, gt1, w0 * gt2))); // cell N-2
+    if (TO_GLOBAL) {
+        st_stream(gbase + (long long)iout * gstride, v0);
+        iout = (iout == 0) ? N - 1 : iout - 1;
+        st_stream(gbase + (long long)iout * gstride, vm1);
+        iout = (iout == 0) ? N - 1 : iout - 1;
+        st_stream(gbase + (long long)iout * gstride, vm2);
+    } else {
+        sc[0] = v0;
+        sc[(N - 1) * PITCH] = vm1;
+        sc[(N - 2) * PITCH] = vm2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Lagrange weights: closed-form polynomials of sll_m_lagrange_interpolation_1d_fast.F90
+// (:59-67,110-121,170-182 even; :239-246,286-295,341-352,405-419,478-494 odd)
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void lagr_coeff(double p, double *pp) {
+    const double p2 = p * p;
+    if constexpr (S == 3) {
+        pp[0] = p * (p - 1.) * 0.5; pp[1] = 1. - p * p; pp[2] = p * (p + 1.) * 0.5;
+    } else if constexpr (S == 5) {
+        pp[0] = (p2 - 1.) * p * (p - 2.) * (1. / 24.);
+        pp[1] = -(p - 1.) * p * (p2 - 4.) * (1. / 6.);
+        pp[2] = (p2 - 1.) * (p2 - 4.) * 0.25;
+        pp[3] = -(p + 1.) * p * (p2 - 4.) * (1. / 6.);
+        pp[4] = (p2 - 1.) * p * (p + 2.) * (1. / 24.);
+    } else if constexpr (S == 7) {
+        pp[0] = p * (p - 3.) * (p2 - 4.) * (p2 - 1.) * (1. / 720.);
+        pp[1] = -p * (p - 2.) * (p2 - 9.) * (p2 - 1.) * (1. / 120.);
+        pp[2] = p * (p - 1.) * (p2 - 9.) * (p2 - 4.) * (1. / 48.);
+        pp[3] = -(p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 36.);
+        pp[4] = (p + 1.) * p * (p2 - 9.) * (p2 - 4.) * (1. / 48.);
+        pp[5] = -(p + 2.) * p * (p2 - 9.) * (p2 - 1.) * (1. / 120.);
+        pp[6] = (p + 3.) * p * (p2 - 4.) * (p2 - 1.) * (1. / 720.);
+    } else if constexpr (S == 9) {
+        pp[0] = p * (p - 4.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 40320.);
+        pp[1] = -p * (p - 3.) * (p2 - 16.) * (p2 - 4.) * (p2 - 1.) * (1. / 5040.);
+        pp[2] = p * (p - 2.) * (p2 - 16.) * (p2 - 9.) * (p2 - 1.) * (1. / 1440.);
+        pp[3] = -p * (p - 1.) * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (1. / 720.);
+        pp[4] = (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 576.);
+        pp[5] = -(p + 1.) * p * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (1. / 720.);
+        pp[6] = (p + 2.) * p * (p2 - 16.) * (p2 - 9.) * (p2 - 1.) * (1. / 1440.);
+        pp[7] = -(p + 3.) * p * (p2 - 16.) * (p2 - 4.) * (p2 - 1.) * (1. / 5040.);
+        pp[8] = (p + 4.) * p * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 40320.);
+    } else if constexpr (S == 11) {
+        pp[0] = p * (p - 5.) * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 3628800.);
+        pp[1] = -p * (p - 4.) * (p2 - 25.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 362880.);
+        pp[2] = p * (p - 3.) * (p2 - 25.) * (p2 - 16.) * (p2 - 4.) * (p2 - 1.) * (1. / 80640.);
+        pp[3] = -p * (p - 2.) * (p2 - 25.) * (p2 - 16.) * (p2 - 9.) * (p2 - 1.) * (1. / 30240.);
+        pp[4] = p * (p - 1.) * (p2 - 25.) * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (1. / 17280.);
+        pp[5] = -(p2 - 25.) * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 14400.);
+        pp[6] = (p + 1.) * p * (p2 - 25.) * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (1. / 17280.);
+        pp[7] = -(p + 2.) * p * (p2 - 25.) * (p2 - 16.) * (p2 - 9.) * (p2 - 1.) * (1. / 30240.);
+        pp[8] = (p + 3.) * p * (p2 - 25.) * (p2 - 16.) * (p2 - 4.) * (p2 - 1.) * (1. / 80640.);
+        pp[9] = -(p + 4.) * p * (p2 - 25.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 362880.);
+        pp[10] = (p + 5.) * p * (p2 - 16.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 3628800.);
+    } else if constexpr (S == 4) {
+        pp[0] = -p * (p - 1.) * (p - 2.) * (1. / 6.);
+        pp[1] = (p2 - 1.) * (p - 2.) * 0.5;
+        pp[2] = -p * (p + 1.) * (p - 2.) * 0.5;
+        pp[3] = p * (p2 - 1.) * (1. / 6.);
+    } else if constexpr (S == 6) {
+        pp[0] = -p * (p2 - 1.) * (p - 2.) * (p - 3.) * (1. / 120.);
+        pp[1] = p * (p - 1.) * (p2 - 4.) * (p - 3.) * (1. / 24.);
+        pp[2] = -(p2 - 1.) * (p2 - 4.) * (p - 3.) * (1. / 12.);
+        pp[3] = p * (p + 1.) * (p2 - 4.) * (p - 3.) * (1. / 12.);
+        pp[4] = -p * (p2 - 1.) * (p + 2.) * (p - 3.) * (1. / 24.);
+        pp[5] = p * (p2 - 1.) * (p2 - 4.) * (1. / 120.);
+    } else if constexpr (S == 8) {
+        pp[0] = -p * (p - 3.) * (p - 4.) * (p2 - 4.) * (p2 - 1.) * (1. / 5040.);
+        pp[1] = p * (p - 2.) * (p - 4.) * (p2 - 9.) * (p2 - 1.) * (1. / 720.);
+        pp[2] = -p * (p - 1.) * (p - 4.) * (p2 - 9.) * (p2 - 4.) * (1. / 240.);
+        pp[3] = (p - 4.) * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 144.);
+        pp[4] = -(p + 1.) * p * (p - 4.) * (p2 - 9.) * (p2 - 4.) * (1. / 144.);
+        pp[5] = (p + 2.) * p * (p - 4.) * (p2 - 9.) * (p2 - 1.) * (1. / 240.);
+        pp[6] = -(p + 3.) * p * (p - 4.) * (p2 - 4.) * (p2 - 1.) * (1. / 720.);
+        pp[7] = p * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 5040.);
+    }
+}
+
+// weights and first stencil offset (mod N) for a line.  Odd S: fixed stencil centred on the grid point,
+// p = whole displacement (fast_disp_fixed_periodic, :609-654).  Even S: centred on the foot cell,
+// pi = floor(p), weights at p - pi (fast_disp_centered_periodicl, :710-769).
+template <int S>
+__device__ __forceinline__ int lagr_setup(double disp, int N, double *pp) {
+    int off;
+    if constexpr ((S & 1) != 0) {
+        lagr_coeff<S>(disp, pp);
+        off = -(S - 1) / 2;
+    } else {
+        const double fl = floor(disp);
+        lagr_coeff<S>(disp - fl, pp);
+        off = -(S / 2 - 1) + (int)fl;
+    }
+    return ((off % N) + N) % N;
+}
+
+// one line from shared memory (sc[k*PITCH]) to global memory with a register window
+template <int S, int PITCH>
+__device__ __forceinline__ void lagrange_line(const double *sc, const int N, const double disp, double *gbase,
+                                              const long long gstride) {
+    double pp[S], w[S];
+    int idx = lagr_setup<S>(disp, N, pp);
+#pragma unroll
+    for (int k = 1; k < S; ++k) {
+        w[k] = sc[idx * PITCH];
+        idx = (idx == N - 1) ? 0 : idx + 1;
+    }
+#pragma unroll 4
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) w[k] = w[k + 1];
+        w[S - 1] = sc[idx * PITCH];
+        idx = (idx == N - 1) ? 0 : idx + 1;
+        double acc = pp[0] * w[0]; // left-to-right sum like lagr_Npt_vec (:393-399)
+#pragma unroll
+        for (int k = 1; k < S; ++k) acc = fma(pp[k], w[k], acc);
+        st_stream(gbase + (long long)i * gstride, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1a/K2a: strided axis (inner > 1).  Block = BW adjacent lines (adjacent in the flattened faster
+// axes, i.e. contiguous in memory row by row); shared tile s[k*BW + t] = f(line t, point k).
+// METHOD 0 = spline, 1 = Lagrange with stencil S.
+// ------------------------------------------------------------------------------------------------
+template <int BW, int METHOD, int S>
+__global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, const long long nlines, const int N,
+                                                        const long long inner, const DispDesc dd, const int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const long long l = (long long)blockIdx.x * BW + tid;
+    const bool active = l < nlines;
+    const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    double *base = f + o * (long long)N * inner + in;
+
+    if (use_tma) { // whole tile inside one `o` and 16-byte tileable (checked by the launcher)
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(N * BW * 8));
+        const double *src0 = base - tid; // line of thread 0
+        for (int j = tid; j < N; j += BW) bulk_g2s(s + (size_t)j * BW, src0 + (long long)j * inner, BW * 8, bar);
+        mbar_wait(bar, 0);
+    } else {
+        if (active)
+            for (int j = 0; j < N; ++j) cp_async8(s + (size_t)j * BW + tid, base + (long long)j * inner);
+        cp_async_wait_all();
+    }
+    if (!active) return;
+    const double disp = disp_of(dd, o, in);
+    if constexpr (METHOD == 0) spline_line<BW, true>(s + tid, N, disp, base, inner);
+    else lagrange_line<S, BW>(s + tid, N, disp, base, inner);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b: spline, contiguous axis (inner == 1).  Block = BW consecutive lines = one contiguous chunk of
+// BW*N doubles.  The tile is transposed on the way in (pitch BW+1: conflict-free for both the
+// coalesced staging and the thread-per-line sweeps) and on the way out, where the integer part of the
+// shift is applied.
+// ------------------------------------------------------------------------------------------------
+template <int BW>
+__global__ void __launch_bounds__(BW) k_spline_contig(double *__restrict__ f, const long long nlines, const int N,
+                                                       const DispDesc dd) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int *dcm = reinterpret_cast<int *>(smem_raw); // BW ints
+    double *s = reinterpret_cast<double *>(smem_raw + 128 + ((BW * 4) / 128) * 128);
+    constexpr int P = BW + 1;
+    const int tid = threadIdx.x;
+    const long long l0 = (long long)blockIdx.x * BW;
+    const int nl = (int)((nlines - l0 < BW) ? (nlines - l0) : BW);
+    double *tile = f + l0 * (long long)N;
+    for (int ln = 0; ln < nl; ++ln)
+        for (int j = tid; j < N; j += BW) cp_async8(s + (size_t)j * P + ln, tile + (long long)ln * N + j);
+    cp_async_wait_all();
+    __syncthreads();
+    if (tid < nl) {
+        const double disp = disp_of(dd, l0 + tid, 0);
+        const int dcell = (int)floor(disp);
+        dcm[tid] = ((dcell % N) + N) % N;
+        spline_line<P, false>(s + tid, N, disp, nullptr, 0);
+    }
+    __syncthreads();
+    for (int ln = 0; ln < nl; ++ln) {
+        const int d = dcm[ln];
+        for (int i = tid; i < N; i += BW) {
+            int kc = i + d;
+            if (kc >= N) kc -= N;
+            st_stream(tile + (long long)ln * N + i, s[(size_t)kc * P + ln]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: Lagrange, contiguous axis.  Tile = LT whole lines in natural layout (one bulk TMA copy),
+// thread per output point, per-line weights in shared memory.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) k_lagrange_contig(double *__restrict__ f, const long long nlines, const int N,
+                                                         const DispDesc dd, const int LT, const int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *tile = reinterpret_cast<double *>(smem_raw + 128);
+    double *wts = tile + (size_t)LT * N;
+    int *offs = reinterpret_cast<int *>(wts + (size_t)LT * S);
+    const int tid = threadIdx.x;
+    const long long l0 = (long long)blockIdx.x * LT;
+    const int nl = (int)((nlines - l0 < LT) ? (nlines - l0) : LT);
+    double *g = f + l0 * (long long)N;
+    const int npts = nl * N;
+    if (use_tma) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(npts * 8));
+            bulk_g2s(tile, g, (uint32_t)(npts * 8), bar);
+        }
+    } else {
+        for (int i = tid; i < npts; i += 256) cp_async8(tile + i, g + i);
+    }
+    for (int ln = tid; ln < nl; ln += 256) {
+        double pp[S];
+        offs[ln] = lagr_setup<S>(disp_of(dd, l0 + ln, 0), N, pp);
+#pragma unroll
+        for (int k = 0; k < S; ++k) wts[ln * S + k] = pp[k];
+    }
+    if (use_tma) mbar_wait(bar, 0);
+    else cp_async_wait_all();
+    __syncthreads();
+    for (int idx = tid; idx < npts; idx += 256) {
+        const int ln = idx / N, i = idx - ln * N;
+        int j = i + offs[ln];
+        if (j >= N) j -= N;
+        const double *row = tile + (size_t)ln * N;
+        const double *w = wts + ln * S;
+        double acc = w[0] * row[j];
+#pragma unroll
+        for (int k = 1; k < S; ++k) {
+            j = (j == N - 1) ? 0 : j + 1;
+            acc = fma(w[k], row[j], acc);
+        }
+        st_stream(g + idx, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static bool g_pw_ready = false;
+static cudaError_t ensure_constants() {
+    if (g_pw_ready) return cudaSuccess;
+    double pw[SLLB_NUM_TERMS];
+    // b/a evaluated like the reference (sqrt of the two constants), then powers by repeated product
+    const double a = sqrt((2.0 + sqrt(3.0)) / 6.0), b = sqrt((2.0 - sqrt(3.0)) / 6.0);
+    double ct = 1.0;
+    for (int i = 0; i < SLLB_NUM_TERMS; ++i) { ct *= -(b / a); pw[i] = ct; }
+    cudaError_t e = cudaMemcpyToSymbol(c_pw, pw, sizeof(pw));
+    if (e == cudaSuccess) g_pw_ready = true;
+    return e;
+}
+
+template <typename K>
+static cudaError_t set_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static const size_t SMEM_MAX = 227 * 1024;
+
+template <int BW, int METHOD, int S>
+static cudaError_t launch_strided_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
+                                    int staging, cudaStream_t st) {
+    size_t smem = 128 + (size_t)N * BW * 8;
+    auto kern = k_advect_strided<BW, METHOD, S>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    bool tma_ok = (inner % BW == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * BW * 8 < (1u << 20));
+    int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
+    long long nblk = (nlines + BW - 1) / BW;
+    kern<<<(unsigned)nblk, BW, smem, st>>>(f, nlines, N, inner, dd, use_tma);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+template <int METHOD, int S>
+static cudaError_t launch_strided(double *f, long long nlines, int N, long long inner, const DispDesc &dd, int staging,
+                                  cudaStream_t st) {
+    // widest tile that fits: BW lanes x N points x 8 B (+128 B header)
+    if ((size_t)N * 32 * 8 + 128 <= SMEM_MAX && (inner >= 32 || nlines >= 32))
+        return launch_strided_t<32, METHOD, S>(f, nlines, N, inner, dd, staging, st);
+    if ((size_t)N * 16 * 8 + 128 <= SMEM_MAX) return launch_strided_t<16, METHOD, S>(f, nlines, N, inner, dd, staging, st);
+    if ((size_t)N * 8 * 8 + 128 <= SMEM_MAX) return launch_strided_t<8, METHOD, S>(f, nlines, N, inner, dd, staging, st);
+    return cudaErrorInvalidValue;
+}
+
+template <int S>
+static cudaError_t launch_lagrange_contig(double *f, long long nlines, int N, const DispDesc &dd, int staging,
+                                          cudaStream_t st) {
+    // lines per tile: aim at ~32 KB tiles, at least 1 line
+    int LT = (int)(4096 / N);
+    if (LT < 1) LT = 1;
+    if (LT > nlines) LT = (int)nlines;
+    size_t smem = 128 + (size_t)LT * N * 8 + (size_t)LT * S * 8 + (size_t)LT * 4 + 16;
+    if (smem > SMEM_MAX) return cudaErrorInvalidValue;
+    auto kern = k_lagrange_contig<S>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    bool tma_ok = (((long long)LT * N) % 2 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && (nlines % LT == 0) &&
+                  ((size_t)LT * N * 8 < (1u << 20));
+    int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
+    long long nblk = (nlines + LT - 1) / LT;
+    kern<<<(unsigned)nblk, 256, smem, st>>>(f, nlines, N, dd, LT, use_tma);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+template <int BW>
+static cudaError_t launch_spline_contig_t(double *f, long long nlines, int N, const DispDesc &dd, cudaStream_t st) {
+    size_t smem = 128 + ((BW * 4) / 128) * 128 + (size_t)N * (BW + 1) * 8;
+    auto kern = k_spline_contig<BW>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    long long nblk = (nlines + BW - 1) / BW;
+    kern<<<(unsigned)nblk, BW, smem, st>>>(f, nlines, N, dd);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
+                          const DispDesc &dd, int staging, cudaStream_t st) {
+    if (n < 8 || outer < 1 || inner < 1) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_constants();
+    if (e != cudaSuccess) return e;
+    const long long nlines = outer * inner;
+    if (nlines > 0x7fffffffLL * 8) return cudaErrorInvalidValue;
+    if (method == METHOD_SPLINE) {
+        if (order != 4) return cudaErrorInvalidValue;
+        if (inner == 1) {
+            if ((size_t)n * 33 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<32>(f, nlines, n, dd, st);
+            if ((size_t)n * 17 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<16>(f, nlines, n, dd, st);
+            if ((size_t)n * 9 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<8>(f, nlines, n, dd, st);
+            return cudaErrorInvalidValue;
+        }
+        return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st);
+    }
+#define LAGR_CASE(SS)                                                                            \
+    case SS:                                                                                     \
+        if (inner == 1) return launch_lagrange_contig<SS>(f, nlines, n, dd, staging, st);       \
+        return launch_strided<1, SS>(f, nlines, n, inner, dd, staging, st);
+    if (method == METHOD_LAGRANGE_FIXED) {
+        switch (order) {
+            LAGR_CASE(3) LAGR_CASE(5) LAGR_CASE(7) LAGR_CASE(9) LAGR_CASE(11)
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    if (method == METHOD_LAGRANGE_CENTERED) {
+        switch (order) {
+            LAGR_CASE(4) LAGR_CASE(6) LAGR_CASE(8)
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: velocity reduction, deterministic two-stage sum.  f is [nv][nx] (x fastest).
+// ------------------------------------------------------------------------------------------------
+static const int RED_CHUNKS = 128;
+size_t reduce_scratch_doubles(long long nx, long long nv) {
+    long long ch = nv < RED_CHUNKS ? nv : RED_CHUNKS;
+    return (size_t)(nx * ch);
+}
+__global__ void __launch_bounds__(128) k_reduce_stage1(const double *__restrict__ f, long long nx, long long nv,
+                                                        int nchunks, double *__restrict__ partial) {
+    const long long x = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (x >= nx) return;
+    const int c = blockIdx.y;
+    const long long v0 = nv * c / nchunks, v1 = nv * (c + 1) / nchunks;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    long long v = v0;
+    for (; v + 3 < v1; v += 4) {
+        a0 += __ldcs(f + x + nx * v);
+        a1 += __ldcs(f + x + nx * (v + 1));
+        a2 += __ldcs(f + x + nx * (v + 2));
+        a3 += __ldcs(f + x + nx * (v + 3));
+    }
+    for (; v < v1; ++v) a0 += __ldcs(f + x + nx * v);
+    partial[(long long)c * nx + x] = (a0 + a1) + (a2 + a3);
+}
+__global__ void k_reduce_stage2(const double *__restrict__ partial, long long nx, int nchunks, double scale,
+                                double *__restrict__ rho) {
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nx) return;
+    double a = 0;
+    for (int c = 0; c < nchunks; ++c) a += partial[(long long)c * nx + x];
+    rho[x] = a * scale;
+}
+cudaError_t launch_reduce_velocity(const double *f, long long nx, long long nv, double scale, double *rho,
+                                   double *scratch, cudaStream_t st) {
+    int nchunks = (int)(nv < RED_CHUNKS ? nv : RED_CHUNKS);
+    dim3 grid((unsigned)((nx + 127) / 128), nchunks);
+    k_reduce_stage1<<<grid, 128, 0, st>>>(f, nx, nv, nchunks, scratch);
+    COUNT_LAUNCH();
+    k_reduce_stage2<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(scratch, nx, nchunks, scale, rho);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: row sums for diagnostics: for each v: (sum_x f, sum_x |f|, sum_x f^2)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_sums(const double *__restrict__ f, long long nx, double *__restrict__ out3) {
+    const long long v = blockIdx.x;
+    const double *row = f + v * nx;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (long long x = threadIdx.x; x < nx; x += 256) {
+        const double t = row[x];
+        s0 += t; s1 += fabs(t); s2 += t * t;
+    }
+    __shared__ double sh[3][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (ln == 0) { sh[0][w] = s0; sh[1][w] = s1; sh[2][w] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double a = 0;
+        for (int i = 0; i < 8; ++i) a += sh[threadIdx.x][i];
+        out3[v * 3 + threadIdx.x] = a;
+    }
+}
+cudaError_t launch_row_sums(const double *f, long long nx, long long nv, double *out3, cudaStream_t st) {
+    k_row_sums<<<(unsigned)nv, 256, 0, st>>>(f, nx, out3);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: spectral multipliers (unnormalised cuFFT: the 1/N factors are folded in here)
+// ------------------------------------------------------------------------------------------------
+// 1D: E_hat(k) = -i rho_hat(k) / (k kx0) / N for k = 1..N/2-1, zero at DC and Nyquist
+// (sll_m_poisson_1d_periodic.F90:148-164)
+__global__ void k_poisson1d(const cufftDoubleComplex *__restrict__ r, int nc, double kx0, cufftDoubleComplex *__restrict__ e) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nc / 2) return;
+    cufftDoubleComplex out = {0.0, 0.0};
+    if (k >= 1 && k <= (nc - 2) / 2) {
+        const double kx = (double)k * kx0;
+        const double sc = (kx / (kx * kx)) / (double)nc;
+        out.x = sc * r[k].y;
+        out.y = -sc * r[k].x;
+    }
+    e[k] = out;
+}
+cudaError_t launch_poisson1d_mult(const cufftDoubleComplex *rho_hat, int nc, double L, cufftDoubleComplex *e_hat,
+                                  cudaStream_t st) {
+    k_poisson1d<<<(nc / 2 + 1 + 127) / 128, 128, 0, st>>>(rho_hat, nc, 2.0 * 3.14159265358979323846 / L, e_hat);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// 2D (sll_m_poisson_2d_periodic.F90:285-310,355-366): kx(1,1) := 1; E1_hat = -i kx/k2 rho_hat,
+// E2_hat = -i ky/k2 rho_hat, phi_hat = rho_hat/k2; ky uses the NEGATIVE Nyquist wavenumber (:299-302).
+// FFTW's c2r drops Im of the i=1 and i=N1/2+1 planes after the complex transform along x2; the same
+// result is obtained from a Hermitian-consistent spectrum: those two columns are replaced by their
+// Hermitian part in x2, X(j) <- (X(j) + conj X(-j))/2.
+__device__ __forceinline__ void p2d_vals(const cufftDoubleComplex *r, int nh, int n2, int i, int j, double kx0,
+                                         double ky0, double &phr, double &phi_, double &e1r, double &e1i, double &e2r,
+                                         double &e2i) {
+    double kx = (double)i * kx0;
+    const double ky = (double)((j < n2 / 2) ? j : j - n2) * ky0;
+    if (i == 0 && j == 0) kx = 1.0;
+    const double k2 = kx * kx + ky * ky;
+    const double kxs = kx / k2, kys = ky / k2;
+    const cufftDoubleComplex v = r[i + (size_t)j * nh];
+    phr = v.x / k2; phi_ = v.y / k2;
+    e1r = kxs * v.y; e1i = -kxs * v.x; // -i kxs (a + ib) = kxs b - i kxs a
+    e2r = kys * v.y; e2i = -kys * v.x;
+}
+__global__ void k_poisson2d(const cufftDoubleComplex *__restrict__ r, int n1, int n2, double kx0, double ky0,
+                            cufftDoubleComplex *__restrict__ ph, cufftDoubleComplex *__restrict__ e1,
+                            cufftDoubleComplex *__restrict__ e2) {
+    const int nh = n1 / 2 + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nh) return;
+    double a[6];
+    p2d_vals(r, nh, n2, i, j, kx0, ky0, a[0], a[1], a[2], a[3], a[4], a[5]);
+    if (i == 0 || 2 * i == n1) {
+        double b[6];
+        const int jm = (j == 0) ? 0 : n2 - j;
+        p2d_vals(r, nh, n2, i, jm, kx0, ky0, b[0], b[1], b[2], b[3], b[4], b[5]);
+#pragma unroll
+        for (int c = 0; c < 6; c += 2) {
+            a[c] = 0.5 * (a[c] + b[c]);
+            a[c + 1] = 0.5 * (a[c + 1] - b[c + 1]);
+        }
+    }
+    const double nrm = 1.0 / ((double)n1 * (double)n2);
+    const size_t idx = i + (size_t)j * nh;
+    if (ph) ph[idx] = make_cuDoubleComplex(a[0] * nrm, a[1] * nrm);
+    if (e1) e1[idx] = make_cuDoubleComplex(a[2] * nrm, a[3] * nrm);
+    if (e2) e2[idx] = make_cuDoubleComplex(a[4] * nrm, a[5] * nrm);
+}
+cudaError_t launch_poisson2d_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, double L1, double L2,
+                                  cufftDoubleComplex *phi_hat, cufftDoubleComplex *e1_hat, cufftDoubleComplex *e2_hat,
+                                  cudaStream_t st) {
+    const double tp = 2.0 * 3.14159265358979323846;
+    dim3 grid((n1 / 2 + 1 + 63) / 64, n2);
+    k_poisson2d<<<grid, 64, 0, st>>>(rho_hat, n1, n2, tp / L1, tp / L2, phi_hat, e1_hat, e2_hat);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// 3D (sll_m_poisson_3d_periodic_par.F90:403-441,1079-1158): phi_hat = rho_hat/(N^3 |k|^2), zero mean;
+// E_d_hat = -i k_d phi_hat with the signed wavenumber and the Nyquist mode of direction d dropped
+// (the reference multiplies it by a purely imaginary factor and keeps the real part).
+__global__ void k_poisson3d(const cufftDoubleComplex *__restrict__ r, int n1, int n2, int n3, double k10, double k20,
+                            double k30, cufftDoubleComplex *__restrict__ ph, cufftDoubleComplex *__restrict__ e1,
+                            cufftDoubleComplex *__restrict__ e2, cufftDoubleComplex *__restrict__ e3) {
+    const int nh = n1 / 2 + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i >= nh) return;
+    const size_t idx = i + (size_t)nh * (j + (size_t)n2 * k);
+    const double f1 = (double)i, f2 = (double)((j < n2 / 2) ? j : n2 - j), f3 = (double)((k < n3 / 2) ? k : n3 - k);
+    const double kx = k10 * f1, ky = k20 * f2, kz = k30 * f3;
+    cufftDoubleComplex p = {0.0, 0.0};
+    if (i + j + k != 0) {
+        const double sc = 1.0 / ((double)n1 * (double)n2 * (double)n3) / (kx * kx + ky * ky + kz * kz);
+        p.x = r[idx].x * sc; p.y = r[idx].y * sc;
+    }
+    if (ph) ph[idx] = p;
+    const double s1 = (2 * i == n1) ? 0.0 : k10 * (double)i;
+    const double s2 = (2 * j == n2) ? 0.0 : k20 * (double)((j < n2 / 2) ? j : j - n2);
+    const double s3 = (2 * k == n3) ? 0.0 : k30 * (double)((k < n3 / 2) ? k : k - n3);
+    if (e1) e1[idx] = make_cuDoubleComplex(s1 * p.y, -s1 * p.x);
+    if (e2) e2[idx] = make_cuDoubleComplex(s2 * p.y, -s2 * p.x);
+    if (e3) e3[idx] = make_cuDoubleComplex(s3 * p.y, -s3 * p.x);
+}
+cudaError_t launch_poisson3d_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, int n3, double L1, double L2,
+                                  double L3, cufftDoubleComplex *phi_hat, cufftDoubleComplex *e1_hat,
+                                  cufftDoubleComplex *e2_hat, cufftDoubleComplex *e3_hat, cudaStream_t st) {
+    const double tp = 2.0 * 3.14159265358979323846;
+    dim3 grid((n1 / 2 + 1 + 31) / 32, n2, n3);
+    k_poisson3d<<<grid, 32, 0, st>>>(rho_hat, n1, n2, n3, tp / L1, tp / L2, tp / L3, phi_hat, e1_hat, e2_hat, e3_hat);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__global__ void k_affine(double *out, long long n, double a0, double a1) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a0 + a1 * (double)i;
+}
+cudaError_t launch_affine(double *out, long long n, double a0, double a1, cudaStream_t st) {
+    k_affine<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, a0, a1);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+__global__ void k_rho_1d1v(double *rho, long long n, double c0, double c1) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rho[i] = c0 - c1 * rho[i];
+}
+cudaError_t launch_rho_1d1v(double *rho, long long n, double c0, double c1, cudaStream_t st) {
+    k_rho_1d1v<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rho, n, c0, c1);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+// single block deterministic sum of squares (fields are small: <= 128^2 or 32^3 values)
+__global__ void __launch_bounds__(1024) k_sum_squares(const double *__restrict__ a, long long n, double *out1) {
+    double s = 0;
+    for (long long i = threadIdx.x; i < n; i += 1024) s += a[i] * a[i];
+    __shared__ double sh[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 32; ++i) t += sh[i];
+        out1[0] = t;
+    }
+}
+cudaError_t launch_sum_squares(const double *a, long long n, double *out1, cudaStream_t st) {
+    k_sum_squares<<<1, 1024, 0, st>>>(a, n, out1);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// K6: box <-> contiguous buffer (column-major order inside the box, like the reference's pack loops)
+__global__ void __launch_bounds__(256) k_pack4d(const double *__restrict__ src, int e0, int e1, int e2, Box4 b,
+                                                double *__restrict__ buf, int unpack, double *__restrict__ dst) {
+    const long long n = (long long)b.n[0] * b.n[1] * b.n[2] * b.n[3];
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
+        long long r = t;
+        const int i0 = (int)(r % b.n[0]); r /= b.n[0];
+        const int i1 = (int)(r % b.n[1]); r /= b.n[1];
+        const int i2 = (int)(r % b.n[2]); r /= b.n[2];
+        const int i3 = (int)r;
+        const long long g = (b.lo[0] + i0) + (long long)e0 * ((b.lo[1] + i1) + (long long)e1 * ((b.lo[2] + i2) + (long long)e2 * (b.lo[3] + i3)));
+        if (unpack) dst[g] = buf[t];
+        else buf[t] = src[g];
+    }
+}
+cudaError_t launch_pack4d(const double *src, const int ext[4], Box4 box, double *buf, cudaStream_t st) {
+    long long n = (long long)box.n[0] * box.n[1] * box.n[2] * box.n[3];
+    if (n <= 0) return cudaSuccess;
+    unsigned nb = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    k_pack4d<<<nb, 256, 0, st>>>(src, ext[0], ext[1], ext[2], box, buf, 0, nullptr);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+cudaError_t launch_unpack4d(double *dst, const int ext[4], Box4 box, const double *buf, cudaStream_t st) {
+    long long n = (long long)box.n[0] * box.n[1] * box.n[2] * box.n[3];
+    if (n <= 0) return cudaSuccess;
+    unsigned nb = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    k_pack4d<<<nb, 256, 0, st>>>(nullptr, ext[0], ext[1], ext[2], box, const_cast<double *>(buf), 1, dst);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+} // namespace sllb

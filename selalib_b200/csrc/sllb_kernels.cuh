@@ -1,0 +1,54 @@
+// Internal interface between the CUDA kernels (sllb_kernels.cu) and the C ABI (sllb_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+namespace sllb {
+
+// Displacement of line (o, in), in cells: scale * v[((o/odiv)%omod)*ostr + ((in/idiv)%imod)*istr]
+struct DispDesc {
+    const double *v;
+    double scale;
+    long long odiv, omod, ostr, idiv, imod, istr;
+};
+
+enum { METHOD_SPLINE = 0, METHOD_LAGRANGE_FIXED = 1, METHOD_LAGRANGE_CENTERED = 2 };
+enum { STAGING_AUTO = 0, STAGING_TMA = 1, STAGING_CPASYNC = 2 };
+
+// K1/K2: one 1D periodic advection on every line of f viewed as [outer][n][inner], in place.
+// Returns cudaSuccess, cudaErrorInvalidValue (bad n / order) or a launch error.
+cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
+                          const DispDesc &dd, int staging, cudaStream_t st);
+
+// K3: rho[x] = scale * sum_v f[x + nx*v]; partial = scratch of reduce_scratch_doubles(nx, nv)
+size_t reduce_scratch_doubles(long long nx, long long nv);
+cudaError_t launch_reduce_velocity(const double *f, long long nx, long long nv, double scale, double *rho,
+                                   double *scratch, cudaStream_t st);
+
+// K8: per velocity index v: s[v] = (sum_x f, sum_x |f|, sum_x f^2)   -> out[3*nv]
+cudaError_t launch_row_sums(const double *f, long long nx, long long nv, double *out3, cudaStream_t st);
+
+// K4: spectral multipliers around cuFFT
+cudaError_t launch_poisson1d_mult(const cufftDoubleComplex *rho_hat, int nc, double L, cufftDoubleComplex *e_hat,
+                                  cudaStream_t st);
+cudaError_t launch_poisson2d_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, double L1, double L2,
+                                  cufftDoubleComplex *phi_hat, cufftDoubleComplex *e1_hat, cufftDoubleComplex *e2_hat,
+                                  cudaStream_t st);
+cudaError_t launch_poisson3d_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, int n3, double L1, double L2,
+                                  double L3, cufftDoubleComplex *phi_hat, cufftDoubleComplex *e1_hat,
+                                  cufftDoubleComplex *e2_hat, cufftDoubleComplex *e3_hat, cudaStream_t st);
+
+// small helpers
+cudaError_t launch_affine(double *out, long long n, double a0, double a1, cudaStream_t st); // out[i]=a0+a1*i
+cudaError_t launch_sum_squares(const double *a, long long n, double *out1, cudaStream_t st);
+cudaError_t launch_rho_1d1v(double *rho, long long n, double c0, double c1, cudaStream_t st); // rho = c0 - c1*rho
+// K6 pack/unpack between a local box array and a contiguous buffer
+struct Box4 { int lo[4]; int n[4]; };   // sub-box origin (local coords) and extents
+cudaError_t launch_pack4d(const double *src, const int ext[4], Box4 box, double *buf, cudaStream_t st);
+cudaError_t launch_unpack4d(double *dst, const int ext[4], Box4 box, const double *buf, cudaStream_t st);
+
+long long launch_count();
+void launch_count_reset();
+
+} // namespace sllb

@@ -1,0 +1,772 @@
+// sllb_sims.cu -- layouts / remap (a13), NCCL communicator, and the time loops of the three
+// simulations the hot path serves, running entirely on the device.
+#include <nccl.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sllb_internal.h"
+
+using namespace sllb;
+
+namespace {
+int check_nccl(ncclResult_t r, const char *what) {
+    if (r == ncclSuccess) return SLLB_OK;
+    return fail(SLLB_ERR_CUDA, std::string(what) + ": " + ncclGetErrorString(r));
+}
+#define SLLB_NCCL(call)                         \
+    do {                                        \
+        int _rc = check_nccl((call), #call);    \
+        if (_rc) return _rc;                    \
+    } while (0)
+
+// split_array_indices, src/parallelization/remap/sll_m_remapper.F90:1860-1939 (0-based, inclusive)
+void split_aux(std::vector<int> &lo, std::vector<int> &hi, int start, int seglen, int mn, int mx) {
+    if (seglen == 1) { lo[start] = mn; hi[start] = mx; return; }
+    const int num = mx - mn + 1;
+    int max1 = (num % 2 == 0) ? mn + num / 2 - 1 : mn + num / 2;
+    split_aux(lo, hi, start, seglen / 2, mn, max1);
+    split_aux(lo, hi, start + seglen / 2, seglen / 2, max1 + 1, mx);
+}
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+} // namespace
+
+extern "C" {
+
+/* sll_s_factorize_in_two_powers_of_two, sll_m_remapper.F90:6452-6476 */
+int sllb_factorize_in_two_powers_of_two(int num_procs, int *f1, int *f2) {
+    if (!f1 || !f2 || !is_pow2(num_procs)) return fail(SLLB_ERR_INVALID, "factorize: num_procs must be a power of two");
+    int exponent = 0;
+    while ((1 << exponent) < num_procs) ++exponent;
+    if (exponent > 0 && exponent % 2 == 0) { *f1 = 1 << (exponent / 2); *f2 = 1 << (exponent / 2); }
+    else if (exponent == 0) { *f1 = 1; *f2 = 1; }
+    else { *f1 = 1 << ((exponent - 1) / 2); *f2 = 1 << ((exponent + 1) / 2); }
+    return SLLB_OK;
+}
+
+/* initialize_layout_with_distributed_4D_array, sll_m_remapper.F90:1345-1487; rank order :1056-1066 */
+int sllb_layout4d_boxes(const int global[4], const int procs[4], int nranks, int *boxes) {
+    if (!global || !procs || !boxes) return fail(SLLB_ERR_INVALID, "layout4d_boxes: null");
+    if ((long long)procs[0] * procs[1] * procs[2] * procs[3] != nranks)
+        return fail(SLLB_ERR_INVALID, "layout4d_boxes: process mesh does not match the number of ranks");
+    std::vector<int> lo[4], hi[4];
+    for (int d = 0; d < 4; ++d) {
+        if (!is_pow2(procs[d])) return fail(SLLB_ERR_INVALID, "layout4d_boxes: process mesh must be powers of two (sll_m_remapper.F90:1389-1397)");
+        if (global[d] < procs[d]) return fail(SLLB_ERR_INVALID, "layout4d_boxes: fewer points than processes along an axis");
+        lo[d].resize(procs[d]); hi[d].resize(procs[d]);
+        split_aux(lo[d], hi[d], 0, procs[d], 0, global[d] - 1);
+    }
+    for (int l = 0; l < procs[3]; ++l) for (int k = 0; k < procs[2]; ++k) for (int j = 0; j < procs[1]; ++j) for (int i = 0; i < procs[0]; ++i) {
+        const int r = i + procs[0] * (j + procs[1] * (k + procs[2] * l));
+        const int c[4] = {i, j, k, l};
+        for (int d = 0; d < 4; ++d) { boxes[r * 8 + 2 * d] = lo[d][c[d]]; boxes[r * 8 + 2 * d + 1] = hi[d][c[d]]; }
+    }
+    return SLLB_OK;
+}
+
+/* box intersections = the remap plan (sll_m_remapper.F90:2073-2157) */
+int sllb_remap4d_plan(const int global[4], const int procs_from[4], const int procs_to[4], int nranks, int rank,
+                      int *send_boxes, int *recv_boxes) {
+    if (rank < 0 || rank >= nranks || !send_boxes || !recv_boxes) return fail(SLLB_ERR_INVALID, "remap4d_plan: bad arguments");
+    std::vector<int> from((size_t)nranks * 8), to((size_t)nranks * 8);
+    SLLB_TRY(sllb_layout4d_boxes(global, procs_from, nranks, from.data()));
+    SLLB_TRY(sllb_layout4d_boxes(global, procs_to, nranks, to.data()));
+    for (int r = 0; r < nranks; ++r)
+        for (int d = 0; d < 4; ++d) {
+            // what I (in the source layout) send to r (its target box); what I (target) receive from r (its source box)
+            send_boxes[r * 8 + 2 * d] = std::max(from[rank * 8 + 2 * d], to[r * 8 + 2 * d]);
+            send_boxes[r * 8 + 2 * d + 1] = std::min(from[rank * 8 + 2 * d + 1], to[r * 8 + 2 * d + 1]);
+            recv_boxes[r * 8 + 2 * d] = std::max(to[rank * 8 + 2 * d], from[r * 8 + 2 * d]);
+            recv_boxes[r * 8 + 2 * d + 1] = std::min(to[rank * 8 + 2 * d + 1], from[r * 8 + 2 * d + 1]);
+        }
+    return SLLB_OK;
+}
+
+/* sll_f_set_process_grid, src/parallelization/decomposition/sll_m_decomposition.F90:2473-2543:
+ * powers of two are distributed starting from the LAST (velocity) dimensions. */
+int sllb_set_process_grid(int nranks, int grid[6]) {
+    if (!grid || !is_pow2(nranks)) return fail(SLLB_ERR_INVALID, "set_process_grid: number of ranks must be a power of two");
+    for (int d = 0; d < 6; ++d) grid[d] = 1;
+    int rem = nranks, d = 5;
+    while (rem > 1) { grid[d] *= 2; rem /= 2; d = (d == 0) ? 5 : d - 1; }
+    return SLLB_OK;
+}
+
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------ */
+/* communicator                                                                                */
+/* ------------------------------------------------------------------------------------------ */
+struct sllb_comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+extern "C" {
+int sllb_comm_unique_id(void *id128) {
+    if (!id128) return fail(SLLB_ERR_INVALID, "comm_unique_id: null");
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    SLLB_NCCL(ncclGetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return SLLB_OK;
+}
+int sllb_comm_create(const void *id128, int nranks, int rank, sllb_comm_t *c) {
+    if (!id128 || !c || nranks < 1 || rank < 0 || rank >= nranks) return fail(SLLB_ERR_INVALID, "comm_create: bad arguments");
+    SLLB_TRY(require_device());
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    sllb_comm *cc = new sllb_comm();
+    cc->nranks = nranks; cc->rank = rank;
+    int rc = check_nccl(ncclCommInitRank(&cc->comm, nranks, id, rank), "ncclCommInitRank");
+    if (rc) { delete cc; return rc; }
+    *c = cc;
+    return SLLB_OK;
+}
+int sllb_comm_destroy(sllb_comm_t c) {
+    if (!c) return SLLB_OK;
+    if (c->comm) ncclCommDestroy(c->comm);
+    delete c;
+    return SLLB_OK;
+}
+int sllb_comm_allreduce_sum(sllb_comm_t c, double *d_buf, int64_t count) {
+    if (!c || !d_buf) return fail(SLLB_ERR_INVALID, "allreduce: null");
+    SLLB_NCCL(ncclAllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, c->comm, 0));
+    return SLLB_OK;
+}
+int sllb_comm_allgather(sllb_comm_t c, const double *d_send, double *d_recv, int64_t count_per_rank) {
+    if (!c || !d_send || !d_recv) return fail(SLLB_ERR_INVALID, "allgather: null");
+    SLLB_NCCL(ncclAllGather(d_send, d_recv, (size_t)count_per_rank, ncclDouble, c->comm, 0));
+    return SLLB_OK;
+}
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------ */
+/* distributed 4D field + remap                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+struct sllb_dist4d {
+    sllb_comm *comm = nullptr;
+    int nranks = 1, rank = 0;
+    int global[4];
+    int procs[2][4];              // [0] x-sequential (axes 2,3 split), [1] v-sequential (axes 0,1 split)
+    std::vector<int> boxes[2];    // all ranks' boxes per layout
+    sllb_field *F[2] = {nullptr, nullptr};
+    DevBuf sendbuf, recvbuf;
+    std::vector<int> sb[2], rb[2]; // plans per direction
+};
+
+static void box_of(const std::vector<int> &boxes, int r, int lo[4], int n[4]) {
+    for (int d = 0; d < 4; ++d) { lo[d] = boxes[r * 8 + 2 * d]; n[d] = boxes[r * 8 + 2 * d + 1] - lo[d] + 1; }
+}
+
+extern "C" {
+int sllb_dist4d_create(sllb_comm_t c, const int global[4], sllb_dist4d_t *D) {
+    if (!global || !D) return fail(SLLB_ERR_INVALID, "dist4d_create: null");
+    SLLB_TRY(require_device());
+    sllb_dist4d *dd = new sllb_dist4d();
+    dd->comm = c;
+    dd->nranks = c ? c->nranks : 1;
+    dd->rank = c ? c->rank : 0;
+    int f1 = 1, f2 = 1;
+    int rc = sllb_factorize_in_two_powers_of_two(dd->nranks, &f1, &f2);
+    if (rc) { delete dd; return rc; }
+    for (int d = 0; d < 4; ++d) dd->global[d] = global[d];
+    const int px[4] = {1, 1, f1, f2}, pv[4] = {f1, f2, 1, 1};
+    memcpy(dd->procs[0], px, sizeof(px));
+    memcpy(dd->procs[1], pv, sizeof(pv));
+    for (int w = 0; w < 2; ++w) {
+        dd->boxes[w].resize((size_t)dd->nranks * 8);
+        rc = sllb_layout4d_boxes(global, dd->procs[w], dd->nranks, dd->boxes[w].data());
+        if (rc) { delete dd; return rc; }
+    }
+    for (int dir = 0; dir < 2; ++dir) {
+        dd->sb[dir].resize((size_t)dd->nranks * 8); dd->rb[dir].resize((size_t)dd->nranks * 8);
+        rc = sllb_remap4d_plan(global, dd->procs[dir], dd->procs[1 - dir], dd->nranks, dd->rank, dd->sb[dir].data(), dd->rb[dir].data());
+        if (rc) { delete dd; return rc; }
+    }
+    int lo[4], n[4];
+    box_of(dd->boxes[0], dd->rank, lo, n);
+    rc = field_alloc(4, n, &dd->F[0]);
+    if (rc) { delete dd; return rc; }
+    if (dd->nranks == 1) {
+        rc = field_wrap(4, n, dd->F[0]->d, &dd->F[1]); // both layouts coincide: no copy, no exchange
+    } else {
+        box_of(dd->boxes[1], dd->rank, lo, n);
+        rc = field_alloc(4, n, &dd->F[1]);
+        if (!rc) rc = dd->sendbuf.ensure((size_t)dd->F[0]->total > (size_t)dd->F[1]->total ? dd->F[0]->total : dd->F[1]->total);
+        if (!rc) rc = dd->recvbuf.ensure(dd->sendbuf.n);
+    }
+    if (rc) { sllb_dist4d_destroy(dd); return rc; }
+    *D = dd;
+    return SLLB_OK;
+}
+int sllb_dist4d_destroy(sllb_dist4d_t D) {
+    if (!D) return SLLB_OK;
+    sllb_field_destroy(D->F[1]);
+    sllb_field_destroy(D->F[0]);
+    delete D;
+    return SLLB_OK;
+}
+int sllb_dist4d_field(sllb_dist4d_t D, int which, sllb_field_t *F) {
+    if (!D || !F || which < 0 || which > 1) return fail(SLLB_ERR_INVALID, "dist4d_field: bad arguments");
+    *F = D->F[which];
+    return SLLB_OK;
+}
+int sllb_dist4d_box(sllb_dist4d_t D, int which, int box[8]) {
+    if (!D || !box || which < 0 || which > 1) return fail(SLLB_ERR_INVALID, "dist4d_box: bad arguments");
+    for (int k = 0; k < 8; ++k) box[k] = D->boxes[which][D->rank * 8 + k];
+    return SLLB_OK;
+}
+/* apply_remap_4D_double (sll_m_remapper.F90:3308-3456): pack per destination, exchange, unpack. */
+int sllb_dist4d_remap(sllb_dist4d_t D, int direction) {
+    if (!D || direction < 0 || direction > 1) return fail(SLLB_ERR_INVALID, "dist4d_remap: bad arguments");
+    if (D->nranks == 1) return SLLB_OK;
+    sllb_field *src = D->F[direction], *dst = D->F[1 - direction];
+    int slo[4], sn[4], dlo[4], dn[4];
+    box_of(D->boxes[direction], D->rank, slo, sn);
+    box_of(D->boxes[1 - direction], D->rank, dlo, dn);
+    const std::vector<int> &sb = D->sb[direction], &rb = D->rb[direction];
+    std::vector<long long> soff(D->nranks + 1, 0), roff(D->nranks + 1, 0);
+    for (int r = 0; r < D->nranks; ++r) {
+        long long cs = 1, cr = 1;
+        for (int d = 0; d < 4; ++d) {
+            cs *= std::max(0, sb[r * 8 + 2 * d + 1] - sb[r * 8 + 2 * d] + 1);
+            cr *= std::max(0, rb[r * 8 + 2 * d + 1] - rb[r * 8 + 2 * d] + 1);
+        }
+        soff[r + 1] = soff[r] + cs; roff[r + 1] = roff[r] + cr;
+        if (cs > 0) {
+            Box4 b;
+            for (int d = 0; d < 4; ++d) { b.lo[d] = sb[r * 8 + 2 * d] - slo[d]; b.n[d] = sb[r * 8 + 2 * d + 1] - sb[r * 8 + 2 * d] + 1; }
+            SLLB_CUDA(launch_pack4d(src->d, sn, b, D->sendbuf.p + soff[r], 0));
+        }
+    }
+    SLLB_NCCL(ncclGroupStart());
+    for (int r = 0; r < D->nranks; ++r) {
+        const long long cs = soff[r + 1] - soff[r], cr = roff[r + 1] - roff[r];
+        if (cs > 0) SLLB_NCCL(ncclSend(D->sendbuf.p + soff[r], (size_t)cs, ncclDouble, r, D->comm->comm, 0));
+        if (cr > 0) SLLB_NCCL(ncclRecv(D->recvbuf.p + roff[r], (size_t)cr, ncclDouble, r, D->comm->comm, 0));
+    }
+    SLLB_NCCL(ncclGroupEnd());
+    for (int r = 0; r < D->nranks; ++r) {
+        if (roff[r + 1] - roff[r] <= 0) continue;
+        Box4 b;
+        for (int d = 0; d < 4; ++d) { b.lo[d] = rb[r * 8 + 2 * d] - dlo[d]; b.n[d] = rb[r * 8 + 2 * d + 1] - rb[r * 8 + 2 * d] + 1; }
+        SLLB_CUDA(launch_unpack4d(dst->d, dn, b, D->recvbuf.p + roff[r], 0));
+    }
+    return SLLB_OK;
+}
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------ */
+/* phase timers (CUDA events on the launch stream)                                              */
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+struct PhaseTimer {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    bool on = false;
+    void begin() { reset(); on = true; }
+    void mark(int phase_just_finished) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, 0);
+        ev.push_back(e); tag.push_back(phase_just_finished);
+    }
+    void collect(double out[4]) {
+        for (int k = 0; k < 4; ++k) out[k] = 0;
+        if (ev.size() < 2) return;
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            if (tag[i] >= 0 && tag[i] < 4) out[tag[i]] += ms;
+        }
+    }
+    void reset() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); tag.clear(); on = false; }
+    ~PhaseTimer() { reset(); }
+};
+} // namespace
+
+/* ------------------------------------------------------------------------------------------ */
+/* 2D2V: sim_bsl_vp_2d2v_cart_poisson_serial                                                    */
+/* simulations/parallel/bsl_vp_2d2v_cart_poisson_serial/sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:650-1364 */
+/* ------------------------------------------------------------------------------------------ */
+struct sllb_sim4d {
+    sllb_sim4d_params_t p;
+    sllb_comm *comm = nullptr;
+    sllb_dist4d *D = nullptr;
+    sllb_poisson *poisson = nullptr;
+    double delta[4];
+    int bx[8], bv[8];  // my boxes in the two layouts
+    DevBuf rho_tile, rho_gather, rho_full, E1, E2, E1loc, E2loc, small;
+    double nrj = 0.0;
+    int istep = 0;
+    PhaseTimer timer;
+    double phase_ms[4] = {0, 0, 0, 0};
+};
+
+__global__ void k_landau4d(double *f, int n0, int n1, int n2, int n3, int lo2, int lo3, double x0min, double x1min,
+                           double x2min, double x3min, double d0, double d1, double d2, double d3, double kx1, double kx2,
+                           double eps) {
+    const long long ntot = (long long)n0 * n1 * n2 * n3;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        const int i0 = (int)(r % n0); r /= n0;
+        const int i1 = (int)(r % n1); r /= n1;
+        const int i2 = (int)(r % n2); r /= n2;
+        const int i3 = (int)r;
+        const double x = x0min + (double)i0 * d0, y = x1min + (double)i1 * d1;
+        const double vx = x2min + (double)(i2 + lo2) * d2, vy = x3min + (double)(i3 + lo3) * d3;
+        const double factor1 = 1.0 + eps * cos(kx1 * x) * cos(kx2 * y);
+        f[t] = (1.0 / (2.0 * 3.14159265358979323846)) * factor1 * exp(-0.5 * (vx * vx + vy * vy));
+    }
+}
+
+static int sim4d_fields(sllb_sim4d *S) {
+    // rho(i1,i2) = delta3*delta4 * sum over (x3,x4) [trapezoid over the duplicated end points == plain sum],
+    // computed in the v-sequential layout; tiles gathered to every rank (split_to_full, :1366-1401).
+    sllb_field *Fv = S->D->F[1];
+    const int N1 = S->p.nc[0], N2 = S->p.nc[1];
+    const int P = S->D->nranks;
+    if (P == 1) {
+        SLLB_TRY(sllb_reduce_velocity(Fv, 2, S->delta[2] * S->delta[3], S->rho_full.p));
+    } else {
+        const long long tile = (long long)Fv->ext[0] * Fv->ext[1];
+        SLLB_TRY(sllb_reduce_velocity(Fv, 2, S->delta[2] * S->delta[3], S->rho_tile.p));
+        SLLB_TRY(sllb_comm_allgather(S->comm, S->rho_tile.p, S->rho_gather.p, tile));
+        const int ext[4] = {N1, N2, 1, 1};
+        for (int r = 0; r < P; ++r) {
+            Box4 b;
+            const int *bb = &S->D->boxes[1][r * 8];
+            b.lo[0] = bb[0]; b.n[0] = bb[1] - bb[0] + 1; b.lo[1] = bb[2]; b.n[1] = bb[3] - bb[2] + 1;
+            b.lo[2] = b.lo[3] = 0; b.n[2] = b.n[3] = 1;
+            SLLB_CUDA(launch_unpack4d(S->rho_full.p, ext, b, S->rho_gather.p + (long long)r * tile, 0));
+        }
+    }
+    SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho_full.p, nullptr, S->E1.p, S->E2.p, nullptr));
+    return SLLB_OK;
+}
+
+// nrj = sum(E1^2 + E2^2) delta1 delta2 over the (N1+1)(N2+1) nodes INCLUDING the periodic duplicates (:1112)
+static int sim4d_nrj(sllb_sim4d *S) {
+    const int N1 = S->p.nc[0], N2 = S->p.nc[1];
+    std::vector<double> e1((size_t)N1 * N2), e2((size_t)N1 * N2);
+    SLLB_CUDA(cudaMemcpy(e1.data(), S->E1.p, e1.size() * 8, cudaMemcpyDeviceToHost));
+    SLLB_CUDA(cudaMemcpy(e2.data(), S->E2.p, e2.size() * 8, cudaMemcpyDeviceToHost));
+    double s = 0;
+    for (int j = 0; j <= N2; ++j) for (int i = 0; i <= N1; ++i) {
+        const size_t k = (size_t)(i % N1) + (size_t)N1 * (j % N2);
+        s += e1[k] * e1[k] + e2[k] * e2[k];
+    }
+    S->nrj = s * S->delta[0] * S->delta[1];
+    return SLLB_OK;
+}
+
+static int sim4d_T(sllb_sim4d *S, double step) {
+    sllb_field *Fx = S->D->F[0];
+    const sllb_sim4d_params_t &p = S->p;
+    // out(x) = in(x - v*step*dt): displacement in cells = -v*step*dt/delta_x  (:1037-1064)
+    SLLB_TRY(sllb_advect_axis_affine(Fx, 0, p.method, p.order, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2],
+                                     -step * p.dt / S->delta[0]));
+    SLLB_TRY(sllb_advect_axis_affine(Fx, 1, p.method, p.order, 3, p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3],
+                                     -step * p.dt / S->delta[1]));
+    return SLLB_OK;
+}
+static int sim4d_V(sllb_sim4d *S, double step) {
+    sllb_field *Fv = S->D->F[1];
+    const sllb_sim4d_params_t &p = S->p;
+    const double *e1 = S->E1.p, *e2 = S->E2.p;
+    if (S->D->nranks > 1) { // my (x1,x2) tile of the replicated field
+        const int ext[4] = {p.nc[0], p.nc[1], 1, 1};
+        Box4 b;
+        b.lo[0] = S->bv[0]; b.n[0] = S->bv[1] - S->bv[0] + 1; b.lo[1] = S->bv[2]; b.n[1] = S->bv[3] - S->bv[2] + 1;
+        b.lo[2] = b.lo[3] = 0; b.n[2] = b.n[3] = 1;
+        SLLB_CUDA(launch_pack4d(S->E1.p, ext, b, S->E1loc.p, 0));
+        SLLB_CUDA(launch_pack4d(S->E2.p, ext, b, S->E2loc.p, 0));
+        e1 = S->E1loc.p; e2 = S->E2loc.p;
+    }
+    // out(v) = in(v - E*step*dt)  (:1137-1166), displacement computed from E inside the kernel (K5)
+    SLLB_TRY(sllb_advect_axis_field(Fv, 2, p.method, p.order, e1, 2, -step * p.dt / S->delta[2]));
+    SLLB_TRY(sllb_advect_axis_field(Fv, 3, p.method, p.order, e2, 2, -step * p.dt / S->delta[3]));
+    return SLLB_OK;
+}
+
+extern "C" {
+
+int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d_t *Sout) {
+    if (!p || !Sout) return fail(SLLB_ERR_INVALID, "sim4d_create: null");
+    if (p->split < 0 || p->split > 2) return fail(SLLB_ERR_UNSUPPORTED, "sim4d_create: split must be Strang VTV (0), Strang TVT (1) or Lie TV (2)");
+    SLLB_TRY(require_device());
+    sllb_sim4d *S = new sllb_sim4d();
+    S->p = *p;
+    S->comm = comm;
+    for (int d = 0; d < 4; ++d) S->delta[d] = (p->xmax[d] - p->xmin[d]) / (double)p->nc[d];
+    int rc = sllb_dist4d_create(comm, p->nc, &S->D);
+    if (!rc) rc = sllb_poisson2d_create(p->nc[0], p->nc[1], p->xmin[0], p->xmax[0], p->xmin[1], p->xmax[1], &S->poisson);
+    if (rc) { sllb_sim4d_destroy(S); return rc; }
+    sllb_dist4d_box(S->D, 0, S->bx);
+    sllb_dist4d_box(S->D, 1, S->bv);
+    const size_t n12 = (size_t)p->nc[0] * p->nc[1];
+    sllb_field *Fv = S->D->F[1];
+    const size_t tile = (size_t)Fv->ext[0] * Fv->ext[1];
+    rc = S->rho_full.ensure(n12);
+    if (!rc) rc = S->E1.ensure(n12);
+    if (!rc) rc = S->E2.ensure(n12);
+    if (!rc) rc = S->rho_tile.ensure(tile);
+    if (!rc) rc = S->rho_gather.ensure(tile * S->D->nranks);
+    if (!rc) rc = S->E1loc.ensure(tile);
+    if (!rc) rc = S->E2loc.ensure(tile);
+    if (!rc) rc = S->small.ensure(16);
+    if (rc) { sllb_sim4d_destroy(S); return rc; }
+    // initial data in the x-sequential layout (sll_f_landau_mode_initializer_4d)
+    sllb_field *Fx = S->D->F[0];
+    k_landau4d<<<148 * 8, 256>>>(Fx->d, Fx->ext[0], Fx->ext[1], Fx->ext[2], Fx->ext[3], S->bx[4], S->bx[6], p->xmin[0],
+                                 p->xmin[1], p->xmin[2], p->xmin[3], S->delta[0], S->delta[1], S->delta[2], S->delta[3],
+                                 p->kx1, p->kx2, p->eps);
+    rc = check_cuda(cudaGetLastError(), "k_landau4d");
+    // E at t = 0 (:851-887)
+    if (!rc) rc = sllb_dist4d_remap(S->D, 0);
+    if (!rc) rc = sim4d_fields(S);
+    if (!rc) rc = sim4d_nrj(S);
+    if (rc) { sllb_sim4d_destroy(S); return rc; }
+    *Sout = S;
+    return SLLB_OK;
+}
+int sllb_sim4d_destroy(sllb_sim4d_t S) {
+    if (!S) return SLLB_OK;
+    sllb_poisson_destroy(S->poisson);
+    sllb_dist4d_destroy(S->D);
+    delete S;
+    return SLLB_OK;
+}
+int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F) {
+    if (!S || !F) return fail(SLLB_ERR_INVALID, "sim4d_field: null");
+    *F = S->D->F[0];
+    return SLLB_OK;
+}
+int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6) {
+    if (!S || !row6) return fail(SLLB_ERR_INVALID, "sim4d_diagnostics: null");
+    sllb_field *Fx = S->D->F[0];
+    const sllb_sim4d_params_t &p = S->p;
+    // second velocity moments; the trapezoid rule over the duplicated end points averages v^2 at both
+    // ends, which for the periodic pair (vmin, vmax) is 0.5 (vmin^2 + vmax^2)
+    std::vector<double> w2;
+    for (int a = 2; a < 4; ++a)
+        for (int i = 0; i < Fx->ext[a]; ++i) {
+            const int ig = i + S->bx[2 * a];
+            double v = p.xmin[a] + ig * S->delta[a];
+            double vv = v * v;
+            if (ig == 0) vv = 0.5 * (p.xmin[a] * p.xmin[a] + p.xmax[a] * p.xmax[a]);
+            w2.push_back(vv);
+        }
+    double m[7];
+    SLLB_TRY(moments_local(Fx, 2, nullptr, w2.data(), m));
+    double loc[4] = {m[0], m[1], m[2], 0.5 * (m[5] + m[6])};
+    if (S->D->nranks > 1) {
+        SLLB_CUDA(cudaMemcpy(S->small.p, loc, sizeof(loc), cudaMemcpyHostToDevice));
+        SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->small.p, 4));
+        SLLB_CUDA(cudaMemcpy(loc, S->small.p, sizeof(loc), cudaMemcpyDeviceToHost));
+    }
+    const double vol = S->delta[0] * S->delta[1] * S->delta[2] * S->delta[3];
+    row6[0] = S->istep * p.dt;
+    row6[1] = S->nrj;
+    row6[2] = loc[3] * vol;
+    row6[3] = loc[0] * vol; row6[4] = loc[1] * vol; row6[5] = loc[2] * vol;
+    return SLLB_OK;
+}
+int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows) {
+    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim4d_run: bad arguments");
+    const sllb_sim4d_params_t &p = S->p;
+    // splitting tables: sll_m_time_splitting_coeff.F90:168-195
+    double steps[3]; int nsub; bool beginT;
+    if (p.split == 0) { steps[0] = 0.5; steps[1] = 1.0; steps[2] = 0.5; nsub = 3; beginT = false; }
+    else if (p.split == 1) { steps[0] = 0.5; steps[1] = 1.0; steps[2] = 0.5; nsub = 3; beginT = true; }
+    else { steps[0] = 1.0; steps[1] = 1.0; nsub = 2; beginT = true; }
+    S->timer.begin();
+    S->timer.mark(-1);
+    for (int it = 0; it < nsteps; ++it) {
+        int isub = 0; bool T = beginT;
+        for (int ss = 0; ss < nsub; ++ss) {
+            if (T) {
+                isub += 1;
+                SLLB_TRY(sim4d_T(S, steps[isub - 1]));
+                S->timer.mark(0);
+            } else {
+                SLLB_TRY(sllb_dist4d_remap(S->D, 0));
+                S->timer.mark(2);
+                SLLB_TRY(sim4d_fields(S));
+                S->timer.mark(1);
+                SLLB_TRY(sim4d_V(S, steps[isub]));
+                S->timer.mark(0);
+                SLLB_TRY(sllb_dist4d_remap(S->D, 1));
+                S->timer.mark(2);
+                isub += 1;
+            }
+            T = !T;
+        }
+        S->istep += 1;
+        if (with_diagnostics) {
+            SLLB_TRY(sim4d_nrj(S));
+            if (rows) SLLB_TRY(sllb_sim4d_diagnostics(S, rows + 6 * it));
+            S->timer.mark(3);
+        }
+    }
+    SLLB_CUDA(cudaDeviceSynchronize());
+    S->timer.collect(S->phase_ms);
+    S->timer.reset();
+    return SLLB_OK;
+}
+int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]) {
+    if (!S || !out) return fail(SLLB_ERR_INVALID, "sim4d_phase_ms: null");
+    for (int k = 0; k < 4; ++k) out[k] = S->phase_ms[k];
+    return SLLB_OK;
+}
+
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------ */
+/* 1D1V: sim_bsl_vp_1d1v_cart (no drive), Strang VTV                                            */
+/* simulations/parallel/bsl_vp_1d1v_cart/sll_m_sim_bsl_vp_1d1v_cart.F90:1066-1907               */
+/* ------------------------------------------------------------------------------------------ */
+struct sllb_sim2d {
+    int nc[2]; double xmin[2], xmax[2], delta[2];
+    int init; double kmode, eps, dt; int method, order;
+    sllb_field *F = nullptr;
+    sllb_poisson *poisson = nullptr;
+    DevBuf rho, E;
+    int istep = 0;
+};
+__global__ void k_init2d(double *f, int n0, int n1, double x0min, double x1min, double d0, double d1, int init,
+                         double kmode, double eps) {
+    const long long ntot = (long long)n0 * n1;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % n0), j = (int)(t / n0);
+        const double x = x0min + i * d0, v = x1min + j * d1;
+        const double fac = 1.0 / sqrt(2.0 * 3.14159265358979323846);
+        f[t] = init == 0 ? fac * (1.0 + eps * cos(kmode * x)) * exp(-0.5 * v * v)
+                         : fac * (1.0 + eps * cos(kmode * x)) * v * v * exp(-0.5 * v * v);
+    }
+}
+static int sim2d_field(sllb_sim2d *S) {
+    // rho = 1 - sum_j f w_j, trapezoid weights over the duplicated v end points == delta_v * plain sum (:937-943,1590-1604)
+    SLLB_TRY(sllb_reduce_velocity(S->F, 1, S->delta[1], S->rho.p));
+    SLLB_CUDA(launch_rho_1d1v(S->rho.p, S->nc[0], 1.0, 1.0, 0));
+    SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, nullptr, S->E.p, nullptr, nullptr));
+    return SLLB_OK;
+}
+extern "C" {
+int sllb_sim2d_create(int nc_x1, int nc_x2, double x1_min, double x1_max, double x2_min, double x2_max, int init,
+                      double kmode, double eps, double dt, int method, int order, sllb_sim2d_t *Sout) {
+    if (!Sout || nc_x1 < 8 || nc_x2 < 8) return fail(SLLB_ERR_INVALID, "sim2d_create: bad arguments");
+    SLLB_TRY(require_device());
+    sllb_sim2d *S = new sllb_sim2d();
+    S->nc[0] = nc_x1; S->nc[1] = nc_x2; S->xmin[0] = x1_min; S->xmax[0] = x1_max; S->xmin[1] = x2_min; S->xmax[1] = x2_max;
+    S->delta[0] = (x1_max - x1_min) / nc_x1; S->delta[1] = (x2_max - x2_min) / nc_x2;
+    S->init = init; S->kmode = kmode; S->eps = eps; S->dt = dt; S->method = method; S->order = order;
+    int rc = field_alloc(2, S->nc, &S->F);
+    if (!rc) rc = sllb_poisson1d_create(nc_x1, x1_min, x1_max, &S->poisson);
+    if (!rc) rc = S->rho.ensure(nc_x1);
+    if (!rc) rc = S->E.ensure(nc_x1);
+    if (!rc) {
+        k_init2d<<<148, 256>>>(S->F->d, nc_x1, nc_x2, x1_min, x2_min, S->delta[0], S->delta[1], init, kmode, eps);
+        rc = check_cuda(cudaGetLastError(), "k_init2d");
+    }
+    if (!rc) rc = sim2d_field(S);
+    if (rc) { sllb_sim2d_destroy(S); return rc; }
+    *Sout = S;
+    return SLLB_OK;
+}
+int sllb_sim2d_destroy(sllb_sim2d_t S) {
+    if (!S) return SLLB_OK;
+    sllb_poisson_destroy(S->poisson);
+    sllb_field_destroy(S->F);
+    delete S;
+    return SLLB_OK;
+}
+int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F) {
+    if (!S || !F) return fail(SLLB_ERR_INVALID, "sim2d_field: null");
+    *F = S->F;
+    return SLLB_OK;
+}
+int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
+    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim2d_run: bad arguments");
+    const double steps[3] = {0.5, 1.0, 0.5};
+    // velocity weights for the moments: trapezoid over duplicated end points (see sim4d diagnostics)
+    std::vector<double> w1(S->nc[1]), w2(S->nc[1]);
+    for (int j = 0; j < S->nc[1]; ++j) {
+        const double v = S->xmin[1] + j * S->delta[1];
+        w1[j] = v; w2[j] = v * v;
+    }
+    w1[0] = 0.5 * (S->xmin[1] + S->xmax[1]);
+    w2[0] = 0.5 * (S->xmin[1] * S->xmin[1] + S->xmax[1] * S->xmax[1]);
+    std::vector<double> hE(S->nc[0]);
+    for (int it = 0; it < nsteps; ++it) {
+        bool T = false;
+        for (int ss = 0; ss < 3; ++ss) {
+            if (T) { // out(x) = in(x - v*step*dt)  (:1570-1585)
+                SLLB_TRY(sllb_advect_axis_affine(S->F, 0, S->method, S->order, 1, S->xmin[1], S->delta[1],
+                                                 -steps[ss] * S->dt / S->delta[0]));
+                SLLB_TRY(sim2d_field(S));
+            } else { // alpha = -E*step, out(v) = in(v + E*step*dt)  (:1656-1686)
+                SLLB_TRY(sllb_advect_axis_field(S->F, 1, S->method, S->order, S->E.p, 1, steps[ss] * S->dt / S->delta[1]));
+            }
+            T = !T;
+        }
+        S->istep += 1;
+        if (rows) {
+            double m[5];
+            SLLB_TRY(moments_local(S->F, 1, w1.data(), w2.data(), m));
+            SLLB_CUDA(cudaMemcpy(hE.data(), S->E.p, hE.size() * 8, cudaMemcpyDeviceToHost));
+            double epot = 0;
+            for (int i = 0; i < S->nc[0]; ++i) epot += hE[i] * hE[i];
+            epot = 0.5 * epot * S->delta[0];
+            const double dv = S->delta[1], dx = S->delta[0];
+            double *r = rows + 8 * it;
+            r[0] = S->istep * S->dt; r[1] = m[0] * dv * dx; r[2] = m[1] * dv * dx; r[3] = m[3] * dv * dx;
+            r[4] = m[2] * dv * dx; r[5] = 0.5 * m[4] * dv * dx; r[6] = epot; r[7] = r[5] + r[6];
+        }
+    }
+    SLLB_CUDA(cudaDeviceSynchronize());
+    return SLLB_OK;
+}
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------ */
+/* 3D3V: sim_bsl_vp_3d3v_cart_dd_slim, Lagrange fixed stencils, single rank                     */
+/* simulations/parallel/bsl_vp_3d3v_cart_dd/sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:278-960      */
+/* ------------------------------------------------------------------------------------------ */
+struct sllb_sim6d {
+    sllb_sim6d_params_t p;
+    double emin[6], emax[6], de[6];
+    sllb_field *F = nullptr;
+    sllb_poisson *poisson = nullptr;
+    DevBuf rho, phi, ex, ey, ez, small;
+    bool started = false;
+    int itime = 0;
+};
+__global__ void k_landau6d(double *f, Ext6 n, double d0, double d1, double d2, double d3, double d4, double d5,
+                           double vmax, double factor, double alpha, double k0, double k1, double k2, double t0, double t1,
+                           double t2) {
+    long long ntot = 1;
+    for (int d = 0; d < 6; ++d) ntot *= n.e[d];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        int i[6];
+        for (int d = 0; d < 6; ++d) { i[d] = (int)(r % n.e[d]); r /= n.e[d]; }
+        const double x0 = d0 * i[0], x1 = d1 * i[1], x2 = d2 * i[2];
+        const double v0 = -vmax + d3 * i[3], v1 = -vmax + d4 * i[4], v2 = -vmax + d5 * i[5];
+        const double a0 = v0 / t0, a1 = v1 / t1, a2 = v2 / t2;
+        f[t] = factor * (1.0 + alpha * (cos(k0 * x0) * cos(k1 * x1) * cos(k2 * x2))) * exp(-0.5 * (a0 * a0 + a1 * a1 + a2 * a2));
+    }
+}
+static int sim6d_fields(sllb_sim6d *S) {
+    // rho = -dV_v sum f (sll_m_sim_6d_utilities.F90:221-244); Poisson + E (:614-616)
+    SLLB_TRY(sllb_reduce_velocity(S->F, 3, -(S->de[3] * S->de[4] * S->de[5]), S->rho.p));
+    SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p));
+    return SLLB_OK;
+}
+static int sim6d_diag(sllb_sim6d *S, double time, double *row14) {
+    const int *n = S->p.n;
+    const double Lx = S->emax[0] - S->emin[0], Ly = S->emax[1] - S->emin[1], Lz = S->emax[2] - S->emin[2];
+    const double vol_x = Lx * Ly * Lz;
+    double volume = 1.0;
+    for (int d = 0; d < 6; ++d) volume *= S->de[d];
+    const double dV = volume / vol_x, dVx = (S->de[0] * S->de[1] * S->de[2]) / vol_x;
+    std::vector<double> w1, w2;
+    for (int a = 3; a < 6; ++a) for (int i = 0; i < n[a]; ++i) { const double v = S->emin[a] + S->de[a] * (double)i; w1.push_back(v); w2.push_back(v * v); }
+    double m[9];
+    SLLB_TRY(moments_local(S->F, 3, w1.data(), w2.data(), m));
+    const long long nx3 = (long long)n[0] * n[1] * n[2];
+    const double *arr[5] = {S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p};
+    for (int a = 0; a < 5; ++a) SLLB_CUDA(launch_sum_squares(arr[a], nx3, S->small.p + a, 0));
+    double ss[5];
+    SLLB_CUDA(cudaMemcpy(ss, S->small.p, sizeof(ss), cudaMemcpyDeviceToHost));
+    row14[0] = time;
+    row14[1] = m[0] * dV; row14[2] = m[2] * dV;
+    for (int a = 0; a < 5; ++a) row14[3 + a] = ss[a] * dVx;
+    for (int a = 0; a < 3; ++a) { row14[8 + a] = m[3 + a] * dV; row14[11 + a] = m[6 + a] * dV; }
+    return SLLB_OK;
+}
+extern "C" {
+int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *Sout) {
+    if (!p || !Sout) return fail(SLLB_ERR_INVALID, "sim6d_create: null");
+    SLLB_TRY(require_device());
+    sllb_sim6d *S = new sllb_sim6d();
+    S->p = *p;
+    for (int d = 0; d < 3; ++d) { S->emin[d] = 0.0; S->emax[d] = p->x_max[d]; S->emin[d + 3] = -p->v_max; S->emax[d + 3] = p->v_max; }
+    for (int d = 0; d < 6; ++d) S->de[d] = (S->emax[d] - S->emin[d]) / (double)p->n[d];
+    const size_t nx3 = (size_t)p->n[0] * p->n[1] * p->n[2];
+    int rc = field_alloc(6, p->n, &S->F);
+    if (!rc) rc = sllb_poisson3d_create(p->n[0], p->n[1], p->n[2], S->emax[0], S->emax[1], S->emax[2], &S->poisson);
+    if (!rc) rc = S->rho.ensure(nx3);
+    if (!rc) rc = S->phi.ensure(nx3);
+    if (!rc) rc = S->ex.ensure(nx3);
+    if (!rc) rc = S->ey.ensure(nx3);
+    if (!rc) rc = S->ez.ensure(nx3);
+    if (!rc) rc = S->small.ensure(16);
+    if (!rc) {
+        Ext6 n;
+        for (int d = 0; d < 6; ++d) n.e[d] = p->n[d];
+        const double twopi = 2.0 * 3.14159265358979323846;
+        const double factor = 1.0 / (pow(sqrt(twopi), 3) * (p->v_thermal[0] * p->v_thermal[1] * p->v_thermal[2]));
+        k_landau6d<<<148 * 8, 256>>>(S->F->d, n, S->de[0], S->de[1], S->de[2], S->de[3], S->de[4], S->de[5], p->v_max, factor,
+                                     p->alpha, p->kx[0], p->kx[1], p->kx[2], p->v_thermal[0], p->v_thermal[1], p->v_thermal[2]);
+        rc = check_cuda(cudaGetLastError(), "k_landau6d");
+    }
+    if (!rc) rc = sim6d_fields(S);
+    if (rc) { sllb_sim6d_destroy(S); return rc; }
+    *Sout = S;
+    return SLLB_OK;
+}
+int sllb_sim6d_destroy(sllb_sim6d_t S) {
+    if (!S) return SLLB_OK;
+    sllb_poisson_destroy(S->poisson);
+    sllb_field_destroy(S->F);
+    delete S;
+    return SLLB_OK;
+}
+int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F) {
+    if (!S || !F) return fail(SLLB_ERR_INVALID, "sim6d_field: null");
+    *F = S->F;
+    return SLLB_OK;
+}
+/* advect_x (:817-865): eta1..3 with disp_eta = -v*dt/dx (:590-592) */
+int sllb_sim6d_advect_x(sllb_sim6d_t S) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_x: null");
+    for (int d = 0; d < 3; ++d)
+        SLLB_TRY(sllb_advect_axis_affine(S->F, d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_x, d + 3, S->emin[d + 3], S->de[d + 3],
+                                         -S->p.delta_t / S->de[d]));
+    return SLLB_OK;
+}
+/* advect_v (:889-958): eta4..6 with displacement E*dt/dv as a 3D field */
+int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_v: null");
+    const double *E[3] = {S->ex.p, S->ey.p, S->ez.p};
+    for (int d = 0; d < 3; ++d)
+        SLLB_TRY(sllb_advect_axis_field(S->F, 3 + d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_v, E[d], 3, dt / S->de[3 + d]));
+    return SLLB_OK;
+}
+int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
+    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run: bad arguments");
+    int row = 0;
+    if (!S->started) {
+        if (rows) SLLB_TRY(sim6d_diag(S, 0.0, rows));
+        row = 1;
+        SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
+        S->started = true;
+    }
+    for (int it = 1; it <= nsteps; ++it) {
+        SLLB_TRY(sllb_sim6d_advect_x(S));
+        SLLB_TRY(sim6d_fields(S));
+        S->itime += 1;
+        if (rows) SLLB_TRY(sim6d_diag(S, (double)S->itime * S->p.delta_t, rows + 14 * (row++)));
+        if (S->p.time_in_phase && it == nsteps) SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
+        else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
+    }
+    SLLB_CUDA(cudaDeviceSynchronize());
+    return SLLB_OK;
+}
+} // extern "C"

@@ -1,0 +1,102 @@
+"""CPU-side checks of the C ABI: the library loads without a GPU, exports every symbol declared in
+include/sll_b200.h, fails loudly (no fallback) when a compute entry point is called without a device,
+and the host-side layout / remap-plan logic reproduces sll_m_remapper's rules."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import selalib_b200 as sb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sll_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sllb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_all_symbols():
+    lib = sb.lib()
+    syms = declared_symbols()
+    assert len(syms) > 50
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert sb.device_count() == 0
+    for ctor in (lambda: sb.Field([16, 16]), lambda: sb.Advector1dPeriodic(32, 0.0, 1.0),
+                 lambda: sb.Poisson([32], [0.0], [1.0]), lambda: sb.Sim2d(32, 32, 0, 1, -1, 1, 0, 0.5, 1e-3, 0.1)):
+        with pytest.raises(sb.SllbError) as e:
+            ctor()
+        assert e.value.code == 4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "selalib_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in txt.replace("no CPU fallback", ""), fn
+
+
+def test_factorize_and_process_grid():
+    # sll_s_factorize_in_two_powers_of_two (sll_m_remapper.F90:6452-6476)
+    assert [sb.factorize_in_two_powers_of_two(p) for p in (1, 2, 4, 8, 16, 32)] == \
+        [(1, 1), (1, 2), (2, 2), (2, 4), (4, 4), (4, 8)]
+    with pytest.raises(sb.SllbError):
+        sb.factorize_in_two_powers_of_two(6)
+    # sll_f_set_process_grid table (sll_m_decomposition.F90:2489-2531)
+    table = {1: (1,) * 6, 2: (1, 1, 1, 1, 1, 2), 4: (1, 1, 1, 1, 2, 2), 8: (1, 1, 1, 2, 2, 2), 16: (1, 1, 2, 2, 2, 2),
+             64: (2,) * 6, 128: (2, 2, 2, 2, 2, 4), 4096: (4,) * 6}
+    for n, g in table.items():
+        assert sb.set_process_grid(n) == g
+
+
+def test_layout_boxes_split_rule():
+    # 129 points over 2 -> 65 + 64 (odd branch, sll_m_remapper.F90:1921); rank = i + P1*(j + P2*(k + P3*l))
+    b = sb.layout4d_boxes([129, 129, 33, 32], [2, 4, 1, 1], 8)
+    assert b[0, 0].tolist() == [0, 64] and b[1, 0].tolist() == [65, 128]
+    assert [b[2 * j, 1].tolist() for j in range(4)] == [[0, 32], [33, 64], [65, 96], [97, 128]]
+    assert (b[:, 2] == [0, 32]).all() and (b[:, 3] == [0, 31]).all()
+    # boxes tile the global array exactly once
+    cover = np.zeros((129, 129), dtype=int)
+    for r in range(8):
+        cover[b[r, 0, 0]:b[r, 0, 1] + 1, b[r, 1, 0]:b[r, 1, 1] + 1] += 1
+    assert (cover == 1).all()
+    with pytest.raises(sb.SllbError):
+        sb.layout4d_boxes([16] * 4, [3, 1, 1, 1], 3)
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 4, 8])
+def test_remap_plan_moves_every_element_once(nranks):
+    """test_remap_4d.F90:118-301: fill with the global linear index, remap, check every element."""
+    g = [12, 9, 8, 10]
+    f1, f2 = sb.factorize_in_two_powers_of_two(nranks)
+    px, pv = [1, 1, f1, f2], [f1, f2, 1, 1]
+    glob = np.arange(np.prod(g), dtype=float).reshape(g, order="F")
+    bx = sb.layout4d_boxes(g, px, nranks)
+    bv = sb.layout4d_boxes(g, pv, nranks)
+    sl = lambda b: tuple(slice(b[d, 0], b[d, 1] + 1) for d in range(4))
+    local_x = [glob[sl(bx[r])].copy(order="F") for r in range(nranks)]
+    local_v = [np.full([bv[r, d, 1] - bv[r, d, 0] + 1 for d in range(4)], -1.0, order="F") for r in range(nranks)]
+    for src in range(nranks):
+        sboxes, _ = sb.remap4d_plan(g, px, pv, nranks, src)
+        for dst in range(nranks):
+            _, rboxes = sb.remap4d_plan(g, px, pv, nranks, dst)
+            s, r = sboxes[dst], rboxes[src]
+            assert (s == r).all()          # both sides agree on the intersection
+            if (s[:, 0] > s[:, 1]).any():
+                continue
+            src_sl = tuple(slice(s[d, 0] - bx[src, d, 0], s[d, 1] + 1 - bx[src, d, 0]) for d in range(4))
+            dst_sl = tuple(slice(s[d, 0] - bv[dst, d, 0], s[d, 1] + 1 - bv[dst, d, 0]) for d in range(4))
+            local_v[dst][dst_sl] = local_x[src][src_sl]
+    for r in range(nranks):
+        assert np.array_equal(local_v[r], glob[sl(bv[r])])
