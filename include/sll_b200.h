@@ -139,6 +139,8 @@ int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, cons
                            int nfield_axes, double scale);
 /* tuning knob: 0 = auto, 1 = TMA bulk staging, 2 = cp.async staging (strided kernels) */
 int sllb_set_staging(int mode);
+/* tuning knob: chunks per line of the strided spline kernel: -1 = auto, 1, 2, 4, 8 */
+int sllb_set_spline_split(int chunks);
 
 /* ---- a14: velocity reduction -> charge density ----------------------------
  * rho[x] = scale * sum over the last (ndim - nx_axes) axes of F.  With periodic cells

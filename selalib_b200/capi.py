@@ -102,6 +102,10 @@ def set_staging(mode):
     _ck(lib().sllb_set_staging(C.c_int(mode)))
 
 
+def set_spline_split(chunks):
+    _ck(lib().sllb_set_spline_split(C.c_int(chunks)))
+
+
 # ---------------------------------------------------------------------------------------------
 # line-granular drop-in objects (mirror sll_t_advector_1d_periodic / sll_c_interpolator_1d)
 # ---------------------------------------------------------------------------------------------

@@ -179,6 +179,13 @@ int sllb_set_staging(int mode) {
     return SLLB_OK;
 }
 
+int sllb_set_spline_split(int chunks) {
+    if (chunks != -1 && chunks != 1 && chunks != 2 && chunks != 4 && chunks != 8)
+        return fail(SLLB_ERR_INVALID, "set_spline_split: chunks must be -1, 1, 2, 4 or 8");
+    g_spline_split = chunks;
+    return SLLB_OK;
+}
+
 /* ---------------- fields ---------------- */
 int sllb_field_create(int ndim, const int *extents, sllb_field_t *F) { return field_alloc(ndim, extents, F); }
 int sllb_field_destroy(sllb_field_t F) {

@@ -295,6 +295,101 @@ __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1a (split): spline on a strided axis with every line cut into P chunks of C = N/P points, one warp
+// per chunk (block = P warps = 32 lines).  The two first-order recurrences are restarted at every chunk
+// boundary with the same 27-term geometric series the reference uses for the periodic wrap
+// (sll_m_cubic_splines.F90:548-556,567-571; truncation (2-sqrt3)^27 = 3.6e-16), so the serial chain per
+// tile is C instead of N steps and P times more warps are resident to hide latency.
+// Chunk [k0,k1) computes g[k] for k = k1+2 .. k0 and emits cells k0+1 .. k1 (mod N).
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restrict__ f, const int N,
+                                                                  const long long inner, const DispDesc dd,
+                                                                  const int use_tma, const long long nlines) {
+    constexpr int BW = 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    const int tid = threadIdx.x, lane = tid & 31, chunk = tid >> 5;
+    const long long l = (long long)blockIdx.x * BW + lane;
+    const bool active = l < nlines;
+    const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    double *base = f + o * (long long)N * inner + in;
+    const int C = N / P, k0 = chunk * C, k1 = k0 + C;
+
+    if (use_tma) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(N * BW * 8));
+        const double *src0 = base - lane;
+        for (int j = tid; j < N; j += 32 * P) bulk_g2s(s + (size_t)j * BW, src0 + (long long)j * inner, BW * 8, bar);
+        mbar_wait(bar, 0);
+    } else {
+        if (active)
+            for (int j = k0; j < k1; ++j) cp_async8(s + (size_t)j * BW + lane, base + (long long)j * inner);
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    const double q = 0.26794919243112270647;
+    double *sc = s + lane;
+    // forward start value from pristine f: e[k0] = f[k0] + sum_i (-q)^{i+1} f[k0-1-i]
+    double e = sc[k0 * BW];
+    {
+        int idx = (k0 == 0) ? N - 1 : k0 - 1;
+#pragma unroll
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            e = fma(c_pw[i], sc[idx * BW], e);
+            idx = (idx == 0) ? N - 1 : idx - 1;
+        }
+    }
+    __syncthreads(); // every chunk has read its warm-up inputs before anybody overwrites f with e
+    sc[k0 * BW] = e;
+#pragma unroll 8
+    for (int k = k0 + 1; k < k1; ++k) {
+        e = fma(-q, e, sc[k * BW]);
+        sc[k * BW] = e;
+    }
+    __syncthreads();
+    if (!active) return;
+    // per-line weights (see spline_line)
+    const double disp = disp_of(dd, o, in);
+    const double r2 = 1.60769515458673623883;
+    const double fl = floor(disp);
+    const int dcell = (int)fl;
+    const double dx = disp - fl, cdx = 1.0 - dx;
+    const double s6 = r2 * (1.0 / 6.0);
+    const double w0 = cdx * cdx * cdx * s6;
+    const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+    const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+    const double w3 = dx * dx * dx * s6;
+    // backward start: g[k1+2] = e[k1+2] + sum_i (-q)^{i+1} e[k1+3+i]   (indices mod N)
+    int i2 = k1 + 2; if (i2 >= N) i2 -= N;
+    int i1 = k1 + 1; if (i1 >= N) i1 -= N;
+    int i0 = k1;     if (i0 >= N) i0 -= N;
+    double g = sc[i2 * BW];
+    {
+        int idx = (i2 == N - 1) ? 0 : i2 + 1;
+#pragma unroll
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            g = fma(c_pw[i], sc[idx * BW], g);
+            idx = (idx == N - 1) ? 0 : idx + 1;
+        }
+    }
+    double a3 = g;                                  // g[k1+2]
+    double a2 = fma(-q, a3, sc[i1 * BW]);           // g[k1+1]
+    double a1 = fma(-q, a2, sc[i0 * BW]);           // g[k1]
+    int iout = ((k1 - dcell) % N + N) % N;          // output index of cell k1 (mod N)
+#pragma unroll 8
+    for (int k = k1 - 1; k >= k0; --k) {
+        const double a0 = fma(-q, a1, sc[k * BW]);
+        const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
+        st_stream(base + (long long)iout * inner, val);
+        iout = (iout == 0) ? N - 1 : iout - 1;
+        a3 = a2; a2 = a1; a1 = a0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1b: spline, contiguous axis (inner == 1).  Block = BW consecutive lines = one contiguous chunk of
 // BW*N doubles.  The tile is transposed on the way in (pitch BW+1: conflict-free for both the
 // coalesced staging and the thread-per-line sweeps) and on the way out, where the integer part of the
@@ -422,6 +517,22 @@ static cudaError_t launch_strided_t(double *f, long long nlines, int N, long lon
     return cudaGetLastError();
 }
 
+int g_spline_split = -1; // -1 auto, else forced P in {1,2,4}
+template <int P>
+static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
+                                         int staging, cudaStream_t st) {
+    size_t smem = 128 + (size_t)N * 32 * 8;
+    auto kern = k_spline_strided_split<P>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    bool tma_ok = (inner % 32 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * 32 * 8 < (1u << 20));
+    int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
+    long long nblk = (nlines + 31) / 32;
+    kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 template <int METHOD, int S>
 static cudaError_t launch_strided(double *f, long long nlines, int N, long long inner, const DispDesc &dd, int staging,
                                   cudaStream_t st) {
@@ -480,6 +591,13 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
             if ((size_t)n * 17 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<16>(f, nlines, n, dd, st);
             if ((size_t)n * 9 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<8>(f, nlines, n, dd, st);
             return cudaErrorInvalidValue;
+        }
+        if ((size_t)n * 32 * 8 + 128 <= SMEM_MAX) {
+            int P = g_spline_split;
+            if (P < 0) P = (n % 4 == 0 && n / 4 >= 32) ? 4 : ((n % 2 == 0 && n / 2 >= 32) ? 2 : 1);
+            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st);
+            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st);
+            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st);
         }
         return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st);
     }

@@ -48,6 +48,7 @@ struct Box4 { int lo[4]; int n[4]; };   // sub-box origin (local coords) and ext
 cudaError_t launch_pack4d(const double *src, const int ext[4], Box4 box, double *buf, cudaStream_t st);
 cudaError_t launch_unpack4d(double *dst, const int ext[4], Box4 box, const double *buf, cudaStream_t st);
 
+extern int g_spline_split; // -1 auto, else lines are cut into this many chunks (1,2,4,8)
 long long launch_count();
 void launch_count_reset();
 
