@@ -257,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
             traffic = json.load(open(tpath)).get("k_advect_strided_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_advect_strided<32,spline> (x2/x3/x4 passes: 3 of 4 axes, 5 of 6 passes per step)",
+    roofline = {"bound": "hbm", "kernel": "k_spline_strided_split<4> (x2/x3/x4 passes: 3 of 4 axes, 5 of 6 passes per step)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * local_pts,
                 "ms_per_launch": t_dom, "ms_per_launch_by_axis": {f"x{a + 1}": kernel_ms[a] for a in axes},
@@ -324,7 +324,7 @@ def run_ours(args, rank, world, local_rank):
                 "config": {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP, "points": int(npts),
                            "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
                            "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap (pack + NCCL send/recv group + unpack)",
-                           "staging": "TMA bulk (cp.async.bulk) for strided axes, cp.async transpose for x1"},
+                           "staging": "TMA bulk (cp.async.bulk, UBLKCP) row copies into shared-memory line tiles"},
                 "phase_ms_per_step": {"advect": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
                                       "remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
