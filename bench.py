@@ -270,6 +270,7 @@ def run_ours(args, rank, world, local_rank):
     lib = sb.lib()
     hp = C.cast(C.c_void_p(host.data_ptr()), C.POINTER(C.c_double))
     assert lib.sllb_field_download(F.h, hp, None) == 0
+    F = S.field()
     row = np.zeros(6)
     e2e_steps = max(1, min(args.steps, env_int("SLLB_E2E_STEPS", 10)))
     barrier()
@@ -277,6 +278,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(e2e_steps):
         assert lib.sllb_field_upload(F.h, hp, None) == 0          # H2D of the step's input state (pinned)
         r = S.run(1, diagnostics=True)                             # one Strang step + diagnostics row (D2H)
+        F = S.field()                                              # x-sequential layout (remap back when N > 1)
         assert lib.sllb_field_download(F.h, hp, None) == 0         # D2H of the step's result
         row = r[0]
     barrier()
@@ -323,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP, "points": int(npts),
                            "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
-                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap (pack + NCCL send/recv group + unpack)",
+                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap (pack + NCCL send/recv group + unpack), 2 remaps per Strang step",
                            "staging": "TMA bulk (cp.async.bulk, UBLKCP) row copies into shared-memory line tiles"},
                 "phase_ms_per_step": {"advect": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
                                       "remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps},

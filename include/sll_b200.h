@@ -213,6 +213,33 @@ int sllb_dist4d_remap(sllb_dist4d_t D, int direction);
 /* ---- a12: 6D slim domain decomposition + halo exchange ----------------------
  * sll_f_set_process_grid (src/parallelization/decomposition/sll_m_decomposition.F90:2473-2543) */
 int sllb_set_process_grid(int nranks, int grid[6]);
+/* sll_t_cartesian_topology_6d + sll_t_decomposition_slim_6d (:124-141,209-227,379-555,835-869): block
+ * decomposition of a global 6D array, rank order of MPI_Cart_create (last axis fastest), periodic ring
+ * neighbours per axis.  procs = NULL or all zeros: sll_f_set_process_grid.  n % procs must be 0 (:846). */
+typedef struct sllb_dd6d *sllb_dd6d_t;
+/* host-only (no device): the block, coordinates and neighbours of `rank`; outputs may be NULL */
+int sllb_dd6d_plan(int nranks, int rank, const int global[6], const int procs_in[6], int procs[6], int coords[6],
+                   int mn[6], int nw[6], int left[6], int right[6]);
+int sllb_dd6d_create(sllb_comm_t c /* NULL = one rank */, const int global[6], const int procs[6], sllb_dd6d_t *D);
+int sllb_dd6d_destroy(sllb_dd6d_t D);
+int sllb_dd6d_field(sllb_dd6d_t D, sllb_field_t *F); /* local block, owned by D */
+/* any output may be NULL: process grid, my coordinates, global offset (0-based) and width of my block,
+ * left / right neighbour ranks per axis */
+int sllb_dd6d_layout(sllb_dd6d_t D, int procs[6], int coords[6], int mn[6], int nw[6], int left[6], int right[6]);
+/* sll_s_apply_halo_exchange_slim_6d_real64 (:1715-2030): fills the left halo (hw_left planes, the last
+ * planes of the left neighbour) and the right halo (hw_right planes, the first planes of the right
+ * neighbour) along `axis`; pack kernel + ncclSend/ncclRecv pair per side, or a local periodic copy when
+ * procs(axis) == 1. Halo buffers are [outer][hw][inner] like the reference's 6D halo arrays. */
+int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right);
+int sllb_dd6d_halo_download(sllb_dd6d_t D, int side /* 0 left, 1 right */, double *host);
+int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms); /* device time of the last exchange */
+/* halo exchange + sll_s_advection_6d_lagrange_dd_slim_advect_eta{axis+1}
+ * (src/semi_lagrangian/advection/sll_m_advection_6d_lagrange_dd_slim.F90:806-2001), fixed odd stencil,
+ * in place on the local block; `disp` indexes the LOCAL block like sllb_advect_axis. */
+int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_t *disp);
+/* tuning / test knob: 1 = also take the halo path (local periodic halo copy + halo-cells kernel, exactly
+ * the reference's sequence) when procs(axis) == 1; default 0 = periodic kernel, same arithmetic */
+int sllb_dd6d_set_force_halo(int on);
 
 /* ---- simulations (time loops of SURVEY.md section 3) --------------------- */
 /* 2D2V sim_bsl_vp_2d2v_cart_poisson_serial on 1..P GPUs.
@@ -233,7 +260,8 @@ int sllb_sim4d_destroy(sllb_sim4d_t S);
 int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows);
 /* row for the current state (time 0 row before any step) */
 int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6);
-int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F); /* local x-sequential field */
+int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F); /* local x-sequential field (remaps into it if needed) */
+int sllb_sim4d_box(sllb_sim4d_t S, int which, int box[8]); /* my box: which = 0 x-sequential, 1 v-sequential */
 /* per-phase device time of the last run() in ms: [advect, reduce+poisson, remap, diag] */
 int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]);
 
@@ -246,9 +274,9 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows);
 int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F);
 int sllb_sim2d_destroy(sllb_sim2d_t S);
 
-/* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (Lagrange fixed stencils), single GPU in this
- * round (velocity-split multi-GPU = next). rows: (nsteps+1) x 14 as the reference's
- * <prefix>.dat (sll_m_sim_6d_utilities.F90:357-364,632-633). */
+/* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (Lagrange fixed stencils) on 1..P GPUs (velocity axes split,
+ * halo exchange per v-advection, rho all-reduced). rows: (nsteps+1) x 14 as the reference's
+ * <prefix>.dat (sll_m_sim_6d_utilities.F90:357-364,632-633); every rank gets the global row. */
 typedef struct sllb_sim6d *sllb_sim6d_t;
 typedef struct {
     int n[6];
@@ -259,10 +287,16 @@ typedef struct {
     int time_in_phase;
 } sllb_sim6d_params_t;
 int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *S);
+/* process_grid: NULL / zeros = sll_f_set_process_grid(nranks) */
+int sllb_sim6d_create_dist(const sllb_sim6d_params_t *p, sllb_comm_t comm, const int process_grid[6], sllb_sim6d_t *S);
 int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows);
-int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F);
+int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F); /* local block */
+int sllb_sim6d_decomposition(sllb_sim6d_t S, sllb_dd6d_t *D);
 int sllb_sim6d_advect_x(sllb_sim6d_t S);
 int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt);
+int sllb_sim6d_fields(sllb_sim6d_t S);                                   /* rho, Poisson, E */
+int sllb_sim6d_diagnostics(sllb_sim6d_t S, double time, double *row14);  /* one row of <prefix>.dat */
+int sllb_sim6d_halo_ms(sllb_sim6d_t S, double *ms, int reset);           /* accumulated halo-exchange device time */
 int sllb_sim6d_destroy(sllb_sim6d_t S);
 
 #ifdef __cplusplus

@@ -368,6 +368,11 @@ class Sim4d:
         _ck(lib().sllb_sim4d_field(self.h, C.byref(f)))
         return Field(handle=f)
 
+    def box(self, which):
+        b = (C.c_int * 8)()
+        _ck(lib().sllb_sim4d_box(self.h, C.c_int(which), b))
+        return np.array(b[:]).reshape(4, 2)
+
     def phase_ms(self):
         out = np.zeros(4)
         _ck(lib().sllb_sim4d_phase_ms(self.h, _p(out)))
@@ -402,16 +407,79 @@ class Sim2d:
             self.h = vp()
 
 
+class Dd6d:
+    """sll_t_decomposition_slim_6d + halo exchange (sll_m_decomposition.F90:835-869,1715-2030)."""
+
+    def __init__(self, comm, global_ext, procs=None):
+        self.h = vp()
+        _ck(lib().sllb_dd6d_create(comm.h if comm is not None else None, _ints(global_ext),
+                                   _ints(procs) if procs is not None else None, C.byref(self.h)))
+        arrs = [(C.c_int * 6)() for _ in range(6)]
+        _ck(lib().sllb_dd6d_layout(self.h, *arrs))
+        self.procs, self.coords, self.mn, self.nw, self.left, self.right = [tuple(a[:]) for a in arrs]
+
+    def field(self):
+        f = vp()
+        _ck(lib().sllb_dd6d_field(self.h, C.byref(f)))
+        return Field(handle=f)
+
+    def halo_exchange(self, axis, hw_left, hw_right):
+        _ck(lib().sllb_dd6d_halo_exchange(self.h, C.c_int(axis), C.c_int(hw_left), C.c_int(hw_right)))
+        self._halo = (axis, hw_left, hw_right)
+
+    def halo(self, side):
+        axis, hl, hr = self._halo
+        shp = list(self.nw); shp[axis] = hl if side == 0 else hr
+        out = np.empty(shp, order="F")
+        if out.size:
+            _ck(lib().sllb_dd6d_halo_download(self.h, C.c_int(side), _p(out)))
+        return out
+
+    def exchange_ms(self):
+        ms = C.c_double(0)
+        _ck(lib().sllb_dd6d_exchange_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def advect_axis(self, axis, stencil, values, scale=1.0, dsel=(1, 1, 0, 1, 1, 0), on_device=False):
+        d = DispT()
+        if on_device:
+            d.values = C.cast(vp(values), dp); d.nvalues = 0; d.values_on_device = 1
+        else:
+            values = np.ascontiguousarray(values, dtype=np.float64)
+            self._keep = values
+            d.values = _p(values); d.nvalues = values.size; d.values_on_device = 0
+        d.scale = scale
+        d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
+        _ck(lib().sllb_dd6d_advect_axis(self.h, C.c_int(axis), C.c_int(stencil), C.byref(d)))
+
+    def destroy(self):
+        if self.h:
+            lib().sllb_dd6d_destroy(self.h)
+            self.h = vp()
+
+
+def dd6d_plan(nranks, rank, global_ext, procs=None):
+    """Host-only decomposition of `rank`: dict(procs, coords, mn, nw, left, right)."""
+    arrs = [(C.c_int * 6)() for _ in range(6)]
+    _ck(lib().sllb_dd6d_plan(C.c_int(nranks), C.c_int(rank), _ints(global_ext), _ints(procs) if procs is not None else None, *arrs))
+    return dict(zip(("procs", "coords", "mn", "nw", "left", "right"), [tuple(a[:]) for a in arrs]))
+
+
+def dd6d_set_force_halo(on):
+    _ck(lib().sllb_dd6d_set_force_halo(C.c_int(1 if on else 0)))
+
+
 class Sim6d:
     def __init__(self, n, v_max, x_max, stencil_x, stencil_v, delta_t, alpha, kx, v_thermal=(1.0, 1.0, 1.0),
-                 time_in_phase=True):
+                 time_in_phase=True, comm=None, process_grid=None):
         p = Sim6dParams()
         p.n[:] = n; p.v_max = v_max; p.x_max[:] = x_max
         p.stencil_x, p.stencil_v, p.delta_t = stencil_x, stencil_v, delta_t
         p.alpha = alpha; p.kx[:] = kx; p.v_thermal[:] = v_thermal
         p.time_in_phase = 1 if time_in_phase else 0
         self.h = vp()
-        _ck(lib().sllb_sim6d_create(C.byref(p), C.byref(self.h)))
+        _ck(lib().sllb_sim6d_create_dist(C.byref(p), comm.h if comm is not None else None,
+                                         _ints(process_grid) if process_grid is not None else None, C.byref(self.h)))
 
     def run(self, nsteps, first=True):
         rows = np.zeros((nsteps + (1 if first else 0), 14))
@@ -423,11 +491,31 @@ class Sim6d:
         _ck(lib().sllb_sim6d_field(self.h, C.byref(f)))
         return Field(handle=f)
 
+    def layout(self):
+        d = vp()
+        _ck(lib().sllb_sim6d_decomposition(self.h, C.byref(d)))
+        arrs = [(C.c_int * 6)() for _ in range(6)]
+        _ck(lib().sllb_dd6d_layout(d, *arrs))
+        return dict(zip(("procs", "coords", "mn", "nw", "left", "right"), [tuple(a[:]) for a in arrs]))
+
     def advect_x(self):
         _ck(lib().sllb_sim6d_advect_x(self.h))
 
     def advect_v(self, dt):
         _ck(lib().sllb_sim6d_advect_v(self.h, C.c_double(dt)))
+
+    def fields(self):
+        _ck(lib().sllb_sim6d_fields(self.h))
+
+    def diagnostics(self, time):
+        row = np.zeros(14)
+        _ck(lib().sllb_sim6d_diagnostics(self.h, C.c_double(time), _p(row)))
+        return row
+
+    def halo_ms(self, reset=True):
+        ms = C.c_double(0)
+        _ck(lib().sllb_sim6d_halo_ms(self.h, C.byref(ms), C.c_int(1 if reset else 0)))
+        return ms.value
 
     def destroy(self):
         if self.h:

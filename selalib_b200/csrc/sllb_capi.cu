@@ -30,6 +30,10 @@ int check_cufft(cufftResult r, const char *what) {
     if (r == CUFFT_SUCCESS) return SLLB_OK;
     return fail(SLLB_ERR_CUDA, std::string(what ? what : "cufft") + ": cufft error " + std::to_string((int)r));
 }
+int check_nccl(ncclResult_t r, const char *what) {
+    if (r == ncclSuccess) return SLLB_OK;
+    return fail(SLLB_ERR_CUDA, std::string(what) + ": " + ncclGetErrorString(r));
+}
 int require_device() {
     if (g_device_ok) return SLLB_OK;
     int n = 0;

@@ -1,0 +1,392 @@
+// sllb_dd6d.cu -- 6D slim domain decomposition, halo exchange (a12) and the 3D3V simulation on 1..P GPUs.
+//
+// Reference: sll_t_cartesian_topology_6d / sll_t_decomposition_slim_6d and
+// sll_s_apply_halo_exchange_slim_6d_real64 (src/parallelization/decomposition/sll_m_decomposition.F90:124-141,
+// 209-227,379-555,835-869,1715-2030), the fixed-stencil whole-array advector
+// (src/semi_lagrangian/advection/sll_m_advection_6d_lagrange_dd_slim.F90:806-2001) and the time loop of
+// simulations/parallel/bsl_vp_3d3v_cart_dd/sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:278-960.
+// MPI_Sendrecv with the ring neighbours becomes a grouped ncclSend/ncclRecv pair per side over NVLink.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sllb_internal.h"
+
+using namespace sllb;
+
+struct sllb_dd6d {
+    sllb_comm *comm = nullptr;
+    int nranks = 1, rank = 0;
+    int global[6], procs[6], coords[6];
+    int mn[6], nw[6];          // global 0-based offset and width of the local block
+    int left[6], right[6];     // ring neighbours per axis (ranks)
+    sllb_field *F = nullptr;
+    DevBuf halo_l, halo_r, send_lo, send_hi;
+    int hw_l = 0, hw_r = 0, halo_axis = -1;
+    double exch_ms = 0.0;      // device time of the last halo exchange (pack + send/recv)
+};
+
+static int g_force_halo = 0; // 1: take the halo-exchange + halo-cells kernel path even when procs(axis) == 1
+
+namespace {
+// MPI_Cart_create ordering (row-major: the LAST dimension varies fastest), sll_m_decomposition.F90:379-555
+int cart_rank(const int procs[6], const int c[6]) {
+    int r = 0;
+    for (int d = 0; d < 6; ++d) r = r * procs[d] + c[d];
+    return r;
+}
+void cart_coords(const int procs[6], int rank, int c[6]) {
+    for (int d = 5; d >= 0; --d) { c[d] = rank % procs[d]; rank /= procs[d]; }
+}
+long long outer_of(const sllb_dd6d *D, int axis) { long long o = 1; for (int d = axis + 1; d < 6; ++d) o *= D->nw[d]; return o; }
+long long inner_of(const sllb_dd6d *D, int axis) { long long i = 1; for (int d = 0; d < axis; ++d) i *= D->nw[d]; return i; }
+} // namespace
+
+extern "C" {
+
+/* host-only: the decomposition of `rank` (no device needed) */
+int sllb_dd6d_plan(int nranks, int rank, const int global[6], const int procs_in[6], int procs[6], int coords[6], int mn[6],
+                   int nw[6], int left[6], int right[6]) {
+    if (!global || nranks < 1 || rank < 0 || rank >= nranks) return fail(SLLB_ERR_INVALID, "dd6d_plan: bad arguments");
+    int pr[6], co[6];
+    bool given = false;
+    if (procs_in) for (int d = 0; d < 6; ++d) if (procs_in[d] > 0) given = true;
+    if (given) {
+        long long prod = 1;
+        for (int d = 0; d < 6; ++d) { pr[d] = procs_in[d] > 0 ? procs_in[d] : 1; prod *= pr[d]; }
+        if (prod != nranks) return fail(SLLB_ERR_INVALID, "dd6d: process grid does not match the number of ranks");
+    } else {
+        SLLB_TRY(sllb_set_process_grid(nranks, pr));
+    }
+    cart_coords(pr, rank, co);
+    for (int d = 0; d < 6; ++d) {
+        // slim decomposition requires n % procs == 0 (sll_m_decomposition.F90:846)
+        if (global[d] < 1 || global[d] % pr[d] != 0)
+            return fail(SLLB_ERR_INVALID, "dd6d: number of cells must be divisible by the number of processes along every axis");
+        int cl[6], cr[6];
+        memcpy(cl, co, sizeof(cl)); memcpy(cr, co, sizeof(cr));
+        cl[d] = (co[d] + pr[d] - 1) % pr[d];
+        cr[d] = (co[d] + 1) % pr[d];
+        if (procs) procs[d] = pr[d];
+        if (coords) coords[d] = co[d];
+        if (nw) nw[d] = global[d] / pr[d];
+        if (mn) mn[d] = co[d] * (global[d] / pr[d]);
+        if (left) left[d] = cart_rank(pr, cl);
+        if (right) right[d] = cart_rank(pr, cr);
+    }
+    return SLLB_OK;
+}
+
+int sllb_dd6d_create(sllb_comm_t c, const int global[6], const int procs_in[6], sllb_dd6d_t *Dout) {
+    if (!global || !Dout) return fail(SLLB_ERR_INVALID, "dd6d_create: null");
+    SLLB_TRY(require_device());
+    sllb_dd6d *D = new sllb_dd6d();
+    D->comm = c;
+    D->nranks = c ? c->nranks : 1;
+    D->rank = c ? c->rank : 0;
+    for (int d = 0; d < 6; ++d) D->global[d] = global[d];
+    int rc = sllb_dd6d_plan(D->nranks, D->rank, global, procs_in, D->procs, D->coords, D->mn, D->nw, D->left, D->right);
+    if (!rc) rc = field_alloc(6, D->nw, &D->F);
+    if (rc) { delete D; return rc; }
+    *Dout = D;
+    return SLLB_OK;
+}
+int sllb_dd6d_set_force_halo(int on) {
+    g_force_halo = on ? 1 : 0;
+    return SLLB_OK;
+}
+int sllb_dd6d_destroy(sllb_dd6d_t D) {
+    if (!D) return SLLB_OK;
+    sllb_field_destroy(D->F);
+    delete D;
+    return SLLB_OK;
+}
+int sllb_dd6d_field(sllb_dd6d_t D, sllb_field_t *F) {
+    if (!D || !F) return fail(SLLB_ERR_INVALID, "dd6d_field: null");
+    *F = D->F;
+    return SLLB_OK;
+}
+int sllb_dd6d_layout(sllb_dd6d_t D, int procs[6], int coords[6], int mn[6], int nw[6], int left[6], int right[6]) {
+    if (!D) return fail(SLLB_ERR_INVALID, "dd6d_layout: null");
+    for (int d = 0; d < 6; ++d) {
+        if (procs) procs[d] = D->procs[d];
+        if (coords) coords[d] = D->coords[d];
+        if (mn) mn[d] = D->mn[d];
+        if (nw) nw[d] = D->nw[d];
+        if (left) left[d] = D->left[d];
+        if (right) right[d] = D->right[d];
+    }
+    return SLLB_OK;
+}
+
+/* sll_s_apply_halo_exchange_slim_6d_real64 (sll_m_decomposition.F90:1715-2030):
+ * right halo (hw_right planes) <- the first planes of the right neighbour, i.e. every rank sends its
+ * first hw_right planes to its LEFT neighbour (:1839-1897); left halo (hw_left planes) <- the last planes
+ * of the left neighbour (:1958-2015).  procs(axis) == 1: local periodic copy (:1840-1861). */
+int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) {
+    if (!D || axis < 0 || axis > 5 || hw_left < 0 || hw_right < 0) return fail(SLLB_ERR_INVALID, "dd6d_halo_exchange: bad arguments");
+    const int n = D->nw[axis];
+    if (hw_left > n || hw_right > n) return fail(SLLB_ERR_INVALID, "dd6d_halo_exchange: halo wider than the local block");
+    const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
+    const size_t cl = (size_t)(outer * hw_left * inner), cr = (size_t)(outer * hw_right * inner);
+    SLLB_TRY(D->halo_l.ensure(cl > 0 ? cl : 1));
+    SLLB_TRY(D->halo_r.ensure(cr > 0 ? cr : 1));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    if (D->procs[axis] == 1) {
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, D->halo_r.p, 0));
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, D->halo_l.p, 0));
+    } else {
+        SLLB_TRY(D->send_lo.ensure(cr > 0 ? cr : 1));
+        SLLB_TRY(D->send_hi.ensure(cl > 0 ? cl : 1));
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, D->send_lo.p, 0));
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, D->send_hi.p, 0));
+        ncclComm_t cm = D->comm->comm;
+        SLLB_NCCL(ncclGroupStart());
+        if (cr > 0) {
+            SLLB_NCCL(ncclSend(D->send_lo.p, cr, ncclDouble, D->left[axis], cm, 0));
+            SLLB_NCCL(ncclRecv(D->halo_r.p, cr, ncclDouble, D->right[axis], cm, 0));
+        }
+        if (cl > 0) {
+            SLLB_NCCL(ncclSend(D->send_hi.p, cl, ncclDouble, D->right[axis], cm, 0));
+            SLLB_NCCL(ncclRecv(D->halo_l.p, cl, ncclDouble, D->left[axis], cm, 0));
+        }
+        SLLB_NCCL(ncclGroupEnd());
+    }
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    D->exch_ms = ms;
+    D->hw_l = hw_left; D->hw_r = hw_right; D->halo_axis = axis;
+    return SLLB_OK;
+}
+int sllb_dd6d_halo_download(sllb_dd6d_t D, int side, double *host) {
+    if (!D || !host || D->halo_axis < 0) return fail(SLLB_ERR_INVALID, "dd6d_halo_download: no halo present");
+    const int hw = side == 0 ? D->hw_l : D->hw_r;
+    const size_t cnt = (size_t)(outer_of(D, D->halo_axis) * hw * inner_of(D, D->halo_axis));
+    if (cnt) SLLB_CUDA(cudaMemcpy(host, side == 0 ? D->halo_l.p : D->halo_r.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    return SLLB_OK;
+}
+int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms) {
+    if (!D || !ms) return fail(SLLB_ERR_INVALID, "dd6d_exchange_ms: null");
+    *ms = D->exch_ms;
+    return SLLB_OK;
+}
+
+/* halo exchange + sll_s_advection_6d_lagrange_dd_slim_advect_eta{axis+1}: fixed odd stencil, in place.
+ * procs(axis) == 1 uses the periodic kernel directly (same arithmetic as the reference's local periodic
+ * halo copy followed by the halo-cells stencil). */
+int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_t *disp) {
+    if (!D || !disp || !disp->values) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis: null");
+    if (axis < 0 || axis > 5) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis: bad axis");
+    if (D->procs[axis] == 1 && !g_force_halo) return sllb_advect_axis(D->F, axis, SLLB_METHOD_LAGRANGE_FIXED, stencil, disp);
+    if (stencil < 3 || stencil > 11 || stencil % 2 == 0) return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: fixed Lagrange stencils 3,5,7,9,11");
+    if (axis == 0) return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: a split contiguous axis (eta1) is not implemented "
+                                                     "(sll_f_set_process_grid splits eta1 only from 64 ranks on)");
+    const int h = (stencil - 1) / 2;
+    SLLB_TRY(sllb_dd6d_halo_exchange(D, axis, h, h));
+    DispDesc dd;
+    if (disp->values_on_device) dd.v = disp->values;
+    else {
+        if (disp->nvalues < 1) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis: nvalues < 1");
+        SLLB_TRY(D->F->disp_scratch.ensure((size_t)disp->nvalues));
+        SLLB_CUDA(cudaMemcpyAsync(D->F->disp_scratch.p, disp->values, (size_t)disp->nvalues * sizeof(double), cudaMemcpyHostToDevice, 0));
+        dd.v = D->F->disp_scratch.p;
+    }
+    dd.scale = disp->scale;
+    dd.odiv = disp->odiv > 0 ? disp->odiv : 1; dd.omod = disp->omod > 0 ? disp->omod : 1; dd.ostr = disp->ostr;
+    dd.idiv = disp->idiv > 0 ? disp->idiv : 1; dd.imod = disp->imod > 0 ? disp->imod : 1; dd.istr = disp->istr;
+    cudaError_t e = launch_lagrange_halo(D->F->d, D->halo_l.p, D->halo_r.p, outer_of(D, axis), D->nw[axis], inner_of(D, axis),
+                                         stencil, dd, g_staging, 0);
+    if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: stencil / block size not implemented"); }
+    return check_cuda(e, "k_lagrange_halo launch");
+}
+
+} // extern "C"
+
+/* ------------------------------------------------------------------------------------------ */
+/* 3D3V: sim_bsl_vp_3d3v_cart_dd_slim, Lagrange fixed stencils, 1..P ranks                      */
+/* ------------------------------------------------------------------------------------------ */
+struct sllb_sim6d {
+    sllb_sim6d_params_t p;
+    double emin[6], emax[6], de[6];
+    sllb_comm *comm = nullptr;
+    sllb_dd6d *D = nullptr;
+    sllb_field *F = nullptr;
+    sllb_poisson *poisson = nullptr;
+    DevBuf rho, phi, ex, ey, ez, small;
+    bool started = false;
+    int itime = 0;
+    double halo_ms = 0.0, advect_ms = 0.0;
+};
+__global__ void k_landau6d(double *f, Ext6 n, Ext6 lo, double d0, double d1, double d2, double d3, double d4, double d5,
+                           double vmax, double factor, double alpha, double k0, double k1, double k2, double t0, double t1,
+                           double t2) {
+    long long ntot = 1;
+    for (int d = 0; d < 6; ++d) ntot *= n.e[d];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        int i[6];
+        for (int d = 0; d < 6; ++d) { i[d] = (int)(r % n.e[d]) + lo.e[d]; r /= n.e[d]; }
+        const double x0 = d0 * i[0], x1 = d1 * i[1], x2 = d2 * i[2];
+        const double v0 = -vmax + d3 * i[3], v1 = -vmax + d4 * i[4], v2 = -vmax + d5 * i[5];
+        const double a0 = v0 / t0, a1 = v1 / t1, a2 = v2 / t2;
+        f[t] = factor * (1.0 + alpha * (cos(k0 * x0) * cos(k1 * x1) * cos(k2 * x2))) * exp(-0.5 * (a0 * a0 + a1 * a1 + a2 * a2));
+    }
+}
+
+extern "C" {
+
+/* rho = -dV_v sum f (sll_m_sim_6d_utilities.F90:203-245), summed over the velocity communicator (:195),
+ * then Poisson and E (sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:605-616) */
+int sllb_sim6d_fields(sllb_sim6d_t S) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_fields: null");
+    SLLB_TRY(sllb_reduce_velocity(S->F, 3, -(S->de[3] * S->de[4] * S->de[5]), S->rho.p));
+    if (S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho.p, (int64_t)S->p.n[0] * S->p.n[1] * S->p.n[2]));
+    SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p));
+    return SLLB_OK;
+}
+/* sll_s_time_history_diagnostics (sll_m_sim_6d_utilities.F90:249-644): time + 13 numbers */
+int sllb_sim6d_diagnostics(sllb_sim6d_t S, double time, double *row14) {
+    if (!S || !row14) return fail(SLLB_ERR_INVALID, "sim6d_diagnostics: null");
+    const int *n = S->p.n;
+    const double Lx = S->emax[0] - S->emin[0], Ly = S->emax[1] - S->emin[1], Lz = S->emax[2] - S->emin[2];
+    const double vol_x = Lx * Ly * Lz;
+    double volume = 1.0;
+    for (int d = 0; d < 6; ++d) volume *= S->de[d];
+    const double dV = volume / vol_x, dVx = (S->de[0] * S->de[1] * S->de[2]) / vol_x;
+    std::vector<double> w1, w2;
+    for (int a = 3; a < 6; ++a)
+        for (int i = 0; i < S->D->nw[a]; ++i) {
+            const double v = S->emin[a] + S->de[a] * (double)(i + S->D->mn[a]);
+            w1.push_back(v); w2.push_back(v * v);
+        }
+    double m[9];
+    SLLB_TRY(moments_local(S->F, 3, w1.data(), w2.data(), m));
+    if (S->D->nranks > 1) {
+        SLLB_CUDA(cudaMemcpy(S->small.p + 5, m, sizeof(m), cudaMemcpyHostToDevice));
+        SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->small.p + 5, 9));
+        SLLB_CUDA(cudaMemcpy(m, S->small.p + 5, sizeof(m), cudaMemcpyDeviceToHost));
+    }
+    const long long nx3 = (long long)n[0] * n[1] * n[2];
+    const double *arr[5] = {S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p};
+    for (int a = 0; a < 5; ++a) SLLB_CUDA(launch_sum_squares(arr[a], nx3, S->small.p + a, 0));
+    double ss[5];
+    SLLB_CUDA(cudaMemcpy(ss, S->small.p, sizeof(ss), cudaMemcpyDeviceToHost));
+    row14[0] = time;
+    row14[1] = m[0] * dV; row14[2] = m[2] * dV;
+    for (int a = 0; a < 5; ++a) row14[3 + a] = ss[a] * dVx;
+    for (int a = 0; a < 3; ++a) { row14[8 + a] = m[3 + a] * dV; row14[11 + a] = m[6 + a] * dV; }
+    return SLLB_OK;
+}
+
+int sllb_sim6d_create_dist(const sllb_sim6d_params_t *p, sllb_comm_t comm, const int process_grid[6], sllb_sim6d_t *Sout) {
+    if (!p || !Sout) return fail(SLLB_ERR_INVALID, "sim6d_create: null");
+    SLLB_TRY(require_device());
+    sllb_sim6d *S = new sllb_sim6d();
+    S->p = *p;
+    S->comm = comm;
+    for (int d = 0; d < 3; ++d) { S->emin[d] = 0.0; S->emax[d] = p->x_max[d]; S->emin[d + 3] = -p->v_max; S->emax[d + 3] = p->v_max; }
+    for (int d = 0; d < 6; ++d) S->de[d] = (S->emax[d] - S->emin[d]) / (double)p->n[d];
+    const size_t nx3 = (size_t)p->n[0] * p->n[1] * p->n[2];
+    int rc = sllb_dd6d_create(comm, p->n, process_grid, &S->D);
+    if (!rc) {
+        S->F = S->D->F;
+        for (int d = 0; d < 3; ++d)
+            if (S->D->procs[d] != 1)
+                rc = fail(SLLB_ERR_UNSUPPORTED, "sim6d_create: process grids that split eta1..3 are not implemented (the reference's "
+                                                "table splits velocity axes only up to 8 ranks, sll_m_decomposition.F90:2489-2498)");
+    }
+    if (!rc) rc = sllb_poisson3d_create(p->n[0], p->n[1], p->n[2], S->emax[0], S->emax[1], S->emax[2], &S->poisson);
+    if (!rc) rc = S->rho.ensure(nx3);
+    if (!rc) rc = S->phi.ensure(nx3);
+    if (!rc) rc = S->ex.ensure(nx3);
+    if (!rc) rc = S->ey.ensure(nx3);
+    if (!rc) rc = S->ez.ensure(nx3);
+    if (!rc) rc = S->small.ensure(16);
+    if (!rc) {
+        Ext6 n, lo;
+        for (int d = 0; d < 6; ++d) { n.e[d] = S->D->nw[d]; lo.e[d] = S->D->mn[d]; }
+        const double twopi = 2.0 * 3.14159265358979323846;
+        const double factor = 1.0 / (pow(sqrt(twopi), 3) * (p->v_thermal[0] * p->v_thermal[1] * p->v_thermal[2]));
+        k_landau6d<<<148 * 8, 256>>>(S->F->d, n, lo, S->de[0], S->de[1], S->de[2], S->de[3], S->de[4], S->de[5], p->v_max, factor,
+                                     p->alpha, p->kx[0], p->kx[1], p->kx[2], p->v_thermal[0], p->v_thermal[1], p->v_thermal[2]);
+        rc = check_cuda(cudaGetLastError(), "k_landau6d");
+    }
+    if (!rc) rc = sllb_sim6d_fields(S);
+    if (rc) { sllb_sim6d_destroy(S); return rc; }
+    *Sout = S;
+    return SLLB_OK;
+}
+int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *Sout) { return sllb_sim6d_create_dist(p, nullptr, nullptr, Sout); }
+int sllb_sim6d_destroy(sllb_sim6d_t S) {
+    if (!S) return SLLB_OK;
+    sllb_poisson_destroy(S->poisson);
+    sllb_dd6d_destroy(S->D);
+    delete S;
+    return SLLB_OK;
+}
+int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F) {
+    if (!S || !F) return fail(SLLB_ERR_INVALID, "sim6d_field: null");
+    *F = S->F;
+    return SLLB_OK;
+}
+int sllb_sim6d_decomposition(sllb_sim6d_t S, sllb_dd6d_t *D) {
+    if (!S || !D) return fail(SLLB_ERR_INVALID, "sim6d_decomposition: null");
+    *D = S->D;
+    return SLLB_OK;
+}
+/* advect_x (:817-865): eta1..3 with disp_eta = -v*dt/dx (:590-592); x is not split, local periodic wrap */
+int sllb_sim6d_advect_x(sllb_sim6d_t S) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_x: null");
+    for (int d = 0; d < 3; ++d)
+        SLLB_TRY(sllb_advect_axis_affine(S->F, d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_x, d + 3,
+                                         S->emin[d + 3] + S->D->mn[d + 3] * S->de[d + 3], S->de[d + 3], -S->p.delta_t / S->de[d]));
+    return SLLB_OK;
+}
+/* advect_v (:889-958): per axis halo exchange, then eta4..6 with displacement E*dt/dv as a 3D field */
+int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_v: null");
+    const double *E[3] = {S->ex.p, S->ey.p, S->ez.p};
+    const long long nx3 = (long long)S->p.n[0] * S->p.n[1] * S->p.n[2];
+    for (int d = 0; d < 3; ++d) {
+        sllb_disp_t ds;
+        memset(&ds, 0, sizeof(ds));
+        ds.values = E[d]; ds.nvalues = nx3; ds.values_on_device = 1; ds.scale = dt / S->de[3 + d];
+        ds.odiv = ds.omod = 1; ds.ostr = 0; ds.idiv = 1; ds.imod = nx3; ds.istr = 1;
+        SLLB_TRY(sllb_dd6d_advect_axis(S->D, 3 + d, S->p.stencil_v, &ds));
+        if (S->D->procs[3 + d] > 1) S->halo_ms += S->D->exch_ms;
+    }
+    return SLLB_OK;
+}
+int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
+    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run: bad arguments");
+    int row = 0;
+    if (!S->started) {
+        if (rows) SLLB_TRY(sllb_sim6d_diagnostics(S, 0.0, rows));
+        row = 1;
+        SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
+        S->started = true;
+    }
+    for (int it = 1; it <= nsteps; ++it) {
+        SLLB_TRY(sllb_sim6d_advect_x(S));
+        SLLB_TRY(sllb_sim6d_fields(S));
+        S->itime += 1;
+        if (rows) SLLB_TRY(sllb_sim6d_diagnostics(S, (double)S->itime * S->p.delta_t, rows + 14 * (row++)));
+        if (S->p.time_in_phase && it == nsteps) SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
+        else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
+    }
+    SLLB_CUDA(cudaDeviceSynchronize());
+    return SLLB_OK;
+}
+int sllb_sim6d_halo_ms(sllb_sim6d_t S, double *ms, int reset) {
+    if (!S || !ms) return fail(SLLB_ERR_INVALID, "sim6d_halo_ms: null");
+    *ms = S->halo_ms;
+    if (reset) S->halo_ms = 0.0;
+    return SLLB_OK;
+}
+} // extern "C"

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cufft.h>
+#include <nccl.h>
 #include <string>
 #include <vector>
 
@@ -33,6 +34,13 @@ extern int g_staging;
         if (_rc) return _rc;                             \
     } while (0)
 
+int check_nccl(ncclResult_t r, const char *what);
+#define SLLB_NCCL(call)                                  \
+    do {                                                 \
+        int _rc = sllb::check_nccl((call), #call);       \
+        if (_rc) return _rc;                             \
+    } while (0)
+
 struct Ext6 { int e[6]; };
 
 // simple owning device buffer
@@ -56,6 +64,11 @@ struct sllb_field {
     sllb::DevBuf red_scratch;    // reduction partials
     sllb::DevBuf stage;          // upload/download staging with duplicates
     sllb::DevBuf rows;           // diagnostics row sums
+};
+
+struct sllb_comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
 };
 
 struct sllb_poisson {

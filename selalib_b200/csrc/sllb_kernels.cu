@@ -480,6 +480,79 @@ __global__ void __launch_bounds__(256) k_lagrange_contig(double *__restrict__ f,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2c: fixed odd Lagrange on a strided axis whose lines are split across ranks: the local piece of N
+// points is extended by H = (S-1)/2 halo planes on each side (left | local | right), exactly the
+// buf_i the reference assembles before sll_s_lagrange_interpolation_1d_fast_disp_fixed_haloc_cells
+// (sll_m_advection_6d_lagrange_dd_slim.F90:1636-1660).  Halo buffers are [outer][H][inner].
+// ------------------------------------------------------------------------------------------------
+template <int BW, int S>
+__global__ void __launch_bounds__(BW) k_lagrange_halo(double *__restrict__ f, const double *__restrict__ hl,
+                                                       const double *__restrict__ hr, const long long nlines,
+                                                       const int N, const long long inner, const DispDesc dd,
+                                                       const int use_tma) {
+    constexpr int H = (S - 1) / 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    const int tid = threadIdx.x;
+    const long long l = (long long)blockIdx.x * BW + tid;
+    const bool active = l < nlines;
+    const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    double *base = f + o * (long long)N * inner + in;
+    const double *lb = hl + o * (long long)H * inner + in;
+    const double *rb = hr + o * (long long)H * inner + in;
+    const int R = N + 2 * H;
+    if (use_tma) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(R * BW * 8));
+        for (int j = tid; j < R; j += BW) {
+            const double *src = (j < H) ? lb - tid + (long long)j * inner
+                              : (j < H + N) ? base - tid + (long long)(j - H) * inner
+                                            : rb - tid + (long long)(j - H - N) * inner;
+            bulk_g2s(s + (size_t)j * BW, src, BW * 8, bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        if (active) {
+            for (int j = 0; j < H; ++j) cp_async8(s + (size_t)j * BW + tid, lb + (long long)j * inner);
+            for (int j = 0; j < N; ++j) cp_async8(s + (size_t)(j + H) * BW + tid, base + (long long)j * inner);
+            for (int j = 0; j < H; ++j) cp_async8(s + (size_t)(j + H + N) * BW + tid, rb + (long long)j * inner);
+        }
+        cp_async_wait_all();
+    }
+    if (!active) return;
+    double pp[S], w[S];
+    lagr_coeff<S>(disp_of(dd, o, in), pp);
+    const double *sc = s + tid;
+#pragma unroll
+    for (int k = 1; k < S; ++k) w[k] = sc[(k - 1) * BW];
+#pragma unroll 4
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) w[k] = w[k + 1];
+        w[S - 1] = sc[(i + S - 1) * BW];
+        double acc = pp[0] * w[0];
+#pragma unroll
+        for (int k = 1; k < S; ++k) acc = fma(pp[k], w[k], acc);
+        st_stream(base + (long long)i * inner, acc);
+    }
+}
+
+// K7: halo pack, buf[o][j][in] = f[o][j0 + j][in] for j < hw; f viewed as [outer][n][inner]
+__global__ void __launch_bounds__(256) k_halo_pack(const double *__restrict__ f, const long long outer, const int n,
+                                                   const long long inner, const int j0, const int hw,
+                                                   double *__restrict__ buf) {
+    const long long chunk = (long long)hw * inner;
+    for (long long o = blockIdx.y; o < outer; o += gridDim.y) {
+        const double *src = f + (o * n + j0) * inner;
+        double *dst = buf + o * chunk;
+        for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < chunk; t += (long long)gridDim.x * 256)
+            dst[t] = __ldcs(src + t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 static bool g_pw_ready = false;
@@ -618,6 +691,50 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
         }
     }
     return cudaErrorInvalidValue;
+}
+
+template <int S>
+static cudaError_t launch_lagrange_halo_t(double *f, const double *hl, const double *hr, long long nlines, int n,
+                                          long long inner, const DispDesc &dd, int staging, cudaStream_t st) {
+    constexpr int BW = 32;
+    const int R = n + (S - 1);
+    size_t smem = 128 + (size_t)R * BW * 8;
+    if (smem > SMEM_MAX) return cudaErrorInvalidValue;
+    auto kern = k_lagrange_halo<BW, S>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    bool tma_ok = (inner % BW == 0) && al16(f) && al16(hl) && al16(hr);
+    int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
+    long long nblk = (nlines + BW - 1) / BW;
+    kern<<<(unsigned)nblk, BW, smem, st>>>(f, hl, hr, nlines, n, inner, dd, use_tma);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
+                                 long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st) {
+    if (n < 1 || outer < 1 || inner < 2) return cudaErrorInvalidValue;
+    const long long nlines = outer * inner;
+    switch (order) {
+    case 3: return launch_lagrange_halo_t<3>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
+    case 5: return launch_lagrange_halo_t<5>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
+    case 7: return launch_lagrange_halo_t<7>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
+    case 9: return launch_lagrange_halo_t<9>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
+    case 11: return launch_lagrange_halo_t<11>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t launch_halo_pack(const double *f, long long outer, int n, long long inner, int j0, int hw, double *buf,
+                             cudaStream_t st) {
+    if (hw <= 0) return cudaSuccess;
+    const long long chunk = (long long)hw * inner;
+    long long gx = (chunk + 1023) / 1024;
+    if (gx > 148 * 8) gx = 148 * 8;
+    long long gy = outer < 65535 ? outer : 65535;
+    while (gx * gy > 148LL * 64 && gx > 1) gx = (gx + 1) / 2;
+    k_halo_pack<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(f, outer, n, inner, j0, hw, buf);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

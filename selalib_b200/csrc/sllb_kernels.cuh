@@ -21,6 +21,13 @@ enum { STAGING_AUTO = 0, STAGING_TMA = 1, STAGING_CPASYNC = 2 };
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
                           const DispDesc &dd, int staging, cudaStream_t st);
 
+// K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]
+cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
+                                 long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st);
+// K7: buf[o][j][in] = f[o][j0+j][in], j < hw
+cudaError_t launch_halo_pack(const double *f, long long outer, int n, long long inner, int j0, int hw, double *buf,
+                             cudaStream_t st);
+
 // K3: rho[x] = scale * sum_v f[x + nx*v]; partial = scratch of reduce_scratch_doubles(nx, nv)
 size_t reduce_scratch_doubles(long long nx, long long nv);
 cudaError_t launch_reduce_velocity(const double *f, long long nx, long long nv, double scale, double *rho,

@@ -1,7 +1,5 @@
 // sllb_sims.cu -- layouts / remap (a13), NCCL communicator, and the time loops of the three
 // simulations the hot path serves, running entirely on the device.
-#include <nccl.h>
-
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -12,16 +10,6 @@
 using namespace sllb;
 
 namespace {
-int check_nccl(ncclResult_t r, const char *what) {
-    if (r == ncclSuccess) return SLLB_OK;
-    return fail(SLLB_ERR_CUDA, std::string(what) + ": " + ncclGetErrorString(r));
-}
-#define SLLB_NCCL(call)                         \
-    do {                                        \
-        int _rc = check_nccl((call), #call);    \
-        if (_rc) return _rc;                    \
-    } while (0)
-
 // split_array_indices, src/parallelization/remap/sll_m_remapper.F90:1860-1939 (0-based, inclusive)
 void split_aux(std::vector<int> &lo, std::vector<int> &hi, int start, int seglen, int mn, int mx) {
     if (seglen == 1) { lo[start] = mn; hi[start] = mx; return; }
@@ -99,10 +87,6 @@ int sllb_set_process_grid(int nranks, int grid[6]) {
 /* ------------------------------------------------------------------------------------------ */
 /* communicator                                                                                */
 /* ------------------------------------------------------------------------------------------ */
-struct sllb_comm {
-    ncclComm_t comm = nullptr;
-    int nranks = 1, rank = 0;
-};
 
 extern "C" {
 int sllb_comm_unique_id(void *id128) {
@@ -304,6 +288,7 @@ struct sllb_sim4d {
     DevBuf rho_tile, rho_gather, rho_full, E1, E2, E1loc, E2loc, small;
     double nrj = 0.0;
     int istep = 0;
+    int layout = 0;    // which copy of f is current: 0 x-sequential, 1 v-sequential
     PhaseTimer timer;
     double phase_ms[4] = {0, 0, 0, 0};
 };
@@ -323,6 +308,17 @@ __global__ void k_landau4d(double *f, int n0, int n1, int n2, int n3, int lo2, i
         const double factor1 = 1.0 + eps * cos(kx1 * x) * cos(kx2 * y);
         f[t] = (1.0 / (2.0 * 3.14159265358979323846)) * factor1 * exp(-0.5 * (vx * vx + vy * vy));
     }
+}
+
+// Bring f into the wanted layout.  The reference remaps back to the x-sequential layout after every V
+// stage (:1171) and forth again before the next one (:1069); when two V stages follow each other (the end of
+// one Strang step and the start of the next) that round trip moves every element back to where it was, so it
+// is skipped here: same values, two remaps per step instead of four.
+static int sim4d_to_layout(sllb_sim4d *S, int want) {
+    if (S->layout == want) return SLLB_OK;
+    SLLB_TRY(sllb_dist4d_remap(S->D, S->layout));
+    S->layout = want;
+    return SLLB_OK;
 }
 
 static int sim4d_fields(sllb_sim4d *S) {
@@ -428,7 +424,7 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
                                  p->kx1, p->kx2, p->eps);
     rc = check_cuda(cudaGetLastError(), "k_landau4d");
     // E at t = 0 (:851-887)
-    if (!rc) rc = sllb_dist4d_remap(S->D, 0);
+    if (!rc) rc = sim4d_to_layout(S, 1);
     if (!rc) rc = sim4d_fields(S);
     if (!rc) rc = sim4d_nrj(S);
     if (rc) { sllb_sim4d_destroy(S); return rc; }
@@ -444,19 +440,25 @@ int sllb_sim4d_destroy(sllb_sim4d_t S) {
 }
 int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F) {
     if (!S || !F) return fail(SLLB_ERR_INVALID, "sim4d_field: null");
+    SLLB_TRY(sim4d_to_layout(S, 0));
     *F = S->D->F[0];
     return SLLB_OK;
 }
+int sllb_sim4d_box(sllb_sim4d_t S, int which, int box[8]) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim4d_box: null");
+    return sllb_dist4d_box(S->D, which, box);
+}
 int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6) {
     if (!S || !row6) return fail(SLLB_ERR_INVALID, "sim4d_diagnostics: null");
-    sllb_field *Fx = S->D->F[0];
+    sllb_field *Fx = S->D->F[S->layout];
+    const int *bx = S->layout == 0 ? S->bx : S->bv;
     const sllb_sim4d_params_t &p = S->p;
     // second velocity moments; the trapezoid rule over the duplicated end points averages v^2 at both
     // ends, which for the periodic pair (vmin, vmax) is 0.5 (vmin^2 + vmax^2)
     std::vector<double> w2;
     for (int a = 2; a < 4; ++a)
         for (int i = 0; i < Fx->ext[a]; ++i) {
-            const int ig = i + S->bx[2 * a];
+            const int ig = i + bx[2 * a];
             double v = p.xmin[a] + ig * S->delta[a];
             double vv = v * v;
             if (ig == 0) vv = 0.5 * (p.xmin[a] * p.xmin[a] + p.xmax[a] * p.xmax[a]);
@@ -492,17 +494,17 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
         for (int ss = 0; ss < nsub; ++ss) {
             if (T) {
                 isub += 1;
+                SLLB_TRY(sim4d_to_layout(S, 0));
+                S->timer.mark(2);
                 SLLB_TRY(sim4d_T(S, steps[isub - 1]));
                 S->timer.mark(0);
             } else {
-                SLLB_TRY(sllb_dist4d_remap(S->D, 0));
+                SLLB_TRY(sim4d_to_layout(S, 1));
                 S->timer.mark(2);
                 SLLB_TRY(sim4d_fields(S));
                 S->timer.mark(1);
                 SLLB_TRY(sim4d_V(S, steps[isub]));
                 S->timer.mark(0);
-                SLLB_TRY(sllb_dist4d_remap(S->D, 1));
-                S->timer.mark(2);
                 isub += 1;
             }
             T = !T;
@@ -634,139 +636,3 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
 }
 } // extern "C"
 
-/* ------------------------------------------------------------------------------------------ */
-/* 3D3V: sim_bsl_vp_3d3v_cart_dd_slim, Lagrange fixed stencils, single rank                     */
-/* simulations/parallel/bsl_vp_3d3v_cart_dd/sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:278-960      */
-/* ------------------------------------------------------------------------------------------ */
-struct sllb_sim6d {
-    sllb_sim6d_params_t p;
-    double emin[6], emax[6], de[6];
-    sllb_field *F = nullptr;
-    sllb_poisson *poisson = nullptr;
-    DevBuf rho, phi, ex, ey, ez, small;
-    bool started = false;
-    int itime = 0;
-};
-__global__ void k_landau6d(double *f, Ext6 n, double d0, double d1, double d2, double d3, double d4, double d5,
-                           double vmax, double factor, double alpha, double k0, double k1, double k2, double t0, double t1,
-                           double t2) {
-    long long ntot = 1;
-    for (int d = 0; d < 6; ++d) ntot *= n.e[d];
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x) {
-        long long r = t;
-        int i[6];
-        for (int d = 0; d < 6; ++d) { i[d] = (int)(r % n.e[d]); r /= n.e[d]; }
-        const double x0 = d0 * i[0], x1 = d1 * i[1], x2 = d2 * i[2];
-        const double v0 = -vmax + d3 * i[3], v1 = -vmax + d4 * i[4], v2 = -vmax + d5 * i[5];
-        const double a0 = v0 / t0, a1 = v1 / t1, a2 = v2 / t2;
-        f[t] = factor * (1.0 + alpha * (cos(k0 * x0) * cos(k1 * x1) * cos(k2 * x2))) * exp(-0.5 * (a0 * a0 + a1 * a1 + a2 * a2));
-    }
-}
-static int sim6d_fields(sllb_sim6d *S) {
-    // rho = -dV_v sum f (sll_m_sim_6d_utilities.F90:221-244); Poisson + E (:614-616)
-    SLLB_TRY(sllb_reduce_velocity(S->F, 3, -(S->de[3] * S->de[4] * S->de[5]), S->rho.p));
-    SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p));
-    return SLLB_OK;
-}
-static int sim6d_diag(sllb_sim6d *S, double time, double *row14) {
-    const int *n = S->p.n;
-    const double Lx = S->emax[0] - S->emin[0], Ly = S->emax[1] - S->emin[1], Lz = S->emax[2] - S->emin[2];
-    const double vol_x = Lx * Ly * Lz;
-    double volume = 1.0;
-    for (int d = 0; d < 6; ++d) volume *= S->de[d];
-    const double dV = volume / vol_x, dVx = (S->de[0] * S->de[1] * S->de[2]) / vol_x;
-    std::vector<double> w1, w2;
-    for (int a = 3; a < 6; ++a) for (int i = 0; i < n[a]; ++i) { const double v = S->emin[a] + S->de[a] * (double)i; w1.push_back(v); w2.push_back(v * v); }
-    double m[9];
-    SLLB_TRY(moments_local(S->F, 3, w1.data(), w2.data(), m));
-    const long long nx3 = (long long)n[0] * n[1] * n[2];
-    const double *arr[5] = {S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p};
-    for (int a = 0; a < 5; ++a) SLLB_CUDA(launch_sum_squares(arr[a], nx3, S->small.p + a, 0));
-    double ss[5];
-    SLLB_CUDA(cudaMemcpy(ss, S->small.p, sizeof(ss), cudaMemcpyDeviceToHost));
-    row14[0] = time;
-    row14[1] = m[0] * dV; row14[2] = m[2] * dV;
-    for (int a = 0; a < 5; ++a) row14[3 + a] = ss[a] * dVx;
-    for (int a = 0; a < 3; ++a) { row14[8 + a] = m[3 + a] * dV; row14[11 + a] = m[6 + a] * dV; }
-    return SLLB_OK;
-}
-extern "C" {
-int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *Sout) {
-    if (!p || !Sout) return fail(SLLB_ERR_INVALID, "sim6d_create: null");
-    SLLB_TRY(require_device());
-    sllb_sim6d *S = new sllb_sim6d();
-    S->p = *p;
-    for (int d = 0; d < 3; ++d) { S->emin[d] = 0.0; S->emax[d] = p->x_max[d]; S->emin[d + 3] = -p->v_max; S->emax[d + 3] = p->v_max; }
-    for (int d = 0; d < 6; ++d) S->de[d] = (S->emax[d] - S->emin[d]) / (double)p->n[d];
-    const size_t nx3 = (size_t)p->n[0] * p->n[1] * p->n[2];
-    int rc = field_alloc(6, p->n, &S->F);
-    if (!rc) rc = sllb_poisson3d_create(p->n[0], p->n[1], p->n[2], S->emax[0], S->emax[1], S->emax[2], &S->poisson);
-    if (!rc) rc = S->rho.ensure(nx3);
-    if (!rc) rc = S->phi.ensure(nx3);
-    if (!rc) rc = S->ex.ensure(nx3);
-    if (!rc) rc = S->ey.ensure(nx3);
-    if (!rc) rc = S->ez.ensure(nx3);
-    if (!rc) rc = S->small.ensure(16);
-    if (!rc) {
-        Ext6 n;
-        for (int d = 0; d < 6; ++d) n.e[d] = p->n[d];
-        const double twopi = 2.0 * 3.14159265358979323846;
-        const double factor = 1.0 / (pow(sqrt(twopi), 3) * (p->v_thermal[0] * p->v_thermal[1] * p->v_thermal[2]));
-        k_landau6d<<<148 * 8, 256>>>(S->F->d, n, S->de[0], S->de[1], S->de[2], S->de[3], S->de[4], S->de[5], p->v_max, factor,
-                                     p->alpha, p->kx[0], p->kx[1], p->kx[2], p->v_thermal[0], p->v_thermal[1], p->v_thermal[2]);
-        rc = check_cuda(cudaGetLastError(), "k_landau6d");
-    }
-    if (!rc) rc = sim6d_fields(S);
-    if (rc) { sllb_sim6d_destroy(S); return rc; }
-    *Sout = S;
-    return SLLB_OK;
-}
-int sllb_sim6d_destroy(sllb_sim6d_t S) {
-    if (!S) return SLLB_OK;
-    sllb_poisson_destroy(S->poisson);
-    sllb_field_destroy(S->F);
-    delete S;
-    return SLLB_OK;
-}
-int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F) {
-    if (!S || !F) return fail(SLLB_ERR_INVALID, "sim6d_field: null");
-    *F = S->F;
-    return SLLB_OK;
-}
-/* advect_x (:817-865): eta1..3 with disp_eta = -v*dt/dx (:590-592) */
-int sllb_sim6d_advect_x(sllb_sim6d_t S) {
-    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_x: null");
-    for (int d = 0; d < 3; ++d)
-        SLLB_TRY(sllb_advect_axis_affine(S->F, d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_x, d + 3, S->emin[d + 3], S->de[d + 3],
-                                         -S->p.delta_t / S->de[d]));
-    return SLLB_OK;
-}
-/* advect_v (:889-958): eta4..6 with displacement E*dt/dv as a 3D field */
-int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
-    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_v: null");
-    const double *E[3] = {S->ex.p, S->ey.p, S->ez.p};
-    for (int d = 0; d < 3; ++d)
-        SLLB_TRY(sllb_advect_axis_field(S->F, 3 + d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_v, E[d], 3, dt / S->de[3 + d]));
-    return SLLB_OK;
-}
-int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
-    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run: bad arguments");
-    int row = 0;
-    if (!S->started) {
-        if (rows) SLLB_TRY(sim6d_diag(S, 0.0, rows));
-        row = 1;
-        SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
-        S->started = true;
-    }
-    for (int it = 1; it <= nsteps; ++it) {
-        SLLB_TRY(sllb_sim6d_advect_x(S));
-        SLLB_TRY(sim6d_fields(S));
-        S->itime += 1;
-        if (rows) SLLB_TRY(sim6d_diag(S, (double)S->itime * S->p.delta_t, rows + 14 * (row++)));
-        if (S->p.time_in_phase && it == nsteps) SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
-        else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
-    }
-    SLLB_CUDA(cudaDeviceSynchronize());
-    return SLLB_OK;
-}
-} // extern "C"

@@ -1,0 +1,127 @@
+"""Multi-GPU checks, one process per GPU (launch with torchrun, 2/4/8 ranks):
+  1. slim 6D halo exchange over NCCL: halos equal the periodic neighbours' planes
+     (reference test: src/parallelization/decomposition/testing/test_decomposition_slim.F90:113-130);
+  2. 4D remap x-seq <-> v-seq over NCCL: every element lands where the layout says
+     (reference test: src/parallelization/remap/testing/test_remap_4d.F90:118-301);
+  3. the 3D3V simulation on P ranks reproduces the golden file (5e-7) and the single-GPU run (1e-12);
+  4. the 2D2V simulation on P ranks reproduces the single-GPU trace and field.
+Prints one JSON line on rank 0 and exits non-zero on any failure."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import selalib_b200 as sb  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    sb.init(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.tensor(list(sb.Comm.unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    comm = sb.Comm(bytes(idt.cpu().tolist()), world, rank)
+    res = {"world": world}
+    ok = True
+
+    # 1. halo exchange
+    g = [4, 4, 4, 8, 8, 8]
+    glob = np.arange(np.prod(g), dtype=np.float64).reshape(g, order="F")
+    D = sb.Dd6d(comm, g)
+    sl = tuple(slice(D.mn[d], D.mn[d] + D.nw[d]) for d in range(6))
+    D.field().upload(np.asfortranarray(glob[sl]))
+    halo_ok = True
+    for axis in range(6):
+        n = D.nw[axis]
+        for hl, hr in ((1, 1), (2, 3), (3, 1), (4, 4)):
+            if max(hl, hr) > n:
+                continue
+            D.halo_exchange(axis, hl, hr)
+            sel = list(sl); sel[axis] = slice(None)
+            er = np.take(glob, [(D.mn[axis] + n + j) % g[axis] for j in range(hr)], axis=axis)[tuple(sel)]
+            el = np.take(glob, [(D.mn[axis] - hl + j) % g[axis] for j in range(hl)], axis=axis)[tuple(sel)]
+            halo_ok = halo_ok and np.array_equal(D.halo(1), er) and np.array_equal(D.halo(0), el)
+    res["procs6d"] = D.procs
+    D.destroy()
+    res["halo_exchange_exact"] = bool(halo_ok)
+    ok = ok and halo_ok
+
+    # 2. remap 4D
+    g4 = [16, 8, 8, 16]
+    glob4 = np.arange(np.prod(g4), dtype=np.float64).reshape(g4, order="F")
+    R = sb.Dist4d(comm, g4)
+    bx, bv = R.box(0), R.box(1)
+    sx = tuple(slice(bx[d, 0], bx[d, 1] + 1) for d in range(4))
+    sv = tuple(slice(bv[d, 0], bv[d, 1] + 1) for d in range(4))
+    R.field(0).upload(np.asfortranarray(glob4[sx]))
+    R.remap(0)
+    r_ok = np.array_equal(R.field(1).download(), glob4[sv])
+    R.field(0).upload(np.zeros_like(np.asfortranarray(glob4[sx])))
+    R.remap(1)
+    r_ok = r_ok and np.array_equal(R.field(0).download(), glob4[sx])
+    R.destroy()
+    res["remap4d_exact"] = bool(r_ok)
+    ok = ok and r_ok
+
+    # 3. 3D3V: golden file + single-GPU run
+    gold = np.loadtxt(os.path.join(ROOT, "tests", "golden", "reffile_bsl_vp_3d3v_cart_dd.dat"))
+    for stencil, n6 in ((3, [16] * 6), (7, [8, 8, 8, 16, 16, 16])):
+        args = (n6, 6.0, [12.5663706144] * 3, stencil, stencil, 0.01, 0.01, [0.499999999998376] * 3)
+        S1 = sb.Sim6d(*args)
+        r1 = S1.run(2)
+        f1 = S1.field().download()
+        S1.destroy()
+        SP = sb.Sim6d(*args, comm=comm)
+        rp = SP.run(2)
+        lay = SP.layout()
+        fp = SP.field().download()
+        SP.destroy()
+        slb = tuple(slice(lay["mn"][d], lay["mn"][d] + lay["nw"][d]) for d in range(6))
+        e_rows = float(np.abs(rp - r1).max())
+        e_f = float(np.abs(fp - f1[slb]).max() / np.abs(f1).max())
+        res[f"sim6d_s{stencil}_rows_vs_1gpu"] = e_rows
+        res[f"sim6d_s{stencil}_f_vs_1gpu"] = e_f
+        ok = ok and e_rows < 1e-12 and e_f < 1e-12
+        if stencil == 3:
+            e_gold = float(np.abs(rp - gold).max())
+            res["sim6d_vs_golden"] = e_gold
+            ok = ok and e_gold < 5e-7
+
+    # 4. 2D2V: P ranks vs single GPU
+    a4 = ([32, 32, 32, 32], [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1)
+    S1 = sb.Sim4d(*a4)
+    r1 = S1.run(3)
+    f1 = S1.field().download()
+    S1.destroy()
+    SP = sb.Sim4d(*a4, comm=comm)
+    rp = SP.run(3)
+    fp = SP.field().download()
+    bxs = SP.box(0)
+    SP.destroy()
+    sx = tuple(slice(bxs[d, 0], bxs[d, 1] + 1) for d in range(4))
+    e_rows = float(np.abs(rp / r1 - 1).max())
+    e_f = float(np.abs(fp - f1[sx]).max() / np.abs(f1).max())
+    res["sim4d_rows_rel_vs_1gpu"] = e_rows
+    res["sim4d_f_vs_1gpu"] = e_f
+    ok = ok and e_rows < 1e-9 and e_f < 1e-12
+
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    res["ok"] = bool(flag.item())
+    if rank == 0:
+        print(json.dumps(res), flush=True)
+    comm.destroy()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
