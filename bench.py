@@ -325,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP, "points": int(npts),
                            "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
-                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap (pack + NCCL send/recv group + unpack), 2 remaps per Strang step",
+                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap fused into the last advection pass of each stage (peer stores over NVLink, CUDA IPC) + all-reduce barrier; 2 remaps per Strang step",
                            "staging": "TMA bulk (cp.async.bulk, UBLKCP) row copies into shared-memory line tiles"},
                 "phase_ms_per_step": {"advect": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
                                       "remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps},

@@ -209,6 +209,14 @@ int sllb_dist4d_field(sllb_dist4d_t D, int which, sllb_field_t *F);
 int sllb_dist4d_box(sllb_dist4d_t D, int which, int box[8]);
 /* direction 0: x-seq -> v-seq, 1: v-seq -> x-seq */
 int sllb_dist4d_remap(sllb_dist4d_t D, int direction);
+/* Fused pass: advect every line of layout `from` along `axis` (whole in that layout) and store the result
+ * straight into the OTHER layout on the ranks that own it there (peer-mapped arrays over NVLink, CUDA IPC),
+ * then a cross-rank barrier.  = advect_1d_constant on every line + apply_remap_4D_double in one kernel.
+ * Needs uniform boxes and peer access (sllb_dist4d_p2p); disp values must be a device pointer. */
+int sllb_dist4d_advect_remap(sllb_dist4d_t D, int from, int axis, int method, int order, const sllb_disp_t *disp);
+int sllb_dist4d_p2p(sllb_dist4d_t D, int *enabled);
+/* 1 (default): the simulations use the fused pass when available; 0: pack + NCCL send/recv + unpack */
+int sllb_set_fused_remap(int on);
 
 /* ---- a12: 6D slim domain decomposition + halo exchange ----------------------
  * sll_f_set_process_grid (src/parallelization/decomposition/sll_m_decomposition.F90:2473-2543) */

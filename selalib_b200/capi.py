@@ -102,6 +102,10 @@ def set_staging(mode):
     _ck(lib().sllb_set_staging(C.c_int(mode)))
 
 
+def set_fused_remap(on):
+    _ck(lib().sllb_set_fused_remap(C.c_int(1 if on else 0)))
+
+
 def set_spline_split(chunks):
     _ck(lib().sllb_set_spline_split(C.c_int(chunks)))
 
@@ -334,6 +338,19 @@ class Dist4d:
 
     def remap(self, direction):
         _ck(lib().sllb_dist4d_remap(self.h, C.c_int(direction)))
+
+    def p2p(self):
+        e = C.c_int(0)
+        _ck(lib().sllb_dist4d_p2p(self.h, C.byref(e)))
+        return bool(e.value)
+
+    def advect_remap(self, src, axis, method, order, values_ptr, scale=1.0, dsel=(1, 1, 0, 1, 1, 0)):
+        """Fused pass: advect layout `src` along `axis`, result lands in the other layout (device disp values)."""
+        d = DispT()
+        d.values = C.cast(vp(values_ptr), dp); d.nvalues = 0; d.values_on_device = 1
+        d.scale = scale
+        d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
+        _ck(lib().sllb_dist4d_advect_remap(self.h, C.c_int(src), C.c_int(axis), C.c_int(method), C.c_int(order), C.byref(d)))
 
     def destroy(self):
         if self.h:

@@ -106,12 +106,12 @@ int field_wrap(int ndim, const int *ext, double *d, sllb_field **F) {
     return SLLB_OK;
 }
 
-int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd) {
+int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap) {
     if (!F || axis < 0 || axis >= F->ndim) return fail(SLLB_ERR_INVALID, "advect_axis: bad field/axis");
     long long inner = 1, outer = 1;
     for (int d = 0; d < axis; ++d) inner *= F->ext[d];
     for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
-    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, 0);
+    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, 0, remap);
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: method/order/line length not implemented (spline: order 4; "
@@ -276,38 +276,50 @@ int sllb_advect_axis(sllb_field_t F, int axis, int method, int order, const sllb
     dd.idiv = disp->idiv > 0 ? disp->idiv : 1; dd.imod = disp->imod > 0 ? disp->imod : 1; dd.istr = disp->istr;
     return advect_axis_dev(F, axis, method, order, dd);
 }
-int sllb_advect_axis_affine(sllb_field_t F, int axis, int method, int order, int v_axis, double vmin, double dv,
-                            double scale) {
+} // extern "C"
+namespace sllb {
+int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv, double scale, DispDesc *dd) {
     if (!F || v_axis < 0 || v_axis >= F->ndim || v_axis == axis)
         return fail(SLLB_ERR_INVALID, "advect_axis_affine: bad v_axis");
     SLLB_TRY(require_device());
     const int nvv = F->ext[v_axis];
     SLLB_TRY(F->disp_scratch.ensure((size_t)nvv));
     SLLB_CUDA(launch_affine(F->disp_scratch.p, nvv, vmin, dv, 0));
-    DispDesc dd;
-    dd.v = F->disp_scratch.p; dd.scale = scale;
-    dd.odiv = dd.omod = dd.idiv = dd.imod = 1; dd.ostr = dd.istr = 0;
+    dd->v = F->disp_scratch.p; dd->scale = scale;
+    dd->odiv = dd->omod = dd->idiv = dd->imod = 1; dd->ostr = dd->istr = 0;
     long long stride = 1;
     if (v_axis > axis) {
         for (int d = axis + 1; d < v_axis; ++d) stride *= F->ext[d];
-        dd.odiv = stride; dd.omod = nvv; dd.ostr = 1;
+        dd->odiv = stride; dd->omod = nvv; dd->ostr = 1;
     } else {
         for (int d = 0; d < v_axis; ++d) stride *= F->ext[d];
-        dd.idiv = stride; dd.imod = nvv; dd.istr = 1;
+        dd->idiv = stride; dd->imod = nvv; dd->istr = 1;
     }
-    return advect_axis_dev(F, axis, method, order, dd);
+    return SLLB_OK;
 }
-int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, const double *d_field, int nfield_axes,
-                           double scale) {
+int make_field_disp(sllb_field *F, int axis, const double *d_field, int nfield_axes, double scale, DispDesc *dd) {
     if (!F || !d_field || nfield_axes < 1 || nfield_axes > axis)
         return fail(SLLB_ERR_INVALID, "advect_axis_field: field axes must be faster than the advected axis");
     SLLB_TRY(require_device());
     long long nf = 1;
     for (int d = 0; d < nfield_axes; ++d) nf *= F->ext[d];
+    dd->v = d_field; dd->scale = scale;
+    dd->odiv = dd->omod = 1; dd->ostr = 0;
+    dd->idiv = 1; dd->imod = nf; dd->istr = 1;
+    return SLLB_OK;
+}
+} // namespace sllb
+extern "C" {
+int sllb_advect_axis_affine(sllb_field_t F, int axis, int method, int order, int v_axis, double vmin, double dv,
+                            double scale) {
     DispDesc dd;
-    dd.v = d_field; dd.scale = scale;
-    dd.odiv = dd.omod = 1; dd.ostr = 0;
-    dd.idiv = 1; dd.imod = nf; dd.istr = 1;
+    SLLB_TRY(make_affine_disp(F, axis, v_axis, vmin, dv, scale, &dd));
+    return advect_axis_dev(F, axis, method, order, dd);
+}
+int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, const double *d_field, int nfield_axes,
+                           double scale) {
+    DispDesc dd;
+    SLLB_TRY(make_field_disp(F, axis, d_field, nfield_axes, scale, &dd));
     return advect_axis_dev(F, axis, method, order, dd);
 }
 

@@ -85,7 +85,9 @@ struct sllb_poisson {
 
 namespace sllb {
 // internal (device-pointer) entry points used by the simulations
-int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd);
+int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr);
+int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv, double scale, DispDesc *dd);
+int make_field_disp(sllb_field *F, int axis, const double *d_field, int nfield_axes, double scale, DispDesc *dd);
 int field_alloc(int ndim, const int *ext, sllb_field **F);
 int field_wrap(int ndim, const int *ext, double *d, sllb_field **F);
 int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out);

@@ -13,6 +13,7 @@
 // writes each point once: 16 B of HBM traffic per point per pass.  All arithmetic is fp64.
 #include "sllb_kernels.cuh"
 #include <cstdio>
+#include <cstring>
 
 namespace sllb {
 
@@ -66,6 +67,66 @@ __device__ __forceinline__ double disp_of(const DispDesc &d, long long o, long l
 }
 
 // ------------------------------------------------------------------------------------------------
+// Where a pass writes its output.  In place: point iout of line (o, in) goes to f[(o*N + iout)*inner + in].
+// Fused remap (RemapDst.on): the pass that ends a splitting stage writes every point straight into the
+// OTHER layout's array on whichever rank owns it there (peer-mapped pointers over NVLink), i.e. the
+// reference's pack + MPI_Alltoall + unpack (apply_remap_4D_double, sll_m_remapper.F90:3308-3456) happens in
+// the store of the advection kernel.  Uniform boxes only (every axis divisible by its process count).
+// The cursor walks the advected-axis index up or down with periodic wrap; `li` is the index inside the
+// destination rank's block, `pc` that rank's coordinate along the advected axis.
+// ------------------------------------------------------------------------------------------------
+struct OutMap {
+    const RemapDst *rd;
+    long long off0, os;   // element offset of (line, li = 0) in the destination array; stride per li
+    int r0, rs, nl, npc;  // rank of the line's fixed coordinates, rank stride per pc, block width, blocks along the axis
+    int pc, li;
+    double *p;
+    __device__ __forceinline__ void seek(int iout) {
+        pc = iout / nl; li = iout - pc * nl;
+        p = rd->base[r0 + pc * rs] + off0 + (long long)li * os;
+    }
+    __device__ __forceinline__ void prev() {
+        if (li > 0) { --li; p -= os; }
+        else { pc = (pc == 0) ? npc - 1 : pc - 1; li = nl - 1; p = rd->base[r0 + pc * rs] + off0 + (long long)li * os; }
+    }
+    __device__ __forceinline__ void next() {
+        if (li < nl - 1) { ++li; p += os; }
+        else { pc = (pc == npc - 1) ? 0 : pc + 1; li = 0; p = rd->base[r0 + pc * rs] + off0; }
+    }
+};
+__device__ __forceinline__ OutMap make_outmap(const RemapDst &rd, const long long o, const long long in, const int N,
+                                              const long long inner) {
+    OutMap m;
+    m.rd = &rd;
+    if (!rd.on) {
+        m.off0 = o * (long long)N * inner + in; m.os = inner;
+        m.r0 = 0; m.rs = 0; m.nl = N; m.npc = 1;
+    } else {
+        const int a = rd.axis;
+        long long ri = in, ro = o, off = 0, ostr = 1;
+        int rank = 0, rstr = 1;
+        m.os = 1; m.rs = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            if (d == a) { m.os = ostr; m.rs = rstr; }
+            else {
+                int c;
+                if (d < a) { c = (int)(ri % rd.se[d]); ri /= rd.se[d]; }
+                else { c = (int)(ro % rd.se[d]); ro /= rd.se[d]; }
+                c += rd.slo[d];
+                const int pcd = c / rd.te[d];
+                off += (long long)(c - pcd * rd.te[d]) * ostr;
+                rank += pcd * rstr;
+            }
+            ostr *= rd.te[d]; rstr *= rd.tp[d];
+        }
+        m.off0 = off; m.r0 = rank; m.nl = rd.te[a]; m.npc = rd.tp[a];
+    }
+    m.pc = 0; m.li = 0; m.p = nullptr;
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Periodic cubic spline on one line held in shared memory (elements at sc[k*PITCH]).
 //
 // Reference recurrences (sll_m_cubic_splines.F90:560-580), a = sqrt((2+sqrt3)/6), b = sqrt((2-sqrt3)/6):
@@ -78,8 +139,7 @@ __device__ __forceinline__ double disp_of(const DispDesc &d, long long o, long l
 __constant__ double c_pw[SLLB_NUM_TERMS]; // (-q)^(i+1)
 
 template <int PITCH, bool TO_GLOBAL>
-__device__ __forceinline__ void spline_line(double *sc, const int N, const double disp, double *gbase,
-                                            const long long gstride) {
+__device__ __forceinline__ void spline_line(double *sc, const int N, const double disp, OutMap *om) {
     const double q = 0.26794919243112270647; // 2 - sqrt(3)
     const double r2 = 1.60769515458673623883; // 6 (2 - sqrt 3) = 1/a^2
     const double fl = floor(disp);
@@ -122,14 +182,13 @@ __device__ __forceinline__ void spline_line(double *sc, const int N, const doubl
     const double gt2 = fma(-q, gt1, sc[(N - 3) * PITCH]);   // g[N-3]
     double a3 = gt0, a2 = gt1, a1 = gt2;
     // output index of cell kc is (kc - dcell) mod N; cells are emitted kc = N-3, N-4, ..., 1
-    int iout = ((N - 3 - dcell) % N + N) % N;
+    if (TO_GLOBAL) om->seek(((N - 3 - dcell) % N + N) % N);
 #pragma unroll 8
     for (int k = N - 4; k >= 0; --k) {
         const double a0 = fma(-q, a1, sc[k * PITCH]);
         const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
-        if (TO_GLOBAL) st_stream(gbase + (long long)iout * gstride, val);
+        if (TO_GLOBAL) { st_stream(om->p, val); om->prev(); }
         else sc[(k + 1) * PITCH] = val; // slot k+1 already consumed
-        iout = (iout == 0) ? N - 1 : iout - 1;
         a3 = a2; a2 = a1; a1 = a0;
     }
     // now a1 = g[0], a2 = g[1], a3 = g[2]
@@ -137,11 +196,9 @@ __device__ __forceinline__ void spline_line(double *sc, const int N, const doubl
     const double vm1 = fma(w3, a2, fma(w2, a1, fma(w1, gt0, w0 * gt1))); // cell N-1
     const double vm2 = fma(w3, a1, fma(w2, gt0, fma(w1, gt1, w0 * gt2))); // cell N-2
     if (TO_GLOBAL) {
-        st_stream(gbase + (long long)iout * gstride, v0);
-        iout = (iout == 0) ? N - 1 : iout - 1;
-        st_stream(gbase + (long long)iout * gstride, vm1);
-        iout = (iout == 0) ? N - 1 : iout - 1;
-        st_stream(gbase + (long long)iout * gstride, vm2);
+        st_stream(om->p, v0); om->prev();
+        st_stream(om->p, vm1); om->prev();
+        st_stream(om->p, vm2);
     } else {
         sc[0] = v0;
         sc[(N - 1) * PITCH] = vm1;
@@ -237,8 +294,7 @@ __device__ __forceinline__ int lagr_setup(double disp, int N, double *pp) {
 
 // one line from shared memory (sc[k*PITCH]) to global memory with a register window
 template <int S, int PITCH>
-__device__ __forceinline__ void lagrange_line(const double *sc, const int N, const double disp, double *gbase,
-                                              const long long gstride) {
+__device__ __forceinline__ void lagrange_line(const double *sc, const int N, const double disp, OutMap *om) {
     double pp[S], w[S];
     int idx = lagr_setup<S>(disp, N, pp);
 #pragma unroll
@@ -246,6 +302,7 @@ __device__ __forceinline__ void lagrange_line(const double *sc, const int N, con
         w[k] = sc[idx * PITCH];
         idx = (idx == N - 1) ? 0 : idx + 1;
     }
+    om->seek(0);
 #pragma unroll 4
     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -255,7 +312,8 @@ __device__ __forceinline__ void lagrange_line(const double *sc, const int N, con
         double acc = pp[0] * w[0]; // left-to-right sum like lagr_Npt_vec (:393-399)
 #pragma unroll
         for (int k = 1; k < S; ++k) acc = fma(pp[k], w[k], acc);
-        st_stream(gbase + (long long)i * gstride, acc);
+        st_stream(om->p, acc);
+        om->next();
     }
 }
 
@@ -266,7 +324,8 @@ __device__ __forceinline__ void lagrange_line(const double *sc, const int N, con
 // ------------------------------------------------------------------------------------------------
 template <int BW, int METHOD, int S>
 __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, const long long nlines, const int N,
-                                                        const long long inner, const DispDesc dd, const int use_tma) {
+                                                        const long long inner, const DispDesc dd, const int use_tma,
+                                                        const __grid_constant__ RemapDst rd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *s = reinterpret_cast<double *>(smem_raw + 128);
@@ -290,8 +349,9 @@ __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, c
     }
     if (!active) return;
     const double disp = disp_of(dd, o, in);
-    if constexpr (METHOD == 0) spline_line<BW, true>(s + tid, N, disp, base, inner);
-    else lagrange_line<S, BW>(s + tid, N, disp, base, inner);
+    OutMap om = make_outmap(rd, o, in, N, inner);
+    if constexpr (METHOD == 0) spline_line<BW, true>(s + tid, N, disp, &om);
+    else lagrange_line<S, BW>(s + tid, N, disp, &om);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -305,7 +365,8 @@ __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, c
 template <int P>
 __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restrict__ f, const int N,
                                                                   const long long inner, const DispDesc dd,
-                                                                  const int use_tma, const long long nlines) {
+                                                                  const int use_tma, const long long nlines,
+                                                                  const __grid_constant__ RemapDst rd) {
     constexpr int BW = 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -378,13 +439,14 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     double a3 = g;                                  // g[k1+2]
     double a2 = fma(-q, a3, sc[i1 * BW]);           // g[k1+1]
     double a1 = fma(-q, a2, sc[i0 * BW]);           // g[k1]
-    int iout = ((k1 - dcell) % N + N) % N;          // output index of cell k1 (mod N)
+    OutMap om = make_outmap(rd, o, in, N, inner);
+    om.seek(((k1 - dcell) % N + N) % N);            // output index of cell k1 (mod N)
 #pragma unroll 8
     for (int k = k1 - 1; k >= k0; --k) {
         const double a0 = fma(-q, a1, sc[k * BW]);
         const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
-        st_stream(base + (long long)iout * inner, val);
-        iout = (iout == 0) ? N - 1 : iout - 1;
+        st_stream(om.p, val);
+        om.prev();
         a3 = a2; a2 = a1; a1 = a0;
     }
 }
@@ -414,7 +476,7 @@ __global__ void __launch_bounds__(BW) k_spline_contig(double *__restrict__ f, co
         const double disp = disp_of(dd, l0 + tid, 0);
         const int dcell = (int)floor(disp);
         dcm[tid] = ((dcell % N) + N) % N;
-        spline_line<P, false>(s + tid, N, disp, nullptr, 0);
+        spline_line<P, false>(s + tid, N, disp, nullptr);
     }
     __syncthreads();
     for (int ln = 0; ln < nl; ++ln) {
@@ -577,7 +639,7 @@ static const size_t SMEM_MAX = 227 * 1024;
 
 template <int BW, int METHOD, int S>
 static cudaError_t launch_strided_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
-                                    int staging, cudaStream_t st) {
+                                    int staging, cudaStream_t st, const RemapDst &rd) {
     size_t smem = 128 + (size_t)N * BW * 8;
     auto kern = k_advect_strided<BW, METHOD, S>;
     cudaError_t e = set_smem(kern, smem);
@@ -585,7 +647,7 @@ static cudaError_t launch_strided_t(double *f, long long nlines, int N, long lon
     bool tma_ok = (inner % BW == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * BW * 8 < (1u << 20));
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + BW - 1) / BW;
-    kern<<<(unsigned)nblk, BW, smem, st>>>(f, nlines, N, inner, dd, use_tma);
+    kern<<<(unsigned)nblk, BW, smem, st>>>(f, nlines, N, inner, dd, use_tma, rd);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
@@ -593,7 +655,7 @@ static cudaError_t launch_strided_t(double *f, long long nlines, int N, long lon
 int g_spline_split = -1; // -1 auto, else forced P in {1,2,4}
 template <int P>
 static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
-                                         int staging, cudaStream_t st) {
+                                         int staging, cudaStream_t st, const RemapDst &rd) {
     size_t smem = 128 + (size_t)N * 32 * 8;
     auto kern = k_spline_strided_split<P>;
     cudaError_t e = set_smem(kern, smem);
@@ -601,19 +663,19 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
     bool tma_ok = (inner % 32 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * 32 * 8 < (1u << 20));
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + 31) / 32;
-    kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines);
+    kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, rd);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
 template <int METHOD, int S>
 static cudaError_t launch_strided(double *f, long long nlines, int N, long long inner, const DispDesc &dd, int staging,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, const RemapDst &rd) {
     // widest tile that fits: BW lanes x N points x 8 B (+128 B header)
     if ((size_t)N * 32 * 8 + 128 <= SMEM_MAX && (inner >= 32 || nlines >= 32))
-        return launch_strided_t<32, METHOD, S>(f, nlines, N, inner, dd, staging, st);
-    if ((size_t)N * 16 * 8 + 128 <= SMEM_MAX) return launch_strided_t<16, METHOD, S>(f, nlines, N, inner, dd, staging, st);
-    if ((size_t)N * 8 * 8 + 128 <= SMEM_MAX) return launch_strided_t<8, METHOD, S>(f, nlines, N, inner, dd, staging, st);
+        return launch_strided_t<32, METHOD, S>(f, nlines, N, inner, dd, staging, st, rd);
+    if ((size_t)N * 16 * 8 + 128 <= SMEM_MAX) return launch_strided_t<16, METHOD, S>(f, nlines, N, inner, dd, staging, st, rd);
+    if ((size_t)N * 8 * 8 + 128 <= SMEM_MAX) return launch_strided_t<8, METHOD, S>(f, nlines, N, inner, dd, staging, st, rd);
     return cudaErrorInvalidValue;
 }
 
@@ -651,8 +713,16 @@ static cudaError_t launch_spline_contig_t(double *f, long long nlines, int N, co
 }
 
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
-                          const DispDesc &dd, int staging, cudaStream_t st) {
+                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap) {
     if (n < 8 || outer < 1 || inner < 1) return cudaErrorInvalidValue;
+    RemapDst rd;
+    if (remap && remap->on) {
+        if (inner == 1) return cudaErrorInvalidValue; // fused remap is implemented for the strided kernels
+        rd = *remap;
+    } else {
+        memset(&rd, 0, sizeof(rd));
+        rd.base[0] = f;
+    }
     cudaError_t e = ensure_constants();
     if (e != cudaSuccess) return e;
     const long long nlines = outer * inner;
@@ -668,16 +738,16 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
         if ((size_t)n * 32 * 8 + 128 <= SMEM_MAX) {
             int P = g_spline_split;
             if (P < 0) P = (n % 4 == 0 && n / 4 >= 32) ? 4 : ((n % 2 == 0 && n / 2 >= 32) ? 2 : 1);
-            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st);
-            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st);
-            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st);
+            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd);
+            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd);
+            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd);
         }
-        return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st);
+        return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st, rd);
     }
 #define LAGR_CASE(SS)                                                                            \
     case SS:                                                                                     \
         if (inner == 1) return launch_lagrange_contig<SS>(f, nlines, n, dd, staging, st);       \
-        return launch_strided<1, SS>(f, nlines, n, inner, dd, staging, st);
+        return launch_strided<1, SS>(f, nlines, n, inner, dd, staging, st, rd);
     if (method == METHOD_LAGRANGE_FIXED) {
         switch (order) {
             LAGR_CASE(3) LAGR_CASE(5) LAGR_CASE(7) LAGR_CASE(9) LAGR_CASE(11)

@@ -16,10 +16,18 @@ struct DispDesc {
 enum { METHOD_SPLINE = 0, METHOD_LAGRANGE_FIXED = 1, METHOD_LAGRANGE_CENTERED = 2 };
 enum { STAGING_AUTO = 0, STAGING_TMA = 1, STAGING_CPASYNC = 2 };
 
+// Fused remap: destination of a pass that writes into the other layout (see OutMap in sllb_kernels.cu).
+struct RemapDst {
+    double *base[8];            // destination array on every rank (peer-mapped); in place: base[0] = f
+    int on, axis;               // on = 0: in place, everything below ignored
+    int se[4], slo[4];          // source layout: local extents and global offset of my box
+    int te[4], tp[4];           // destination layout: local extents (uniform boxes) and process mesh
+};
+
 // K1/K2: one 1D periodic advection on every line of f viewed as [outer][n][inner], in place.
 // Returns cudaSuccess, cudaErrorInvalidValue (bad n / order) or a launch error.
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
-                          const DispDesc &dd, int staging, cudaStream_t st);
+                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap = nullptr);
 
 // K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]
 cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,

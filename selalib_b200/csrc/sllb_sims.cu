@@ -1,6 +1,7 @@
 // sllb_sims.cu -- layouts / remap (a13), NCCL communicator, and the time loops of the three
 // simulations the hot path serves, running entirely on the device.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -139,10 +140,97 @@ struct sllb_dist4d {
     sllb_field *F[2] = {nullptr, nullptr};
     DevBuf sendbuf, recvbuf;
     std::vector<int> sb[2], rb[2]; // plans per direction
+    // fused remap: every rank's two layout arrays mapped into this process (CUDA IPC over NVLink)
+    bool p2p = false;
+    double *peer[2][8];
+    std::vector<void *> ipc_opened;
+    DevBuf flag;                   // 1 double: all-reduce used as the cross-rank barrier
 };
+
+int g_fused_remap = 1; // 1: advect + remap in one kernel over peer memory when possible, 0: pack + NCCL + unpack
+
+// Map every rank's F[0] and F[1] into this process.  cudaIpcGetMemHandle names the whole allocation, so the
+// offset of the array inside it travels with the handle.
+static int dist4d_setup_p2p(sllb_dist4d *D) {
+    D->p2p = false;
+    if (D->nranks < 2 || D->nranks > 8) return SLLB_OK;
+    for (int w = 0; w < 2; ++w)
+        for (int d = 0; d < 4; ++d)
+            if (D->global[d] % D->procs[w][d] != 0) return SLLB_OK; // non-uniform boxes: NCCL path
+    const char *env = getenv("SLLB_FUSED_REMAP");
+    if (env && env[0] == '0') return SLLB_OK;
+    typedef int (*getrange_t)(unsigned long long *, size_t *, unsigned long long);
+    getrange_t get_range = nullptr;
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn)
+            get_range = reinterpret_cast<getrange_t>(fn);
+        else cudaGetLastError();
+    }
+    struct Slot { cudaIpcMemHandle_t h; long long offset; long long ok; };
+    static_assert(sizeof(Slot) % 8 == 0, "slot size");
+    const int P = D->nranks;
+    std::vector<Slot> mine(2), all((size_t)2 * P);
+    int good = 1;
+    for (int w = 0; w < 2; ++w) {
+        unsigned long long base = 0; size_t size = 0;
+        memset(&mine[w], 0, sizeof(Slot));
+        if (!get_range || get_range(&base, &size, (unsigned long long)(uintptr_t)D->F[w]->d) != 0) { good = 0; continue; }
+        if (cudaIpcGetMemHandle(&mine[w].h, reinterpret_cast<void *>((uintptr_t)base)) != cudaSuccess) { cudaGetLastError(); good = 0; continue; }
+        mine[w].offset = (long long)((unsigned long long)(uintptr_t)D->F[w]->d - base);
+    }
+    mine[0].ok = mine[1].ok = good;
+    char *dsend = nullptr, *drecv = nullptr;
+    SLLB_CUDA(cudaMalloc(&dsend, 2 * sizeof(Slot)));
+    SLLB_CUDA(cudaMalloc(&drecv, (size_t)2 * P * sizeof(Slot)));
+    SLLB_CUDA(cudaMemcpy(dsend, mine.data(), 2 * sizeof(Slot), cudaMemcpyHostToDevice));
+    SLLB_NCCL(ncclAllGather(dsend, drecv, 2 * sizeof(Slot), ncclChar, D->comm->comm, 0));
+    SLLB_CUDA(cudaMemcpy(all.data(), drecv, (size_t)2 * P * sizeof(Slot), cudaMemcpyDeviceToHost));
+    cudaFree(dsend); cudaFree(drecv);
+    for (int r = 0; r < P; ++r) if (!all[2 * r].ok) good = 0;
+    if (good) {
+        for (int r = 0; r < P && good; ++r)
+            for (int w = 0; w < 2; ++w) {
+                if (r == D->rank) { D->peer[w][r] = D->F[w]->d; continue; }
+                void *ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[2 * r + w].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+                D->ipc_opened.push_back(ptr);
+                D->peer[w][r] = reinterpret_cast<double *>(static_cast<char *>(ptr) + all[2 * r + w].offset);
+            }
+    }
+    // everybody must agree, otherwise nobody uses the fused path
+    SLLB_TRY(D->flag.ensure(2));
+    double h = good ? 0.0 : 1.0;
+    SLLB_CUDA(cudaMemcpy(D->flag.p, &h, sizeof(double), cudaMemcpyHostToDevice));
+    SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
+    SLLB_CUDA(cudaMemcpy(&h, D->flag.p, sizeof(double), cudaMemcpyDeviceToHost));
+    D->p2p = (h == 0.0);
+    return SLLB_OK;
+}
 
 static void box_of(const std::vector<int> &boxes, int r, int lo[4], int n[4]) {
     for (int d = 0; d < 4; ++d) { lo[d] = boxes[r * 8 + 2 * d]; n[d] = boxes[r * 8 + 2 * d + 1] - lo[d] + 1; }
+}
+
+static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int method, int order, const DispDesc &dd) {
+    if (!D->p2p || !g_fused_remap) return fail(SLLB_ERR_UNSUPPORTED, "dist4d_advect_remap: peer mapping not available (use advect + sllb_dist4d_remap)");
+    const int to = 1 - from;
+    if (D->procs[from][axis] != 1) return fail(SLLB_ERR_INVALID, "dist4d_advect_remap: the advected axis must be whole in the source layout");
+    RemapDst rd;
+    memset(&rd, 0, sizeof(rd));
+    for (int r = 0; r < D->nranks; ++r) rd.base[r] = D->peer[to][r];
+    rd.on = 1; rd.axis = axis;
+    for (int d = 0; d < 4; ++d) {
+        rd.se[d] = D->F[from]->ext[d];
+        rd.slo[d] = D->boxes[from][D->rank * 8 + 2 * d];
+        rd.tp[d] = D->procs[to][d];
+        rd.te[d] = D->global[d] / D->procs[to][d];
+    }
+    SLLB_TRY(advect_axis_dev(D->F[from], axis, method, order, dd, &rd));
+    // all ranks' stores into my destination array are complete once every rank's kernel has finished
+    SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
+    return SLLB_OK;
 }
 
 extern "C" {
@@ -182,12 +270,35 @@ int sllb_dist4d_create(sllb_comm_t c, const int global[4], sllb_dist4d_t *D) {
         if (!rc) rc = dd->sendbuf.ensure((size_t)dd->F[0]->total > (size_t)dd->F[1]->total ? dd->F[0]->total : dd->F[1]->total);
         if (!rc) rc = dd->recvbuf.ensure(dd->sendbuf.n);
     }
+    if (!rc && dd->nranks > 1) rc = dist4d_setup_p2p(dd);
     if (rc) { sllb_dist4d_destroy(dd); return rc; }
     *D = dd;
     return SLLB_OK;
 }
+int sllb_dist4d_p2p(sllb_dist4d_t D, int *enabled) {
+    if (!D || !enabled) return fail(SLLB_ERR_INVALID, "dist4d_p2p: null");
+    *enabled = (D->p2p && g_fused_remap) ? 1 : 0;
+    return SLLB_OK;
+}
+int sllb_set_fused_remap(int on) {
+    g_fused_remap = on ? 1 : 0;
+    return SLLB_OK;
+}
+/* One advection pass along `axis` of the layout `from` whose stores land in the OTHER layout on the owning
+ * ranks (peer memory over NVLink), followed by a cross-rank barrier: advect_1d_constant on every line +
+ * apply_remap_4D_double (sll_m_remapper.F90:3308-3456) in one kernel. */
+int sllb_dist4d_advect_remap(sllb_dist4d_t D, int from, int axis, int method, int order, const sllb_disp_t *disp) {
+    if (!D || !disp || !disp->values || from < 0 || from > 1 || axis < 0 || axis > 3) return fail(SLLB_ERR_INVALID, "dist4d_advect_remap: bad arguments");
+    if (!disp->values_on_device) return fail(SLLB_ERR_INVALID, "dist4d_advect_remap: displacement values must be on the device");
+    DispDesc dd;
+    dd.v = disp->values; dd.scale = disp->scale;
+    dd.odiv = disp->odiv > 0 ? disp->odiv : 1; dd.omod = disp->omod > 0 ? disp->omod : 1; dd.ostr = disp->ostr;
+    dd.idiv = disp->idiv > 0 ? disp->idiv : 1; dd.imod = disp->imod > 0 ? disp->imod : 1; dd.istr = disp->istr;
+    return dist4d_advect_remap_dev(D, from, axis, method, order, dd);
+}
 int sllb_dist4d_destroy(sllb_dist4d_t D) {
     if (!D) return SLLB_OK;
+    for (void *ptr : D->ipc_opened) cudaIpcCloseMemHandle(ptr);
     sllb_field_destroy(D->F[1]);
     sllb_field_destroy(D->F[0]);
     delete D;
@@ -361,17 +472,24 @@ static int sim4d_nrj(sllb_sim4d *S) {
     return SLLB_OK;
 }
 
-static int sim4d_T(sllb_sim4d *S, double step) {
+// `fuse`: the stage's last pass writes straight into the other layout (advect + remap in one kernel)
+static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     sllb_field *Fx = S->D->F[0];
     const sllb_sim4d_params_t &p = S->p;
     // out(x) = in(x - v*step*dt): displacement in cells = -v*step*dt/delta_x  (:1037-1064)
     SLLB_TRY(sllb_advect_axis_affine(Fx, 0, p.method, p.order, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2],
                                      -step * p.dt / S->delta[0]));
-    SLLB_TRY(sllb_advect_axis_affine(Fx, 1, p.method, p.order, 3, p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3],
-                                     -step * p.dt / S->delta[1]));
+    DispDesc dd;
+    SLLB_TRY(make_affine_disp(Fx, 1, 3, p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3], -step * p.dt / S->delta[1], &dd));
+    if (fuse) {
+        SLLB_TRY(dist4d_advect_remap_dev(S->D, 0, 1, p.method, p.order, dd));
+        S->layout = 1;
+    } else {
+        SLLB_TRY(advect_axis_dev(Fx, 1, p.method, p.order, dd));
+    }
     return SLLB_OK;
 }
-static int sim4d_V(sllb_sim4d *S, double step) {
+static int sim4d_V(sllb_sim4d *S, double step, bool fuse) {
     sllb_field *Fv = S->D->F[1];
     const sllb_sim4d_params_t &p = S->p;
     const double *e1 = S->E1.p, *e2 = S->E2.p;
@@ -386,7 +504,14 @@ static int sim4d_V(sllb_sim4d *S, double step) {
     }
     // out(v) = in(v - E*step*dt)  (:1137-1166), displacement computed from E inside the kernel (K5)
     SLLB_TRY(sllb_advect_axis_field(Fv, 2, p.method, p.order, e1, 2, -step * p.dt / S->delta[2]));
-    SLLB_TRY(sllb_advect_axis_field(Fv, 3, p.method, p.order, e2, 2, -step * p.dt / S->delta[3]));
+    DispDesc dd;
+    SLLB_TRY(make_field_disp(Fv, 3, e2, 2, -step * p.dt / S->delta[3], &dd));
+    if (fuse) {
+        SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, p.method, p.order, dd));
+        S->layout = 0;
+    } else {
+        SLLB_TRY(advect_axis_dev(Fv, 3, p.method, p.order, dd));
+    }
     return SLLB_OK;
 }
 
@@ -489,21 +614,27 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
     else { steps[0] = 1.0; steps[1] = 1.0; nsub = 2; beginT = true; }
     S->timer.begin();
     S->timer.mark(-1);
+    const bool can_fuse = S->D->p2p && g_fused_remap && S->D->nranks > 1;
     for (int it = 0; it < nsteps; ++it) {
         int isub = 0; bool T = beginT;
         for (int ss = 0; ss < nsub; ++ss) {
+            // the stage after this one (possibly the first stage of the next step) is of the other kind
+            // <=> f is needed in the other layout next: fuse the remap into this stage's last pass
+            const bool last_stage = (it == nsteps - 1 && ss == nsub - 1);
+            const bool nextT = (ss == nsub - 1) ? beginT : !T;
+            const bool fuse = can_fuse && !last_stage && (nextT != T);
             if (T) {
                 isub += 1;
                 SLLB_TRY(sim4d_to_layout(S, 0));
                 S->timer.mark(2);
-                SLLB_TRY(sim4d_T(S, steps[isub - 1]));
+                SLLB_TRY(sim4d_T(S, steps[isub - 1], fuse));
                 S->timer.mark(0);
             } else {
                 SLLB_TRY(sim4d_to_layout(S, 1));
                 S->timer.mark(2);
                 SLLB_TRY(sim4d_fields(S));
                 S->timer.mark(1);
-                SLLB_TRY(sim4d_V(S, steps[isub]));
+                SLLB_TRY(sim4d_V(S, steps[isub], fuse));
                 S->timer.mark(0);
                 isub += 1;
             }

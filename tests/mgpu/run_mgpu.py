@@ -71,6 +71,38 @@ def main():
     res["remap4d_exact"] = bool(r_ok)
     ok = ok and r_ok
 
+    # 2b. fused advect + remap (peer stores over NVLink) == in-place advect followed by the NCCL remap, bit for bit
+    g4 = [64, 32, 32, 64]
+    rng = np.random.default_rng(20261017)
+    glob4 = np.asfortranarray(rng.standard_normal(g4))
+    R = sb.Dist4d(comm, g4)
+    res["p2p"] = R.p2p()
+    if R.p2p():
+        fused_ok = True
+        for src, axis, method, order in ((0, 1, sb.METHOD_SPLINE, 4), (1, 3, sb.METHOD_SPLINE, 4),
+                                         (0, 1, sb.METHOD_LAGRANGE_FIXED, 5), (1, 3, sb.METHOD_LAGRANGE_CENTERED, 6)):
+            b = R.box(src)
+            sl4 = tuple(slice(b[d, 0], b[d, 1] + 1) for d in range(4))
+            ext = R.field(src).extents
+            if src == 0:   # x-advection: displacement per x4 index (local)
+                disp = torch.linspace(-2.7, 3.1, ext[3], dtype=torch.float64, device="cuda") + 0.01 * rank
+                dsel = (ext[2], ext[3], 1, 1, 1, 0)
+            else:          # v-advection: displacement per (x1, x2) local
+                disp = torch.sin(torch.arange(ext[0] * ext[1], dtype=torch.float64, device="cuda") + rank) * 1.9
+                dsel = (1, 1, 0, 1, ext[0] * ext[1], 1)
+            R.field(src).upload(np.asfortranarray(glob4[sl4]))
+            R.field(src).advect_axis(axis, method, order, disp.data_ptr(), 0.7, dsel, on_device=True)
+            R.remap(src)
+            ref = R.field(1 - src).download()
+            R.field(1 - src).upload(np.zeros_like(ref))
+            R.field(src).upload(np.asfortranarray(glob4[sl4]))
+            R.advect_remap(src, axis, method, order, disp.data_ptr(), 0.7, dsel)
+            sb.synchronize()
+            fused_ok = fused_ok and np.array_equal(R.field(1 - src).download(), ref)
+        res["fused_remap_exact"] = bool(fused_ok)
+        ok = ok and fused_ok
+    R.destroy()
+
     # 3. 3D3V: golden file + single-GPU run
     gold = np.loadtxt(os.path.join(ROOT, "tests", "golden", "reffile_bsl_vp_3d3v_cart_dd.dat"))
     for stencil, n6 in ((3, [16] * 6), (7, [8, 8, 8, 16, 16, 16])):
@@ -112,6 +144,15 @@ def main():
     res["sim4d_rows_rel_vs_1gpu"] = e_rows
     res["sim4d_f_vs_1gpu"] = e_f
     ok = ok and e_rows < 1e-9 and e_f < 1e-12
+    # same run through the unfused path (pack + NCCL send/recv + unpack): identical values
+    sb.set_fused_remap(False)
+    SQ = sb.Sim4d(*a4, comm=comm)
+    rq = SQ.run(3)
+    fq = SQ.field().download()
+    SQ.destroy()
+    sb.set_fused_remap(True)
+    res["sim4d_fused_equals_nccl_path"] = bool(np.array_equal(rq, rp) and np.array_equal(fq, fp))
+    ok = ok and res["sim4d_fused_equals_nccl_path"]
 
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -52,7 +52,7 @@ def test_halo_exchange_single_rank_is_periodic_copy(sb):
 @pytest.mark.parametrize("staging", [0, 2])
 def test_halo_cells_kernel_vs_oracle(sb, orc, stencil, staging):
     rng = np.random.default_rng(SEED + stencil)
-    shape = (32, 4, 2, 12, 6, 16)          # inner of every axis >= 1 is a multiple of 32: TMA path
+    shape = (32, 6, 2, 12, 6, 16)          # inner of every axis >= 1 is a multiple of 32: TMA path
     f0 = np.asfortranarray(rng.standard_normal(shape))
     E = rng.uniform(-1.2, 1.2, shape[0] * shape[1] * shape[2])
     nx3 = shape[0] * shape[1] * shape[2]
