@@ -137,6 +137,18 @@ int sllb_advect_axis_affine(sllb_field_t F, int axis, int method, int order, int
  * `nfield_axes` axes of F (v-advection; K5) */
 int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, const double *d_field,
                            int nfield_axes, double scale);
+/* K1c: the x1 and the x2 pass of a T stage in ONE sweep over f: every contiguous (axis 0, axis 1) plane is
+ * staged in shared memory, both periodic cubic-spline advections are applied there and the plane is written
+ * once (the two displacements must be constant over a plane, as alpha = v3*step, alpha = v4*step of
+ * sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:1037-1064 are).  d_rho != NULL (DEVICE, extents[0]*extents[1]):
+ * also returns rho = rho_scale * sum over the remaining axes of the result, i.e. the reduction that follows
+ * the T stage (sll_m_reduction.F90:187-272), without another sweep.  Same values as two sllb_advect_axis
+ * calls to rounding (restart series evaluated in Horner form).  SLLB_ERR_UNSUPPORTED when the plane does not
+ * fit (extents multiples of 32, <= 16384 points) -- call sllb_advect_axis twice instead. */
+int sllb_advect_plane(sllb_field_t F, int method, int order, const sllb_disp_t *disp0, const sllb_disp_t *disp1,
+                      double rho_scale, double *d_rho);
+/* tuning knob: on = 0 disables K1c inside the simulations; points_per_thread 0 (auto), 16 or 32 */
+int sllb_set_plane_kernel(int on, int points_per_thread);
 /* tuning knob: 0 = auto, 1 = TMA bulk staging, 2 = cp.async staging (strided kernels) */
 int sllb_set_staging(int mode);
 /* tuning knob: chunks per line of the strided spline kernel: -1 = auto, 1, 2, 4, 8 */

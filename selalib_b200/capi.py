@@ -102,6 +102,10 @@ def set_staging(mode):
     _ck(lib().sllb_set_staging(C.c_int(mode)))
 
 
+def set_plane_kernel(on, points_per_thread=0):
+    _ck(lib().sllb_set_plane_kernel(C.c_int(1 if on else 0), C.c_int(points_per_thread)))
+
+
 def set_fused_remap(on):
     _ck(lib().sllb_set_fused_remap(C.c_int(1 if on else 0)))
 
@@ -210,6 +214,28 @@ class Field:
         d.scale = scale
         d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
         _ck(lib().sllb_advect_axis(self.h, C.c_int(axis), C.c_int(method), C.c_int(order), C.byref(d)))
+
+    def advect_plane(self, values0, dsel0, scale0, values1, dsel1, scale1, rho_scale=None):
+        """K1c: spline passes along axes 0 and 1 in one sweep; returns rho (host) when rho_scale is given."""
+        ds = []
+        keep = []
+        for values, dsel, scale in ((values0, dsel0, scale0), (values1, dsel1, scale1)):
+            d = DispT()
+            values = np.ascontiguousarray(values, dtype=np.float64)
+            keep.append(values)
+            d.values = _p(values); d.nvalues = values.size; d.values_on_device = 0; d.scale = scale
+            d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
+            ds.append(d)
+        rho_dev = None
+        if rho_scale is not None:
+            import torch
+            rho_dev = torch.empty(self.extents[0] * self.extents[1], dtype=torch.float64, device="cuda")
+        _ck(lib().sllb_advect_plane(self.h, C.c_int(METHOD_SPLINE), C.c_int(4), C.byref(ds[0]), C.byref(ds[1]),
+                                    C.c_double(rho_scale if rho_scale is not None else 0.0),
+                                    C.cast(vp(rho_dev.data_ptr()), dp) if rho_dev is not None else None))
+        if rho_dev is not None:
+            return rho_dev.cpu().numpy().reshape(self.extents[:2], order="F")
+        return None
 
     def advect_axis_affine(self, axis, method, order, v_axis, vmin, dv, scale):
         _ck(lib().sllb_advect_axis_affine(self.h, C.c_int(axis), C.c_int(method), C.c_int(order), C.c_int(v_axis),

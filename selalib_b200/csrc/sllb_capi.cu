@@ -106,18 +106,43 @@ int field_wrap(int ndim, const int *ext, double *d, sllb_field **F) {
     return SLLB_OK;
 }
 
-int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap) {
+int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap,
+                    double *linesum) {
     if (!F || axis < 0 || axis >= F->ndim) return fail(SLLB_ERR_INVALID, "advect_axis: bad field/axis");
     long long inner = 1, outer = 1;
     for (int d = 0; d < axis; ++d) inner *= F->ext[d];
     for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
-    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, 0, remap);
+    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, 0, remap, linesum);
+    if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: line sums are produced by the chunked strided spline kernel only"); }
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: method/order/line length not implemented (spline: order 4; "
                                           "Lagrange fixed: 3,5,7,9,11; centred: 4,6,8; 8 <= n, line must fit shared memory)");
     }
     return check_cuda(e, "advect kernel launch");
+}
+
+// K1c: spline passes along axes 0 and 1 on every plane in one sweep (+ optional rho = scale * sum over the
+// other axes of the result).  SLLB_ERR_UNSUPPORTED when the shape / displacement pattern does not fit.
+int g_plane_kernel = 1;
+int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho) {
+    if (!F || F->ndim < 2) return fail(SLLB_ERR_INVALID, "advect_plane: bad field");
+    if (!g_plane_kernel) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: disabled (sllb_set_plane_kernel)");
+    const int n1 = F->ext[0], n2 = F->ext[1];
+    long long nplanes = 1;
+    for (int d = 2; d < F->ndim; ++d) nplanes *= F->ext[d];
+    double *partial = nullptr;
+    int nparts = 0;
+    if (d_rho) {
+        nparts = plane_grid(n1, n2, nplanes);
+        SLLB_TRY(F->red_scratch.ensure((size_t)nparts * n1 * n2));
+        partial = F->red_scratch.p;
+    }
+    cudaError_t e = launch_spline_plane(F->d, n1, n2, nplanes, dd0, dd1, partial, 0);
+    if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: plane shape or displacement pattern not supported"); }
+    SLLB_TRY(check_cuda(e, "k_spline_plane launch"));
+    if (d_rho) SLLB_CUDA(launch_sum_partials(partial, (long long)n1 * n2, nparts, rho_scale, d_rho, 0));
+    return SLLB_OK;
 }
 
 int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out) {
@@ -180,6 +205,14 @@ void sllb_launch_count_reset(void) { launch_count_reset(); }
 int sllb_set_staging(int mode) {
     if (mode < 0 || mode > 2) return fail(SLLB_ERR_INVALID, "set_staging: mode must be 0,1,2");
     g_staging = mode;
+    return SLLB_OK;
+}
+
+int sllb_set_plane_kernel(int on, int points_per_thread) {
+    if (points_per_thread != 0 && points_per_thread != 16 && points_per_thread != 32)
+        return fail(SLLB_ERR_INVALID, "set_plane_kernel: points_per_thread must be 0 (auto), 16 or 32");
+    g_plane_kernel = on ? 1 : 0;
+    g_plane_ept = points_per_thread;
     return SLLB_OK;
 }
 
@@ -323,6 +356,32 @@ int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, cons
     return advect_axis_dev(F, axis, method, order, dd);
 }
 
+static int to_dispdesc(sllb_field_t F, const sllb_disp_t *disp, DevBuf &scratch, DispDesc *dd) {
+    if (!disp || !disp->values) return fail(SLLB_ERR_INVALID, "displacement: null");
+    if (disp->values_on_device) dd->v = disp->values;
+    else {
+        if (disp->nvalues < 1) return fail(SLLB_ERR_INVALID, "displacement: nvalues < 1");
+        SLLB_TRY(scratch.ensure((size_t)disp->nvalues));
+        SLLB_CUDA(cudaMemcpyAsync(scratch.p, disp->values, (size_t)disp->nvalues * sizeof(double), cudaMemcpyHostToDevice, 0));
+        dd->v = scratch.p;
+    }
+    dd->scale = disp->scale;
+    dd->odiv = disp->odiv > 0 ? disp->odiv : 1; dd->omod = disp->omod > 0 ? disp->omod : 1; dd->ostr = disp->ostr;
+    dd->idiv = disp->idiv > 0 ? disp->idiv : 1; dd->imod = disp->imod > 0 ? disp->imod : 1; dd->istr = disp->istr;
+    (void)F;
+    return SLLB_OK;
+}
+int sllb_advect_plane(sllb_field_t F, int method, int order, const sllb_disp_t *disp0, const sllb_disp_t *disp1,
+                      double rho_scale, double *d_rho) {
+    if (!F) return fail(SLLB_ERR_INVALID, "advect_plane: null field");
+    if (method != SLLB_METHOD_SPLINE || order != 4) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: cubic splines only");
+    SLLB_TRY(require_device());
+    DispDesc d0, d1;
+    SLLB_TRY(to_dispdesc(F, disp0, F->disp_scratch, &d0));
+    SLLB_TRY(to_dispdesc(F, disp1, F->disp_scratch2, &d1));
+    return advect_plane_dev(F, d0, d1, rho_scale, d_rho);
+}
+
 /* ---------------- reductions ---------------- */
 int sllb_reduce_velocity(sllb_field_t F, int nx_axes, double scale, double *d_rho) {
     if (!F || !d_rho || nx_axes < 1 || nx_axes >= F->ndim) return fail(SLLB_ERR_INVALID, "reduce_velocity: bad arguments");
@@ -338,11 +397,10 @@ int sllb_reduce_velocity_host(sllb_field_t F, int nx_axes, double scale, double 
     if (!F || !h_rho || nx_axes < 1 || nx_axes >= F->ndim) return fail(SLLB_ERR_INVALID, "reduce_velocity: bad arguments");
     long long nx = 1;
     for (int d = 0; d < nx_axes; ++d) nx *= F->ext[d];
-    DevBuf tmp;
     SLLB_TRY(require_device());
-    SLLB_TRY(tmp.ensure((size_t)nx));
-    SLLB_TRY(sllb_reduce_velocity(F, nx_axes, scale, tmp.p));
-    SLLB_CUDA(cudaMemcpy(h_rho, tmp.p, (size_t)nx * sizeof(double), cudaMemcpyDeviceToHost));
+    SLLB_TRY(F->rho_scratch.ensure((size_t)nx));
+    SLLB_TRY(sllb_reduce_velocity(F, nx_axes, scale, F->rho_scratch.p));
+    SLLB_CUDA(cudaMemcpy(h_rho, F->rho_scratch.p, (size_t)nx * sizeof(double), cudaMemcpyDeviceToHost));
     return SLLB_OK;
 }
 int sllb_moments(sllb_field_t F, int nv, const double *w1, const double *w2, double *out) {

@@ -61,6 +61,8 @@ struct sllb_field {
     double *d = nullptr;
     bool owns = true;
     sllb::DevBuf disp_scratch;   // uploaded displacement values
+    sllb::DevBuf disp_scratch2;  // second displacement (plane kernel)
+    sllb::DevBuf rho_scratch;    // device rho of the host-returning reduction
     sllb::DevBuf red_scratch;    // reduction partials
     sllb::DevBuf stage;          // upload/download staging with duplicates
     sllb::DevBuf rows;           // diagnostics row sums
@@ -85,7 +87,10 @@ struct sllb_poisson {
 
 namespace sllb {
 // internal (device-pointer) entry points used by the simulations
-int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr);
+int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr,
+                    double *linesum = nullptr);
+int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho);
+extern int g_plane_kernel;
 int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv, double scale, DispDesc *dd);
 int make_field_disp(sllb_field *F, int axis, const double *d_field, int nfield_axes, double scale, DispDesc *dd);
 int field_alloc(int ndim, const int *ext, sllb_field **F);

@@ -362,15 +362,17 @@ __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, c
 // tile is C instead of N steps and P times more warps are resident to hide latency.
 // Chunk [k0,k1) computes g[k] for k = k1+2 .. k0 and emits cells k0+1 .. k1 (mod N).
 // ------------------------------------------------------------------------------------------------
-template <int P>
+template <int P, bool REMAP>
 __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restrict__ f, const int N,
                                                                   const long long inner, const DispDesc dd,
                                                                   const int use_tma, const long long nlines,
+                                                                  double *__restrict__ linesum,
                                                                   const __grid_constant__ RemapDst rd) {
     constexpr int BW = 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    double *part = reinterpret_cast<double *>(smem_raw + 128);          // [P][32] chunk sums (linesum only)
+    double *s = reinterpret_cast<double *>(smem_raw + 128 + P * 32 * 8);
     const int tid = threadIdx.x, lane = tid & 31, chunk = tid >> 5;
     const long long l = (long long)blockIdx.x * BW + lane;
     const bool active = l < nlines;
@@ -411,43 +413,74 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
         sc[k * BW] = e;
     }
     __syncthreads();
-    if (!active) return;
-    // per-line weights (see spline_line)
-    const double disp = disp_of(dd, o, in);
-    const double r2 = 1.60769515458673623883;
-    const double fl = floor(disp);
-    const int dcell = (int)fl;
-    const double dx = disp - fl, cdx = 1.0 - dx;
-    const double s6 = r2 * (1.0 / 6.0);
-    const double w0 = cdx * cdx * cdx * s6;
-    const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
-    const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
-    const double w3 = dx * dx * dx * s6;
-    // backward start: g[k1+2] = e[k1+2] + sum_i (-q)^{i+1} e[k1+3+i]   (indices mod N)
-    int i2 = k1 + 2; if (i2 >= N) i2 -= N;
-    int i1 = k1 + 1; if (i1 >= N) i1 -= N;
-    int i0 = k1;     if (i0 >= N) i0 -= N;
-    double g = sc[i2 * BW];
-    {
-        int idx = (i2 == N - 1) ? 0 : i2 + 1;
+    double total = 0.0;
+    if (active) {
+        // per-line weights (see spline_line)
+        const double disp = disp_of(dd, o, in);
+        const double r2 = 1.60769515458673623883;
+        const double fl = floor(disp);
+        const int dcell = (int)fl;
+        const double dx = disp - fl, cdx = 1.0 - dx;
+        const double s6 = r2 * (1.0 / 6.0);
+        const double w0 = cdx * cdx * cdx * s6;
+        const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+        const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+        const double w3 = dx * dx * dx * s6;
+        // backward start: g[k1+2] = e[k1+2] + sum_i (-q)^{i+1} e[k1+3+i]   (indices mod N)
+        int i2 = k1 + 2; if (i2 >= N) i2 -= N;
+        int i1 = k1 + 1; if (i1 >= N) i1 -= N;
+        int i0 = k1;     if (i0 >= N) i0 -= N;
+        double g = sc[i2 * BW];
+        {
+            int idx = (i2 == N - 1) ? 0 : i2 + 1;
 #pragma unroll
-        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
-            g = fma(c_pw[i], sc[idx * BW], g);
-            idx = (idx == N - 1) ? 0 : idx + 1;
+            for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+                g = fma(c_pw[i], sc[idx * BW], g);
+                idx = (idx == N - 1) ? 0 : idx + 1;
+            }
+        }
+        double a3 = g;                                  // g[k1+2]
+        double a2 = fma(-q, a3, sc[i1 * BW]);           // g[k1+1]
+        double a1 = fma(-q, a2, sc[i0 * BW]);           // g[k1]
+        const int iout0 = ((k1 - dcell) % N + N) % N;   // output index of cell k1 (mod N)
+        if constexpr (REMAP) {
+            OutMap om = make_outmap(rd, o, in, N, inner);
+            om.seek(iout0);
+#pragma unroll 8
+            for (int k = k1 - 1; k >= k0; --k) {
+                const double a0 = fma(-q, a1, sc[k * BW]);
+                const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
+                st_stream(om.p, val);
+                total += val;
+                om.prev();
+                a3 = a2; a2 = a1; a1 = a0;
+            }
+        } else {
+            double *p = base + (long long)iout0 * inner;
+            double *const ptop = base + (long long)(N - 1) * inner;
+            int iout = iout0;
+#pragma unroll 8
+            for (int k = k1 - 1; k >= k0; --k) {
+                const double a0 = fma(-q, a1, sc[k * BW]);
+                const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
+                st_stream(p, val);
+                total += val;
+                p = (iout == 0) ? ptop : p - inner;
+                iout = (iout == 0) ? N - 1 : iout - 1;
+                a3 = a2; a2 = a1; a1 = a0;
+            }
         }
     }
-    double a3 = g;                                  // g[k1+2]
-    double a2 = fma(-q, a3, sc[i1 * BW]);           // g[k1+1]
-    double a1 = fma(-q, a2, sc[i0 * BW]);           // g[k1]
-    OutMap om = make_outmap(rd, o, in, N, inner);
-    om.seek(((k1 - dcell) % N + N) % N);            // output index of cell k1 (mod N)
-#pragma unroll 8
-    for (int k = k1 - 1; k >= k0; --k) {
-        const double a0 = fma(-q, a1, sc[k * BW]);
-        const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
-        st_stream(om.p, val);
-        om.prev();
-        a3 = a2; a2 = a1; a1 = a0;
+    // optional: sum of every advected line (charge-density reduction fused into the pass, see K3b)
+    if (linesum != nullptr) {
+        part[chunk * 32 + lane] = total;
+        __syncthreads();
+        if (chunk == 0 && active) {
+            double t = part[lane];
+#pragma unroll
+            for (int c = 1; c < P; ++c) t += part[c * 32 + lane];
+            linesum[l] = t;
+        }
     }
 }
 
@@ -486,6 +519,247 @@ __global__ void __launch_bounds__(BW) k_spline_contig(double *__restrict__ f, co
             if (kc >= N) kc -= N;
             st_stream(tile + (long long)ln * N + i, s[(size_t)kc * P + ln]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b (split): spline, contiguous axis.  Block = 32 consecutive lines = one contiguous chunk of 32*N
+// doubles, brought in by ONE bulk TMA copy in its natural layout s[line*N + k].  Thread (lane = line,
+// warp = chunk) runs the two recurrences over C = N/P points of its line, restarted with the reference's
+// 27-term series like K1a.  Because the line is periodic the chunk boundaries may sit anywhere: line l
+// starts its chunks at k = l mod 16, so the 32 lanes of a warp touch 16 different bank pairs at every step
+// (conflict-free for 8-byte words) although the pitch N is a multiple of 16.  The result of cell k+1 is
+// parked in slot k (the slot just consumed), and the tile leaves through coalesced stores that apply the
+// integer part of the shift.
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(32 * P) k_spline_contig_split(double *__restrict__ f, const long long nlines, const int N,
+                                                                 const DispDesc dd) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    int *rot = reinterpret_cast<int *>(smem_raw + 16); // 32 ints: slot of output point 0 per line
+    double *s = reinterpret_cast<double *>(smem_raw + 256);
+    const int tid = threadIdx.x, lane = tid & 31, chunk = tid >> 5;
+    const long long l0 = (long long)blockIdx.x * 32;
+    const int nl = (int)((nlines - l0 < 32) ? (nlines - l0) : 32);
+    double *tile = f + l0 * (long long)N;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)((size_t)nl * N * 8));
+        bulk_g2s(s, tile, (uint32_t)((size_t)nl * N * 8), bar);
+    }
+    const bool active = lane < nl;
+    const int C = N / P;
+    int k0 = chunk * C + (lane & 15);
+    if (k0 >= N) k0 -= N;
+    double *sc = s + (size_t)(active ? lane : 0) * N;
+    const double q = 0.26794919243112270647;
+    double disp = 0.0;
+    if (active) disp = disp_of(dd, l0 + lane, 0);
+    mbar_wait(bar, 0);
+    // forward restart from pristine f: e[k0] = f[k0] + sum_i (-q)^{i+1} f[k0-1-i]
+    double e = sc[k0];
+    {
+        int idx = (k0 == 0) ? N - 1 : k0 - 1;
+#pragma unroll
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            e = fma(c_pw[i], sc[idx], e);
+            idx = (idx == 0) ? N - 1 : idx - 1;
+        }
+    }
+    __syncthreads();
+    if (active) {
+        sc[k0] = e;
+        int k = k0;
+#pragma unroll 8
+        for (int t = 1; t < C; ++t) {
+            k = (k == N - 1) ? 0 : k + 1;
+            e = fma(-q, e, sc[k]);
+            sc[k] = e;
+        }
+    }
+    __syncthreads();
+    // backward restart: with k1 = k0 + C, g[k1+2] = e[k1+2] + sum_i (-q)^{i+1} e[k1+3+i]   (indices mod N)
+    int i0 = k0 + C; if (i0 >= N) i0 -= N;
+    int i1 = (i0 == N - 1) ? 0 : i0 + 1;
+    int i2 = (i1 == N - 1) ? 0 : i1 + 1;
+    double g = sc[i2];
+    {
+        int idx = (i2 == N - 1) ? 0 : i2 + 1;
+#pragma unroll
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            g = fma(c_pw[i], sc[idx], g);
+            idx = (idx == N - 1) ? 0 : idx + 1;
+        }
+    }
+    double a3 = g;                             // g[k1+2]
+    double a2 = fma(-q, a3, sc[i1]);           // g[k1+1]
+    double a1 = fma(-q, a2, sc[i0]);           // g[k1]
+    __syncthreads(); // every chunk holds its start values before anybody overwrites e with results
+    if (active) {
+        const double r2 = 1.60769515458673623883;
+        const double fl = floor(disp);
+        const double dx = disp - fl, cdx = 1.0 - dx;
+        const double s6 = r2 * (1.0 / 6.0);
+        const double w0 = cdx * cdx * cdx * s6;
+        const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+        const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+        const double w3 = dx * dx * dx * s6;
+        if (chunk == 0) {
+            // output point i takes cell (i + dcell) mod N, which is parked in slot (i + dcell - 1) mod N
+            const int dcell = (int)fl;
+            rot[lane] = (((dcell - 1) % N) + N) % N;
+        }
+        int k = i0;
+#pragma unroll 8
+        for (int t = 0; t < C; ++t) {
+            k = (k == 0) ? N - 1 : k - 1;
+            const double a0 = fma(-q, a1, sc[k]);
+            sc[k] = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
+            a3 = a2; a2 = a1; a1 = a0;
+        }
+    }
+    __syncthreads();
+    for (int ln = chunk; ln < nl; ln += P) {
+        const int r = rot[ln];
+        const double *row = s + (size_t)ln * N;
+        double *orow = tile + (long long)ln * N;
+        for (int i = lane; i < N; i += 32) {
+            int kc = i + r;
+            if (kc >= N) kc -= N;
+            st_stream(orow + i, row[kc]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1c: the whole T stage in one sweep.  The x1 pass and the x2 pass of a splitting stage act on the same
+// contiguous (x1,x2) plane of f and their displacements are constant over that plane (alpha = v3*step,
+// alpha = v4*step: sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:1037-1064), so a persistent CTA stages one
+// N1 x N2 plane (one bulk TMA copy), runs both periodic spline solves + shift-evaluates in shared memory
+// and writes the plane once: two advection passes for 16 B of HBM traffic per point.  Optionally the CTA
+// also accumulates its planes into a per-CTA partial charge density (the reduction over x3,x4 that follows
+// the T stage, sll_m_reduction.F90:187-272), so rho needs no extra sweep over f.
+// Threads = N1*N2/16: every line is cut into chunks of 16 points (27-term restarts as in K1a).  Pass A runs
+// along x1 (rows, skewed chunk starts for conflict-free banks), pass B along x2 (columns).  Each pass parks
+// cell k+1 in slot k, so after both passes out(i1,i2) sits at slot (i1+r1, i2+r2) with r = dcell-1 (mod N).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void plane_pass(double *sc, const int stride, const int N, const int k0, const int C,
+                                           const double disp) {
+    const double q = 0.26794919243112270647;
+    // restart values: the 27-term series of the reference in Horner form, i.e. the recurrence itself started
+    // 27 points upstream from zero (no coefficient table: it would be hoisted into 54 registers here)
+    double e;
+    {
+        int idx = k0 - SLLB_NUM_TERMS;
+        while (idx < 0) idx += N;
+        e = sc[idx * stride];
+#pragma unroll 9
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            idx = (idx == N - 1) ? 0 : idx + 1;
+            e = fma(-q, e, sc[idx * stride]);
+        }
+    }
+    __syncthreads();
+    sc[k0 * stride] = e;
+    int k = k0;
+#pragma unroll 4
+    for (int t = 1; t < C; ++t) {
+        k = (k == N - 1) ? 0 : k + 1;
+        e = fma(-q, e, sc[k * stride]);
+        sc[k * stride] = e;
+    }
+    __syncthreads();
+    int i0 = k0 + C; if (i0 >= N) i0 -= N;
+    const int i1 = (i0 == N - 1) ? 0 : i0 + 1;
+    const int i2 = (i1 == N - 1) ? 0 : i1 + 1;
+    double g;
+    {
+        int idx = i2 + SLLB_NUM_TERMS;
+        while (idx >= N) idx -= N;
+        g = sc[idx * stride];
+#pragma unroll 9
+        for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
+            idx = (idx == 0) ? N - 1 : idx - 1;
+            g = fma(-q, g, sc[idx * stride]);
+        }
+    }
+    double a3 = g;
+    double a2 = fma(-q, a3, sc[i1 * stride]);
+    double a1 = fma(-q, a2, sc[i0 * stride]);
+    __syncthreads();
+    const double r2 = 1.60769515458673623883;
+    const double fl = floor(disp);
+    const double dx = disp - fl, cdx = 1.0 - dx;
+    const double s6 = r2 * (1.0 / 6.0);
+    const double w0 = cdx * cdx * cdx * s6;
+    const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+    const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+    const double w3 = dx * dx * dx * s6;
+    k = i0;
+#pragma unroll 4
+    for (int t = 0; t < C; ++t) {
+        k = (k == 0) ? N - 1 : k - 1;
+        const double a0 = fma(-q, a1, sc[k * stride]);
+        sc[k * stride] = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1 parked in slot k
+        a3 = a2; a2 = a1; a1 = a0;
+    }
+    __syncthreads();
+}
+
+// EPT = plane points per thread = chunk length; RHO: keep the per-thread partial sums (EPT registers)
+template <int EPT, bool RHO>
+__global__ void __launch_bounds__(16384 / EPT, 1) k_spline_plane(double *__restrict__ f, const int N1, const int N2,
+                                                                 const long long nplanes, const DispDesc dd1,
+                                                                 const DispDesc dd2, double *__restrict__ rho_partial) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, T = blockDim.x;
+    const int npl = N1 * N2;
+    constexpr int C = EPT;
+    const int PA = N1 / C, PB = N2 / C;              // chunks per line in pass A / B
+    // pass A: line = x2 index (row of N1 contiguous points); pass B: line = x1 index (column, stride N1)
+    const int lineA = (w / PA) * 32 + lane, chA = w % PA;
+    int k0A = chA * C + (lane & 15); if (k0A >= N1) k0A -= N1;
+    const int lineB = (w / PB) * 32 + lane, chB = w % PB;
+    const int k0B = chB * C;
+    double acc[RHO ? EPT : 1];
+#pragma unroll
+    for (int j = 0; j < (RHO ? EPT : 1); ++j) acc[j] = 0.0;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t phase = 0;
+    for (long long pl = blockIdx.x; pl < nplanes; pl += gridDim.x) {
+        double *gp = f + pl * (long long)npl;
+        if (tid == 0) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
+            bulk_g2s(s, gp, (uint32_t)(npl * 8), bar);
+        }
+        const double d1 = disp_of(dd1, pl * N2, 0); // constant over the plane (checked by the launcher)
+        const double d2 = disp_of(dd2, pl, 0);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        plane_pass(s + (size_t)lineA * N1, 1, N1, k0A, C, d1);
+        plane_pass(s + lineB, N1, N2, k0B, C, d2);
+        const int r1 = ((((int)floor(d1) - 1) % N1) + N1) % N1;
+        const int r2 = ((((int)floor(d2) - 1) % N2) + N2) % N2;
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int idx = tid + j * T;
+            const int i2 = idx / N1, i1 = idx - i2 * N1;
+            int c1 = i1 + r1; if (c1 >= N1) c1 -= N1;
+            int c2 = i2 + r2; if (c2 >= N2) c2 -= N2;
+            const double v = s[(size_t)c2 * N1 + c1];
+            st_stream(gp + idx, v);
+            if constexpr (RHO) acc[j] += v;
+        }
+        __syncthreads(); // the plane has left shared memory before the next bulk copy lands
+    }
+    if constexpr (RHO) {
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) rho_partial[(long long)blockIdx.x * npl + tid + j * T] = acc[j];
     }
 }
 
@@ -655,15 +929,23 @@ static cudaError_t launch_strided_t(double *f, long long nlines, int N, long lon
 int g_spline_split = -1; // -1 auto, else forced P in {1,2,4}
 template <int P>
 static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
-                                         int staging, cudaStream_t st, const RemapDst &rd) {
-    size_t smem = 128 + (size_t)N * 32 * 8;
-    auto kern = k_spline_strided_split<P>;
-    cudaError_t e = set_smem(kern, smem);
-    if (e != cudaSuccess) return e;
+                                         int staging, cudaStream_t st, const RemapDst &rd, double *linesum) {
+    size_t smem = 128 + (size_t)P * 32 * 8 + (size_t)N * 32 * 8;
     bool tma_ok = (inner % 32 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * 32 * 8 < (1u << 20));
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + 31) / 32;
-    kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, rd);
+    cudaError_t e;
+    if (rd.on) {
+        auto kern = k_spline_strided_split<P, true>;
+        e = set_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd);
+    } else {
+        auto kern = k_spline_strided_split<P, false>;
+        e = set_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd);
+    }
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
@@ -712,8 +994,74 @@ static cudaError_t launch_spline_contig_t(double *f, long long nlines, int N, co
     return cudaGetLastError();
 }
 
+template <int P>
+static cudaError_t launch_spline_contig_split_t(double *f, long long nlines, int N, const DispDesc &dd, cudaStream_t st) {
+    size_t smem = 256 + (size_t)N * 32 * 8;
+    auto kern = k_spline_contig_split<P>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    long long nblk = (nlines + 31) / 32;
+    kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, nlines, N, dd);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// K1c launcher.  Returns cudaErrorNotSupported when the plane does not fit the kernel's assumptions (the
+// caller then runs the two passes separately).
+int g_plane_ept = 0; // tuning knob: 0 auto, 16 or 32 points per thread
+static int plane_ept(int n1, int n2, bool rho) {
+    if (rho) return 32;
+    if (g_plane_ept == 16 || g_plane_ept == 32) return g_plane_ept;
+    return 32;
+}
+int plane_grid(int n1, int n2, long long nplanes) {
+    const size_t smem = 128 + (size_t)n1 * n2 * 8;
+    const int threads = n1 * n2 / plane_ept(n1, n2, true);
+    int per_sm = (int)(SMEM_MAX / (smem + 1024));
+    if (per_sm * threads > 2048) per_sm = 2048 / threads;
+    if (per_sm < 1) per_sm = 1;
+    long long g = 148LL * per_sm;
+    return (int)(nplanes < g ? nplanes : g);
+}
+cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, const DispDesc &dd1, const DispDesc &dd2,
+                                double *rho_partial, cudaStream_t st) {
+    if (n1 % 32 != 0 || n2 % 32 != 0 || n1 < 32 || n2 < 32) return cudaErrorNotSupported;
+    const int ept = plane_ept(n1, n2, rho_partial != nullptr);
+    const int threads = n1 * n2 / ept;
+    if (threads > 16384 / ept || threads < 32) return cudaErrorNotSupported;
+    const size_t smem = 128 + (size_t)n1 * n2 * 8;
+    if (smem > SMEM_MAX || (size_t)n1 * n2 * 8 >= (1u << 20)) return cudaErrorNotSupported;
+    if ((reinterpret_cast<uintptr_t>(f) & 15) != 0) return cudaErrorNotSupported;
+    // both displacements must be constant over a plane
+    const bool c1 = (dd1.istr == 0 || dd1.imod == 1) && (dd1.ostr == 0 || dd1.omod == 1 || dd1.odiv % n2 == 0);
+    const bool c2 = (dd2.istr == 0 || dd2.imod == 1);
+    if (!c1 || !c2) return cudaErrorNotSupported;
+    cudaError_t e = ensure_constants();
+    if (e != cudaSuccess) return e;
+    const int grid = plane_grid(n1, n2, nplanes);
+#define SLLB_PLANE_LAUNCH(E, R)                                                                         \
+    do {                                                                                                \
+        e = set_smem(k_spline_plane<E, R>, smem);                                                       \
+        if (e != cudaSuccess) return e;                                                                 \
+        k_spline_plane<E, R><<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial);  \
+    } while (0)
+    if (rho_partial) SLLB_PLANE_LAUNCH(32, true);
+    else if (ept == 16) SLLB_PLANE_LAUNCH(16, false);
+    else SLLB_PLANE_LAUNCH(32, false);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+__global__ void k_reduce_stage2(const double *__restrict__ partial, long long nx, int nchunks, double scale,
+                                double *__restrict__ rho);
+// rho[x] = scale * sum_b partial[b][x]
+cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts, double scale, double *rho, cudaStream_t st) {
+    k_reduce_stage2<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(partial, nx, nparts, scale, rho);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
-                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap) {
+                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap, double *linesum) {
     if (n < 8 || outer < 1 || inner < 1) return cudaErrorInvalidValue;
     RemapDst rd;
     if (remap && remap->on) {
@@ -729,21 +1077,35 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
     if (nlines > 0x7fffffffLL * 8) return cudaErrorInvalidValue;
     if (method == METHOD_SPLINE) {
         if (order != 4) return cudaErrorInvalidValue;
+        if (inner == 1 && linesum) return cudaErrorNotSupported;
         if (inner == 1) {
+            // split kernel: one bulk TMA copy per 32-line tile (16-byte granularity) and P chunks per line
+            const bool tile_ok = (size_t)n * 32 * 8 + 256 <= SMEM_MAX && (size_t)n * 32 * 8 < (1u << 20) &&
+                                 (reinterpret_cast<uintptr_t>(f) & 15) == 0 && staging != STAGING_CPASYNC &&
+                                 (n % 2 == 0 || (nlines % 32 == 0)) && ((nlines % 32) * n) % 2 == 0;
+            if (tile_ok && g_spline_split != 1) {
+                int P = g_spline_split;
+                if (P < 0) P = (n % 4 == 0 && n / 4 >= 32) ? 4 : ((n % 2 == 0 && n / 2 >= 32) ? 2 : 0);
+                if (P == 8 && n % 8 == 0 && n / 8 >= 30) return launch_spline_contig_split_t<8>(f, nlines, n, dd, st);
+                if (P == 4 && n % 4 == 0 && n / 4 >= 30) return launch_spline_contig_split_t<4>(f, nlines, n, dd, st);
+                if (P == 2 && n % 2 == 0 && n / 2 >= 30) return launch_spline_contig_split_t<2>(f, nlines, n, dd, st);
+            }
             if ((size_t)n * 33 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<32>(f, nlines, n, dd, st);
             if ((size_t)n * 17 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<16>(f, nlines, n, dd, st);
             if ((size_t)n * 9 * 8 + 256 <= SMEM_MAX) return launch_spline_contig_t<8>(f, nlines, n, dd, st);
             return cudaErrorInvalidValue;
         }
-        if ((size_t)n * 32 * 8 + 128 <= SMEM_MAX) {
+        if ((size_t)n * 32 * 8 + 128 + 8 * 32 * 8 <= SMEM_MAX) {
             int P = g_spline_split;
             if (P < 0) P = (n % 4 == 0 && n / 4 >= 32) ? 4 : ((n % 2 == 0 && n / 2 >= 32) ? 2 : 1);
-            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd);
-            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd);
-            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd);
+            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd, linesum);
+            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd, linesum);
+            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd, linesum);
         }
+        if (linesum) return cudaErrorNotSupported; // line sums come from the chunked kernel only
         return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st, rd);
     }
+    if (linesum) return cudaErrorNotSupported;
 #define LAGR_CASE(SS)                                                                            \
     case SS:                                                                                     \
         if (inner == 1) return launch_lagrange_contig<SS>(f, nlines, n, dd, staging, st);       \

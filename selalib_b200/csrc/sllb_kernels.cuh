@@ -27,7 +27,17 @@ struct RemapDst {
 // K1/K2: one 1D periodic advection on every line of f viewed as [outer][n][inner], in place.
 // Returns cudaSuccess, cudaErrorInvalidValue (bad n / order) or a launch error.
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
-                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap = nullptr);
+                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap = nullptr,
+                          double *linesum = nullptr);
+// linesum (strided spline passes only, else cudaErrorNotSupported): linesum[line] = sum of the advected line
+
+// K1c: both passes of a T stage (axes 0 and 1) on every contiguous n1 x n2 plane in one sweep, optionally
+// accumulating per-CTA partial sums over the planes: rho_partial[plane_grid(...)][n1*n2].
+// cudaErrorNotSupported when the plane shape / displacement pattern does not fit.
+int plane_grid(int n1, int n2, long long nplanes);
+cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, const DispDesc &dd1, const DispDesc &dd2,
+                                double *rho_partial, cudaStream_t st);
+cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts, double scale, double *rho, cudaStream_t st);
 
 // K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]
 cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
@@ -63,6 +73,7 @@ struct Box4 { int lo[4]; int n[4]; };   // sub-box origin (local coords) and ext
 cudaError_t launch_pack4d(const double *src, const int ext[4], Box4 box, double *buf, cudaStream_t st);
 cudaError_t launch_unpack4d(double *dst, const int ext[4], Box4 box, const double *buf, cudaStream_t st);
 
+extern int g_plane_ept;    // plane kernel: 0 auto, 16 or 32 points per thread
 extern int g_spline_split; // -1 auto, else lines are cut into this many chunks (1,2,4,8)
 long long launch_count();
 void launch_count_reset();

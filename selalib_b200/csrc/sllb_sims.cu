@@ -396,7 +396,10 @@ struct sllb_sim4d {
     sllb_poisson *poisson = nullptr;
     double delta[4];
     int bx[8], bv[8];  // my boxes in the two layouts
-    DevBuf rho_tile, rho_gather, rho_full, E1, E2, E1loc, E2loc, small;
+    DevBuf rho_tile, rho_gather, rho_full, E1, E2, E1loc, E2loc, small, linesum;
+    // where the charge density of the current f can be had without another sweep over f:
+    // 0 nothing (reduce f), 1 rho_full already holds it (T stage plane kernel), 2 line sums of the last x4 pass
+    int rho_state = 0;
     double nrj = 0.0;
     int istep = 0;
     int layout = 0;    // which copy of f is current: 0 x-sequential, 1 v-sequential
@@ -438,11 +441,20 @@ static int sim4d_fields(sllb_sim4d *S) {
     sllb_field *Fv = S->D->F[1];
     const int N1 = S->p.nc[0], N2 = S->p.nc[1];
     const int P = S->D->nranks;
-    if (P == 1) {
-        SLLB_TRY(sllb_reduce_velocity(Fv, 2, S->delta[2] * S->delta[3], S->rho_full.p));
+    const double scale = S->delta[2] * S->delta[3];
+    const long long tile = (long long)Fv->ext[0] * Fv->ext[1];
+    double *rho_local = (P == 1) ? S->rho_full.p : S->rho_tile.p;
+    if (S->rho_state == 1 && P == 1) {
+        // rho_full was accumulated by the plane kernel during the T stage
+    } else if (S->rho_state == 2) {
+        // sum over x4 came out of the last x4 pass; finish the sum over x3 (K3 on a [x1 x2][x3] array)
+        SLLB_TRY(Fv->red_scratch.ensure(reduce_scratch_doubles(tile, Fv->ext[2])));
+        SLLB_CUDA(launch_reduce_velocity(S->linesum.p, tile, Fv->ext[2], scale, rho_local, Fv->red_scratch.p, 0));
     } else {
-        const long long tile = (long long)Fv->ext[0] * Fv->ext[1];
-        SLLB_TRY(sllb_reduce_velocity(Fv, 2, S->delta[2] * S->delta[3], S->rho_tile.p));
+        SLLB_TRY(sllb_reduce_velocity(Fv, 2, scale, rho_local));
+    }
+    S->rho_state = 0;
+    if (P > 1) {
         SLLB_TRY(sllb_comm_allgather(S->comm, S->rho_tile.p, S->rho_gather.p, tile));
         const int ext[4] = {N1, N2, 1, 1};
         for (int r = 0; r < P; ++r) {
@@ -476,6 +488,19 @@ static int sim4d_nrj(sllb_sim4d *S) {
 static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     sllb_field *Fx = S->D->F[0];
     const sllb_sim4d_params_t &p = S->p;
+    S->rho_state = 0;
+    // single GPU, cubic splines: both passes and the charge density in one sweep (K1c)
+    if (S->D->nranks == 1 && p.method == SLLB_METHOD_SPLINE && g_plane_kernel) {
+        DispDesc d0, d1;
+        SLLB_TRY(Fx->disp_scratch2.ensure((size_t)Fx->ext[3]));
+        SLLB_TRY(make_affine_disp(Fx, 0, 2, p.xmin[2], S->delta[2], -step * p.dt / S->delta[0], &d0));
+        SLLB_CUDA(launch_affine(Fx->disp_scratch2.p, Fx->ext[3], p.xmin[3], S->delta[3], 0));
+        d1.v = Fx->disp_scratch2.p; d1.scale = -step * p.dt / S->delta[1];
+        d1.odiv = Fx->ext[2]; d1.omod = Fx->ext[3]; d1.ostr = 1; d1.idiv = d1.imod = 1; d1.istr = 0;
+        int rc = advect_plane_dev(Fx, d0, d1, S->delta[2] * S->delta[3], S->rho_full.p);
+        if (rc == SLLB_OK) { S->rho_state = 1; return SLLB_OK; }
+        if (rc != SLLB_ERR_UNSUPPORTED) return rc;
+    }
     // out(x) = in(x - v*step*dt): displacement in cells = -v*step*dt/delta_x  (:1037-1064)
     SLLB_TRY(sllb_advect_axis_affine(Fx, 0, p.method, p.order, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2],
                                      -step * p.dt / S->delta[0]));
@@ -506,11 +531,21 @@ static int sim4d_V(sllb_sim4d *S, double step, bool fuse) {
     SLLB_TRY(sllb_advect_axis_field(Fv, 2, p.method, p.order, e1, 2, -step * p.dt / S->delta[2]));
     DispDesc dd;
     SLLB_TRY(make_field_disp(Fv, 3, e2, 2, -step * p.dt / S->delta[3], &dd));
+    S->rho_state = 0;
     if (fuse) {
         SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, p.method, p.order, dd));
         S->layout = 0;
     } else {
-        SLLB_TRY(advect_axis_dev(Fv, 3, p.method, p.order, dd));
+        // f stays in this layout, so the next thing that happens to it is another V stage: hand its charge
+        // density over as line sums of this pass (sum over x4 per (x1,x2,x3) line) instead of re-reading f
+        int rc = SLLB_ERR_UNSUPPORTED;
+        if (p.method == SLLB_METHOD_SPLINE && g_plane_kernel) {
+            rc = S->linesum.ensure((size_t)Fv->ext[0] * Fv->ext[1] * Fv->ext[2]);
+            if (!rc) rc = advect_axis_dev(Fv, 3, p.method, p.order, dd, nullptr, S->linesum.p);
+            if (rc == SLLB_OK) S->rho_state = 2;
+        }
+        if (rc == SLLB_ERR_UNSUPPORTED) rc = advect_axis_dev(Fv, 3, p.method, p.order, dd);
+        if (rc) return rc;
     }
     return SLLB_OK;
 }
@@ -565,6 +600,7 @@ int sllb_sim4d_destroy(sllb_sim4d_t S) {
 }
 int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F) {
     if (!S || !F) return fail(SLLB_ERR_INVALID, "sim4d_field: null");
+    S->rho_state = 0; // the caller may overwrite f through the handle
     SLLB_TRY(sim4d_to_layout(S, 0));
     *F = S->D->F[0];
     return SLLB_OK;

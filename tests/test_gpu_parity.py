@@ -222,6 +222,95 @@ def test_spline_strided_split_kernel(sb, orc, split, staging):
         sb.set_staging(0)
 
 
+@pytest.mark.parametrize("split", [1, 2, 4, 8, -1])
+def test_spline_contig_split_kernel(sb, orc, split):
+    """the chunked contiguous-axis spline kernel (one bulk TMA copy per 32-line tile, skewed chunk starts):
+    every split factor, full and ragged tiles, large integer shifts, line lengths with and without the
+    multiple-of-16 pitch, and the fallbacks (odd N, cp.async staging)."""
+    rng = np.random.default_rng(SEED + 200 + split)
+    sb.set_spline_split(split)
+    try:
+        for shape in [(128, 32, 4), (128, 37), (64, 33, 3), (256, 40), (100, 50), (72, 64), (65, 31), (512, 32), (32, 96)]:
+            f0 = np.asfortranarray(rng.standard_normal(shape))
+            F = sb.Field(shape)
+            nl = int(np.prod(shape[1:]))
+            disp = rng.uniform(-1.5 * shape[0], 1.5 * shape[0], nl)
+            dsel = (1, nl, 1, 1, 1, 0)
+            ref = orc.advect_axis(f0.copy(order="F"), 0, "spline", 4, disp, dsel)
+            for staging in (0, 2):
+                sb.set_staging(staging)
+                F.upload(f0)
+                F.advect_axis(0, sb.METHOD_SPLINE, 4, disp, 1.0, dsel)
+                assert relerr(F.download(), ref) < TOL, (shape, split, staging)
+            F.destroy()
+    finally:
+        sb.set_spline_split(-1)
+        sb.set_staging(0)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 5, 3), (64, 64, 7, 5), (32, 64, 4, 3), (128, 64, 3, 2), (64, 32, 150)])
+@pytest.mark.parametrize("ept", [0, 16, 32])
+def test_advect_plane_kernel(sb, orc, shape, ept):
+    """K1c: x1 and x2 passes (+ the charge density) in one sweep == two oracle passes + a plain sum."""
+    rng = np.random.default_rng(SEED + 300 + sum(shape))
+    f0 = np.asfortranarray(rng.standard_normal(shape))
+    nd = len(shape)
+    n3 = shape[2]
+    n4 = shape[3] if nd > 3 else 1
+    v3 = rng.uniform(-70, 70, n3)
+    v4 = rng.uniform(-70, 70, n4)
+    d0 = (shape[1], n3, 1, 1, 1, 0)            # axis-0 lines: o = x2 + N2*(x3 + N3*x4) -> x3
+    d1 = (n3, n4, 1, 1, 1, 0)                  # axis-1 lines: o = x3 + N3*x4 -> x4
+    ref = orc.advect_axis(f0.copy(order="F"), 0, "spline", 4, v3 * 0.9, d0)
+    ref = orc.advect_axis(ref, 1, "spline", 4, v4 * 1.1, d1)
+    F = sb.Field(shape)
+    sb.set_plane_kernel(True, ept)
+    try:
+        F.upload(f0)
+        rho = F.advect_plane(v3, d0, 0.9, v4, d1, 1.1, rho_scale=0.25)
+        out = F.download()
+        assert relerr(out, ref) < TOL
+        rho_ref = 0.25 * ref.reshape(shape[0], shape[1], -1).sum(axis=2)
+        assert np.abs(rho - rho_ref).max() < 1e-12 * np.abs(ref).max() * (n3 * n4)
+        F.upload(f0)
+        assert F.advect_plane(v3, d0, 0.9, v4, d1, 1.1) is None
+        assert relerr(F.download(), ref) < TOL
+    finally:
+        sb.set_plane_kernel(True, 0)
+    F.destroy()
+
+
+def test_advect_plane_kernel_unsupported(sb):
+    F = sb.Field((48, 40, 4))
+    with pytest.raises(sb.SllbError) as ei:
+        F.advect_plane(np.zeros(4), (40, 4, 1, 1, 1, 0), 1.0, np.zeros(1), (1, 1, 0, 1, 1, 0), 1.0)
+    assert ei.value.code == 2
+    F.destroy()
+    F = sb.Field((64, 64, 4))
+    with pytest.raises(sb.SllbError) as ei:   # displacement varying inside a plane
+        F.advect_plane(np.zeros(64), (1, 64, 1, 1, 1, 0), 1.0, np.zeros(1), (1, 1, 0, 1, 1, 0), 1.0)
+    assert ei.value.code == 2
+    F.destroy()
+
+
+def test_sim4d_fused_stage_kernels_match_separate_passes(sb):
+    """the T-stage plane kernel + line-sum charge density vs. the separate passes + full reduction"""
+    a4 = ([32, 64, 32, 32], [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-2, 0.1)
+    out = {}
+    for on in (True, False):
+        sb.set_plane_kernel(on)
+        try:
+            S = sb.Sim4d(*a4)
+            rows = S.run(4)
+            f = S.field().download()
+            S.destroy()
+        finally:
+            sb.set_plane_kernel(True)
+        out[on] = (rows, f)
+    assert np.abs(out[True][0] / out[False][0] - 1).max() < 1e-10
+    assert relerr(out[True][1], out[False][1]) < TOL
+
+
 def test_advect_axis_6d(sb, orc):
     rng = np.random.default_rng(SEED)
     shape = (8, 10, 8, 8, 12, 8)
