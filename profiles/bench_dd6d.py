@@ -1,0 +1,118 @@
+"""C5: 3D3V Landau damping 32^6 fp64, domain-decomposed fixed-stencil Lagrange advection (7-point), halo exchange
+over NCCL send/recv.  One process per GPU (torchrun); prints one JSON line on rank 0.
+
+  value       = 6D point-updates/s per advection pass over the timed steps (6 passes per step: eta1..eta6,
+                plus the rho reduction, all-reduce and 32^3 Poisson solve inside the timed region)
+  x_pass_ms   = mean device time of one x pass (no communication: x is not split up to 8 ranks)
+  v_pass_ms   = mean device time of one v pass (halo pack + send/recv + halo-cells kernel)
+  halo_ms     = part of a v pass spent in pack + NCCL send/recv (CUDA events around the exchange)
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import selalib_b200 as sb  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--stencil", type=int, default=7)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    sb.init(local)
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.tensor(list(sb.Comm.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = sb.Comm(bytes(idt.cpu().tolist()), world, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = a.n
+    S = sb.Sim6d([n] * 6, 6.0, [4 * np.pi] * 3, a.stencil, a.stencil, 0.01, 0.01, [0.5] * 3, comm=comm)
+    lay = S.layout()
+    S.run(a.warmup, first=True)
+    S.halo_ms()
+    barrier()
+    sb.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rows = S.run(a.steps, first=False)
+    e1.record()
+    barrier()
+    ms = maxr(e0.elapsed_time(e1))
+    launches = sb.launch_count()
+    npts = float(n) ** 6
+    # separate timings of the x stage and the v stage
+    reps = 3
+    S.halo_ms()
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for _ in range(reps):
+        S.advect_x()
+    x1.record()
+    barrier()
+    x_ms = maxr(x0.elapsed_time(x1)) / (3 * reps)
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    S.halo_ms()
+    v0.record()
+    for _ in range(reps):
+        S.advect_v(0.01)
+    v1.record()
+    barrier()
+    v_ms = maxr(v0.elapsed_time(v1)) / (3 * reps)
+    nsplit = sum(1 for p in lay["procs"][3:] if p > 1)
+    halo_ms = maxr(S.halo_ms()) / max(1, nsplit * reps)
+    local_pts = float(np.prod(lay["nw"]))
+    peak = 6452.5
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    if rank == 0:
+        hw = (a.stencil - 1) // 2
+        halo_bytes = 2 * hw * local_pts / lay["nw"][5] * 8 if world > 1 else 0
+        print(json.dumps({
+            "metric": "6D phase-space point-updates/s per advection pass", "value": 6 * npts * a.steps / (ms * 1e-3),
+            "unit": "point-updates/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "scaling": "strong", "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D3V Landau damping {n}^6 fp64, Lagrange fixed {a.stencil}-point in all six directions, "
+                                   "dt=0.01, landau_prod alpha=0.01 k=0.5, L=4pi, v_max=6 (sim_bsl_vp_3d3v_cart_dd_slim semantics)",
+                       "process_grid": lay["procs"], "local_block": lay["nw"]},
+            "x_pass_ms": x_ms, "x_pass_gbs": 16 * local_pts / (x_ms * 1e-3) / 1e9, "x_pass_frac_of_measured_hbm": 16 * local_pts / (x_ms * 1e-3) / 1e9 / peak,
+            "v_pass_ms": v_ms, "halo_ms_per_split_pass": halo_ms,
+            "halo_bytes_sent_per_split_pass": halo_bytes,
+            "halo_gbs_per_direction": (halo_bytes / 2) / (halo_ms * 1e-3) / 1e9 if halo_ms > 0 else None,
+            "gpu_launches": int(launches), "mass": float(rows[-1, 1]), "l2": float(rows[-1, 2])}), flush=True)
+    S.destroy()
+    if comm is not None:
+        comm.destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

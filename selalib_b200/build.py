@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libsllb200.so")
-SOURCES = ["sllb_kernels.cu", "sllb_capi.cu", "sllb_sims.cu", "sllb_dd6d.cu"]
+SOURCES = ["sllb_kernels.cu", "sllb_capi.cu", "sllb_sims.cu", "sllb_dd6d.cu", "sllb_compat6d.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -21,7 +21,8 @@ def _stale():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sll_b200.h"), __file__]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sll_b200.h"),
+                                                         os.path.join(HERE, "..", "include", "sll_b200_sim6d_compat.h"), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

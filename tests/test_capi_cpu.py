@@ -14,15 +14,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "sll_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(sllb_[a-z0-9_]+)\s*\(", src)))
+    syms = set()
+    for hdr in ("sll_b200.h", "sll_b200_sim6d_compat.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b((?:sllb_|sim_bsl_vp_3d3v_cart_dd_slim_|sll_s_)[a-z0-9_]+)\s*\(", src))
+    return sorted(syms)
 
 
 def test_library_loads_and_exports_all_symbols():
     lib = sb.lib()
     syms = declared_symbols()
-    assert len(syms) > 50
+    assert len(syms) > 80 and "sim_bsl_vp_3d3v_cart_dd_slim_init" in syms and "sll_s_halt_collective" in syms
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, missing
 
@@ -100,3 +103,17 @@ def test_remap_plan_moves_every_element_once(nranks):
             local_v[dst][dst_sl] = local_x[src][src_sl]
     for r in range(nranks):
         assert np.array_equal(local_v[r], glob[sl(bv[r])])
+
+
+def test_compat6d_check_reads_reference_format(tmp_path):
+    """sll_s_check_diagnostics semantics on the golden file itself (host only): identical -> PASSED,
+    perturbed beyond 5e-7 -> FAILED."""
+    lib = sb.lib()
+    gold = os.path.join(ROOT, "tests", "golden", "reffile_bsl_vp_3d3v_cart_dd.dat")
+    assert lib.sllb_sim6d_compat_check(gold.encode(), gold.encode()) == 0
+    rows = np.loadtxt(gold)
+    rows[1, 3] += 1e-6
+    bad = tmp_path / "bad.dat"
+    np.savetxt(bad, rows)
+    assert lib.sllb_sim6d_compat_check(gold.encode(), str(bad).encode()) != 0
+    assert lib.sllb_sim6d_compat_check(gold.encode(), str(tmp_path / "missing.dat").encode()) != 0

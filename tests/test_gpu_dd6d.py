@@ -117,3 +117,28 @@ def test_sim6d_golden_through_halo_path(sb):
         sb.dd6d_set_force_halo(False)
     assert np.abs(rows - gold).max() < 5e-7
     assert np.array_equal(rows, r0) and np.array_equal(f, f0)   # identical arithmetic, bit for bit
+
+
+def test_cpp_interface_of_the_reference_simulation(sb, tmp_path):
+    """Our restatement of simulations/parallel/bsl_vp_3d3v_cart_dd/test_cpp_interface.cpp: a C++ host drives the
+    simulation through the reference's own C symbols (namelist in, <prefix>.dat out) and the result is checked
+    against the golden file with the reference's tolerance; passes on the string 'works in cpp' like the CTest."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "selalib_b200", "lib")
+    exe = str(tmp_path / "test_cpp_interface_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_cpp_interface_b200.cpp"), "-o", exe,
+                           "-L" + libdir, "-lsllb200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, os.path.join(root, "tests", "golden", "param_6d_golden.nml"),
+                          os.path.join(root, "tests", "golden", "reffile_bsl_vp_3d3v_cart_dd.dat")],
+                         cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "PASSED." in out.stdout and "works in cpp" in out.stdout
+    # the file is in the reference's e20.12 layout: 3 rows of 14 numbers, 20 columns each
+    lines = open(tmp_path / "vp_3d3v_dd_b200.dat").read().splitlines()
+    assert len(lines) == 3 and all(len(ln) == 280 for ln in lines)
+    gold = np.loadtxt(os.path.join(root, "tests", "golden", "reffile_bsl_vp_3d3v_cart_dd.dat"))
+    assert np.abs(np.loadtxt(tmp_path / "vp_3d3v_dd_b200.dat") - gold).max() < 5e-7
+    assert lines[0].startswith("  0.000000000000E+00  0.999999986099E+00")
