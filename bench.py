@@ -327,8 +327,10 @@ def run_ours(args, rank, world, local_rank):
                            "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
                            "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap fused into the last advection pass of each stage (peer stores over NVLink, CUDA IPC) + all-reduce barrier; 2 remaps per Strang step",
                            "staging": "TMA bulk (cp.async.bulk, UBLKCP) row copies into shared-memory line tiles"},
-                "phase_ms_per_step": {"advect": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
-                                      "remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps},
+                "phase_ms_per_step": {"advect_local_passes": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
+                                      "nccl_remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps,
+                                      "advect_fused_remap_passes": phase[4] / args.steps,
+                                      "barrier_after_fused_pass": phase[5] / args.steps},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "check": {"mass": float(row[3]), "field_energy": float(row[1])}}
         print(json.dumps(line), flush=True)

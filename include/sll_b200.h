@@ -260,6 +260,10 @@ int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_
 /* tuning / test knob: 1 = also take the halo path (local periodic halo copy + halo-cells kernel, exactly
  * the reference's sequence) when procs(axis) == 1; default 0 = periodic kernel, same arithmetic */
 int sllb_dd6d_set_force_halo(int on);
+/* 1 (default): when peer mapping is available (CUDA IPC, <= 8 ranks, halo <= 5 planes) the pack kernel stores the
+ * edge planes straight into the neighbour's halo buffer over NVLink; 0: pack + ncclSend/ncclRecv */
+int sllb_dd6d_set_halo_p2p(int on);
+int sllb_dd6d_p2p(sllb_dd6d_t D, int *enabled);
 
 /* ---- simulations (time loops of SURVEY.md section 3) --------------------- */
 /* 2D2V sim_bsl_vp_2d2v_cart_poisson_serial on 1..P GPUs.
@@ -284,6 +288,8 @@ int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F); /* local x-sequential fie
 int sllb_sim4d_box(sllb_sim4d_t S, int which, int box[8]); /* my box: which = 0 x-sequential, 1 v-sequential */
 /* per-phase device time of the last run() in ms: [advect, reduce+poisson, remap, diag] */
 int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]);
+/* finer: [local passes, reduce+poisson, NCCL remap, diag, fused advect+remap kernels, barriers after them] */
+int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]);
 
 /* 1D1V sim_bsl_vp_1d1v_cart (single GPU). init 0 Landau, 1 two-stream. rows: nsteps x 8
  * (time, mass, l1, momentum, l2, ekin, epot, etot; sll_m_sim_bsl_vp_1d1v_cart.F90:1783) */

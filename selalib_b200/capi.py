@@ -417,8 +417,8 @@ class Sim4d:
         return np.array(b[:]).reshape(4, 2)
 
     def phase_ms(self):
-        out = np.zeros(4)
-        _ck(lib().sllb_sim4d_phase_ms(self.h, _p(out)))
+        out = np.zeros(6)
+        _ck(lib().sllb_sim4d_phase_ms6(self.h, _p(out)))
         return out
 
     def destroy(self):
@@ -466,6 +466,11 @@ class Dd6d:
         _ck(lib().sllb_dd6d_field(self.h, C.byref(f)))
         return Field(handle=f)
 
+    def p2p(self):
+        e = C.c_int(0)
+        _ck(lib().sllb_dd6d_p2p(self.h, C.byref(e)))
+        return bool(e.value)
+
     def halo_exchange(self, axis, hw_left, hw_right):
         _ck(lib().sllb_dd6d_halo_exchange(self.h, C.c_int(axis), C.c_int(hw_left), C.c_int(hw_right)))
         self._halo = (axis, hw_left, hw_right)
@@ -506,6 +511,10 @@ def dd6d_plan(nranks, rank, global_ext, procs=None):
     arrs = [(C.c_int * 6)() for _ in range(6)]
     _ck(lib().sllb_dd6d_plan(C.c_int(nranks), C.c_int(rank), _ints(global_ext), _ints(procs) if procs is not None else None, *arrs))
     return dict(zip(("procs", "coords", "mn", "nw", "left", "right"), [tuple(a[:]) for a in arrs]))
+
+
+def dd6d_set_halo_p2p(on):
+    _ck(lib().sllb_dd6d_set_halo_p2p(C.c_int(1 if on else 0)))
 
 
 def dd6d_set_force_halo(on):

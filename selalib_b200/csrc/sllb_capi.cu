@@ -49,6 +49,70 @@ int require_device() {
     return SLLB_OK;
 }
 
+// Peer mapping over CUDA IPC: every rank contributes `count` device buffers; on return peers[r*count + k] is
+// rank r's k-th buffer mapped into this process (my own pointers for r == me).  cudaIpcGetMemHandle names a
+// whole allocation, so the offset of each buffer inside its allocation travels with the handle.  *ok is false
+// (on every rank) when any rank could not export or open a handle; callers then keep to NCCL.
+int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<void *> &peers,
+                     std::vector<void *> &opened, bool *ok) {
+    *ok = false;
+    if (!comm || comm->nranks < 2) return SLLB_OK;
+    typedef int (*getrange_t)(unsigned long long *, size_t *, unsigned long long);
+    getrange_t get_range = nullptr;
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn)
+            get_range = reinterpret_cast<getrange_t>(fn);
+        else cudaGetLastError();
+    }
+    struct Slot { cudaIpcMemHandle_t h; long long offset; long long ok; };
+    static_assert(sizeof(Slot) % 8 == 0, "slot size");
+    const int P = comm->nranks;
+    std::vector<Slot> my((size_t)count), all((size_t)count * P);
+    int good = 1;
+    for (int k = 0; k < count; ++k) {
+        unsigned long long base = 0; size_t size = 0;
+        memset(&my[k], 0, sizeof(Slot));
+        if (!get_range || get_range(&base, &size, (unsigned long long)(uintptr_t)mine[k]) != 0) { good = 0; continue; }
+        if (cudaIpcGetMemHandle(&my[k].h, reinterpret_cast<void *>((uintptr_t)base)) != cudaSuccess) { cudaGetLastError(); good = 0; continue; }
+        my[k].offset = (long long)((unsigned long long)(uintptr_t)mine[k] - base);
+    }
+    for (int k = 0; k < count; ++k) my[k].ok = good;
+    char *dsend = nullptr, *drecv = nullptr;
+    SLLB_CUDA(cudaMalloc(&dsend, (size_t)count * sizeof(Slot)));
+    SLLB_CUDA(cudaMalloc(&drecv, (size_t)count * P * sizeof(Slot)));
+    SLLB_CUDA(cudaMemcpy(dsend, my.data(), (size_t)count * sizeof(Slot), cudaMemcpyHostToDevice));
+    SLLB_NCCL(ncclAllGather(dsend, drecv, (size_t)count * sizeof(Slot), ncclChar, comm->comm, 0));
+    SLLB_CUDA(cudaMemcpy(all.data(), drecv, (size_t)count * P * sizeof(Slot), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < P; ++r) if (!all[(size_t)r * count].ok) good = 0;
+    peers.assign((size_t)count * P, nullptr);
+    if (good) {
+        // several buffers of one rank may live in the same allocation: open each distinct handle once
+        for (int r = 0; r < P && good; ++r)
+            for (int k = 0; k < count; ++k) {
+                if (r == comm->rank) { peers[(size_t)r * count + k] = mine[k]; continue; }
+                void *ptr = nullptr;
+                for (int j = 0; j < k; ++j)
+                    if (memcmp(&all[(size_t)r * count + j].h, &all[(size_t)r * count + k].h, sizeof(cudaIpcMemHandle_t)) == 0)
+                        ptr = static_cast<char *>(peers[(size_t)r * count + j]) - all[(size_t)r * count + j].offset;
+                if (!ptr) {
+                    if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r * count + k].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+                    opened.push_back(ptr);
+                }
+                peers[(size_t)r * count + k] = static_cast<char *>(ptr) + all[(size_t)r * count + k].offset;
+            }
+    }
+    // everybody must agree, otherwise nobody uses peer stores
+    double h = good ? 0.0 : 1.0, *dflag = reinterpret_cast<double *>(dsend);
+    SLLB_CUDA(cudaMemcpy(dflag, &h, sizeof(double), cudaMemcpyHostToDevice));
+    SLLB_NCCL(ncclAllReduce(dflag, dflag, 1, ncclDouble, ncclSum, comm->comm, 0));
+    SLLB_CUDA(cudaMemcpy(&h, dflag, sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dsend); cudaFree(drecv);
+    *ok = (h == 0.0);
+    return SLLB_OK;
+}
+
 int DevBuf::ensure(size_t count) {
     if (count <= n && p) return SLLB_OK;
     release();

@@ -7,6 +7,7 @@
 // simulations/parallel/bsl_vp_3d3v_cart_dd/sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:278-960.
 // MPI_Sendrecv with the ring neighbours becomes a grouped ncclSend/ncclRecv pair per side over NVLink.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -23,11 +24,22 @@ struct sllb_dd6d {
     int left[6], right[6];     // ring neighbours per axis (ranks)
     sllb_field *F = nullptr;
     DevBuf halo_l, halo_r, send_lo, send_hi;
+    double *cur_l = nullptr, *cur_r = nullptr; // halo planes of the last exchange
     int hw_l = 0, hw_r = 0, halo_axis = -1;
+    // peer path: double-buffered halo arrays of every rank mapped into this process; the pack kernel stores the
+    // edge planes straight into the neighbour's halo buffer over NVLink (no send buffer, no NCCL copy)
+    bool p2p = false;
+    DevBuf pbuf[4];                       // [parity*2 + side], side 0 = left halo, 1 = right halo
+    size_t pcap = 0;                      // capacity of each in doubles
+    std::vector<void *> peers, ipc_opened;
+    DevBuf flag;
+    int parity = 0;
     double exch_ms = 0.0;      // device time of the last halo exchange (pack + send/recv)
 };
 
-static int g_force_halo = 0; // 1: take the halo-exchange + halo-cells kernel path even when procs(axis) == 1
+static int g_force_halo = 0;
+static int g_halo_p2p = 1;   // 1: peer stores when available, 0: pack + ncclSend/ncclRecv
+static const int HALO_P2P_HW_MAX = 5; // widest halo (stencil 11) the peer buffers are sized for // 1: take the halo-exchange + halo-cells kernel path even when procs(axis) == 1
 
 namespace {
 // MPI_Cart_create ordering (row-major: the LAST dimension varies fastest), sll_m_decomposition.F90:379-555
@@ -88,8 +100,39 @@ int sllb_dd6d_create(sllb_comm_t c, const int global[6], const int procs_in[6], 
     for (int d = 0; d < 6; ++d) D->global[d] = global[d];
     int rc = sllb_dd6d_plan(D->nranks, D->rank, global, procs_in, D->procs, D->coords, D->mn, D->nw, D->left, D->right);
     if (!rc) rc = field_alloc(6, D->nw, &D->F);
-    if (rc) { delete D; return rc; }
+    if (!rc && D->nranks > 1 && D->nranks <= 8) {
+        const char *env = getenv("SLLB_HALO_P2P");
+        if (!(env && env[0] == '0')) {
+            // largest halo over the split axes: HW_MAX planes
+            size_t cap = 0;
+            for (int d = 1; d < 6; ++d)
+                if (D->procs[d] > 1) {
+                    const int hw = HALO_P2P_HW_MAX < D->nw[d] ? HALO_P2P_HW_MAX : D->nw[d];
+                    const size_t c = (size_t)(D->F->total / D->nw[d]) * hw;
+                    if (c > cap) cap = c;
+                }
+            if (cap > 0) {
+                void *mine[4];
+                for (int k = 0; k < 4 && !rc; ++k) { rc = D->pbuf[k].ensure(cap); mine[k] = D->pbuf[k].p; }
+                if (!rc) rc = D->flag.ensure(2);
+                bool ok = false;
+                if (!rc) rc = peer_map_buffers(D->comm, mine, 4, D->peers, D->ipc_opened, &ok);
+                D->p2p = ok;
+                D->pcap = cap;
+            }
+        }
+    }
+    if (rc) { sllb_dd6d_destroy(D); return rc; }
     *Dout = D;
+    return SLLB_OK;
+}
+int sllb_dd6d_set_halo_p2p(int on) {
+    g_halo_p2p = on ? 1 : 0;
+    return SLLB_OK;
+}
+int sllb_dd6d_p2p(sllb_dd6d_t D, int *enabled) {
+    if (!D || !enabled) return fail(SLLB_ERR_INVALID, "dd6d_p2p: null");
+    *enabled = (D->p2p && g_halo_p2p) ? 1 : 0;
     return SLLB_OK;
 }
 int sllb_dd6d_set_force_halo(int on) {
@@ -98,6 +141,7 @@ int sllb_dd6d_set_force_halo(int on) {
 }
 int sllb_dd6d_destroy(sllb_dd6d_t D) {
     if (!D) return SLLB_OK;
+    for (void *ptr : D->ipc_opened) cudaIpcCloseMemHandle(ptr);
     sllb_field_destroy(D->F);
     delete D;
     return SLLB_OK;
@@ -130,14 +174,30 @@ int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) 
     if (hw_left > n || hw_right > n) return fail(SLLB_ERR_INVALID, "dd6d_halo_exchange: halo wider than the local block");
     const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
     const size_t cl = (size_t)(outer * hw_left * inner), cr = (size_t)(outer * hw_right * inner);
-    SLLB_TRY(D->halo_l.ensure(cl > 0 ? cl : 1));
-    SLLB_TRY(D->halo_r.ensure(cr > 0 ? cr : 1));
+    const bool peer_path = D->p2p && g_halo_p2p && D->procs[axis] > 1 && cl <= D->pcap && cr <= D->pcap;
+    if (!peer_path) {
+        SLLB_TRY(D->halo_l.ensure(cl > 0 ? cl : 1));
+        SLLB_TRY(D->halo_r.ensure(cr > 0 ? cr : 1));
+        D->cur_l = D->halo_l.p; D->cur_r = D->halo_r.p;
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, 0);
     if (D->procs[axis] == 1) {
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, D->halo_r.p, 0));
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, D->halo_l.p, 0));
+    } else if (peer_path) {
+        // my first planes are the RIGHT halo of my left neighbour, my last planes the LEFT halo of my right
+        // neighbour: store them there directly.  Buffers alternate between exchanges, so a neighbour that is
+        // still reading the previous halo is not disturbed; the all-reduce is the cross-rank barrier.
+        const int par = D->parity;
+        double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 4 + par * 2 + 1]);
+        double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 4 + par * 2 + 0]);
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, dst_r, 0));
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, dst_l, 0));
+        SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
+        D->cur_l = D->pbuf[par * 2 + 0].p; D->cur_r = D->pbuf[par * 2 + 1].p;
+        D->parity ^= 1;
     } else {
         SLLB_TRY(D->send_lo.ensure(cr > 0 ? cr : 1));
         SLLB_TRY(D->send_hi.ensure(cl > 0 ? cl : 1));
@@ -168,7 +228,7 @@ int sllb_dd6d_halo_download(sllb_dd6d_t D, int side, double *host) {
     if (!D || !host || D->halo_axis < 0) return fail(SLLB_ERR_INVALID, "dd6d_halo_download: no halo present");
     const int hw = side == 0 ? D->hw_l : D->hw_r;
     const size_t cnt = (size_t)(outer_of(D, D->halo_axis) * hw * inner_of(D, D->halo_axis));
-    if (cnt) SLLB_CUDA(cudaMemcpy(host, side == 0 ? D->halo_l.p : D->halo_r.p, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    if (cnt) SLLB_CUDA(cudaMemcpy(host, side == 0 ? D->cur_l : D->cur_r, cnt * sizeof(double), cudaMemcpyDeviceToHost));
     return SLLB_OK;
 }
 int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms) {
@@ -200,7 +260,7 @@ int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_
     dd.scale = disp->scale;
     dd.odiv = disp->odiv > 0 ? disp->odiv : 1; dd.omod = disp->omod > 0 ? disp->omod : 1; dd.ostr = disp->ostr;
     dd.idiv = disp->idiv > 0 ? disp->idiv : 1; dd.imod = disp->imod > 0 ? disp->imod : 1; dd.istr = disp->istr;
-    cudaError_t e = launch_lagrange_halo(D->F->d, D->halo_l.p, D->halo_r.p, outer_of(D, axis), D->nw[axis], inner_of(D, axis),
+    cudaError_t e = launch_lagrange_halo(D->F->d, D->cur_l, D->cur_r, outer_of(D, axis), D->nw[axis], inner_of(D, axis),
                                          stencil, dd, g_staging, 0);
     if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: stencil / block size not implemented"); }
     return check_cuda(e, "k_lagrange_halo launch");

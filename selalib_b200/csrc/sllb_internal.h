@@ -86,6 +86,8 @@ struct sllb_poisson {
 };
 
 namespace sllb {
+int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<void *> &peers,
+                     std::vector<void *> &opened, bool *ok);
 // internal (device-pointer) entry points used by the simulations
 int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr,
                     double *linesum = nullptr);

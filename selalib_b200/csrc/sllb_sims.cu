@@ -129,6 +129,38 @@ int sllb_comm_allgather(sllb_comm_t c, const double *d_send, double *d_recv, int
 } // extern "C"
 
 /* ------------------------------------------------------------------------------------------ */
+/* phase timers (CUDA events on the launch stream)                                              */
+/* ------------------------------------------------------------------------------------------ */
+namespace {
+struct PhaseTimer {
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    bool on = false;
+    void begin() { reset(); on = true; }
+    void mark(int phase_just_finished) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, 0);
+        ev.push_back(e); tag.push_back(phase_just_finished);
+    }
+    void collect(double out[6]) {
+        for (int k = 0; k < 6; ++k) out[k] = 0;
+        if (ev.size() < 2) return;
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            if (tag[i] >= 0 && tag[i] < 6) out[tag[i]] += ms;
+        }
+    }
+    void reset() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); tag.clear(); on = false; }
+    ~PhaseTimer() { reset(); }
+};
+} // namespace
+static void phase_mark(PhaseTimer *t, int tag) { if (t) t->mark(tag); }
+
+/* ------------------------------------------------------------------------------------------ */
 /* distributed 4D field + remap                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 struct sllb_dist4d {
@@ -149,8 +181,7 @@ struct sllb_dist4d {
 
 int g_fused_remap = 1; // 1: advect + remap in one kernel over peer memory when possible, 0: pack + NCCL + unpack
 
-// Map every rank's F[0] and F[1] into this process.  cudaIpcGetMemHandle names the whole allocation, so the
-// offset of the array inside it travels with the handle.
+// Map every rank's F[0] and F[1] into this process (CUDA IPC, see peer_map_buffers).
 static int dist4d_setup_p2p(sllb_dist4d *D) {
     D->p2p = false;
     if (D->nranks < 2 || D->nranks > 8) return SLLB_OK;
@@ -159,53 +190,15 @@ static int dist4d_setup_p2p(sllb_dist4d *D) {
             if (D->global[d] % D->procs[w][d] != 0) return SLLB_OK; // non-uniform boxes: NCCL path
     const char *env = getenv("SLLB_FUSED_REMAP");
     if (env && env[0] == '0') return SLLB_OK;
-    typedef int (*getrange_t)(unsigned long long *, size_t *, unsigned long long);
-    getrange_t get_range = nullptr;
-    {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn)
-            get_range = reinterpret_cast<getrange_t>(fn);
-        else cudaGetLastError();
-    }
-    struct Slot { cudaIpcMemHandle_t h; long long offset; long long ok; };
-    static_assert(sizeof(Slot) % 8 == 0, "slot size");
-    const int P = D->nranks;
-    std::vector<Slot> mine(2), all((size_t)2 * P);
-    int good = 1;
-    for (int w = 0; w < 2; ++w) {
-        unsigned long long base = 0; size_t size = 0;
-        memset(&mine[w], 0, sizeof(Slot));
-        if (!get_range || get_range(&base, &size, (unsigned long long)(uintptr_t)D->F[w]->d) != 0) { good = 0; continue; }
-        if (cudaIpcGetMemHandle(&mine[w].h, reinterpret_cast<void *>((uintptr_t)base)) != cudaSuccess) { cudaGetLastError(); good = 0; continue; }
-        mine[w].offset = (long long)((unsigned long long)(uintptr_t)D->F[w]->d - base);
-    }
-    mine[0].ok = mine[1].ok = good;
-    char *dsend = nullptr, *drecv = nullptr;
-    SLLB_CUDA(cudaMalloc(&dsend, 2 * sizeof(Slot)));
-    SLLB_CUDA(cudaMalloc(&drecv, (size_t)2 * P * sizeof(Slot)));
-    SLLB_CUDA(cudaMemcpy(dsend, mine.data(), 2 * sizeof(Slot), cudaMemcpyHostToDevice));
-    SLLB_NCCL(ncclAllGather(dsend, drecv, 2 * sizeof(Slot), ncclChar, D->comm->comm, 0));
-    SLLB_CUDA(cudaMemcpy(all.data(), drecv, (size_t)2 * P * sizeof(Slot), cudaMemcpyDeviceToHost));
-    cudaFree(dsend); cudaFree(drecv);
-    for (int r = 0; r < P; ++r) if (!all[2 * r].ok) good = 0;
-    if (good) {
-        for (int r = 0; r < P && good; ++r)
-            for (int w = 0; w < 2; ++w) {
-                if (r == D->rank) { D->peer[w][r] = D->F[w]->d; continue; }
-                void *ptr = nullptr;
-                if (cudaIpcOpenMemHandle(&ptr, all[2 * r + w].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
-                D->ipc_opened.push_back(ptr);
-                D->peer[w][r] = reinterpret_cast<double *>(static_cast<char *>(ptr) + all[2 * r + w].offset);
-            }
-    }
-    // everybody must agree, otherwise nobody uses the fused path
+    void *mine[2] = {D->F[0]->d, D->F[1]->d};
+    std::vector<void *> peers;
+    bool ok = false;
     SLLB_TRY(D->flag.ensure(2));
-    double h = good ? 0.0 : 1.0;
-    SLLB_CUDA(cudaMemcpy(D->flag.p, &h, sizeof(double), cudaMemcpyHostToDevice));
-    SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
-    SLLB_CUDA(cudaMemcpy(&h, D->flag.p, sizeof(double), cudaMemcpyDeviceToHost));
-    D->p2p = (h == 0.0);
+    SLLB_TRY(peer_map_buffers(D->comm, mine, 2, peers, D->ipc_opened, &ok));
+    if (ok)
+        for (int r = 0; r < D->nranks; ++r)
+            for (int w = 0; w < 2; ++w) D->peer[w][r] = static_cast<double *>(peers[(size_t)r * 2 + w]);
+    D->p2p = ok;
     return SLLB_OK;
 }
 
@@ -213,7 +206,8 @@ static void box_of(const std::vector<int> &boxes, int r, int lo[4], int n[4]) {
     for (int d = 0; d < 4; ++d) { lo[d] = boxes[r * 8 + 2 * d]; n[d] = boxes[r * 8 + 2 * d + 1] - lo[d] + 1; }
 }
 
-static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int method, int order, const DispDesc &dd) {
+static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int method, int order, const DispDesc &dd,
+                                   PhaseTimer *timer = nullptr) {
     if (!D->p2p || !g_fused_remap) return fail(SLLB_ERR_UNSUPPORTED, "dist4d_advect_remap: peer mapping not available (use advect + sllb_dist4d_remap)");
     const int to = 1 - from;
     if (D->procs[from][axis] != 1) return fail(SLLB_ERR_INVALID, "dist4d_advect_remap: the advected axis must be whole in the source layout");
@@ -227,9 +221,12 @@ static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int metho
         rd.tp[d] = D->procs[to][d];
         rd.te[d] = D->global[d] / D->procs[to][d];
     }
+    phase_mark(timer, 0);
     SLLB_TRY(advect_axis_dev(D->F[from], axis, method, order, dd, &rd));
+    phase_mark(timer, 4);
     // all ranks' stores into my destination array are complete once every rank's kernel has finished
     SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
+    phase_mark(timer, 5);
     return SLLB_OK;
 }
 
@@ -354,36 +351,6 @@ int sllb_dist4d_remap(sllb_dist4d_t D, int direction) {
 }
 } // extern "C"
 
-/* ------------------------------------------------------------------------------------------ */
-/* phase timers (CUDA events on the launch stream)                                              */
-/* ------------------------------------------------------------------------------------------ */
-namespace {
-struct PhaseTimer {
-    std::vector<cudaEvent_t> ev;
-    std::vector<int> tag;
-    bool on = false;
-    void begin() { reset(); on = true; }
-    void mark(int phase_just_finished) {
-        if (!on) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, 0);
-        ev.push_back(e); tag.push_back(phase_just_finished);
-    }
-    void collect(double out[4]) {
-        for (int k = 0; k < 4; ++k) out[k] = 0;
-        if (ev.size() < 2) return;
-        cudaEventSynchronize(ev.back());
-        for (size_t i = 1; i < ev.size(); ++i) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            if (tag[i] >= 0 && tag[i] < 4) out[tag[i]] += ms;
-        }
-    }
-    void reset() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); tag.clear(); on = false; }
-    ~PhaseTimer() { reset(); }
-};
-} // namespace
 
 /* ------------------------------------------------------------------------------------------ */
 /* 2D2V: sim_bsl_vp_2d2v_cart_poisson_serial                                                    */
@@ -404,7 +371,7 @@ struct sllb_sim4d {
     int istep = 0;
     int layout = 0;    // which copy of f is current: 0 x-sequential, 1 v-sequential
     PhaseTimer timer;
-    double phase_ms[4] = {0, 0, 0, 0};
+    double phase_ms[6] = {0, 0, 0, 0, 0, 0}; // local passes, rho+poisson, NCCL remap, diagnostics, fused passes, barriers
 };
 
 __global__ void k_landau4d(double *f, int n0, int n1, int n2, int n3, int lo2, int lo3, double x0min, double x1min,
@@ -507,7 +474,7 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     DispDesc dd;
     SLLB_TRY(make_affine_disp(Fx, 1, 3, p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3], -step * p.dt / S->delta[1], &dd));
     if (fuse) {
-        SLLB_TRY(dist4d_advect_remap_dev(S->D, 0, 1, p.method, p.order, dd));
+        SLLB_TRY(dist4d_advect_remap_dev(S->D, 0, 1, p.method, p.order, dd, &S->timer));
         S->layout = 1;
     } else {
         SLLB_TRY(advect_axis_dev(Fx, 1, p.method, p.order, dd));
@@ -533,7 +500,7 @@ static int sim4d_V(sllb_sim4d *S, double step, bool fuse) {
     SLLB_TRY(make_field_disp(Fv, 3, e2, 2, -step * p.dt / S->delta[3], &dd));
     S->rho_state = 0;
     if (fuse) {
-        SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, p.method, p.order, dd));
+        SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, p.method, p.order, dd, &S->timer));
         S->layout = 0;
     } else {
         // f stays in this layout, so the next thing that happens to it is another V stage: hand its charge
@@ -688,9 +655,15 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
     S->timer.reset();
     return SLLB_OK;
 }
+int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]) {
+    if (!S || !out) return fail(SLLB_ERR_INVALID, "sim4d_phase_ms6: null");
+    for (int k = 0; k < 6; ++k) out[k] = S->phase_ms[k];
+    return SLLB_OK;
+}
 int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]) {
     if (!S || !out) return fail(SLLB_ERR_INVALID, "sim4d_phase_ms: null");
     for (int k = 0; k < 4; ++k) out[k] = S->phase_ms[k];
+    out[0] += S->phase_ms[4]; out[2] += S->phase_ms[5];
     return SLLB_OK;
 }
 

@@ -50,7 +50,21 @@ def main():
             el = np.take(glob, [(D.mn[axis] - hl + j) % g[axis] for j in range(hl)], axis=axis)[tuple(sel)]
             halo_ok = halo_ok and np.array_equal(D.halo(1), er) and np.array_equal(D.halo(0), el)
     res["procs6d"] = D.procs
+    res["halo_p2p"] = D.p2p()
     D.destroy()
+    # same exchange through pack + ncclSend/ncclRecv
+    sb.dd6d_set_halo_p2p(False)
+    D = sb.Dd6d(comm, g)
+    D.field().upload(np.asfortranarray(glob[sl]))
+    for axis in range(3, 6):
+        n = D.nw[axis]
+        D.halo_exchange(axis, 2, 3)
+        sel = list(sl); sel[axis] = slice(None)
+        er = np.take(glob, [(D.mn[axis] + n + j) % g[axis] for j in range(3)], axis=axis)[tuple(sel)]
+        el = np.take(glob, [(D.mn[axis] - 2 + j) % g[axis] for j in range(2)], axis=axis)[tuple(sel)]
+        halo_ok = halo_ok and np.array_equal(D.halo(1), er) and np.array_equal(D.halo(0), el)
+    D.destroy()
+    sb.dd6d_set_halo_p2p(True)
     res["halo_exchange_exact"] = bool(halo_ok)
     ok = ok and halo_ok
 
@@ -122,6 +136,16 @@ def main():
         res[f"sim6d_s{stencil}_rows_vs_1gpu"] = e_rows
         res[f"sim6d_s{stencil}_f_vs_1gpu"] = e_f
         ok = ok and e_rows < 1e-12 and e_f < 1e-12
+        # halo exchange by peer stores == halo exchange by NCCL send/recv, bit for bit
+        sb.dd6d_set_halo_p2p(False)
+        SQ = sb.Sim6d(*args, comm=comm)
+        rq = SQ.run(2)
+        fq = SQ.field().download()
+        SQ.destroy()
+        sb.dd6d_set_halo_p2p(True)
+        same = bool(np.array_equal(rq, rp) and np.array_equal(fq, fp))
+        res[f"sim6d_s{stencil}_p2p_equals_nccl"] = same
+        ok = ok and same
         if stencil == 3:
             e_gold = float(np.abs(rp - gold).max())
             res["sim6d_vs_golden"] = e_gold
