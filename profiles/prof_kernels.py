@@ -20,6 +20,7 @@ for _ in range(reps):
     F.advect_axis(2, sb.METHOD_SPLINE, 4, E, 1.0, (1, 1, 0, 1, n * n, 1))
     F.advect_axis(3, sb.METHOD_SPLINE, 4, E, 1.0, (1, 1, 0, 1, n * n, 1))
     F.reduce_velocity(2, 1.0)
+    F.advect_plane(v, (n, n, 1, 1, 1, 0), 1.0, v, (n, n, 1, 1, 1, 0), 1.0, rho_scale=1.0)
     F.advect_axis(1, sb.METHOD_LAGRANGE_FIXED, 7, v, 0.3, (1, n, 1, 1, 1, 0))
     F.advect_axis(0, sb.METHOD_LAGRANGE_FIXED, 7, v, 0.3, (n, n, 1, 1, 1, 0))
 sb.synchronize()

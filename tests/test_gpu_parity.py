@@ -566,3 +566,56 @@ def test_full_size_properties_2d2v_64(sb):
         F.advect_axis(axis, m, o, disp, 0.3, (1, 1, 0, 1, 1, 0) if axis else (1, n, 1, 1, 1, 0))
     assert np.abs(F.download() - 1).max() < 1e-14
     S.destroy()
+
+
+# ---------------------------------------------------------------------------------------------
+# committed golden vectors (tests/golden/oracle_*.npz)
+# ---------------------------------------------------------------------------------------------
+def test_committed_golden_vectors(sb):
+    """the CUDA path against COMMITTED oracle outputs (no oracle call on this box)"""
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    d = np.load(os.path.join(G, "oracle_advect4d.npz"))
+    f0 = np.asfortranarray(d["f0"])
+    codes = {"spline": sb.METHOD_SPLINE, "lagrange_fixed": sb.METHOD_LAGRANGE_FIXED, "lagrange_centered": sb.METHOD_LAGRANGE_CENTERED}
+    F = sb.Field(f0.shape)
+    n = 0
+    for key in d.files:
+        if "_axis" not in key:
+            continue
+        name, axis = key.rsplit("_axis", 1)
+        axis = int(axis)
+        method = name.rstrip("0123456789")
+        order = int(name[len(method):])
+        F.upload(f0)
+        F.advect_axis(axis, codes[method], order, d[f"disp{axis}"], 1.0, tuple(int(v) for v in d[f"dsel{axis}"]))
+        assert relerr(F.download(), d[key]) < TOL, key
+        n += 1
+    assert n == 8
+    F.destroy()
+    ln = np.load(os.path.join(G, "oracle_lines.npz"))
+    adv = sb.Advector1dPeriodic(64, 0.0, 2 * np.pi, sb.ADV_PERIODIC_SPLINE, 4)
+    assert relerr(adv.advect_1d_constant(1.3, 0.1, ln["line"]), ln["adv_spline"]) < TOL
+    adv.delete()
+    adv = sb.Advector1dPeriodic(64, 0.0, 2 * np.pi, sb.ADV_PERIODIC_LAGRANGE, 6)
+    assert relerr(adv.advect_1d_constant(1.3, 0.1, ln["line"]), ln["adv_lagrange6"]) < TOL
+    adv.delete()
+    itp = sb.Interpolator1d(sb.INTERP_CUBIC_SPLINE, 65, 0.0, 2 * np.pi)
+    assert relerr(itp.interpolate_array_disp(65, ln["line"], -1.2 * (2 * np.pi / 64)), ln["spline_disp"]) < TOL
+    itp.delete()
+    po = np.load(os.path.join(G, "oracle_poisson.npz"))
+    P = sb.Poisson([16, 12], [0.0, 0.0], [4 * np.pi, 2 * np.pi])
+    _, e1, e2 = P.solve(po["rho2"])
+    assert np.abs(e1 - po["e1"]).max() < 1e-12 * np.abs(po["e1"]).max()
+    assert np.abs(e2 - po["e2"]).max() < 1e-12 * np.abs(po["e2"]).max()
+    P.destroy()
+    tr = np.load(os.path.join(G, "oracle_traces.npz"))
+    S = sb.Sim4d([16, 16, 32, 32], [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1)
+    rows = S.run(5)
+    S.destroy()
+    assert np.abs(rows / tr["rows4"][1:] - 1).max() < 1e-8
+    S2 = sb.Sim2d(64, 64, 0.0, 4 * np.pi, -6.0, 6.0, 0, 0.5, 1e-3, 0.1)
+    r2 = S2.run(20)
+    S2.destroy()
+    sel = [0, 1, 2, 4, 5, 6, 7]   # the momentum column is ~1e-17: compared absolutely
+    assert np.abs(r2[:, sel] / tr["rows2"][:, sel] - 1).max() < 1e-8
+    assert np.abs(r2[:, 3] - tr["rows2"][:, 3]).max() < 1e-12
