@@ -53,6 +53,12 @@ def lib():
         if not os.path.exists(_SO):
             raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(selalib_b200 has no CPU fallback)")
+        try:
+            # torch bundles a newer NCCL under the same soname (libnccl.so.2); it has to be the one that gets
+            # loaded, otherwise a later `import torch` in this process fails to resolve its NCCL symbols
+            import torch  # noqa: F401
+        except Exception:
+            pass
         _LIB = C.CDLL(_SO, mode=C.RTLD_GLOBAL)
         _LIB.sllb_last_error.restype = C.c_char_p
         _LIB.sllb_launch_count.restype = C.c_int64

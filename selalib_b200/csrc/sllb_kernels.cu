@@ -764,6 +764,188 @@ __global__ void __launch_bounds__(16384 / EPT, 1) k_spline_plane(double *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1c, register-resident variant.  Same job as k_spline_plane, organised around the shared-memory pipe,
+// which is what bounds the in-place variant (5.7 shared accesses per point per pass):
+//   * a thread keeps its chunk of 32 points in registers through both sweeps of a pass: one shared read and
+//     one shared write per point per pass;
+//   * the sweeps start from zero inside every chunk; the exact start values arrive afterwards from the
+//     neighbouring chunk as one scalar each (end value of the previous chunk for the forward sweep, first
+//     value of the next one for the backward sweep) and enter through the same 27-term geometric series the
+//     reference truncates at (sll_m_cubic_splines.F90:548-571): e[j] += (-q)^(j+1) e_prev_end, j < 27;
+//   * pass A scatters its results to their final x1 positions, pass B shifts its chunk grid by the integer
+//     part of the x2 displacement, so every thread owns fixed output points (x1, 32*chunk + j): the results go
+//     from registers straight to global memory (coalesced rows) and into fixed charge-density accumulators
+//     (12 in registers, 20 in shared memory);
+//   * the plane is dead in shared memory as soon as pass B has loaded it, so the bulk TMA copy of the next
+//     plane is issued there and overlaps the arithmetic and the stores of pass B.
+// ------------------------------------------------------------------------------------------------
+#define SLLB_PR_C 32     // chunk length = points per thread
+#define SLLB_PR_ACCR 12  // charge-density accumulators kept in registers (the other 20 live in shared memory: 227 KB budget)
+
+// two sweeps + evaluation on a register-resident chunk g[0..31]; exch: [0..nchunks*nlines) end values,
+// then 3 arrays of first values.  `line` / `nlines` / `ch` / `nch` identify the chunk for the exchange.
+__device__ __forceinline__ void chunk_solve(double (&g)[SLLB_PR_C], double *exch, const int line, const int nlines,
+                                            const int ch, const int nch, const double dx) {
+    constexpr int C = SLLB_PR_C;
+    const double q = 0.26794919243112270647;
+    double *e_end = exch, *g0 = exch + (size_t)nlines * nch, *g1 = g0 + (size_t)nlines * nch, *g2 = g1 + (size_t)nlines * nch;
+#pragma unroll
+    for (int j = 1; j < C; ++j) g[j] = fma(-q, g[j - 1], g[j]);
+    e_end[ch * nlines + line] = g[C - 1];
+    __syncthreads();
+    {
+        const int cp = (ch == 0) ? nch - 1 : ch - 1;
+        const double ep = e_end[cp * nlines + line];
+#pragma unroll
+        for (int j = 0; j < SLLB_NUM_TERMS; ++j) g[j] = fma(c_pw[j], ep, g[j]);
+    }
+#pragma unroll
+    for (int j = C - 2; j >= 0; --j) g[j] = fma(-q, g[j + 1], g[j]);
+    g0[ch * nlines + line] = g[0];
+    g1[ch * nlines + line] = g[1];
+    g2[ch * nlines + line] = g[2];
+    __syncthreads();
+    const int cn = (ch == nch - 1) ? 0 : ch + 1;
+    const double n0 = g0[cn * nlines + line], n1 = g1[cn * nlines + line], n2 = g2[cn * nlines + line];
+#pragma unroll
+    for (int j = 0; j < SLLB_NUM_TERMS; ++j) g[C - 1 - j] = fma(c_pw[j], n0, g[C - 1 - j]);
+    const double r2 = 1.60769515458673623883;
+    const double cdx = 1.0 - dx, s6 = r2 * (1.0 / 6.0);
+    const double w0 = cdx * cdx * cdx * s6;
+    const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+    const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+    const double w3 = dx * dx * dx * s6;
+    // g[j] <- value of cell (k0 + j + 1): w0 g[j] + w1 g[j+1] + w2 g[j+2] + w3 g[j+3]
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const double b1 = (j + 1 < C) ? g[j + 1] : n0;
+        const double b2 = (j + 2 < C) ? g[j + 2] : ((j + 2 == C) ? n0 : n1);
+        const double b3 = (j + 3 < C) ? g[j + 3] : ((j + 3 == C) ? n0 : ((j + 3 == C + 1) ? n1 : n2));
+        g[j] = fma(w3, b3, fma(w2, b2, fma(w1, b1, w0 * g[j])));
+    }
+}
+
+template <bool RHO>
+__global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1, const int N2,
+                                                           const long long nplanes, const DispDesc dd1,
+                                                           const DispDesc dd2, double *__restrict__ rho_partial) {
+    constexpr int C = SLLB_PR_C;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, T = blockDim.x;
+    const int npl = N1 * N2;
+    double *exch = s + npl;                    // 4 * T doubles
+    double *accs = exch + 4 * (size_t)T;       // RHO: (C - ACCR) * T doubles
+    const int PA = N1 / C, PB = N2 / C;
+    const int rowA = (w / PA) * 32 + lane, chA = w % PA; // pass A: row = x2 index, chunk along x1
+    const int colB = (w / PB) * 32 + lane, chB = w % PB; // pass B: column = x1 index, chunk along x2
+    double acc[SLLB_PR_ACCR];
+#pragma unroll
+    for (int j = 0; j < SLLB_PR_ACCR; ++j) acc[j] = 0.0;
+    if (RHO)
+        for (int j = 0; j < C - SLLB_PR_ACCR; ++j) accs[(size_t)j * T + tid] = 0.0;
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    uint32_t phase = 0;
+    long long pl = blockIdx.x;
+    if (tid == 0 && pl < nplanes) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
+        bulk_g2s(s, f + pl * (long long)npl, (uint32_t)(npl * 8), bar);
+    }
+    for (; pl < nplanes; pl += gridDim.x) {
+        double *gp = f + pl * (long long)npl;
+        const double d1 = disp_of(dd1, pl * N2, 0); // constant over the plane (checked by the launcher)
+        const double d2 = disp_of(dd2, pl, 0);
+        const double fl1 = floor(d1), fl2 = floor(d2);
+        double g[C];
+        // ---- pass A: rows ----
+        int k0 = chA * C + (lane & 15);        // skewed chunk start: conflict-free banks with pitch N1
+        if (k0 >= N1) k0 -= N1;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        {
+            const double *row = s + (size_t)rowA * N1;
+            int k = k0;
+#pragma unroll
+            for (int j = 0; j < C; ++j) { g[j] = row[k]; k = (k == N1 - 1) ? 0 : k + 1; }
+        }
+        chunk_solve(g, exch, rowA, N2, chA, PA, d1 - fl1);
+        {
+            // cell k0+j+1 is output point (k0 + j + 1 - dcell1) mod N1
+            double *row = s + (size_t)rowA * N1;
+            int i1 = (int)(((long long)k0 + 1 - (long long)fl1) % N1);
+            if (i1 < 0) i1 += N1;
+#pragma unroll
+            for (int j = 0; j < C; ++j) { row[i1] = g[j]; i1 = (i1 == N1 - 1) ? 0 : i1 + 1; }
+        }
+        __syncthreads();
+        // ---- pass B: columns; the chunk grid is shifted so that this thread's cells are points 32*chB + j ----
+        {
+            int k = (int)(((long long)chB * C - 1 + (long long)fl2) % N2);
+            if (k < 0) k += N2;
+            const double *col = s + colB;
+#pragma unroll
+            for (int j = 0; j < C; ++j) { g[j] = col[(size_t)k * N1]; k = (k == N2 - 1) ? 0 : k + 1; }
+        }
+        // (the first barrier inside chunk_solve also says: every thread has read the plane)
+        {
+            constexpr double q = 0.26794919243112270647;
+#pragma unroll
+            for (int j = 1; j < C; ++j) g[j] = fma(-q, g[j - 1], g[j]);
+            exch[chB * N1 + colB] = g[C - 1];
+            __syncthreads();
+            const long long nxt = pl + gridDim.x;
+            if (tid == 0 && nxt < nplanes) { // the plane is dead in shared memory: fetch the next one
+                mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
+                bulk_g2s(s, f + nxt * (long long)npl, (uint32_t)(npl * 8), bar);
+            }
+            double *e_end = exch, *g0 = exch + (size_t)N1 * PB, *g1 = g0 + (size_t)N1 * PB, *g2 = g1 + (size_t)N1 * PB;
+            {
+                const int cp = (chB == 0) ? PB - 1 : chB - 1;
+                const double ep = e_end[cp * N1 + colB];
+#pragma unroll
+                for (int j = 0; j < SLLB_NUM_TERMS; ++j) g[j] = fma(c_pw[j], ep, g[j]);
+            }
+#pragma unroll
+            for (int j = C - 2; j >= 0; --j) g[j] = fma(-q, g[j + 1], g[j]);
+            g0[chB * N1 + colB] = g[0];
+            g1[chB * N1 + colB] = g[1];
+            g2[chB * N1 + colB] = g[2];
+            __syncthreads();
+            const int cn = (chB == PB - 1) ? 0 : chB + 1;
+            const double n0 = g0[cn * N1 + colB], n1 = g1[cn * N1 + colB], n2 = g2[cn * N1 + colB];
+#pragma unroll
+            for (int j = 0; j < SLLB_NUM_TERMS; ++j) g[C - 1 - j] = fma(c_pw[j], n0, g[C - 1 - j]);
+            const double dx = d2 - fl2, cdx = 1.0 - dx, s6 = 1.60769515458673623883 * (1.0 / 6.0);
+            const double w0 = cdx * cdx * cdx * s6;
+            const double w1 = (1.0 + 3.0 * cdx + 3.0 * cdx * cdx - 3.0 * cdx * cdx * cdx) * s6;
+            const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
+            const double w3 = dx * dx * dx * s6;
+            double *out = gp + (size_t)(chB * C) * N1 + colB;
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const double b1 = (j + 1 < C) ? g[j + 1] : n0;
+                const double b2 = (j + 2 < C) ? g[j + 2] : ((j + 2 == C) ? n0 : n1);
+                const double b3 = (j + 3 < C) ? g[j + 3] : ((j + 3 == C) ? n0 : ((j + 3 == C + 1) ? n1 : n2));
+                const double v = fma(w3, b3, fma(w2, b2, fma(w1, b1, w0 * g[j])));
+                st_stream(out + (size_t)j * N1, v);
+                if constexpr (RHO) {
+                    if (j < SLLB_PR_ACCR) acc[j] += v;
+                    else accs[(size_t)(j - SLLB_PR_ACCR) * T + tid] += v;
+                }
+            }
+        }
+        __syncthreads(); // exchange arrays are reused by the next plane
+    }
+    if constexpr (RHO) {
+        double *rp = rho_partial + (long long)blockIdx.x * npl + (size_t)(chB * C) * N1 + colB;
+#pragma unroll
+        for (int j = 0; j < C; ++j) rp[(size_t)j * N1] = (j < SLLB_PR_ACCR) ? acc[j] : accs[(size_t)(j - SLLB_PR_ACCR) * T + tid];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b: Lagrange, contiguous axis.  Tile = LT whole lines in natural layout (one bulk TMA copy),
 // thread per output point, per-line weights in shared memory.
 // ------------------------------------------------------------------------------------------------
@@ -1008,17 +1190,22 @@ static cudaError_t launch_spline_contig_split_t(double *f, long long nlines, int
 
 // K1c launcher.  Returns cudaErrorNotSupported when the plane does not fit the kernel's assumptions (the
 // caller then runs the two passes separately).
-int g_plane_ept = 0; // tuning knob: 0 auto, 16 or 32 points per thread
+int g_plane_ept = 0; // tuning knob: 0 auto (register-resident variant), 16 or 32: in-place variant with that many points per thread
 static int plane_ept(int n1, int n2, bool rho) {
-    if (rho) return 32;
-    if (g_plane_ept == 16 || g_plane_ept == 32) return g_plane_ept;
+    if (g_plane_ept == 16 && !rho) return 16;
     return 32;
 }
+static size_t plane_smem(int n1, int n2, bool rho) {
+    const size_t T = (size_t)n1 * n2 / SLLB_PR_C;
+    if (g_plane_ept != 0) return 128 + (size_t)n1 * n2 * 8;
+    return 128 + (size_t)n1 * n2 * 8 + 4 * T * 8 + (rho ? (SLLB_PR_C - SLLB_PR_ACCR) * T * 8 : 0);
+}
 int plane_grid(int n1, int n2, long long nplanes) {
-    const size_t smem = 128 + (size_t)n1 * n2 * 8;
-    const int threads = n1 * n2 / plane_ept(n1, n2, true);
+    const size_t smem = plane_smem(n1, n2, true);
+    const int threads = n1 * n2 / 32;
     int per_sm = (int)(SMEM_MAX / (smem + 1024));
     if (per_sm * threads > 2048) per_sm = 2048 / threads;
+    if (g_plane_ept == 0 && per_sm * threads * 128 > 65536) per_sm = 65536 / (threads * 128);
     if (per_sm < 1) per_sm = 1;
     long long g = 148LL * per_sm;
     return (int)(nplanes < g ? nplanes : g);
@@ -1026,10 +1213,11 @@ int plane_grid(int n1, int n2, long long nplanes) {
 cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, const DispDesc &dd1, const DispDesc &dd2,
                                 double *rho_partial, cudaStream_t st) {
     if (n1 % 32 != 0 || n2 % 32 != 0 || n1 < 32 || n2 < 32) return cudaErrorNotSupported;
-    const int ept = plane_ept(n1, n2, rho_partial != nullptr);
+    const bool rho = rho_partial != nullptr;
+    const int ept = plane_ept(n1, n2, rho);
     const int threads = n1 * n2 / ept;
     if (threads > 16384 / ept || threads < 32) return cudaErrorNotSupported;
-    const size_t smem = 128 + (size_t)n1 * n2 * 8;
+    const size_t smem = plane_smem(n1, n2, rho);
     if (smem > SMEM_MAX || (size_t)n1 * n2 * 8 >= (1u << 20)) return cudaErrorNotSupported;
     if ((reinterpret_cast<uintptr_t>(f) & 15) != 0) return cudaErrorNotSupported;
     // both displacements must be constant over a plane
@@ -1039,15 +1227,18 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
     cudaError_t e = ensure_constants();
     if (e != cudaSuccess) return e;
     const int grid = plane_grid(n1, n2, nplanes);
-#define SLLB_PLANE_LAUNCH(E, R)                                                                         \
-    do {                                                                                                \
-        e = set_smem(k_spline_plane<E, R>, smem);                                                       \
-        if (e != cudaSuccess) return e;                                                                 \
-        k_spline_plane<E, R><<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial);  \
+#define SLLB_PLANE_LAUNCH(KERN)                                                              \
+    do {                                                                                     \
+        e = set_smem(KERN, smem);                                                            \
+        if (e != cudaSuccess) return e;                                                      \
+        KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial);        \
     } while (0)
-    if (rho_partial) SLLB_PLANE_LAUNCH(32, true);
-    else if (ept == 16) SLLB_PLANE_LAUNCH(16, false);
-    else SLLB_PLANE_LAUNCH(32, false);
+    if (g_plane_ept == 0) {
+        if (rho) SLLB_PLANE_LAUNCH(k_spline_plane_r<true>);
+        else SLLB_PLANE_LAUNCH(k_spline_plane_r<false>);
+    } else if (rho) SLLB_PLANE_LAUNCH((k_spline_plane<32, true>));
+    else if (ept == 16) SLLB_PLANE_LAUNCH((k_spline_plane<16, false>));
+    else SLLB_PLANE_LAUNCH((k_spline_plane<32, false>));
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
