@@ -246,7 +246,36 @@ def run_ours(args, rank, world, local_rank):
         a1.record()
         torch.cuda.synchronize()
         kernel_ms[axis] = a0.elapsed_time(a1) / reps
-    strided = [kernel_ms[a] for a in axes if a != 0]
+    # the T stage runs as ONE kernel on a single GPU (x1 pass + x2 pass + charge density, K1c): time it too
+    plane_ms = None
+    if world == 1:
+        from selalib_b200.capi import DispT, dp as _dp, vp as _vp
+        import ctypes as _C
+
+        def _disp(dsel):
+            d = DispT()
+            d.values = _C.cast(_vp(dispv.data_ptr()), _dp); d.nvalues = 0; d.values_on_device = 1; d.scale = 1.0
+            d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = dsel
+            return d
+        pd0, pd1 = _disp((ext[1], ext[2], 1, 1, 1, 0)), _disp((ext[2], ext[3], 1, 1, 1, 0))
+        rho_t = torch.empty(ext[0] * ext[1], dtype=torch.float64, device="cuda")
+
+        def plane_call():
+            assert sb.lib().sllb_advect_plane(F.h, 0, 4, _C.byref(pd0), _C.byref(pd1), _C.c_double(1.0),
+                                              _C.cast(_vp(rho_t.data_ptr()), _dp)) == 0, sb.last_error()
+        for _ in range(3):
+            plane_call()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            plane_call()
+        a1.record()
+        torch.cuda.synchronize()
+        plane_ms = a0.elapsed_time(a1) / reps
+    # dominant kernel: the strided spline pass (x3 and x4 passes of both V stages = 4 of the 6 passes of a step
+    # on one GPU; x2, x3, x4 passes on several GPUs)
+    strided = [kernel_ms[a] for a in axes if a >= 2] or [kernel_ms[a] for a in axes if a != 0]
     t_dom = sum(strided) / len(strided)
     peak, peak_src = measured_peak()
     achieved = 16.0 * local_pts / (t_dom * 1e-3) / 1e9
@@ -255,13 +284,20 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("k_advect_strided_bytes_per_launch")
+            if traffic is not None:
+                traffic = traffic * local_pts / float(NSIDE) ** 4   # captured on the 128^4 field
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_spline_strided_split<4> (x2/x3/x4 passes: 3 of 4 axes, 5 of 6 passes per step)",
+    roofline = {"bound": "hbm", "kernel": "k_spline_strided_split<4> (x3 and x4 passes: 4 of the 6 passes of a step; the other two "
+                                          "are the single k_spline_plane_r launch of the T stage)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * local_pts,
                 "ms_per_launch": t_dom, "ms_per_launch_by_axis": {f"x{a + 1}": kernel_ms[a] for a in axes},
                 "gbs_by_axis": {f"x{a + 1}": 16.0 * local_pts / (kernel_ms[a] * 1e-3) / 1e9 for a in axes},
+                "t_stage_plane_kernel": None if plane_ms is None else {
+                    "kernel": "k_spline_plane_r<rho> (x1 pass + x2 pass + charge density in one sweep)", "ms_per_launch": plane_ms,
+                    "algorithmic_bytes_per_launch": 32.0 * local_pts, "achieved_gbs_at_16B_per_point_per_pass": 32.0 * local_pts / (plane_ms * 1e-3) / 1e9,
+                    "hbm_bytes_moved_per_launch": 16.0 * local_pts, "hbm_gbs": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9},
                 "timing": f"CUDA events on the launch stream, {reps} launches after 3 warm-ups, field {ext} "
                           f"({local_pts * 8 / 1e9:.2f} GB > L2)"}
 
@@ -326,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
                 "config": {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP, "points": int(npts),
                            "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
                            "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap fused into the last advection pass of each stage (peer stores over NVLink, CUDA IPC) + all-reduce barrier; 2 remaps per Strang step",
-                           "staging": "TMA bulk (cp.async.bulk, UBLKCP) row copies into shared-memory line tiles"},
+                           "staging": "TMA bulk copies (cp.async.bulk, UBLKCP): 256 B rows of 32-line tiles (V stage), whole 128x128 planes (T stage)"},
                 "phase_ms_per_step": {"advect_local_passes": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
                                       "nccl_remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps,
                                       "advect_fused_remap_passes": phase[4] / args.steps,
