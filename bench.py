@@ -377,6 +377,9 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; rank 0 must print ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

@@ -20,6 +20,8 @@ import selalib_b200 as sb  # noqa: E402
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=32)
     ap.add_argument("--stencil", type=int, default=7)

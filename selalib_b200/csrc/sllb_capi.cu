@@ -189,7 +189,8 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
 // K1c: spline passes along axes 0 and 1 on every plane in one sweep (+ optional rho = scale * sum over the
 // other axes of the result).  SLLB_ERR_UNSUPPORTED when the shape / displacement pattern does not fit.
 int g_plane_kernel = 1;
-int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho) {
+int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
+                     const RemapDst *remap) {
     if (!F || F->ndim < 2) return fail(SLLB_ERR_INVALID, "advect_plane: bad field");
     if (!g_plane_kernel) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: disabled (sllb_set_plane_kernel)");
     const int n1 = F->ext[0], n2 = F->ext[1];
@@ -202,7 +203,7 @@ int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, do
         SLLB_TRY(F->red_scratch.ensure((size_t)nparts * n1 * n2));
         partial = F->red_scratch.p;
     }
-    cudaError_t e = launch_spline_plane(F->d, n1, n2, nplanes, dd0, dd1, partial, 0);
+    cudaError_t e = launch_spline_plane(F->d, n1, n2, nplanes, dd0, dd1, partial, 0, remap);
     if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: plane shape or displacement pattern not supported"); }
     SLLB_TRY(check_cuda(e, "k_spline_plane launch"));
     if (d_rho) SLLB_CUDA(launch_sum_partials(partial, (long long)n1 * n2, nparts, rho_scale, d_rho, 0));

@@ -91,7 +91,8 @@ int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<
 // internal (device-pointer) entry points used by the simulations
 int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr,
                     double *linesum = nullptr);
-int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho);
+int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
+                     const RemapDst *remap = nullptr);
 extern int g_plane_kernel;
 int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv, double scale, DispDesc *dd);
 int make_field_disp(sllb_field *F, int axis, const double *d_field, int nfield_axes, double scale, DispDesc *dd);

@@ -825,10 +825,11 @@ __device__ __forceinline__ void chunk_solve(double (&g)[SLLB_PR_C], double *exch
     }
 }
 
-template <bool RHO>
+template <bool RHO, bool REMAP>
 __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1, const int N2,
                                                            const long long nplanes, const DispDesc dd1,
-                                                           const DispDesc dd2, double *__restrict__ rho_partial) {
+                                                           const DispDesc dd2, double *__restrict__ rho_partial,
+                                                           const __grid_constant__ RemapDst rd) {
     constexpr int C = SLLB_PR_C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -923,13 +924,20 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
             const double w2 = (1.0 + 3.0 * dx + 3.0 * dx * dx - 3.0 * dx * dx * dx) * s6;
             const double w3 = dx * dx * dx * s6;
             double *out = gp + (size_t)(chB * C) * N1 + colB;
+            OutMap om;
+            if constexpr (REMAP) {
+                // this thread's points are the x2 line (o = plane, in = x1) of the source layout: same map as K1a
+                om = make_outmap(rd, pl, colB, N2, N1);
+                om.seek(chB * C);
+            }
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const double b1 = (j + 1 < C) ? g[j + 1] : n0;
                 const double b2 = (j + 2 < C) ? g[j + 2] : ((j + 2 == C) ? n0 : n1);
                 const double b3 = (j + 3 < C) ? g[j + 3] : ((j + 3 == C) ? n0 : ((j + 3 == C + 1) ? n1 : n2));
                 const double v = fma(w3, b3, fma(w2, b2, fma(w1, b1, w0 * g[j])));
-                st_stream(out + (size_t)j * N1, v);
+                if constexpr (REMAP) { st_stream(om.p, v); om.next(); }
+                else st_stream(out + (size_t)j * N1, v);
                 if constexpr (RHO) {
                     if (j < SLLB_PR_ACCR) acc[j] += v;
                     else accs[(size_t)(j - SLLB_PR_ACCR) * T + tid] += v;
@@ -1211,8 +1219,16 @@ int plane_grid(int n1, int n2, long long nplanes) {
     return (int)(nplanes < g ? nplanes : g);
 }
 cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, const DispDesc &dd1, const DispDesc &dd2,
-                                double *rho_partial, cudaStream_t st) {
+                                double *rho_partial, cudaStream_t st, const RemapDst *remap) {
     if (n1 % 32 != 0 || n2 % 32 != 0 || n1 < 32 || n2 < 32) return cudaErrorNotSupported;
+    RemapDst rd;
+    if (remap && remap->on) {
+        if (g_plane_ept != 0 || remap->axis != 1) return cudaErrorNotSupported;
+        rd = *remap;
+    } else {
+        memset(&rd, 0, sizeof(rd));
+        rd.base[0] = f;
+    }
     const bool rho = rho_partial != nullptr;
     const int ept = plane_ept(n1, n2, rho);
     const int threads = n1 * n2 / ept;
@@ -1227,6 +1243,12 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
     cudaError_t e = ensure_constants();
     if (e != cudaSuccess) return e;
     const int grid = plane_grid(n1, n2, nplanes);
+#define SLLB_PLANE_LAUNCH_R(KERN)                                                            \
+    do {                                                                                     \
+        e = set_smem(KERN, smem);                                                            \
+        if (e != cudaSuccess) return e;                                                      \
+        KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial, rd);    \
+    } while (0)
 #define SLLB_PLANE_LAUNCH(KERN)                                                              \
     do {                                                                                     \
         e = set_smem(KERN, smem);                                                            \
@@ -1234,8 +1256,13 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
         KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial);        \
     } while (0)
     if (g_plane_ept == 0) {
-        if (rho) SLLB_PLANE_LAUNCH(k_spline_plane_r<true>);
-        else SLLB_PLANE_LAUNCH(k_spline_plane_r<false>);
+        if (rd.on) {
+            if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true>));
+            else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, true>));
+        } else {
+            if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false>));
+            else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, false>));
+        }
     } else if (rho) SLLB_PLANE_LAUNCH((k_spline_plane<32, true>));
     else if (ept == 16) SLLB_PLANE_LAUNCH((k_spline_plane<16, false>));
     else SLLB_PLANE_LAUNCH((k_spline_plane<32, false>));

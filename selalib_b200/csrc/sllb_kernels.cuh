@@ -36,7 +36,7 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
 // cudaErrorNotSupported when the plane shape / displacement pattern does not fit.
 int plane_grid(int n1, int n2, long long nplanes);
 cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, const DispDesc &dd1, const DispDesc &dd2,
-                                double *rho_partial, cudaStream_t st);
+                                double *rho_partial, cudaStream_t st, const RemapDst *remap = nullptr);
 cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts, double scale, double *rho, cudaStream_t st);
 
 // K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]

@@ -206,12 +206,9 @@ static void box_of(const std::vector<int> &boxes, int r, int lo[4], int n[4]) {
     for (int d = 0; d < 4; ++d) { lo[d] = boxes[r * 8 + 2 * d]; n[d] = boxes[r * 8 + 2 * d + 1] - lo[d] + 1; }
 }
 
-static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int method, int order, const DispDesc &dd,
-                                   PhaseTimer *timer = nullptr) {
-    if (!D->p2p || !g_fused_remap) return fail(SLLB_ERR_UNSUPPORTED, "dist4d_advect_remap: peer mapping not available (use advect + sllb_dist4d_remap)");
+static void dist4d_remap_dst(sllb_dist4d *D, int from, int axis, RemapDst *rdp) {
     const int to = 1 - from;
-    if (D->procs[from][axis] != 1) return fail(SLLB_ERR_INVALID, "dist4d_advect_remap: the advected axis must be whole in the source layout");
-    RemapDst rd;
+    RemapDst &rd = *rdp;
     memset(&rd, 0, sizeof(rd));
     for (int r = 0; r < D->nranks; ++r) rd.base[r] = D->peer[to][r];
     rd.on = 1; rd.axis = axis;
@@ -221,6 +218,13 @@ static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int metho
         rd.tp[d] = D->procs[to][d];
         rd.te[d] = D->global[d] / D->procs[to][d];
     }
+}
+static int dist4d_advect_remap_dev(sllb_dist4d *D, int from, int axis, int method, int order, const DispDesc &dd,
+                                   PhaseTimer *timer = nullptr) {
+    if (!D->p2p || !g_fused_remap) return fail(SLLB_ERR_UNSUPPORTED, "dist4d_advect_remap: peer mapping not available (use advect + sllb_dist4d_remap)");
+    if (D->procs[from][axis] != 1) return fail(SLLB_ERR_INVALID, "dist4d_advect_remap: the advected axis must be whole in the source layout");
+    RemapDst rd;
+    dist4d_remap_dst(D, from, axis, &rd);
     phase_mark(timer, 0);
     SLLB_TRY(advect_axis_dev(D->F[from], axis, method, order, dd, &rd));
     phase_mark(timer, 4);
@@ -411,8 +415,8 @@ static int sim4d_fields(sllb_sim4d *S) {
     const double scale = S->delta[2] * S->delta[3];
     const long long tile = (long long)Fv->ext[0] * Fv->ext[1];
     double *rho_local = (P == 1) ? S->rho_full.p : S->rho_tile.p;
-    if (S->rho_state == 1 && P == 1) {
-        // rho_full was accumulated by the plane kernel during the T stage
+    if (S->rho_state == 1) {
+        // rho_full was accumulated by the plane kernel during the T stage (and all-reduced over the ranks)
     } else if (S->rho_state == 2) {
         // sum over x4 came out of the last x4 pass; finish the sum over x3 (K3 on a [x1 x2][x3] array)
         SLLB_TRY(Fv->red_scratch.ensure(reduce_scratch_doubles(tile, Fv->ext[2])));
@@ -420,8 +424,9 @@ static int sim4d_fields(sllb_sim4d *S) {
     } else {
         SLLB_TRY(sllb_reduce_velocity(Fv, 2, scale, rho_local));
     }
+    const bool have_full = (S->rho_state == 1);
     S->rho_state = 0;
-    if (P > 1) {
+    if (P > 1 && !have_full) {
         SLLB_TRY(sllb_comm_allgather(S->comm, S->rho_tile.p, S->rho_gather.p, tile));
         const int ext[4] = {N1, N2, 1, 1};
         for (int r = 0; r < P; ++r) {
@@ -456,16 +461,32 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     sllb_field *Fx = S->D->F[0];
     const sllb_sim4d_params_t &p = S->p;
     S->rho_state = 0;
-    // single GPU, cubic splines: both passes and the charge density in one sweep (K1c)
-    if (S->D->nranks == 1 && p.method == SLLB_METHOD_SPLINE && g_plane_kernel) {
+    // cubic splines: both passes and the charge density in one sweep (K1c); on several GPUs the same kernel also
+    // stores into the v-sequential layout of the owning ranks when the next stage is a V stage (`fuse`)
+    if (p.method == SLLB_METHOD_SPLINE && g_plane_kernel) {
         DispDesc d0, d1;
         SLLB_TRY(Fx->disp_scratch2.ensure((size_t)Fx->ext[3]));
-        SLLB_TRY(make_affine_disp(Fx, 0, 2, p.xmin[2], S->delta[2], -step * p.dt / S->delta[0], &d0));
-        SLLB_CUDA(launch_affine(Fx->disp_scratch2.p, Fx->ext[3], p.xmin[3], S->delta[3], 0));
+        SLLB_TRY(make_affine_disp(Fx, 0, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2], -step * p.dt / S->delta[0], &d0));
+        SLLB_CUDA(launch_affine(Fx->disp_scratch2.p, Fx->ext[3], p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3], 0));
         d1.v = Fx->disp_scratch2.p; d1.scale = -step * p.dt / S->delta[1];
         d1.odiv = Fx->ext[2]; d1.omod = Fx->ext[3]; d1.ostr = 1; d1.idiv = d1.imod = 1; d1.istr = 0;
-        int rc = advect_plane_dev(Fx, d0, d1, S->delta[2] * S->delta[3], S->rho_full.p);
-        if (rc == SLLB_OK) { S->rho_state = 1; return SLLB_OK; }
+        RemapDst rd;
+        if (fuse) dist4d_remap_dst(S->D, 0, 1, &rd);
+        S->timer.mark(0);
+        int rc = advect_plane_dev(Fx, d0, d1, S->delta[2] * S->delta[3], S->rho_full.p, fuse ? &rd : nullptr);
+        if (rc == SLLB_OK) {
+            if (fuse) {
+                S->timer.mark(4);
+                // rho_full holds the sum over MY planes: the all-reduce completes it and is the barrier of the remap
+                SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho_full.p, (int64_t)p.nc[0] * p.nc[1]));
+                S->timer.mark(5);
+                S->layout = 1;
+            } else if (S->D->nranks > 1) {
+                SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho_full.p, (int64_t)p.nc[0] * p.nc[1]));
+            }
+            S->rho_state = 1;
+            return SLLB_OK;
+        }
         if (rc != SLLB_ERR_UNSUPPORTED) return rc;
     }
     // out(x) = in(x - v*step*dt): displacement in cells = -v*step*dt/delta_x  (:1037-1064)

@@ -20,6 +20,8 @@ import selalib_b200 as sb  # noqa: E402
 
 
 def main():
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     sb.init(local)
