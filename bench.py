@@ -202,6 +202,8 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     n = NSIDE
+    if os.environ.get("SLLB_REMAP_ROTATION") is not None:
+        sb.set_remap_rotation(env_int("SLLB_REMAP_ROTATION", 1))
     sampler = ClockSampler(local_rank) if rank == 0 else None
     S = sb.Sim4d([n] * 4, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, split=0, method=sb.METHOD_SPLINE, order=4, comm=comm)
     npts = float(n) ** 4
@@ -217,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = sb.launch_count()
-    phase = S.phase_ms().tolist()
+    phase = S.phase_ms8().tolist()
     value = PASSES_PER_STEP * npts * args.steps / (ms * 1e-3)
 
     # ---- per-kernel timing for the roofline (CUDA events on the launch stream, local field) ------
@@ -365,8 +367,11 @@ def run_ours(args, rank, world, local_rank):
                            "staging": "TMA bulk copies (cp.async.bulk, UBLKCP): 256 B rows of 32-line tiles (V stage), whole 128x128 planes (T stage)"},
                 "phase_ms_per_step": {"advect_local_passes": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
                                       "nccl_remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps,
-                                      "advect_fused_remap_passes": phase[4] / args.steps,
-                                      "barrier_after_fused_pass": phase[5] / args.steps},
+                                      "advect_fused_remap_passes": (phase[4] + phase[6]) / args.steps,
+                                      "barrier_after_fused_pass": (phase[5] + phase[7]) / args.steps,
+                                      "fused_V_pass_x4+remap": phase[4] / args.steps, "barrier_after_V": phase[5] / args.steps,
+                                      "fused_T_plane_x1+x2+rho+remap": phase[6] / args.steps,
+                                      "allreduce_rho_after_T": phase[7] / args.steps},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "check": {"mass": float(row[3]), "field_energy": float(row[1])}}
         print(json.dumps(line), flush=True)

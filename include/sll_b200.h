@@ -53,6 +53,12 @@ void sllb_launch_count_reset(void);
  *  src/interpolation/periodic_interpolation/sll_m_periodic_interp.F90:38-41) */
 #define SLLB_ADV_PERIODIC_SPLINE 0
 #define SLLB_ADV_PERIODIC_LAGRANGE 1
+/* sll_t_advector_1d_bsl (src/semi_lagrangian/advection/sll_m_advection_1d_BSL.F90:40-54,152-164) wired as in the
+ * reference's test_advection_1d_bsl.F90: explicit-Euler characteristics with sll_p_periodic
+ * (sll_m_characteristics_1d_explicit_euler.F90:157-189) + sll_t_cubic_spline_interpolator_1d%interpolate_array.
+ * For a constant advection field the feet are x_i - A*dt folded into the period, i.e. one shift per line:
+ * the same fused kernel serves it.  `order` is ignored (cubic). */
+#define SLLB_ADV_BSL 2
 
 /* interpolator kinds (sll_c_interpolator_1d implementations) */
 #define SLLB_INTERP_CUBIC_SPLINE 0      /* sll_t_cubic_spline_interpolator_1d */
@@ -73,7 +79,8 @@ void sllb_launch_count_reset(void);
  * (sll_m_advection_1d_periodic.F90:57-130) and the abstract interface
  * (sll_m_advection_1d_base.F90:53-68).  out(x_i) = in(x_i - A*dt); `in` may alias
  * `out`; n = num_cells or num_cells+1 (the duplicate is filled when n > num_cells).
- * kind PERIODIC_SPLINE supports order 4; PERIODIC_LAGRANGE supports order 4,6,8. */
+ * kind PERIODIC_SPLINE supports order 4; PERIODIC_LAGRANGE supports order 4,6,8; BSL: n = num_cells+1 points as the
+ * reference object is built on npts grid points (n = num_cells also accepted). */
 typedef struct sllb_adv1d *sllb_adv1d_t;
 int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int order, sllb_adv1d_t *h);
 int sllb_adv1d_advect_constant(sllb_adv1d_t h, double A, double dt, const double *in, double *out, int n);
@@ -229,6 +236,9 @@ int sllb_dist4d_advect_remap(sllb_dist4d_t D, int from, int axis, int method, in
 int sllb_dist4d_p2p(sllb_dist4d_t D, int *enabled);
 /* 1 (default): the simulations use the fused pass when available; 0: pack + NCCL send/recv + unpack */
 int sllb_set_fused_remap(int on);
+/* 1 (default): a fused pass starts its sweep at a rank-dependent tile so that at every moment the senders are
+ * spread evenly over the receivers (no NVLink ingress hot spot); 0: every rank sweeps in the same order */
+int sllb_set_remap_rotation(int on);
 
 /* ---- a12: 6D slim domain decomposition + halo exchange ----------------------
  * sll_f_set_process_grid (src/parallelization/decomposition/sll_m_decomposition.F90:2473-2543) */
@@ -290,6 +300,9 @@ int sllb_sim4d_box(sllb_sim4d_t S, int which, int box[8]); /* my box: which = 0 
 int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]);
 /* finer: [local passes, reduce+poisson, NCCL remap, diag, fused advect+remap kernels, barriers after them] */
 int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]);
+/* finest: [local passes, reduce+poisson, NCCL remap, diag, fused V-stage pass (x4 + remap), barrier after it,
+ *          fused T-stage plane kernel (x1 + x2 + rho + remap), all-reduce (rho + barrier) after it] */
+int sllb_sim4d_phase_ms8(sllb_sim4d_t S, double out[8]);
 
 /* 1D1V sim_bsl_vp_1d1v_cart (single GPU). init 0 Landau, 1 two-stream. rows: nsteps x 8
  * (time, mass, l1, momentum, l2, ekin, epot, etot; sll_m_sim_bsl_vp_1d1v_cart.F90:1783) */

@@ -82,6 +82,15 @@ def advect_1d_periodic_constant(kind, num_cells, xmin, xmax, order, A, dt, inp):
     return out
 
 
+def advect_1d_bsl_constant(npts, eta_min, eta_max, A, dt, inp, fast=1):
+    """sll_t_advector_1d_bsl%advect_1d_constant with explicit-Euler periodic characteristics + cubic-spline interpolator"""
+    inp = _f(inp); out = np.empty_like(inp)
+    assert inp.size == npts
+    lib().orc_advect_1d_bsl_constant(C.c_int(npts), C.c_double(eta_min), C.c_double(eta_max), C.c_int(fast),
+                                     C.c_double(A), C.c_double(dt), _p(inp), _p(out))
+    return out
+
+
 def lagr_coeff(s, p):
     pp = np.zeros(11)
     rc = lib().orc_lagr_coeff(C.c_int(s), C.c_double(p), _p(pp))

@@ -418,6 +418,35 @@ void orc_advect_1d_periodic_constant(int kind, int num_cells, double xmin, doubl
     free(tmp);
 }
 
+/* a4: sll_t_advector_1d_bsl%advect_1d_constant, src/semi_lagrangian/advection/sll_m_advection_1d_BSL.F90:152-164,
+ * with the objects the reference's own test wires in (test_advection_1d_BSL.F90): characteristics =
+ * sll_t_charac_1d_explicit_euler with sll_p_periodic (feet = eta - dt*A, folded back into [eta_min, eta_max) by
+ * sll_f_process_outside_point_periodic when outside or on the border;
+ * src/time_integration/characteristics/sll_m_characteristics_1d_explicit_euler.F90:157-189,
+ * sll_m_characteristics_1d_base.F90:84-108) and interp = sll_t_cubic_spline_interpolator_1d%interpolate_array
+ * (compute_interpolant + eval_array, sll_m_cubic_spline_interpolator_1d.F90:97-109).
+ * npts = num_cells + 1 points, eta_coords(i) = eta_min + (i-1)*delta (:109-113). */
+void orc_advect_1d_bsl_constant(int npts, double eta_min, double eta_max, int fast, double A, double dt,
+                                const double *input, double *output) {
+    double *C = (double *)malloc(sizeof(double) * (npts + 3));
+    double *feet = (double *)malloc(sizeof(double) * npts);
+    double delta_eta = (eta_max - eta_min) / (double)(npts - 1);
+    for (int i = 0; i < npts; ++i) {
+        double eta = eta_min + (double)i * delta_eta;
+        double o = eta - dt * A;
+        if (o <= eta_min || o >= eta_max) {
+            double e = (o - eta_min) / (eta_max - eta_min);
+            e = e - floor(e);
+            if (e == 1.0) e = 0.0;
+            o = eta_min + e * (eta_max - eta_min);
+        }
+        feet[i] = o;
+    }
+    orc_spline_compute_interpolant_periodic(input, npts, fast, C);
+    spline_eval_array(C, npts, eta_min, eta_max, feet, output, npts);
+    free(C); free(feet);
+}
+
 /* ------------------------------------------------------------------------- */
 /* a10: sll_m_lagrange_interpolation_1d_fast                                   */
 /* ------------------------------------------------------------------------- */

@@ -92,5 +92,57 @@ int main() {
             }
         }
     }
+        // ---- both directions at once (the all-to-all is bidirectional): device 0 -> 1 and 1 -> 0 concurrently ----
+    {
+        double *src1, *peer0;
+        CK(cudaSetDevice(1)); CK(cudaDeviceEnablePeerAccess(0, 0)); CK(cudaMalloc(&src1, bytes)); CK(cudaMemset(src1, 1, bytes));
+        CK(cudaSetDevice(0)); CK(cudaMalloc(&peer0, bytes));
+        cudaEvent_t a1, b1; CK(cudaSetDevice(1)); cudaEventCreate(&a1); cudaEventCreate(&b1); CK(cudaSetDevice(0));
+        for (int vec = 1; vec <= 2; ++vec) {
+            const long long row_elems = 32 * vec, nrows = bytes / 8 / row_elems, stride = nrows / 4096 * row_elems;
+            float ms0 = 0, ms1 = 0;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaSetDevice(0)); cudaEventRecord(a);
+                if (vec == 1) k_store<1><<<148 * 16, 256>>>(peer, src, nrows, row_elems, stride);
+                else k_store<2><<<148 * 16, 256>>>(peer, src, nrows, row_elems, stride);
+                cudaEventRecord(b);
+                CK(cudaSetDevice(1)); cudaEventRecord(a1);
+                if (vec == 1) k_store<1><<<148 * 16, 256>>>(peer0, src1, nrows, row_elems, stride);
+                else k_store<2><<<148 * 16, 256>>>(peer0, src1, nrows, row_elems, stride);
+                cudaEventRecord(b1);
+                CK(cudaSetDevice(0)); cudaEventSynchronize(b); cudaEventElapsedTime(&ms0, a, b);
+                CK(cudaSetDevice(1)); cudaEventSynchronize(b1); cudaEventElapsedTime(&ms1, a1, b1);
+                CK(cudaSetDevice(0));
+            }
+            char name[128];
+            snprintf(name, sizeof(name), "bidirectional st.cs %2d B/lane %3d B rows: dev0 / dev1", 8 * vec, 256 * vec);
+            report(name, ms0); report(name, ms1);
+        }
+        {
+            float ms0 = 0, ms1 = 0;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaSetDevice(0)); cudaEventRecord(a); CK(cudaMemcpyPeerAsync(peer, 1, src, 0, bytes, 0)); cudaEventRecord(b);
+                CK(cudaSetDevice(1)); cudaEventRecord(a1); CK(cudaMemcpyPeerAsync(peer0, 0, src1, 1, bytes, 0)); cudaEventRecord(b1);
+                CK(cudaSetDevice(0)); cudaEventSynchronize(b); cudaEventElapsedTime(&ms0, a, b);
+                CK(cudaSetDevice(1)); cudaEventSynchronize(b1); cudaEventElapsedTime(&ms1, a1, b1);
+                CK(cudaSetDevice(0));
+            }
+            report("bidirectional cudaMemcpyPeerAsync: dev0", ms0); report("bidirectional cudaMemcpyPeerAsync: dev1", ms1);
+        }
+        for (int piece : {512, 16384}) {
+            const long long np = bytes / piece;
+            float ms0 = 0, ms1 = 0;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaSetDevice(0)); cudaEventRecord(a); k_bulk<<<148 * 8, 128, piece>>>(peer, np, piece); cudaEventRecord(b);
+                CK(cudaSetDevice(1)); cudaEventRecord(a1); k_bulk<<<148 * 8, 128, piece>>>(peer0, np, piece); cudaEventRecord(b1);
+                CK(cudaSetDevice(0)); cudaEventSynchronize(b); cudaEventElapsedTime(&ms0, a, b);
+                CK(cudaSetDevice(1)); cudaEventSynchronize(b1); cudaEventElapsedTime(&ms1, a1, b1);
+                CK(cudaSetDevice(0));
+            }
+            char name[128];
+            snprintf(name, sizeof(name), "bidirectional TMA bulk store %5d B pieces: dev0 / dev1", piece);
+            report(name, ms0); report(name, ms1);
+        }
+    }
     return 0;
 }

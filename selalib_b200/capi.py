@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "lib", "libsllb200.so")
 
 METHOD_SPLINE, METHOD_LAGRANGE_FIXED, METHOD_LAGRANGE_CENTERED = 0, 1, 2
-ADV_PERIODIC_SPLINE, ADV_PERIODIC_LAGRANGE = 0, 1
+ADV_PERIODIC_SPLINE, ADV_PERIODIC_LAGRANGE, ADV_BSL = 0, 1, 2
 (INTERP_CUBIC_SPLINE, INTERP_LAGRANGE_CENTERED, INTERP_LAGRANGE_FIXED, INTERP_PERIODIC_SPLINE,
  INTERP_PERIODIC_LAGRANGE) = range(5)
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 1, 2, 3, 4
@@ -116,6 +116,10 @@ def set_fused_remap(on):
     _ck(lib().sllb_set_fused_remap(C.c_int(1 if on else 0)))
 
 
+def set_remap_rotation(on):
+    _ck(lib().sllb_set_remap_rotation(C.c_int(1 if on else 0)))
+
+
 def set_spline_split(chunks):
     _ck(lib().sllb_set_spline_split(C.c_int(chunks)))
 
@@ -124,7 +128,8 @@ def set_spline_split(chunks):
 # line-granular drop-in objects (mirror sll_t_advector_1d_periodic / sll_c_interpolator_1d)
 # ---------------------------------------------------------------------------------------------
 class Advector1dPeriodic:
-    """sll_t_advector_1d_periodic (sll_m_advection_1d_periodic.F90:41-130)."""
+    """sll_t_advector_1d_periodic (sll_m_advection_1d_periodic.F90:41-130); kind=ADV_BSL: sll_t_advector_1d_bsl
+    (sll_m_advection_1d_BSL.F90) with explicit-Euler periodic characteristics + cubic-spline interpolator."""
 
     def __init__(self, num_cells, xmin, xmax, kind=ADV_PERIODIC_SPLINE, order=4):
         self.h = vp()
@@ -425,6 +430,11 @@ class Sim4d:
     def phase_ms(self):
         out = np.zeros(6)
         _ck(lib().sllb_sim4d_phase_ms6(self.h, _p(out)))
+        return out
+
+    def phase_ms8(self):
+        out = np.zeros(8)
+        _ck(lib().sllb_sim4d_phase_ms8(self.h, _p(out)))
         return out
 
     def destroy(self):

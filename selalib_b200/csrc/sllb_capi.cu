@@ -281,6 +281,11 @@ int sllb_set_plane_kernel(int on, int points_per_thread) {
     return SLLB_OK;
 }
 
+int sllb_set_remap_rotation(int on) {
+    g_remap_rotation = on ? 1 : 0;
+    return SLLB_OK;
+}
+
 int sllb_set_spline_split(int chunks) {
     if (chunks != -1 && chunks != 1 && chunks != 2 && chunks != 4 && chunks != 8)
         return fail(SLLB_ERR_INVALID, "set_spline_split: chunks must be -1, 1, 2, 4 or 8");
@@ -626,6 +631,8 @@ int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int ord
         if (order != 4 && order != 6 && order != 8)
             return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_lagrange implemented for order 4, 6, 8");
         method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = order;
+    } else if (kind == SLLB_ADV_BSL) {
+        method = SLLB_METHOD_SPLINE; stencil = 4;
     } else return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: advector kind not implemented");
     SLLB_TRY(require_device());
     sllb_adv1d *a = new sllb_adv1d();
@@ -641,6 +648,12 @@ int sllb_adv1d_advect_constant(sllb_adv1d_t h, double A, double dt, const double
     if (n != h->num_cells && n != h->num_cells + 1) return fail(SLLB_ERR_INVALID, "advect_constant: n must be num_cells or num_cells+1");
     SLLB_TRY(require_device());
     /* shift = A*dt/(xmax-xmin)*num_cells (sll_m_advection_1d_periodic.F90:117); out(j) = interp(j - shift) */
+    if (h->kind == SLLB_ADV_BSL) {
+        /* feet = eta_i - dt*A folded into [eta_min, eta_max) (explicit Euler, periodic), then the interpolant is
+         * evaluated there: out(i) = S(x_i - A*dt), displacement in cells = -A*dt/delta */
+        const double delta = (h->xmax - h->xmin) / (double)h->num_cells;
+        return line_shift(h->line, h->method, h->stencil, -(A * dt) / delta, in, out, n);
+    }
     const double shift = A * dt / (h->xmax - h->xmin) * (double)h->num_cells;
     return line_shift(h->line, h->method, h->stencil, -shift, in, out, n);
 }

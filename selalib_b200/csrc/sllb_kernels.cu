@@ -374,7 +374,9 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     double *part = reinterpret_cast<double *>(smem_raw + 128);          // [P][32] chunk sums (linesum only)
     double *s = reinterpret_cast<double *>(smem_raw + 128 + P * 32 * 8);
     const int tid = threadIdx.x, lane = tid & 31, chunk = tid >> 5;
-    const long long l = (long long)blockIdx.x * BW + lane;
+    unsigned bid = blockIdx.x;
+    if constexpr (REMAP) { bid += (unsigned)rd.block_rot; if (bid >= gridDim.x) bid -= gridDim.x; }
+    const long long l = (long long)bid * BW + lane;
     const bool active = l < nlines;
     const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
     double *base = f + o * (long long)N * inner + in;
@@ -1117,6 +1119,19 @@ static cudaError_t launch_strided_t(double *f, long long nlines, int N, long lon
 }
 
 int g_spline_split = -1; // -1 auto, else forced P in {1,2,4}
+int g_remap_rotation = 1; // fused remap: 1 = ranks start their sweep at different destination ranks
+// A fused pass walks its tiles with the slowest non-advected axis outermost.  When the destination layout splits
+// that axis, every rank would store to the same group of receivers at the same time (all senders into
+// 1/tp of the receivers: their NVLink ingress is the bottleneck, the other receivers idle).  Rotating the start
+// tile by rank/tp of the sweep spreads the senders evenly over the receivers at every moment.
+static int remap_block_rotation(const RemapDst &rd, long long nblk) {
+    if (!rd.on || !g_remap_rotation) return 0;
+    int slow = 3;
+    if (slow == rd.axis) slow = 2;
+    const int tp = rd.tp[slow];
+    if (tp <= 1 || nblk % tp != 0) return 0;
+    return (int)((rd.rank % tp) * (nblk / tp));
+}
 template <int P>
 static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
                                          int staging, cudaStream_t st, const RemapDst &rd, double *linesum) {
@@ -1129,7 +1144,9 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
         auto kern = k_spline_strided_split<P, true>;
         e = set_smem(kern, smem);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd);
+        RemapDst rr = rd;
+        rr.block_rot = remap_block_rotation(rd, nblk);
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr);
     } else {
         auto kern = k_spline_strided_split<P, false>;
         e = set_smem(kern, smem);

@@ -22,6 +22,9 @@ struct RemapDst {
     int on, axis;               // on = 0: in place, everything below ignored
     int se[4], slo[4];          // source layout: local extents and global offset of my box
     int te[4], tp[4];           // destination layout: local extents (uniform boxes) and process mesh
+    int block_rot;              // tiles are visited starting from this one (set by the launcher from `rank`): ranks
+                                // start at different destination ranks so no receiver is hit by everybody at once
+    int rank;                   // my rank (seed of the rotation)
 };
 
 // K1/K2: one 1D periodic advection on every line of f viewed as [outer][n][inner], in place.
@@ -74,6 +77,7 @@ cudaError_t launch_pack4d(const double *src, const int ext[4], Box4 box, double 
 cudaError_t launch_unpack4d(double *dst, const int ext[4], Box4 box, const double *buf, cudaStream_t st);
 
 extern int g_plane_ept;    // plane kernel: 0 auto, 16 or 32 points per thread
+extern int g_remap_rotation; // fused remap: rank-dependent start tile
 extern int g_spline_split; // -1 auto, else lines are cut into this many chunks (1,2,4,8)
 long long launch_count();
 void launch_count_reset();

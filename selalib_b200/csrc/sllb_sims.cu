@@ -144,14 +144,14 @@ struct PhaseTimer {
         cudaEventRecord(e, 0);
         ev.push_back(e); tag.push_back(phase_just_finished);
     }
-    void collect(double out[6]) {
-        for (int k = 0; k < 6; ++k) out[k] = 0;
+    void collect(double out[8]) {
+        for (int k = 0; k < 8; ++k) out[k] = 0;
         if (ev.size() < 2) return;
         cudaEventSynchronize(ev.back());
         for (size_t i = 1; i < ev.size(); ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            if (tag[i] >= 0 && tag[i] < 6) out[tag[i]] += ms;
+            if (tag[i] >= 0 && tag[i] < 8) out[tag[i]] += ms;
         }
     }
     void reset() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); tag.clear(); on = false; }
@@ -211,7 +211,7 @@ static void dist4d_remap_dst(sllb_dist4d *D, int from, int axis, RemapDst *rdp) 
     RemapDst &rd = *rdp;
     memset(&rd, 0, sizeof(rd));
     for (int r = 0; r < D->nranks; ++r) rd.base[r] = D->peer[to][r];
-    rd.on = 1; rd.axis = axis;
+    rd.on = 1; rd.axis = axis; rd.rank = D->rank; rd.block_rot = 0;
     for (int d = 0; d < 4; ++d) {
         rd.se[d] = D->F[from]->ext[d];
         rd.slo[d] = D->boxes[from][D->rank * 8 + 2 * d];
@@ -375,7 +375,9 @@ struct sllb_sim4d {
     int istep = 0;
     int layout = 0;    // which copy of f is current: 0 x-sequential, 1 v-sequential
     PhaseTimer timer;
-    double phase_ms[6] = {0, 0, 0, 0, 0, 0}; // local passes, rho+poisson, NCCL remap, diagnostics, fused passes, barriers
+    // local passes, rho+poisson, NCCL remap, diagnostics, fused V-stage pass, barrier after it, fused T-stage plane
+    // kernel, all-reduce (rho + barrier) after it
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 __global__ void k_landau4d(double *f, int n0, int n1, int n2, int n3, int lo2, int lo3, double x0min, double x1min,
@@ -476,10 +478,10 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
         int rc = advect_plane_dev(Fx, d0, d1, S->delta[2] * S->delta[3], S->rho_full.p, fuse ? &rd : nullptr);
         if (rc == SLLB_OK) {
             if (fuse) {
-                S->timer.mark(4);
+                S->timer.mark(6);
                 // rho_full holds the sum over MY planes: the all-reduce completes it and is the barrier of the remap
                 SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho_full.p, (int64_t)p.nc[0] * p.nc[1]));
-                S->timer.mark(5);
+                S->timer.mark(7);
                 S->layout = 1;
             } else if (S->D->nranks > 1) {
                 SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho_full.p, (int64_t)p.nc[0] * p.nc[1]));
@@ -679,12 +681,18 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
 int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]) {
     if (!S || !out) return fail(SLLB_ERR_INVALID, "sim4d_phase_ms6: null");
     for (int k = 0; k < 6; ++k) out[k] = S->phase_ms[k];
+    out[4] += S->phase_ms[6]; out[5] += S->phase_ms[7];
+    return SLLB_OK;
+}
+int sllb_sim4d_phase_ms8(sllb_sim4d_t S, double out[8]) {
+    if (!S || !out) return fail(SLLB_ERR_INVALID, "sim4d_phase_ms8: null");
+    for (int k = 0; k < 8; ++k) out[k] = S->phase_ms[k];
     return SLLB_OK;
 }
 int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]) {
     if (!S || !out) return fail(SLLB_ERR_INVALID, "sim4d_phase_ms: null");
     for (int k = 0; k < 4; ++k) out[k] = S->phase_ms[k];
-    out[0] += S->phase_ms[4]; out[2] += S->phase_ms[5];
+    out[0] += S->phase_ms[4] + S->phase_ms[6]; out[2] += S->phase_ms[5] + S->phase_ms[7];
     return SLLB_OK;
 }
 

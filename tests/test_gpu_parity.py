@@ -72,6 +72,24 @@ def test_advector_periodic_lagrange(sb, orc, order):
     adv.delete()
 
 
+@pytest.mark.parametrize("n", [32, 64, 200])
+def test_advector_bsl(sb, orc, n):
+    """a4: sll_t_advector_1d_bsl%advect_1d_constant (explicit-Euler periodic characteristics + cubic-spline
+    interpolate_array) against the oracle's restatement of that object chain."""
+    rng = np.random.default_rng(SEED + 7 * n)
+    xmin, xmax = -1.0, 2.5
+    adv = sb.Advector1dPeriodic(n, xmin, xmax, sb.ADV_BSL, 4)
+    for A, dt in [(1.0, 0.1), (-0.37, 0.3), (0.0, 0.1), (55.5, 0.2), (3.5 / n, 1.0)]:
+        f = rng.standard_normal(n + 1); f[-1] = f[0]
+        ref = orc.advect_1d_bsl_constant(n + 1, xmin, xmax, A, dt, f)
+        out = adv.advect_1d_constant(A, dt, f)
+        assert out.shape == (n + 1,)
+        assert relerr(out, ref) < TOL
+    ones = np.ones(n + 1)                                  # test_advection_1d_bsl.F90: err < 1e-15 on input = 1
+    assert np.abs(adv.advect_1d_constant(1.0, 0.1, ones) - 1.0).max() < 2e-15
+    adv.delete()
+
+
 def test_advector_unsupported(sb):
     with pytest.raises(sb.SllbError) as e:
         sb.Advector1dPeriodic(64, 0.0, 1.0, sb.ADV_PERIODIC_SPLINE, 8)

@@ -196,3 +196,18 @@ def test_sim4d_runs_and_conserves_mass():
     # FFT periodic advector (the sims' default SLL_SPLINES) agrees with the direct spline
     rows_fft = orc.sim4d(nc, [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1, 3, method=1)
     assert np.abs(rows_fft - rows).max() / np.abs(rows).max() < 1e-12
+
+
+def test_bsl_advector_kat():
+    """a4: test_advection_1d_bsl.F90: input = 1, A = 1, dt = 0.1, 32 cells on [0,1] -> err < 1e-15; and the BSL chain
+    (explicit-Euler periodic feet + interpolate_array) agrees with the constant-shift evaluation (eval_disp) and
+    with the sims' FFT advector."""
+    n = 32
+    out = orc.advect_1d_bsl_constant(n + 1, 0.0, 1.0, 1.0, 0.1, np.ones(n + 1))
+    assert np.abs(out - 1.0).max() < 1e-15
+    f = RNG.standard_normal(n + 1); f[-1] = f[0]
+    for A, dt in [(1.0, 0.1), (-0.37, 0.3), (12.1, 0.2)]:
+        a = orc.advect_1d_bsl_constant(n + 1, 0.0, 1.0, A, dt, f)
+        b = orc.spline_interpolate_array_disp(f, 0.0, 1.0, -A * dt)
+        c = orc.advect_1d_periodic_constant("spline", n, 0.0, 1.0, 4, A, dt, f)
+        assert np.abs(a - b).max() < 1e-13 and np.abs(a - c).max() < 1e-13
