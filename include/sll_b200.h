@@ -161,6 +161,23 @@ int sllb_set_staging(int mode);
 /* tuning knob: chunks per line of the strided spline kernel: -1 = auto, 1, 2, 4, 8 */
 int sllb_set_spline_split(int chunks);
 
+/* ---- (f)1: LOCAL cubic spline with halo cells ------------------------------
+ * sll_t_advection_6d_spline_dd_slim (src/semi_lagrangian/advection/sll_m_advection_6d_spline_dd_slim.F90) on top of
+ * sll_m_cubic_spline_halo_1d (src/interpolation/interpolators/sll_m_cubic_spline_halo_1d.F90:69-200): every rank
+ * interpolates its piece of a line with a spline whose two start values are series truncated after NUM_TERMS = 15
+ * terms (:11; truncation 2.6e-9 relative, the reference's own test tolerance is 4e-9), so results depend on the
+ * decomposition exactly as in the reference.  out(i) = S(x_i + disp), disp = shift + alpha, alpha in [0,1).
+ * The reference cuts the monotonic displacement array of eta1..3 into blocks of equal integer part
+ * (make_blocks_spline :202-287); indices with disp == 0 are in no block and the line stays untouched. */
+#define SLLB_SHIFT_SKIP INT32_MIN
+/* host only: shift[j] = integer displacement of index j's block or SLLB_SHIFT_SKIP, alpha[j] = disp - floor(disp)
+ * (alpha / nblocks may be NULL) */
+int sllb_spline_dd_blocks(int n, const double *disp, int32_t *shift, double *alpha, int *nblocks);
+/* one pass along `axis` of a field whose axis is whole on this rank (procs(axis) == 1: the halo is the periodic image).
+ * shift: HOST table indexed like disp->values (from sllb_spline_dd_blocks), or NULL = floor(disp) per line
+ * (the eta4..6 rule, :1098-1102).  SLLB_ERR_UNSUPPORTED when the axis has <= 15 points (:79). */
+int sllb_advect_axis_spline_dd(sllb_field_t F, int axis, const sllb_disp_t *disp, const int32_t *shift);
+
 /* ---- a14: velocity reduction -> charge density ----------------------------
  * rho[x] = scale * sum over the last (ndim - nx_axes) axes of F.  With periodic cells
  * only, the trapezoid rule over the duplicated end points
@@ -267,6 +284,19 @@ int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms); /* device time of the last
  * (src/semi_lagrangian/advection/sll_m_advection_6d_lagrange_dd_slim.F90:806-2001), fixed odd stencil,
  * in place on the local block; `disp` indexes the LOCAL block like sllb_advect_axis. */
 int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_t *disp);
+/* (f)1 on a decomposed block: sll_s_advection_6d_spline_dd_slim_[f]advect_eta{axis+1}.  Split axis: K9p computes the
+ * neighbours' parts of the boundary sums (prepare_exchange), they travel with hw_left / hw_right halo planes
+ * (sll_s_apply_bc_exchange_slim_6d_real64 + halo exchange, peer stores over NVLink or ncclSend/ncclRecv), then the
+ * local spline runs on halo | block | halo.  Every line's shift must lie in [-hw_left, hw_right-1] (the reference's
+ * eta4..6 use 1, 1: shifts 0 and -1, :1082-1087).  Unsplit axis: same as sllb_advect_axis_spline_dd. */
+int sllb_dd6d_advect_axis_spline(sllb_dd6d_t D, int axis, const sllb_disp_t *disp, const int32_t *shift, int hw_left,
+                                 int hw_right);
+/* make_blocks_lagrange (sll_m_advection_6d_lagrange_dd_slim.F90:202-286), host only: the blocks of equal integer
+ * displacement of the centred Lagrange x-advection and the halo widths each block exchanges,
+ * halo_width[2*b] = stencil/2 - box - 1 (left), halo_width[2*b+1] = stencil/2 + box (right).  box[j] = block's integer
+ * displacement or SLLB_SHIFT_SKIP (disp == 0: untouched line).  SLLB_ERR_INVALID when a displacement leaves
+ * [-stencil/2, stencil/2) (the reference's SLL_ASSERT :232-235).  halo_width holds up to `stencil` blocks. */
+int sllb_lagrange_dd_blocks(int n, int stencil, const double *disp, int32_t *box, int *nblocks, int *halo_width);
 /* tuning / test knob: 1 = also take the halo path (local periodic halo copy + halo-cells kernel, exactly
  * the reference's sequence) when procs(axis) == 1; default 0 = periodic kernel, same arithmetic */
 int sllb_dd6d_set_force_halo(int on);
@@ -313,7 +343,7 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows);
 int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F);
 int sllb_sim2d_destroy(sllb_sim2d_t S);
 
-/* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (Lagrange fixed stencils) on 1..P GPUs (velocity axes split,
+/* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (fixed / centred Lagrange or local splines) on 1..P GPUs (velocity axes split,
  * halo exchange per v-advection, rho all-reduced). rows: (nsteps+1) x 14 as the reference's
  * <prefix>.dat (sll_m_sim_6d_utilities.F90:357-364,632-633); every rank gets the global row. */
 typedef struct sllb_sim6d *sllb_sim6d_t;
@@ -324,7 +354,16 @@ typedef struct {
     double delta_t;
     double alpha, kx[3], v_thermal[3]; /* landau_prod */
     int time_in_phase;
+    /* interpolator_type of the namelist (sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:363-372):
+     * SLLB_ADVECTOR_FIXED    "fixed":    Lagrange, odd stencils stencil_x / stencil_v in all six directions;
+     * SLLB_ADVECTOR_CENTERED "centered": eta1..3 by the variable-block centred Lagrange advector (even stencil_x,
+     *                        fadvect_eta1..3, sll_m_advection_6d_lagrange_dd_slim.F90:173-322), eta4..6 fixed stencil_v;
+     * SLLB_ADVECTOR_SPLINE   "spline":   local cubic splines (sll_t_advection_6d_spline_dd_slim), stencils ignored */
+    int advector;
 } sllb_sim6d_params_t;
+#define SLLB_ADVECTOR_FIXED 0
+#define SLLB_ADVECTOR_CENTERED 1
+#define SLLB_ADVECTOR_SPLINE 2
 int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *S);
 /* process_grid: NULL / zeros = sll_f_set_process_grid(nranks) */
 int sllb_sim6d_create_dist(const sllb_sim6d_params_t *p, sllb_comm_t comm, const int process_grid[6], sllb_sim6d_t *S);

@@ -18,8 +18,8 @@ ip = C.POINTER(C.c_int)
 
 def build(force=False):
     so = os.path.join(_HERE, "liborc.so")
-    src = os.path.join(_HERE, "sll_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, n) for n in ("sll_oracle.c", "sll_oracle_halo.c", "Makefile")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return so
 
@@ -194,15 +194,17 @@ def advect_axis_sub(f, axis, method, order, disp, dsel, frac):
 
 
 def sim6d(n, v_max, xmax, stencil_x, stencil_v, delta_t, nsteps, alpha, kx, vth=(1.0, 1.0, 1.0),
-          time_in_phase=True, want_f=False):
+          time_in_phase=True, want_f=False, advector=0, vblk=(1, 1, 1)):
+    """advector: 0 fixed, 1 centered, 2 spline; vblk: emulated ring ranks along eta4..6 (local splines depend on it)"""
     nn = (C.c_int * 6)(*n)
     rows = np.zeros((nsteps + 1, 14))
     f = np.zeros(tuple(n), order="F") if want_f else None
-    rc = lib().orc_sim6d_run(nn, C.c_double(v_max), (C.c_double * 3)(*xmax), C.c_int(stencil_x), C.c_int(stencil_v),
-                             C.c_double(delta_t), C.c_int(nsteps), C.c_double(alpha), (C.c_double * 3)(*kx),
-                             (C.c_double * 3)(*vth), C.c_int(1 if time_in_phase else 0), _p(rows),
-                             _p(f) if want_f else None)
-    assert rc == 0
+    lib().orc_sim6d_run_ex.restype = C.c_int
+    rc = lib().orc_sim6d_run_ex(nn, C.c_double(v_max), (C.c_double * 3)(*xmax), C.c_int(stencil_x), C.c_int(stencil_v),
+                                C.c_double(delta_t), C.c_int(nsteps), C.c_double(alpha), (C.c_double * 3)(*kx),
+                                (C.c_double * 3)(*vth), C.c_int(1 if time_in_phase else 0), _p(rows),
+                                _p(f) if want_f else None, C.c_int(advector), (C.c_int * 3)(*vblk))
+    assert rc == 0, rc
     return (rows, f) if want_f else rows
 
 
@@ -227,3 +229,68 @@ def sim2d(nc_x1, nc_x2, x1_min, x1_max, x2_min, x2_max, init, kmode, eps, dt, ns
                              _p(f) if want_f else None, _p(E))
     assert rc == 0
     return (rows, f, E) if want_f else rows
+
+
+# ---- local cubic spline with halo cells (sll_m_cubic_spline_halo_1d, sll_m_advection_6d_spline_dd_slim) ----
+SKIP = -2 ** 31
+
+
+def halo_prepare_exchange(fdata, si):
+    fdata = _f(fdata); d0 = C.c_double(); c2 = C.c_double()
+    lib().orc_halo_prepare_exchange(_p(fdata), C.c_int(si), C.c_int(fdata.size), C.byref(d0), C.byref(c2))
+    return d0.value, c2.value
+
+
+def halo_finish_boundary_conditions(fdata, si, d0, c2):
+    fdata = _f(fdata); d0 = C.c_double(d0); c2 = C.c_double(c2)
+    lib().orc_halo_finish_boundary_conditions(_p(fdata), C.c_int(si), C.c_int(fdata.size), C.byref(d0), C.byref(c2))
+    return d0.value, c2.value
+
+
+def halo_compute_interpolant(fin, np_):
+    fin = _f(fin); d = np.zeros(np_ + 3); coeffs = np.zeros(np_ + 3)
+    lib().orc_halo_compute_interpolant(_p(fin), C.c_int(np_), _p(d), _p(coeffs))
+    return coeffs
+
+
+def halo_eval_disp(coeffs, alpha, np_):
+    coeffs = _f(coeffs); out = np.zeros(np_)
+    lib().orc_halo_eval_disp(_p(coeffs), C.c_double(alpha), C.c_int(np_), _p(out))
+    return out
+
+
+def halo_periodic(data, alpha):
+    """sll_s_cubic_spline_halo_1d_periodic on the n periodic cells of `data`"""
+    n = data.size
+    fin = np.zeros(n + 3); fin[:n] = data
+    out = np.zeros(n)
+    lib().orc_halo_periodic(_p(fin), C.c_double(alpha), C.c_int(n), _p(out))
+    return out
+
+
+def make_blocks_spline(disp):
+    disp = _f(disp); n = disp.size
+    shift = np.zeros(n, dtype=np.int32); alpha = np.zeros(n)
+    lib().orc_make_blocks_spline.restype = C.c_int
+    nb = lib().orc_make_blocks_spline(C.c_int(n), _p(disp), shift.ctypes.data_as(ip), _p(alpha))
+    return shift, alpha, nb
+
+
+def spline_dd_advect_axis(f, axis, nblk, disp, dsel, shifts=None):
+    """Local-spline pass along `axis` of the Fortran-ordered array f (in place) with the axis cut into nblk ring
+    pieces; disp / shifts indexed like advect_axis."""
+    assert f.flags.f_contiguous
+    shape = f.shape
+    inner = int(np.prod(shape[:axis], dtype=np.int64))
+    outer = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    disp = _f(disp)
+    L = C.c_long
+    sh = None
+    if shifts is not None:
+        sh = np.ascontiguousarray(shifts, dtype=np.int32)
+    lib().orc_spline_dd_advect_axis.restype = C.c_int
+    rc = lib().orc_spline_dd_advect_axis(_p(f), L(outer), C.c_int(shape[axis]), L(inner), C.c_int(nblk), _p(disp),
+                                         sh.ctypes.data_as(ip) if sh is not None else None, *[L(int(v)) for v in dsel])
+    if rc != 0:
+        raise ValueError("local spline needs more than 15 points per piece")
+    return f

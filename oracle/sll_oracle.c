@@ -958,9 +958,60 @@ static void diagnostics6d(const double *f, const int n[6], const double vmin[3],
 /* Runs init + `nsteps` steps; writes (nsteps+1) rows of 14 numbers (time + 13) to `rows`.
  * landau_prod initial data: sll_m_distribution_function_initializer_6d.F90:547-564,689-702;
  * local grid :312-335.  f (if non-NULL) receives the final distribution. */
+/* advector (interpolator_type, sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:363-372): 0 "fixed", 1 "centered" (eta1..3 by
+ * fadvect_eta1..3 of the Lagrange advector: blocks of make_blocks_lagrange, centered_halo_cells on halo|f|halo with the
+ * halo a periodic copy when the axis is not split, i.e. centered_periodicl arithmetic; lines with zero displacement
+ * belong to no block), 2 "spline" (sll_t_advection_6d_spline_dd_slim; vblk[d] = number of ring ranks along eta4+d the
+ * run is emulated for, the local spline depends on it). */
+int orc_spline_dd_advect_axis(double *f, long outer, int n, long inner, int nblk, const double *dvals, const int *shifts,
+                              long odiv, long omod, long ostr, long idiv, long imodn, long istr);
+int orc_make_blocks_spline(int n, const double *disp_in, int *shift, double *alpha);
+int orc_sim6d_run_ex(const int n[6], double v_max, const double xmax[3], int stencil_x, int stencil_v,
+                     double delta_t, int nsteps, double alpha, const double kx[3], const double vth[3],
+                     int time_in_phase, double *rows, double *f_out, int advector, const int vblk[3]);
 int orc_sim6d_run(const int n[6], double v_max, const double xmax[3], int stencil_x, int stencil_v,
                   double delta_t, int nsteps, double alpha, const double kx[3], const double vth[3],
                   int time_in_phase, double *rows, double *f_out) {
+    const int one[3] = {1, 1, 1};
+    return orc_sim6d_run_ex(n, v_max, xmax, stencil_x, stencil_v, delta_t, nsteps, alpha, kx, vth, time_in_phase, rows,
+                            f_out, 0, one);
+}
+/* x-advection along eta(id+1) of the non-"fixed" advectors, displacement array over the conjugate velocity index */
+static void advect6d_x_blocks(double *f, const int n[6], int id, int advector, int stencil_x, const double *disp) {
+    long inner = 1, outer = 1, stride_o = 1;
+    for (int d = 0; d < id; ++d) inner *= n[d];
+    for (int d = id + 1; d < 6; ++d) outer *= n[d];
+    for (int d = id + 1; d < id + 3; ++d) stride_o *= n[d];
+    int nv = n[id + 3];
+    int *shift = (int *)malloc(sizeof(int) * nv);
+    double *al = (double *)malloc(sizeof(double) * nv);
+    orc_make_blocks_spline(nv, disp, shift, al); /* make_blocks_lagrange walks the array identically (:237-283) */
+    if (advector == 2) {
+        orc_spline_dd_advect_axis(f, outer, n[id], inner, 1, disp, shift, stride_o, nv, 1, 1, 1, 0);
+    } else {
+        int nn = n[id];
+#pragma omp parallel
+        {
+            double *lin = (double *)malloc(sizeof(double) * 4 * (nn + 2));
+            double *lout = lin + nn + 1, *scratch = lout + nn + 1;
+#pragma omp for schedule(static) collapse(2)
+            for (long o = 0; o < outer; ++o)
+                for (long in = 0; in < inner; ++in) {
+                    long l = (o / stride_o) % nv;
+                    if (shift[l] == (-2147483647 - 1)) continue;
+                    double *base = f + o * (long)nn * inner + in;
+                    for (int i = 0; i < nn; ++i) lin[i] = base[(long)i * inner];
+                    advect_line(4, stencil_x, nn, lin, lout, disp[l], scratch);
+                    for (int i = 0; i < nn; ++i) base[(long)i * inner] = lout[i];
+                }
+            free(lin);
+        }
+    }
+    free(shift); free(al);
+}
+int orc_sim6d_run_ex(const int n[6], double v_max, const double xmax[3], int stencil_x, int stencil_v,
+                     double delta_t, int nsteps, double alpha, const double kx[3], const double vth[3],
+                     int time_in_phase, double *rows, double *f_out, int advector, const int vblk[3]) {
     long ntot = 1; for (int d = 0; d < 6; ++d) ntot *= n[d];
     long nx3 = (long)n[0] * n[1] * n[2];
     double eta_min[6] = {0, 0, 0, -v_max, -v_max, -v_max};
@@ -1003,13 +1054,19 @@ int orc_sim6d_run(const int n[6], double v_max, const double xmax[3], int stenci
         orc_poisson_3d_periodic_solve(n[0], n[1], n[2], Lx, Ly, Lz, rho, phi, ex, ey, ez); } while (0)
 #define ADVECT_V(dtv) do { const double *E3[3] = {ex, ey, ez}; \
         for (int d = 0; d < 3; ++d) { for (long i = 0; i < nx3; ++i) dfield[i] = E3[d][i] * (dtv) / de[3 + d]; \
-            advect6d_axis(f, n, 3 + d, stencil_v, dfield, 1); } } while (0)
+            if (advector == 2) { long inn = nx3, out = 1; for (int a = 3; a < 3 + d; ++a) inn *= n[a]; \
+                for (int a = 4 + d; a < 6; ++a) out *= n[a]; \
+                if (orc_spline_dd_advect_axis(f, out, n[3 + d], inn, vblk[d], dfield, NULL, 1, 1, 0, 1, nx3, 1)) return -2; } \
+            else advect6d_axis(f, n, 3 + d, stencil_v, dfield, 1); } } while (0)
     FIELDS();
     rows[0] = 0.0;
     diagnostics6d(f, n, vmin3, dv3, dV, dVx, rho, phi, ex, ey, ez, rows + 1);
     ADVECT_V(0.5 * delta_t);
     for (int it = 1; it <= nsteps; ++it) {
-        for (int d = 0; d < 3; ++d) advect6d_axis(f, n, d, stencil_x, dispx[d], 0);
+        for (int d = 0; d < 3; ++d) {
+            if (advector == 0) advect6d_axis(f, n, d, stencil_x, dispx[d], 0);
+            else advect6d_x_blocks(f, n, d, advector, stencil_x, dispx[d]);
+        }
         FIELDS();
         rows[14 * it] = (double)it * delta_t;
         diagnostics6d(f, n, vmin3, dv3, dV, dVx, rho, phi, ex, ey, ez, rows + 14 * it + 1);

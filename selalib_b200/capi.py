@@ -8,6 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "lib", "libsllb200.so")
 
 METHOD_SPLINE, METHOD_LAGRANGE_FIXED, METHOD_LAGRANGE_CENTERED = 0, 1, 2
+ADVECTOR_FIXED, ADVECTOR_CENTERED, ADVECTOR_SPLINE = 0, 1, 2
+SHIFT_SKIP = -2 ** 31
 ADV_PERIODIC_SPLINE, ADV_PERIODIC_LAGRANGE, ADV_BSL = 0, 1, 2
 (INTERP_CUBIC_SPLINE, INTERP_LAGRANGE_CENTERED, INTERP_LAGRANGE_FIXED, INTERP_PERIODIC_SPLINE,
  INTERP_PERIODIC_LAGRANGE) = range(5)
@@ -40,7 +42,7 @@ class Sim6dParams(C.Structure):
     _fields_ = [("n", C.c_int * 6), ("v_max", C.c_double), ("x_max", C.c_double * 3),
                 ("stencil_x", C.c_int), ("stencil_v", C.c_int), ("delta_t", C.c_double),
                 ("alpha", C.c_double), ("kx", C.c_double * 3), ("v_thermal", C.c_double * 3),
-                ("time_in_phase", C.c_int)]
+                ("time_in_phase", C.c_int), ("advector", C.c_int)]
 
 
 _LIB = None
@@ -182,6 +184,36 @@ class Interpolator1d:
 # ---------------------------------------------------------------------------------------------
 # batched device-resident API
 # ---------------------------------------------------------------------------------------------
+def _disp(owner, values, scale, dsel, on_device=False):
+    d = DispT()
+    if on_device:
+        d.values = C.cast(vp(values), dp); d.nvalues = 0; d.values_on_device = 1
+    else:
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        owner._keep = values
+        d.values = _p(values); d.nvalues = values.size; d.values_on_device = 0
+    d.scale = scale
+    d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
+    return d
+
+
+def spline_dd_blocks(disp):
+    """make_blocks_spline: (shift int32[n], alpha[n], nblocks)"""
+    disp = np.ascontiguousarray(disp, dtype=np.float64)
+    shift = np.zeros(disp.size, dtype=np.int32); alpha = np.zeros(disp.size); nb = C.c_int(0)
+    _ck(lib().sllb_spline_dd_blocks(C.c_int(disp.size), _p(disp), shift.ctypes.data_as(C.POINTER(C.c_int32)), _p(alpha), C.byref(nb)))
+    return shift, alpha, nb.value
+
+
+def lagrange_dd_blocks(disp, stencil):
+    """make_blocks_lagrange: (box int32[n], nblocks, halo widths (nblocks, 2))"""
+    disp = np.ascontiguousarray(disp, dtype=np.float64)
+    box = np.zeros(disp.size, dtype=np.int32); nb = C.c_int(0); hw = (C.c_int * (2 * stencil + 2))()
+    _ck(lib().sllb_lagrange_dd_blocks(C.c_int(disp.size), C.c_int(stencil), _p(disp), box.ctypes.data_as(C.POINTER(C.c_int32)),
+                                      C.byref(nb), hw))
+    return box, nb.value, np.array(hw[:2 * nb.value]).reshape(-1, 2)
+
+
 class Field:
     def __init__(self, extents=None, handle=None):
         self.owns = handle is None
@@ -225,6 +257,15 @@ class Field:
         d.scale = scale
         d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
         _ck(lib().sllb_advect_axis(self.h, C.c_int(axis), C.c_int(method), C.c_int(order), C.byref(d)))
+
+    def advect_axis_spline_dd(self, axis, values, dsel=(1, 1, 0, 1, 1, 0), scale=1.0, shift=None):
+        """local cubic spline (NUM_TERMS = 15) along an unsplit axis; shift: int32 table indexed like values or None"""
+        d = _disp(self, values, scale, dsel)
+        sh = None
+        if shift is not None:
+            sh = np.ascontiguousarray(shift, dtype=np.int32)
+            assert sh.size == d.nvalues
+        _ck(lib().sllb_advect_axis_spline_dd(self.h, C.c_int(axis), C.byref(d), sh.ctypes.data_as(C.POINTER(C.c_int32)) if sh is not None else None))
 
     def advect_plane(self, values0, dsel0, scale0, values1, dsel1, scale1, rho_scale=None):
         """K1c: spline passes along axes 0 and 1 in one sweep; returns rho (host) when rho_scale is given."""
@@ -516,6 +557,15 @@ class Dd6d:
         d.odiv, d.omod, d.ostr, d.idiv, d.imod, d.istr = [int(v) for v in dsel]
         _ck(lib().sllb_dd6d_advect_axis(self.h, C.c_int(axis), C.c_int(stencil), C.byref(d)))
 
+    def advect_axis_spline(self, axis, values, scale=1.0, dsel=(1, 1, 0, 1, 1, 0), shift=None, hw=(1, 1), on_device=False):
+        d = _disp(self, values, scale, dsel, on_device)
+        sh = None
+        if shift is not None:
+            sh = np.ascontiguousarray(shift, dtype=np.int32)
+        _ck(lib().sllb_dd6d_advect_axis_spline(self.h, C.c_int(axis), C.byref(d),
+                                               sh.ctypes.data_as(C.POINTER(C.c_int32)) if sh is not None else None,
+                                               C.c_int(hw[0]), C.c_int(hw[1])))
+
     def destroy(self):
         if self.h:
             lib().sllb_dd6d_destroy(self.h)
@@ -539,12 +589,13 @@ def dd6d_set_force_halo(on):
 
 class Sim6d:
     def __init__(self, n, v_max, x_max, stencil_x, stencil_v, delta_t, alpha, kx, v_thermal=(1.0, 1.0, 1.0),
-                 time_in_phase=True, comm=None, process_grid=None):
+                 time_in_phase=True, comm=None, process_grid=None, advector=ADVECTOR_FIXED):
         p = Sim6dParams()
         p.n[:] = n; p.v_max = v_max; p.x_max[:] = x_max
         p.stencil_x, p.stencil_v, p.delta_t = stencil_x, stencil_v, delta_t
         p.alpha = alpha; p.kx[:] = kx; p.v_thermal[:] = v_thermal
         p.time_in_phase = 1 if time_in_phase else 0
+        p.advector = advector
         self.h = vp()
         _ck(lib().sllb_sim6d_create_dist(C.byref(p), comm.h if comm is not None else None,
                                          _ints(process_grid) if process_grid is not None else None, C.byref(self.h)))

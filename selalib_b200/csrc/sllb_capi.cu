@@ -426,7 +426,9 @@ int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, cons
     return advect_axis_dev(F, axis, method, order, dd);
 }
 
-static int to_dispdesc(sllb_field_t F, const sllb_disp_t *disp, DevBuf &scratch, DispDesc *dd) {
+} // extern "C"
+namespace sllb {
+int to_dispdesc(const sllb_disp_t *disp, DevBuf &scratch, DispDesc *dd) {
     if (!disp || !disp->values) return fail(SLLB_ERR_INVALID, "displacement: null");
     if (disp->values_on_device) dd->v = disp->values;
     else {
@@ -438,8 +440,88 @@ static int to_dispdesc(sllb_field_t F, const sllb_disp_t *disp, DevBuf &scratch,
     dd->scale = disp->scale;
     dd->odiv = disp->odiv > 0 ? disp->odiv : 1; dd->omod = disp->omod > 0 ? disp->omod : 1; dd->ostr = disp->ostr;
     dd->idiv = disp->idiv > 0 ? disp->idiv : 1; dd->imod = disp->imod > 0 ? disp->imod : 1; dd->istr = disp->istr;
-    (void)F;
     return SLLB_OK;
+}
+// integer shift table of the local-spline advector: HOST int32[n] -> device (kept in F's scratch); NULL stays NULL
+int upload_shift(sllb_field *F, const int32_t *shift, long long n, const int **d_shift) {
+    *d_shift = nullptr;
+    if (!shift) return SLLB_OK;
+    if (n < 1) return fail(SLLB_ERR_INVALID, "shift table: nvalues < 1");
+    SLLB_TRY(F->shift_scratch.ensure((size_t)(n + 1) / 2));
+    SLLB_CUDA(cudaMemcpyAsync(F->shift_scratch.p, shift, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+    *d_shift = reinterpret_cast<const int *>(F->shift_scratch.p);
+    return SLLB_OK;
+}
+} // namespace sllb
+extern "C" {
+/* make_blocks_spline (sll_m_advection_6d_spline_dd_slim.F90:202-287), host only: the reference walks the monotonic
+ * displacement array once and cuts it into blocks of equal integer part; indices with abs(disp) == 0 belong to no
+ * block and stay untouched.  The walk is restated literally (including which block an exactly integer displacement
+ * lands in) so that the per-index shift table drives the kernels exactly like the reference's block loop. */
+int sllb_spline_dd_blocks(int n, const double *disp, int32_t *shift, double *alpha, int *nblocks) {
+    if (n < 1 || !disp || !shift) return fail(SLLB_ERR_INVALID, "spline_dd_blocks: bad arguments");
+    for (int j = 0; j < n; ++j) shift[j] = SLLB_SHIFT_SKIP;
+    auto D = [&](int j) { return disp[j - 1]; }; // 1-based like the reference
+    int bl = 1;
+    if (n > 1 && fabs(D(bl)) == 0.0) bl = bl + 1;
+    const int box1 = (int)floor(D(bl));
+    bl = n;
+    if (n > 1 && fabs(D(bl)) == 0.0) bl = bl - 1;
+    const int box2 = (int)floor(D(bl));
+    const int blocks = abs(box2 - box1) + 1;
+    int j = 1;
+    for (int b = 1; b <= blocks; ++b) {
+        if (j <= n && fabs(D(j)) == 0.0) j = j + 1;
+        const int si = (box1 > box2) ? box1 - b + 1 : box1 + b - 1;
+        const int jstart = j;
+        if (box1 > box2) { while (j <= n && D(j) > (double)si) ++j; }
+        else { while (j <= n && D(j) < (double)(si + 1)) ++j; }
+        const int jend = (j - 1 >= 1 && fabs(D(j - 1)) == 0.0) ? j - 2 : j - 1;
+        for (int k = jstart; k <= jend; ++k) shift[k - 1] = si;
+    }
+    if (alpha) for (int k = 0; k < n; ++k) alpha[k] = disp[k] - floor(disp[k]);
+    if (nblocks) *nblocks = blocks;
+    return SLLB_OK;
+}
+int sllb_lagrange_dd_blocks(int n, int stencil, const double *disp, int32_t *box, int *nblocks, int *halo_width) {
+    if (n < 1 || !disp || !box || stencil < 2 || stencil % 2 != 0) return fail(SLLB_ERR_INVALID, "lagrange_dd_blocks: bad arguments");
+    int nb = 0;
+    SLLB_TRY(sllb_spline_dd_blocks(n, disp, box, nullptr, &nb)); // same walk (:237-283 == spline :219-277)
+    int first = 1, last = n;
+    if (n > 1 && fabs(disp[0]) == 0.0) first = 2;
+    if (n > 1 && fabs(disp[n - 1]) == 0.0) last = n - 1;
+    const int box1 = (int)floor(disp[first - 1]), box2 = (int)floor(disp[last - 1]);
+    for (int b : {box1, box2})
+        if (b < -stencil / 2 || b >= stencil / 2)
+            return fail(SLLB_ERR_INVALID, "lagrange_dd_blocks: displacement too large for the stencil (box outside [-stencil/2, stencil/2))");
+    if (halo_width)
+        for (int b = 0; b < nb; ++b) {
+            const int bx = (box1 > box2) ? box1 - b : box1 + b;
+            halo_width[2 * b] = stencil / 2 - bx - 1;
+            halo_width[2 * b + 1] = stencil / 2 + bx;
+        }
+    if (nblocks) *nblocks = nb;
+    return SLLB_OK;
+}
+/* local cubic spline (NUM_TERMS = 15) along an axis that is NOT split: the ring neighbour is the line itself */
+int sllb_advect_axis_spline_dd(sllb_field_t F, int axis, const sllb_disp_t *disp, const int32_t *shift) {
+    if (!F || axis < 0 || axis >= F->ndim) return fail(SLLB_ERR_INVALID, "advect_axis_spline_dd: bad arguments");
+    SLLB_TRY(require_device());
+    DispDesc dd;
+    SLLB_TRY(to_dispdesc(disp, F->disp_scratch, &dd));
+    const int *d_shift = nullptr;
+    SLLB_TRY(upload_shift(F, shift, disp->nvalues, &d_shift));
+    long long inner = 1, outer = 1;
+    for (int d = 0; d < axis; ++d) inner *= F->ext[d];
+    for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
+    cudaError_t e = launch_spline_dd(F->d, outer, F->ext[axis], inner, dd, d_shift, nullptr, 0, nullptr, 0, nullptr, nullptr,
+                                     g_staging, 0);
+    if (e == cudaErrorInvalidValue) {
+        cudaGetLastError();
+        return fail(SLLB_ERR_UNSUPPORTED, "advect_axis_spline_dd: the local spline needs more than 15 points per line "
+                                          "(SLL_ASSERT_ALWAYS(num_points > NUM_TERMS), sll_m_cubic_spline_halo_1d.F90:79)");
+    }
+    return check_cuda(e, "k_spline_dd launch");
 }
 int sllb_advect_plane(sllb_field_t F, int method, int order, const sllb_disp_t *disp0, const sllb_disp_t *disp1,
                       double rho_scale, double *d_rho) {
@@ -447,8 +529,8 @@ int sllb_advect_plane(sllb_field_t F, int method, int order, const sllb_disp_t *
     if (method != SLLB_METHOD_SPLINE || order != 4) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: cubic splines only");
     SLLB_TRY(require_device());
     DispDesc d0, d1;
-    SLLB_TRY(to_dispdesc(F, disp0, F->disp_scratch, &d0));
-    SLLB_TRY(to_dispdesc(F, disp1, F->disp_scratch2, &d1));
+    SLLB_TRY(to_dispdesc(disp0, F->disp_scratch, &d0));
+    SLLB_TRY(to_dispdesc(disp1, F->disp_scratch2, &d1));
     return advect_plane_dev(F, d0, d1, rho_scale, d_rho);
 }
 

@@ -214,7 +214,10 @@ void sim_bsl_vp_3d3v_cart_dd_slim_init(void **sim, const char *filename) {
     for (int d = 0; d < 3; ++d) c->p.x_max[d] = get_real(nml, "domain_dims", xm[d], 12.5663706144);
     if (get_str(nml, "advect_params", "bc_type", "sll_p_periodic") != "sll_p_periodic") die(fun, "bc_type not implemented (sll_p_periodic only)");
     const std::string itype = get_str(nml, "advect_params", "interpolator_type", "fixed");
-    if (itype != "fixed") die(fun, "Interpolator type not implemented (fixed Lagrange only on the B200 path).");
+    if (itype == "fixed") c->p.advector = SLLB_ADVECTOR_FIXED;
+    else if (itype == "centered") c->p.advector = SLLB_ADVECTOR_CENTERED;
+    else if (itype == "spline" || itype == "splines") c->p.advector = SLLB_ADVECTOR_SPLINE;
+    else die(fun, "Interpolator type not implemented.");
     c->p.stencil_v = get_int(nml, "advect_params", "stencil", 7);
     c->p.stencil_x = get_int(nml, "advect_params", "stencil_x", c->p.stencil_v);
     c->prefix = get_str(nml, "output", "file_prefix", "vp_3d3v_dd");

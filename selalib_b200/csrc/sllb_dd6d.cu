@@ -29,7 +29,10 @@ struct sllb_dd6d {
     // peer path: double-buffered halo arrays of every rank mapped into this process; the pack kernel stores the
     // edge planes straight into the neighbour's halo buffer over NVLink (no send buffer, no NCCL copy)
     bool p2p = false;
-    DevBuf pbuf[4];                       // [parity*2 + side], side 0 = left halo, 1 = right halo
+    DevBuf pbuf[8];                       // [parity*2 + side], side 0 = left halo, 1 = right halo; 4 + same: the
+                                          // local spline's boundary sums per line (bc_left, bc_right)
+    size_t bcap = 0;                      // capacity of each boundary-sum buffer in doubles
+    DevBuf bc_l, bc_r, bc_send_r, bc_send_l; // NCCL / single-rank path of the boundary sums
     size_t pcap = 0;                      // capacity of each in doubles
     std::vector<void *> peers, ipc_opened;
     DevBuf flag;
@@ -112,13 +115,18 @@ int sllb_dd6d_create(sllb_comm_t c, const int global[6], const int procs_in[6], 
                     if (c > cap) cap = c;
                 }
             if (cap > 0) {
-                void *mine[4];
+                size_t bcap = 0; // one value per line of the longest split axis
+                for (int d = 1; d < 6; ++d)
+                    if (D->procs[d] > 1 && (size_t)(D->F->total / D->nw[d]) > bcap) bcap = (size_t)(D->F->total / D->nw[d]);
+                void *mine[8];
                 for (int k = 0; k < 4 && !rc; ++k) { rc = D->pbuf[k].ensure(cap); mine[k] = D->pbuf[k].p; }
+                for (int k = 4; k < 8 && !rc; ++k) { rc = D->pbuf[k].ensure(bcap); mine[k] = D->pbuf[k].p; }
                 if (!rc) rc = D->flag.ensure(2);
                 bool ok = false;
-                if (!rc) rc = peer_map_buffers(D->comm, mine, 4, D->peers, D->ipc_opened, &ok);
+                if (!rc) rc = peer_map_buffers(D->comm, mine, 8, D->peers, D->ipc_opened, &ok);
                 D->p2p = ok;
                 D->pcap = cap;
+                D->bcap = bcap;
             }
         }
     }
@@ -191,8 +199,8 @@ int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) 
         // neighbour: store them there directly.  Buffers alternate between exchanges, so a neighbour that is
         // still reading the previous halo is not disturbed; the all-reduce is the cross-rank barrier.
         const int par = D->parity;
-        double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 4 + par * 2 + 1]);
-        double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 4 + par * 2 + 0]);
+        double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 8 + par * 2 + 1]);
+        double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + par * 2 + 0]);
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, dst_r, 0));
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, dst_l, 0));
         SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
@@ -266,6 +274,64 @@ int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_
     return check_cuda(e, "k_lagrange_halo launch");
 }
 
+/* sll_s_advection_6d_spline_dd_slim_[f]advect_eta{axis+1} (sll_m_advection_6d_spline_dd_slim.F90:291-515,976-1203):
+ *   prepare_exchange on every line (K9p)  ->  bc exchange + halo exchange  ->  finish_boundary_conditions,
+ *   compute_interpolant, eval_disp (K9).  The boundary sums ride on the same barrier as the halo planes. */
+int sllb_dd6d_advect_axis_spline(sllb_dd6d_t D, int axis, const sllb_disp_t *disp, const int32_t *shift, int hw_left,
+                                 int hw_right) {
+    if (!D || !disp || !disp->values) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis_spline: null");
+    if (axis < 0 || axis > 5) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis_spline: bad axis");
+    if (D->procs[axis] == 1 && !g_force_halo) return sllb_advect_axis_spline_dd(D->F, axis, disp, shift);
+    if (axis == 0) return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis_spline: a split contiguous axis (eta1) is not implemented");
+    if (hw_left < 0 || hw_right < 0 || hw_left + hw_right < 1) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis_spline: halo widths must cover shifts -hw_left..hw_right-1");
+    const int np = D->nw[axis];
+    if (np < spline_dd_min_points(hw_left, hw_right))
+        return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis_spline: too few local points for the 15-term boundary series "
+                                          "(SLL_ASSERT_ALWAYS(num_points > NUM_TERMS), sll_m_cubic_spline_halo_1d.F90:79)");
+    const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
+    const size_t nlines = (size_t)(outer * inner);
+    DispDesc dd;
+    SLLB_TRY(to_dispdesc(disp, D->F->disp_scratch, &dd));
+    const int *d_shift = nullptr;
+    SLLB_TRY(upload_shift(D->F, shift, disp->nvalues, &d_shift));
+    const size_t cl = (size_t)(outer * hw_left * inner), cr = (size_t)(outer * hw_right * inner);
+    const bool peer_path = D->p2p && g_halo_p2p && D->procs[axis] > 1 && cl <= D->pcap && cr <= D->pcap && nlines <= D->bcap;
+    const double *bc_l = nullptr, *bc_r = nullptr;
+    if (peer_path) {
+        // my top cells feed the d_0 of my RIGHT neighbour (its bc_left), my bottom cells the c_np2 of my LEFT
+        // neighbour (its bc_right): K9p stores them there; the halo exchange below ends with the barrier
+        const int par = D->parity;
+        double *dst_for_right = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + 4 + par * 2 + 0]);
+        double *dst_for_left = static_cast<double *>(D->peers[(size_t)D->left[axis] * 8 + 4 + par * 2 + 1]);
+        SLLB_CUDA(launch_spline_dd_prepare(D->F->d, outer, np, inner, dd, d_shift, hw_left, hw_right, dst_for_right, dst_for_left, 0));
+        bc_l = D->pbuf[4 + par * 2 + 0].p; bc_r = D->pbuf[4 + par * 2 + 1].p;
+        SLLB_TRY(sllb_dd6d_halo_exchange(D, axis, hw_left, hw_right));
+    } else if (D->procs[axis] == 1) {
+        SLLB_TRY(D->bc_l.ensure(nlines)); SLLB_TRY(D->bc_r.ensure(nlines));
+        SLLB_CUDA(launch_spline_dd_prepare(D->F->d, outer, np, inner, dd, d_shift, hw_left, hw_right, D->bc_l.p, D->bc_r.p, 0));
+        bc_l = D->bc_l.p; bc_r = D->bc_r.p;
+        SLLB_TRY(sllb_dd6d_halo_exchange(D, axis, hw_left, hw_right));
+    } else {
+        SLLB_TRY(D->bc_l.ensure(nlines)); SLLB_TRY(D->bc_r.ensure(nlines));
+        SLLB_TRY(D->bc_send_r.ensure(nlines)); SLLB_TRY(D->bc_send_l.ensure(nlines));
+        SLLB_CUDA(launch_spline_dd_prepare(D->F->d, outer, np, inner, dd, d_shift, hw_left, hw_right, D->bc_send_r.p, D->bc_send_l.p, 0));
+        ncclComm_t cm = D->comm->comm;
+        SLLB_NCCL(ncclGroupStart());
+        SLLB_NCCL(ncclSend(D->bc_send_r.p, nlines, ncclDouble, D->right[axis], cm, 0));
+        SLLB_NCCL(ncclRecv(D->bc_l.p, nlines, ncclDouble, D->left[axis], cm, 0));
+        SLLB_NCCL(ncclSend(D->bc_send_l.p, nlines, ncclDouble, D->left[axis], cm, 0));
+        SLLB_NCCL(ncclRecv(D->bc_r.p, nlines, ncclDouble, D->right[axis], cm, 0));
+        SLLB_NCCL(ncclGroupEnd());
+        bc_l = D->bc_l.p; bc_r = D->bc_r.p;
+        SLLB_TRY(sllb_dd6d_halo_exchange(D, axis, hw_left, hw_right));
+    }
+    // hw_left may be 0 (all shifts >= 0): the kernel still wants a valid pointer
+    const double *hl = D->cur_l ? D->cur_l : D->cur_r;
+    cudaError_t e = launch_spline_dd(D->F->d, outer, np, inner, dd, d_shift, hl, hw_left, D->cur_r, hw_right, bc_l, bc_r, g_staging, 0);
+    if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis_spline: block size not implemented"); }
+    return check_cuda(e, "k_spline_dd_strided launch");
+}
+
 } // extern "C"
 
 /* ------------------------------------------------------------------------------------------ */
@@ -282,6 +348,11 @@ struct sllb_sim6d {
     bool started = false;
     int itime = 0;
     double halo_ms = 0.0, advect_ms = 0.0;
+    // spline / centred advectors: per x axis the displacement -v dt/dx of the local velocity indices, as the reference
+    // stores it (sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:590-592), and the block table of make_blocks_spline
+    std::vector<double> disp_x[3];
+    std::vector<int32_t> shift_x[3];
+    int hw_x[3][2] = {{0, 1}, {0, 1}, {0, 1}}; // halo widths that cover every block's shift: max(-si), max(si+1)
 };
 __global__ void k_landau6d(double *f, Ext6 n, Ext6 lo, double d0, double d1, double d2, double d3, double d4, double d5,
                            double vmax, double factor, double alpha, double k0, double k1, double k2, double t0, double t1,
@@ -377,6 +448,28 @@ int sllb_sim6d_create_dist(const sllb_sim6d_params_t *p, sllb_comm_t comm, const
                                      p->alpha, p->kx[0], p->kx[1], p->kx[2], p->v_thermal[0], p->v_thermal[1], p->v_thermal[2]);
         rc = check_cuda(cudaGetLastError(), "k_landau6d");
     }
+    if (!rc && p->advector != SLLB_ADVECTOR_FIXED && p->advector != SLLB_ADVECTOR_CENTERED && p->advector != SLLB_ADVECTOR_SPLINE)
+        rc = fail(SLLB_ERR_UNSUPPORTED, "sim6d_create: Interpolator type not implemented.");
+    if (!rc && p->advector != SLLB_ADVECTOR_FIXED)
+        for (int d = 0; d < 3 && !rc; ++d) {
+            const int nv = S->D->nw[d + 3];
+            S->disp_x[d].resize(nv); S->shift_x[d].resize(nv);
+            for (int l = 0; l < nv; ++l) {
+                const double v = S->emin[d + 3] + S->de[d + 3] * (double)(l + S->D->mn[d + 3]); // sll_s_set_local_grid
+                S->disp_x[d][l] = -v * p->delta_t / S->de[d];
+            }
+            if (p->advector == SLLB_ADVECTOR_SPLINE) rc = sllb_spline_dd_blocks(nv, S->disp_x[d].data(), S->shift_x[d].data(), nullptr, nullptr);
+            else rc = sllb_lagrange_dd_blocks(nv, p->stencil_x, S->disp_x[d].data(), S->shift_x[d].data(), nullptr, nullptr);
+            int hl = 0, hr = 0;
+            for (int l = 0; l < nv; ++l) {
+                const int si = S->shift_x[d][l];
+                if (si == SLLB_SHIFT_SKIP) continue;
+                if (-si > hl) hl = -si;
+                if (si + 1 > hr) hr = si + 1;
+            }
+            if (hl + hr < 1) hr = 1;
+            S->hw_x[d][0] = hl; S->hw_x[d][1] = hr;
+        }
     if (!rc) rc = sllb_sim6d_fields(S);
     if (rc) { sllb_sim6d_destroy(S); return rc; }
     *Sout = S;
@@ -403,6 +496,21 @@ int sllb_sim6d_decomposition(sllb_sim6d_t S, sllb_dd6d_t *D) {
 /* advect_x (:817-865): eta1..3 with disp_eta = -v*dt/dx (:590-592); x is not split, local periodic wrap */
 int sllb_sim6d_advect_x(sllb_sim6d_t S) {
     if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_x: null");
+    if (S->p.advector != SLLB_ADVECTOR_FIXED) {
+        // fadvect_eta1..3 (:866-880): the displacement array of the conjugate velocity axis, block by block in the
+        // reference, line by line here (the block only fixes the integer part, carried by the shift table)
+        for (int d = 0; d < 3; ++d) {
+            sllb_disp_t ds;
+            memset(&ds, 0, sizeof(ds));
+            ds.values = S->disp_x[d].data(); ds.nvalues = (int64_t)S->disp_x[d].size(); ds.values_on_device = 0; ds.scale = 1.0;
+            long long stride = 1;
+            for (int a = d + 1; a < d + 3; ++a) stride *= S->D->nw[a];
+            ds.odiv = stride; ds.omod = S->D->nw[d + 3]; ds.ostr = 1; ds.idiv = 1; ds.imod = 1; ds.istr = 0;
+            if (S->p.advector == SLLB_ADVECTOR_SPLINE) SLLB_TRY(sllb_dd6d_advect_axis_spline(S->D, d, &ds, S->shift_x[d].data(), S->hw_x[d][0], S->hw_x[d][1]));
+            else SLLB_TRY(sllb_advect_axis(S->F, d, SLLB_METHOD_LAGRANGE_CENTERED, S->p.stencil_x, &ds));
+        }
+        return SLLB_OK;
+    }
     for (int d = 0; d < 3; ++d)
         SLLB_TRY(sllb_advect_axis_affine(S->F, d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_x, d + 3,
                                          S->emin[d + 3] + S->D->mn[d + 3] * S->de[d + 3], S->de[d + 3], -S->p.delta_t / S->de[d]));
@@ -418,7 +526,9 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
         memset(&ds, 0, sizeof(ds));
         ds.values = E[d]; ds.nvalues = nx3; ds.values_on_device = 1; ds.scale = dt / S->de[3 + d];
         ds.odiv = ds.omod = 1; ds.ostr = 0; ds.idiv = 1; ds.imod = nx3; ds.istr = 1;
-        SLLB_TRY(sllb_dd6d_advect_axis(S->D, 3 + d, S->p.stencil_v, &ds));
+        // splines: halo of one plane on both sides, shifts 0 and -1 (:1082-1087); else fixed Lagrange
+        if (S->p.advector == SLLB_ADVECTOR_SPLINE) SLLB_TRY(sllb_dd6d_advect_axis_spline(S->D, 3 + d, &ds, nullptr, 1, 1));
+        else SLLB_TRY(sllb_dd6d_advect_axis(S->D, 3 + d, S->p.stencil_v, &ds));
         if (S->D->procs[3 + d] > 1) S->halo_ms += S->D->exch_ms;
     }
     return SLLB_OK;

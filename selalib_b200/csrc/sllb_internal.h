@@ -66,6 +66,7 @@ struct sllb_field {
     sllb::DevBuf red_scratch;    // reduction partials
     sllb::DevBuf stage;          // upload/download staging with duplicates
     sllb::DevBuf rows;           // diagnostics row sums
+    sllb::DevBuf shift_scratch;  // uploaded integer shift table (local spline)
 };
 
 struct sllb_comm {
@@ -98,5 +99,7 @@ int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv
 int make_field_disp(sllb_field *F, int axis, const double *d_field, int nfield_axes, double scale, DispDesc *dd);
 int field_alloc(int ndim, const int *ext, sllb_field **F);
 int field_wrap(int ndim, const int *ext, double *d, sllb_field **F);
+int to_dispdesc(const sllb_disp_t *disp, DevBuf &scratch, DispDesc *dd);
+int upload_shift(sllb_field *F, const int32_t *shift, long long n, const int **d_shift);
 int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out);
 } // namespace sllb

@@ -12,6 +12,7 @@
 // mbarrier, or cp.async when the tile is not 16-byte tileable), solves / evaluates in the block and
 // writes each point once: 16 B of HBM traffic per point per pass.  All arithmetic is fp64.
 #include "sllb_kernels.cuh"
+#include "sllb_device.cuh"
 #include <cstdio>
 #include <cstring>
 
@@ -20,51 +21,8 @@ namespace sllb {
 static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 void launch_count_reset() { g_launches = 0; }
+void count_launch() { ++g_launches; }
 #define COUNT_LAUNCH() (++g_launches)
-
-// ------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + 1D bulk TMA (cp.async.bulk) + cp.async
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy (TMA engine, SASS UBLKCP), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-// streaming store: written once, not re-read by this pass
-__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
-
-__device__ __forceinline__ double disp_of(const DispDesc &d, long long o, long long in) {
-    return d.scale * d.v[((o / d.odiv) % d.omod) * d.ostr + ((in / d.idiv) % d.imod) * d.istr];
-}
 
 // ------------------------------------------------------------------------------------------------
 // Where a pass writes its output.  In place: point iout of line (o, in) goes to f[(o*N + iout)*inner + in].

@@ -45,6 +45,22 @@ cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts,
 // K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]
 cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
                                  long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st);
+// K9: local cubic spline with halo cells (sll_m_cubic_spline_halo_1d, NUM_TERMS = 15) on every line of f viewed as
+// [outer][np][inner], in place.  halo_l == nullptr: the axis is not split, the ring neighbour is the line itself
+// (periodic wrap, one kernel).  Otherwise halo_l / halo_r are [outer][hwl|hwr][inner] planes of the neighbours and
+// bc_l / bc_r [outer][inner] the neighbours' parts of the two boundary sums (launch_spline_dd_prepare on their side).
+// d_shift: optional DEVICE table of integer shifts indexed like dd.v (INT_MIN = leave the line untouched);
+// nullptr = floor(displacement).  cudaErrorInvalidValue: too few points (np <= 15, or a neighbour sum would leave
+// the neighbour's block), cudaErrorNotSupported: split contiguous axis.
+int spline_dd_min_points(int hwl, int hwr);
+cudaError_t launch_spline_dd(double *f, long long outer, int np, long long inner, const DispDesc &dd, const int *d_shift,
+                             const double *halo_l, int hwl, const double *halo_r, int hwr, const double *bc_l,
+                             const double *bc_r, int staging, cudaStream_t st);
+// K9p: for_right[line] / for_left[line] = the parts of the right neighbour's d_0 sum / the left neighbour's c_np2 sum
+// made of MY cells (sll_s_cubic_spline_halo_1d_prepare_exchange)
+cudaError_t launch_spline_dd_prepare(const double *f, long long outer, int np, long long inner, const DispDesc &dd,
+                                     const int *d_shift, int hwl, int hwr, double *for_right, double *for_left,
+                                     cudaStream_t st);
 // K7: buf[o][j][in] = f[o][j0+j][in], j < hw
 cudaError_t launch_halo_pack(const double *f, long long outer, int n, long long inner, int j0, int hw, double *buf,
                              cudaStream_t st);

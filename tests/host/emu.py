@@ -1,0 +1,33 @@
+"""Builds and loads tests/host/spline15_host.cpp: the per-line device functions of K9 compiled for the host
+(test infrastructure; lets the CPU suite check the CUDA path's arithmetic against the oracle)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libspline15_host.so")
+        deps = [os.path.join(_HERE, "spline15_host.cpp"),
+                os.path.join(_HERE, "..", "..", "selalib_b200", "csrc", "sllb_spline15.cuh")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, deps[0]])
+        _LIB = C.CDLL(so)
+        _LIB.emu_spline_dd_line.restype = C.c_int
+    return _LIB
+
+
+def spline_dd_line(line, nblk, si, alpha, hwl=1, hwr=1, mode=0):
+    line = np.ascontiguousarray(line, dtype=np.float64)
+    out = np.empty_like(line)
+    dp = C.POINTER(C.c_double)
+    rc = lib().emu_spline_dd_line(line.ctypes.data_as(dp), out.ctypes.data_as(dp), C.c_int(line.size), C.c_int(nblk),
+                                  C.c_int(si), C.c_double(alpha), C.c_int(hwl), C.c_int(hwr), C.c_int(mode))
+    assert rc == 0, rc
+    return out

@@ -1,0 +1,57 @@
+// Host emulation of K9 (selalib_b200/csrc/sllb_spline15.cuh compiled with g++): TEST INFRASTRUCTURE.
+// Emulates, line by line, what k_spline_dd_prepare + k_spline_dd_strided / k_spline_dd_contig do with the shared-memory
+// tile (pitch 1 here), for an axis cut into nblk ring pieces, so the per-line arithmetic of the CUDA path can be checked
+// against the oracle in the CPU test suite.  The GPU parity tests check the kernels themselves.
+#define SLLB_HOST_EMULATION 1
+#include "../../selalib_b200/csrc/sllb_spline15.cuh"
+
+#include <climits>
+#include <cstring>
+#include <vector>
+
+using namespace sllb;
+
+static void init_consts() {
+    static bool ready = false;
+    if (ready) return;
+    const double a = sqrt((2.0 + sqrt(3.0)) / 6.0), b = sqrt((2.0 - sqrt(3.0)) / 6.0);
+    for (int i = 0; i <= SLLB_HALO_TERMS; ++i) c_hpw[i] = pow(-(b / a), (double)i);
+    ready = true;
+}
+
+extern "C" {
+// line of n = nblk*np points; mode 0: strided kernel (TO_GLOBAL), 1: contiguous kernel (parked results + rotation).
+// nblk == 1 -> WRAP kernels; nblk > 1 -> prepare + halo rows + non-WRAP kernel per piece.
+int emu_spline_dd_line(const double *lin, double *lout, int n, int nblk, int si, double alpha, int hwl, int hwr, int mode) {
+    init_consts();
+    const int np = n / nblk;
+    if (si == INT_MIN) { memcpy(lout, lin, sizeof(double) * n); return 0; }
+    if (nblk == 1) {
+        std::vector<double> tile(lin, lin + n);
+        double sd, sc;
+        spline15_sums<1, true>(tile.data(), n, si, 0.0, 0.0, &sd, &sc);
+        if (mode == 0) spline15_line<1, true, true>(tile.data(), n, si, alpha, sd, sc, lout, 1);
+        else {
+            spline15_line<1, true, false>(tile.data(), n, si, alpha, sd, sc, nullptr, 0);
+            const int r = wrap_idx(si, n);
+            for (int i = 0; i < n; ++i) { int kc = i + r; if (kc >= n) kc -= n; lout[i] = tile[kc]; }
+        }
+        return 0;
+    }
+    if (mode != 0) return -1;
+    if (si < -hwl || si > hwr - 1) return -2;
+    std::vector<double> for_right(nblk), for_left(nblk);
+    for (int r = 0; r < nblk; ++r) spline15_prepare(lin + (long)r * np, 1, np, si, &for_right[r], &for_left[r]);
+    for (int r = 0; r < nblk; ++r) {
+        const int left = (r + nblk - 1) % nblk, right = (r + 1) % nblk;
+        std::vector<double> tile(hwl + np + hwr);
+        for (int j = 0; j < hwl; ++j) tile[j] = lin[(long)left * np + np - hwl + j];       // last planes of the left neighbour
+        for (int j = 0; j < np; ++j) tile[hwl + j] = lin[(long)r * np + j];
+        for (int j = 0; j < hwr; ++j) tile[hwl + np + j] = lin[(long)right * np + j];      // first planes of the right neighbour
+        double *x0 = tile.data() + hwl, sd, sc;
+        spline15_sums<1, false>(x0, np, si, for_right[left], for_left[right], &sd, &sc);
+        spline15_line<1, false, true>(x0, np, si, alpha, sd, sc, lout + (long)r * np, 1);
+    }
+    return 0;
+}
+}

@@ -153,6 +153,34 @@ def main():
             res["sim6d_vs_golden"] = e_gold
             ok = ok and e_gold < 5e-7
 
+    # 3b. local splines (sll_t_advection_6d_spline_dd_slim): the P-rank result depends on the decomposition through the
+    #     15-term boundary series; it must match the oracle's emulation of exactly this process grid to 1e-12, through
+    #     peer stores and through ncclSend/ncclRecv
+    from oracle import orc
+    pg = sb.set_process_grid(world)
+    ns = [16, 16, 16] + [18 * pg[d] for d in (3, 4, 5)]   # > 15 + 2 local points along every split axis
+    sargs = (ns, 6.0, [4 * np.pi] * 3, 3, 3, 0.05, 0.01, [0.5] * 3)
+    for p2p in (True, False):
+        sb.dd6d_set_halo_p2p(p2p)
+        SS = sb.Sim6d(*sargs, comm=comm, advector=sb.ADVECTOR_SPLINE)
+        lay = SS.layout()
+        rs = SS.run(2)
+        fs = SS.field().download()
+        SS.destroy()
+        if rank == 0 and p2p:
+            orows, of = orc.sim6d(ns, 6.0, [4 * np.pi] * 3, 3, 3, 0.05, 2, 0.01, [0.5] * 3, want_f=True, advector=2,
+                                  vblk=lay["procs"][3:])
+            np.save("/tmp/_sllb_spline_of.npy", of); np.save("/tmp/_sllb_spline_or.npy", orows)
+        dist.barrier()
+        of = np.load("/tmp/_sllb_spline_of.npy"); orows = np.load("/tmp/_sllb_spline_or.npy")
+        sls = tuple(slice(lay["mn"][d], lay["mn"][d] + lay["nw"][d]) for d in range(6))
+        e_f = float(np.abs(fs - of[sls]).max() / np.abs(of).max())
+        e_r = float(np.abs(rs[:, [1, 2, 3, 4, 5, 6, 7, 11, 12, 13]] / orows[:, [1, 2, 3, 4, 5, 6, 7, 11, 12, 13]] - 1).max())
+        res["sim6d_spline_f_vs_oracle_" + ("p2p" if p2p else "nccl")] = e_f
+        res["sim6d_spline_rows_vs_oracle_" + ("p2p" if p2p else "nccl")] = e_r
+        ok = ok and e_f < 1e-11 and e_r < 1e-9
+    sb.dd6d_set_halo_p2p(True)
+
     # 4. 2D2V: P ranks vs single GPU
     a4 = ([32, 32, 32, 32], [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1)
     S1 = sb.Sim4d(*a4)

@@ -117,3 +117,32 @@ def test_compat6d_check_reads_reference_format(tmp_path):
     np.savetxt(bad, rows)
     assert lib.sllb_sim6d_compat_check(gold.encode(), str(bad).encode()) != 0
     assert lib.sllb_sim6d_compat_check(gold.encode(), str(tmp_path / "missing.dat").encode()) != 0
+
+
+def test_spline_dd_blocks_host_plan():
+    """sllb_spline_dd_blocks / sllb_lagrange_dd_blocks (host only) against the literal restatement of
+    make_blocks_spline (sll_m_advection_6d_spline_dd_slim.F90:202-287) and make_blocks_lagrange
+    (sll_m_advection_6d_lagrange_dd_slim.F90:202-286)"""
+    from oracle import orc
+    rng = np.random.default_rng(20261017)
+    for n in (16, 32, 33):
+        v = -6.0 + 12.0 / n * np.arange(n)
+        for fac in (0.04, 0.2, 0.45, -0.3, 0.25):      # 0.25: displacements that are exactly integer
+            disp = -v * fac
+            shift, alpha, nb = sb.spline_dd_blocks(disp)
+            oshift, oalpha, onb = orc.make_blocks_spline(disp)
+            assert np.array_equal(shift, oshift) and nb == onb
+            assert np.array_equal(alpha, oalpha)
+    # monotonic random displacements without zeros
+    disp = np.sort(rng.uniform(-2.7, 1.9, 40))
+    for d in (disp, disp[::-1].copy()):
+        shift, _, nb = sb.spline_dd_blocks(d)
+        oshift, _, onb = orc.make_blocks_spline(d)
+        assert np.array_equal(shift, oshift) and nb == onb
+    # centred Lagrange: halo widths stencil/2 - box - 1, stencil/2 + box per block (:239-240,257-258)
+    v = -6.0 + 12.0 / 32 * np.arange(32)
+    box, nb, hw = sb.lagrange_dd_blocks(-v * 0.3, 6)
+    assert nb == 4 and np.array_equal(hw, [[1, 4], [2, 3], [3, 2], [4, 1]])
+    assert box[16] == sb.SHIFT_SKIP and box[0] == 1 and box[-1] == -2
+    with pytest.raises(sb.SllbError):
+        sb.lagrange_dd_blocks(-v * 0.3, 2)          # displacement leaves [-stencil/2, stencil/2)
