@@ -292,5 +292,6 @@ def spline_dd_advect_axis(f, axis, nblk, disp, dsel, shifts=None):
     rc = lib().orc_spline_dd_advect_axis(_p(f), L(outer), C.c_int(shape[axis]), L(inner), C.c_int(nblk), _p(disp),
                                          sh.ctypes.data_as(ip) if sh is not None else None, *[L(int(v)) for v in dsel])
     if rc != 0:
-        raise ValueError("local spline needs more than 15 points per piece")
+        raise ValueError("local spline: too few points per piece for the 15-term boundary series (np > 15, np >= 16 - si, "
+                         "np >= 17 + si)")
     return f

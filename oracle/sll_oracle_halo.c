@@ -201,6 +201,7 @@ int orc_spline_dd_advect_axis(double *f, long outer, int n, long inner, int nblk
     if (nblk < 1 || n % nblk != 0 || n / nblk <= HALO_NUM_TERMS) return -1; /* SLL_ASSERT_ALWAYS(num_points > NUM_TERMS) */
     halo_consts();
     const int np = n / nblk;
+    int bad = 0;
 #pragma omp parallel
     {
         double *lin = (double *)malloc(sizeof(double) * (2 * (size_t)n + 2 * nblk + 3 * (np + 3) + 8));
@@ -213,6 +214,10 @@ int orc_spline_dd_advect_axis(double *f, long outer, int n, long inner, int nblk
                 double dc = dvals[idx];
                 int si = shifts ? shifts[idx] : (int)floor(dc);
                 if (si == ORC_SKIP) continue;
+                /* the neighbour sums must stay inside the neighbour's piece: prepare_exchange reads fdata(np+si-15)
+                 * and fdata(2+si+15) (:83-103); the reference only asserts np > 15 and reads out of bounds beyond
+                 * that, so such lines are refused here instead of being compared against garbage */
+                if (np < 16 - si || np < 17 + si) { bad = 1; continue; }
                 double alpha = dc - floor(dc);
                 for (int i = 0; i < n; ++i) lin[i] = base[(long)i * inner];
                 halo_line(lin, lout, n, nblk, si, alpha, work);
@@ -220,5 +225,5 @@ int orc_spline_dd_advect_axis(double *f, long outer, int n, long inner, int nblk
             }
         free(lin);
     }
-    return 0;
+    return bad ? -3 : 0;
 }

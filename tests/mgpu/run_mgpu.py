@@ -158,7 +158,7 @@ def main():
     #     peer stores and through ncclSend/ncclRecv
     from oracle import orc
     pg = sb.set_process_grid(world)
-    ns = [16, 16, 16] + [18 * pg[d] for d in (3, 4, 5)]   # > 15 + 2 local points along every split axis
+    ns = [18, 18, 18] + [18 * pg[d] for d in (3, 4, 5)]   # > 15 + 2 local points along every split axis
     sargs = (ns, 6.0, [4 * np.pi] * 3, 3, 3, 0.05, 0.01, [0.5] * 3)
     for p2p in (True, False):
         sb.dd6d_set_halo_p2p(p2p)

@@ -100,6 +100,10 @@ def test_too_few_points_rejected():
     f = np.asfortranarray(RNG.standard_normal((2, 30, 2)))
     with pytest.raises(ValueError):
         orc.spline_dd_advect_axis(f, 1, 2, np.zeros(2) + 0.3, (1, 1, 0, 1, 2, 1))
+    f = np.asfortranarray(RNG.standard_normal((2, 18, 2)))
+    orc.spline_dd_advect_axis(f, 1, 1, np.zeros(2) - 1.7, (1, 1, 0, 1, 2, 1))       # si = -2: 18 >= 16 + 2
+    with pytest.raises(ValueError):
+        orc.spline_dd_advect_axis(f, 1, 1, np.zeros(2) - 2.7, (1, 1, 0, 1, 2, 1))   # si = -3: out of bounds in the reference
 
 
 # ---- the CUDA path's per-line functions (sllb_spline15.cuh) compiled for the host, against the oracle -------------
