@@ -18,7 +18,7 @@ ip = C.POINTER(C.c_int)
 
 def build(force=False):
     so = os.path.join(_HERE, "liborc.so")
-    srcs = [os.path.join(_HERE, n) for n in ("sll_oracle.c", "sll_oracle_halo.c", "Makefile")]
+    srcs = [os.path.join(_HERE, n) for n in ("sll_oracle.c", "sll_oracle_halo.c", "sll_oracle_split.c", "Makefile")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return so
@@ -208,14 +208,60 @@ def sim6d(n, v_max, xmax, stencil_x, stencil_v, delta_t, nsteps, alpha, kx, vth=
     return (rows, f) if want_f else rows
 
 
-def sim4d(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split=0, method=0, order=4, want_f=False):
+SPLIT_CASES = ["SLL_STRANG_VTV", "SLL_STRANG_TVT", "SLL_LIE_TV", "SLL_LIE_VT", "SLL_TRIPLE_JUMP_TVT", "SLL_TRIPLE_JUMP_VTV",
+               "SLL_ORDER6_VTV", "SLL_ORDER6_TVT", "SLL_ORDER6VP_TVT", "SLL_ORDER6VP_VTV", "SLL_ORDER6VPnew_TVT",
+               "SLL_ORDER6VPnew1_VTV", "SLL_ORDER6VPnew2_VTV", "SLL_ORDER6VP2D_VTV", "SLL_ORDER6VPOT_VTV",
+               "SLL_ORDER6VPOTnew1_VTV", "SLL_ORDER6VPOTnew2_VTV", "SLL_ORDER6VPOTnew3_VTV"]
+
+
+def splitting_coeff(split, dt):
+    """(steps, split_begin_T, dim_split_V) of sll_f_new_time_splitting_coeff for case number / name `split`"""
+    if isinstance(split, str):
+        split = SPLIT_CASES.index(split)
+    s = np.zeros(32); nb = C.c_int(); bt = C.c_int(); dv = C.c_int()
+    lib().orc_splitting_coeff.restype = C.c_int
+    rc = lib().orc_splitting_coeff(C.c_int(split), C.c_double(dt), _p(s), C.byref(nb), C.byref(bt), C.byref(dv))
+    if rc != 0:
+        raise ValueError("split_case not defined")
+    nT = (nb.value + (1 if bt.value else 0)) // 2
+    nV = nb.value - nT
+    return s[:nT + nV * dv.value].copy(), bool(bt.value), dv.value
+
+
+def compute_w_hermite(r, s):
+    w = np.zeros(s - r + 1)
+    lib().orc_compute_w_hermite(C.c_int(r), C.c_int(s), _p(w))
+    return w
+
+
+def compute_jacobian(E1, E2, factor, r=-2, s=2):
+    E1 = np.asfortranarray(E1, dtype=np.float64); E2 = np.asfortranarray(E2, dtype=np.float64)
+    jac = np.zeros_like(E1, order="F")
+    lib().orc_compute_jacobian(_p(E1), _p(E2), C.c_int(E1.shape[0] - 1), C.c_int(E1.shape[1] - 1), C.c_double(factor),
+                               C.c_int(r), C.c_int(s), _p(jac))
+    return jac
+
+
+def sim4d(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split=0, method=0, order=4, want_f=False, stencil=(-2, 2),
+          want_jac=False):
+    """split: case number (0 Strang VTV, 1 Strang TVT, 2 Lie TV, ... see SPLIT_CASES) or the namelist's name"""
+    if isinstance(split, str):
+        split = SPLIT_CASES.index(split)
     rows = np.zeros((nsteps + 1, 6))
+    jac = np.zeros((nsteps + 1, 2))
     f = np.zeros(tuple(c + 1 for c in nc), order="F") if want_f else None
-    rc = lib().orc_sim4d_run((C.c_int * 4)(*nc), (C.c_double * 4)(*xmin), (C.c_double * 4)(*xmax), C.c_double(kx1),
-                             C.c_double(kx2), C.c_double(eps), C.c_double(dt), C.c_int(nsteps), C.c_int(split),
-                             C.c_int(method), C.c_int(order), _p(rows), _p(f) if want_f else None)
-    assert rc == 0
-    return (rows, f) if want_f else rows
+    lib().orc_sim4d_run_ex.restype = C.c_int
+    rc = lib().orc_sim4d_run_ex((C.c_int * 4)(*nc), (C.c_double * 4)(*xmin), (C.c_double * 4)(*xmax), C.c_double(kx1),
+                                C.c_double(kx2), C.c_double(eps), C.c_double(dt), C.c_int(nsteps), C.c_int(split),
+                                C.c_int(method), C.c_int(order), _p(rows), _p(f) if want_f else None,
+                                C.c_int(stencil[0]), C.c_int(stencil[1]), _p(jac))
+    assert rc == 0, rc
+    out = (rows,)
+    if want_f:
+        out += (f,)
+    if want_jac:
+        out += (jac,)
+    return out if len(out) > 1 else rows
 
 
 def sim2d(nc_x1, nc_x2, x1_min, x1_max, x2_min, x2_max, init, kmode, eps, dt, nsteps, method=0, order=4,

@@ -1104,16 +1104,29 @@ static void advect_dup_line(int method, int order, int nc, double xmin, double x
     }
 }
 
+int orc_splitting_coeff(int split, double dt, double *s, int *nb_split_step, int *split_begin_T, int *dim_split_V);
+void orc_compute_jacobian(const double *E1, const double *E2, int nc1, int nc2, double factor, int r, int s, double *jac);
+int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
+                     double eps, double dt, int nsteps, int split, int method, int order, double *rows,
+                     double *f_out, int stencil_r, int stencil_s, double *jac_rows);
 int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
                   double eps, double dt, int nsteps, int split, int method, int order, double *rows,
                   double *f_out) {
+    return orc_sim4d_run_ex(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split, method, order, rows, f_out, -2, 2, NULL);
+}
+/* split: case numbering of sll_oracle_split.c (0 Strang VTV ... 17); stencil_r/s: finite-difference stencil of
+ * compute_jacobian (namelist defaults -2, 2, :366-367); jac_rows (may be NULL): (nsteps+1) x 2 = thdiag columns 6, 7
+ * (max|jacobian_E|, nrj_jac) */
+int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
+                     double eps, double dt, int nsteps, int split, int method, int order, double *rows,
+                     double *f_out, int stencil_r, int stencil_s, double *jac_rows) {
     int np[4]; long ntot = 1;
     double delta[4];
     for (int d = 0; d < 4; ++d) { np[d] = nc[d] + 1; ntot *= np[d]; delta[d] = (xmax[d] - xmin[d]) / (double)nc[d]; }
     double *f = (double *)malloc(sizeof(double) * ntot);
     long n12 = (long)np[0] * np[1];
-    double *rho = (double *)malloc(sizeof(double) * n12 * 3);
-    double *E1 = rho + n12, *E2 = E1 + n12;
+    double *rho = (double *)malloc(sizeof(double) * n12 * 6);
+    double *E1 = rho + n12, *E2 = E1 + n12, *jacE = E2 + n12, *K1 = jacE + n12, *K2 = K1 + n12;
     if (!f || !rho) return -1;
 #define F4D(a, b, c, d) f[(a) + (long)np[0] * ((b) + (long)np[1] * ((c) + (long)np[2] * (d)))]
     /* sll_f_landau_mode_initializer_4d, sll_m_common_array_initializers.F90:948-993 */
@@ -1126,15 +1139,22 @@ int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], d
             F4D(i1, i2, i3, i4) = (1.0 / (2.0 * ORC_PI)) * factor1 * exp(-0.5 * (vx * vx + vy * vy));
         }
     }
-    double steps[3]; int nsub; int beginT;
-    if (split == 0) { steps[0] = 0.5; steps[1] = 1.0; steps[2] = 0.5; nsub = 3; beginT = 0; }
-    else if (split == 1) { steps[0] = 0.5; steps[1] = 1.0; steps[2] = 0.5; nsub = 3; beginT = 1; }
-    else { steps[0] = 1.0; steps[1] = 1.0; nsub = 2; beginT = 1; }
-    double nrj = 0;
+    double steps[32]; int nsub; int beginT; int dimV;
+    if (orc_splitting_coeff(split, dt, steps, &nsub, &beginT, &dimV)) return -2;
+    double nrj = 0, nrj_jac = 0, jac_max = 0;
+    /* fields of a V stage (:1110-1126): E from rho, jacobian_E from E, and with dim_split_V == 2 the second field pair
+     * from the Poisson solve of jacobian_E */
 #define FIELD4() do { orc_reduction_4d_to_2d_direction34(f, np[0], np[1], np[2], np[3], delta[2], delta[3], rho); \
         orc_poisson_2d_periodic_solve_e(nc[0], nc[1], xmin[0], xmax[0], xmin[1], xmax[1], rho, np[0], np[1], E1, E2, NULL); \
-        nrj = 0; for (long i = 0; i < n12; ++i) nrj += E1[i] * E1[i] + E2[i] * E2[i]; nrj *= delta[0] * delta[1]; } while (0)
+        nrj = 0; for (long i = 0; i < n12; ++i) nrj += E1[i] * E1[i] + E2[i] * E2[i]; nrj *= delta[0] * delta[1]; \
+        orc_compute_jacobian(E1, E2, nc[0], nc[1], 4.0 / (delta[0] * delta[1]), stencil_r, stencil_s, jacE); \
+        jac_max = 0; for (long i = 0; i < n12; ++i) if (fabs(jacE[i]) > jac_max) jac_max = fabs(jacE[i]); \
+        nrj_jac = 0; \
+        if (dimV == 2) { orc_poisson_2d_periodic_solve_e(nc[0], nc[1], xmin[0], xmax[0], xmin[1], xmax[1], jacE, np[0], np[1], K1, K2, NULL); \
+            for (long i = 0; i < n12; ++i) nrj_jac += K1[i] * K1[i] + K2[i] * K2[i]; nrj_jac *= delta[0] * delta[1]; } } while (0)
     FIELD4();
+    if (dimV == 2) { /* the t = 0 row sums field_x2 unsquared, twice (:905) */
+        nrj_jac = 0; for (long i = 0; i < n12; ++i) nrj_jac += K1[i] * K1[i] + K2[i] + K2[i]; nrj_jac *= delta[0] * delta[1]; }
     /* row 0 (:983-997): time, nrj, ekin(analytic = L1*L2), mass0... we emit the same
      * three integrals as later rows, computed, for a uniform table */
     int maxnp = 0; for (int d = 0; d < 4; ++d) if (np[d] > maxnp) maxnp = np[d];
@@ -1168,7 +1188,7 @@ int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], d
                     }
                 } else {
                     FIELD4();
-                    double st = steps[isub];
+                    double st = steps[isub], st2 = (dimV == 2) ? steps[isub + 1] : 0.0;
 #pragma omp parallel
                     {
                         double *line = (double *)malloc(sizeof(double) * (4 * maxnp + 32));
@@ -1176,12 +1196,14 @@ int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], d
 #pragma omp for collapse(2) schedule(static)
                         for (int i2 = 0; i2 < np[1]; ++i2) for (int i1 = 0; i1 < np[0]; ++i1) {
                             double a3 = 0.0; a3 = a3 + E1[i1 + (long)np[0] * i2] * st;
+                            if (dimV == 2) a3 = a3 + K1[i1 + (long)np[0] * i2] * st2;
                             for (int i4 = 0; i4 < np[3]; ++i4) {
                                 for (int i = 0; i < np[2]; ++i) line[i] = F4D(i1, i2, i, i4);
                                 advect_dup_line(method, order, nc[2], xmin[2], xmax[2], a3, dt, line, scr);
                                 for (int i = 0; i < np[2]; ++i) F4D(i1, i2, i, i4) = line[i];
                             }
                             double a4 = 0.0; a4 = a4 + E2[i1 + (long)np[0] * i2] * st;
+                            if (dimV == 2) a4 = a4 + K2[i1 + (long)np[0] * i2] * st2;
                             for (int i3 = 0; i3 < np[2]; ++i3) {
                                 for (int i = 0; i < np[3]; ++i) line[i] = F4D(i1, i2, i3, i);
                                 advect_dup_line(method, order, nc[3], xmin[3], xmax[3], a4, dt, line, scr);
@@ -1190,7 +1212,7 @@ int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], d
                         }
                         free(line);
                     }
-                    isub += 1;
+                    isub += dimV;
                 }
                 T = !T;
             }
@@ -1216,6 +1238,7 @@ int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], d
         }
         double *r = rows + 6 * it;
         r[0] = it * dt; r[1] = nrj; r[2] = ekin; r[3] = i0; r[4] = i1n; r[5] = i2n;
+        if (jac_rows) { jac_rows[2 * it] = jac_max; jac_rows[2 * it + 1] = nrj_jac; }
     }
     if (f_out) memcpy(f_out, f, sizeof(double) * ntot);
     free(f); free(rho);
