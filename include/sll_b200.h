@@ -305,9 +305,42 @@ int sllb_dd6d_set_force_halo(int on);
 int sllb_dd6d_set_halo_p2p(int on);
 int sllb_dd6d_p2p(sllb_dd6d_t D, int *enabled);
 
+/* ---- a17 / (f)3: operator-splitting schedules ------------------------------
+ * sll_f_new_time_splitting_coeff (src/time_integration/splitting_methods/sll_m_time_splitting_coeff.F90:86-594):
+ * every split_case the 2D2V simulation's namelist accepts (sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:514-554). */
+#define SLLB_SPLIT_STRANG_VTV 0
+#define SLLB_SPLIT_STRANG_TVT 1
+#define SLLB_SPLIT_LIE_TV 2
+#define SLLB_SPLIT_LIE_VT 3
+#define SLLB_SPLIT_TRIPLE_JUMP_TVT 4
+#define SLLB_SPLIT_TRIPLE_JUMP_VTV 5
+#define SLLB_SPLIT_ORDER6_VTV 6
+#define SLLB_SPLIT_ORDER6_TVT 7
+#define SLLB_SPLIT_ORDER6VP_TVT 8
+#define SLLB_SPLIT_ORDER6VP_VTV 9
+#define SLLB_SPLIT_ORDER6VPNEW_TVT 10
+#define SLLB_SPLIT_ORDER6VPNEW1_VTV 11 /* the simulation's default (:342) */
+#define SLLB_SPLIT_ORDER6VPNEW2_VTV 12
+#define SLLB_SPLIT_ORDER6VP2D_VTV 13
+#define SLLB_SPLIT_ORDER6VPOT_VTV 14     /* 14..17: dim_split_V = 2, V stages also move along the modified potential */
+#define SLLB_SPLIT_ORDER6VPOTNEW1_VTV 15
+#define SLLB_SPLIT_ORDER6VPOTNEW2_VTV 16
+#define SLLB_SPLIT_ORDER6VPOTNEW3_VTV 17
+#define SLLB_SPLIT_MAX_STEPS 32
+/* host only.  name = the namelist string, e.g. "SLL_ORDER6VPnew1_VTV" */
+int sllb_splitting_case_from_name(const char *name, int *split_case);
+const char *sllb_splitting_case_name(int split_case);
+/* steps[SLLB_SPLIT_MAX_STEPS] = split_step(:) as sll_t_splitting_coeff holds it (one entry per T stage, dim_split_V
+ * entries per V stage; *nsteps of them); dt enters the Vlasov-Poisson order-6 weights.  Outputs may be NULL. */
+int sllb_splitting_coeff(int split_case, double dt, double *steps, int *nsteps, int *nb_split_step, int *split_begin_T,
+                         int *dim_split_V);
+/* sll_s_compute_w_hermite (src/semi_lagrangian/fcisl/sll_m_fcisl.F90:413-486): first-derivative weights on the
+ * stencil r..s (r < 0 < s), w[k - r]; used by compute_jacobian (...poisson_serial.F90:1403-1436) */
+int sllb_compute_w_hermite(int r, int s, double *w);
+
 /* ---- simulations (time loops of SURVEY.md section 3) --------------------- */
 /* 2D2V sim_bsl_vp_2d2v_cart_poisson_serial on 1..P GPUs.
- * split: 0 Strang VTV, 1 Strang TVT, 2 Lie TV. method/order as SLLB_METHOD_*. */
+ * split: SLLB_SPLIT_* (0 Strang VTV, 1 Strang TVT, 2 Lie TV, ...). method/order as SLLB_METHOD_*. */
 typedef struct sllb_sim4d *sllb_sim4d_t;
 typedef struct {
     int nc[4];
@@ -316,6 +349,7 @@ typedef struct {
     double dt;
     int split;
     int method, order;
+    int stencil_r, stencil_s; /* finite-difference stencil of compute_jacobian; 0, 0 = the namelist default -2, 2 (:366-367) */
 } sllb_sim4d_params_t;
 int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm /* NULL = single GPU */, sllb_sim4d_t *S);
 int sllb_sim4d_destroy(sllb_sim4d_t S);
@@ -324,6 +358,9 @@ int sllb_sim4d_destroy(sllb_sim4d_t S);
 int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows);
 /* row for the current state (time 0 row before any step) */
 int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6);
+/* the 13 columns of the reference's thdiag file for the current state (:998-1010 at t = 0, :1262-1275 later):
+ * time, nrj, ekin, nrj0, ekin0, max|jacobian_E|, nrj_jac, int f, int |f|, int f^2, mass0, mass0, l20 */
+int sllb_sim4d_thdiag(sllb_sim4d_t S, double *row13);
 int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F); /* local x-sequential field (remaps into it if needed) */
 int sllb_sim4d_box(sllb_sim4d_t S, int which, int box[8]); /* my box: which = 0 x-sequential, 1 v-sequential */
 /* per-phase device time of the last run() in ms: [advect, reduce+poisson, remap, diag] */

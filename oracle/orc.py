@@ -243,24 +243,24 @@ def compute_jacobian(E1, E2, factor, r=-2, s=2):
 
 
 def sim4d(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split=0, method=0, order=4, want_f=False, stencil=(-2, 2),
-          want_jac=False):
+          want_thdiag=False):
     """split: case number (0 Strang VTV, 1 Strang TVT, 2 Lie TV, ... see SPLIT_CASES) or the namelist's name"""
     if isinstance(split, str):
         split = SPLIT_CASES.index(split)
     rows = np.zeros((nsteps + 1, 6))
-    jac = np.zeros((nsteps + 1, 2))
+    thd = np.zeros((nsteps + 1, 13))
     f = np.zeros(tuple(c + 1 for c in nc), order="F") if want_f else None
     lib().orc_sim4d_run_ex.restype = C.c_int
     rc = lib().orc_sim4d_run_ex((C.c_int * 4)(*nc), (C.c_double * 4)(*xmin), (C.c_double * 4)(*xmax), C.c_double(kx1),
                                 C.c_double(kx2), C.c_double(eps), C.c_double(dt), C.c_int(nsteps), C.c_int(split),
                                 C.c_int(method), C.c_int(order), _p(rows), _p(f) if want_f else None,
-                                C.c_int(stencil[0]), C.c_int(stencil[1]), _p(jac))
+                                C.c_int(stencil[0]), C.c_int(stencil[1]), _p(thd))
     assert rc == 0, rc
     out = (rows,)
     if want_f:
         out += (f,)
-    if want_jac:
-        out += (jac,)
+    if want_thdiag:
+        out += (thd,)
     return out if len(out) > 1 else rows
 
 

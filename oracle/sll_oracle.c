@@ -1108,18 +1108,18 @@ int orc_splitting_coeff(int split, double dt, double *s, int *nb_split_step, int
 void orc_compute_jacobian(const double *E1, const double *E2, int nc1, int nc2, double factor, int r, int s, double *jac);
 int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
                      double eps, double dt, int nsteps, int split, int method, int order, double *rows,
-                     double *f_out, int stencil_r, int stencil_s, double *jac_rows);
+                     double *f_out, int stencil_r, int stencil_s, double *thdiag);
 int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
                   double eps, double dt, int nsteps, int split, int method, int order, double *rows,
                   double *f_out) {
     return orc_sim4d_run_ex(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split, method, order, rows, f_out, -2, 2, NULL);
 }
 /* split: case numbering of sll_oracle_split.c (0 Strang VTV ... 17); stencil_r/s: finite-difference stencil of
- * compute_jacobian (namelist defaults -2, 2, :366-367); jac_rows (may be NULL): (nsteps+1) x 2 = thdiag columns 6, 7
- * (max|jacobian_E|, nrj_jac) */
+ * compute_jacobian (namelist defaults -2, 2, :366-367); thdiag (may be NULL): (nsteps+1) x 13, the rows of the
+ * reference's thdiag file (:998-1010 at t = 0 with the analytic mass0 / l20 of SLL_LANDAU :449-452, :1262-1275 later) */
 int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
                      double eps, double dt, int nsteps, int split, int method, int order, double *rows,
-                     double *f_out, int stencil_r, int stencil_s, double *jac_rows) {
+                     double *f_out, int stencil_r, int stencil_s, double *thdiag) {
     int np[4]; long ntot = 1;
     double delta[4];
     for (int d = 0; d < 4; ++d) { np[d] = nc[d] + 1; ntot *= np[d]; delta[d] = (xmax[d] - xmin[d]) / (double)nc[d]; }
@@ -1238,7 +1238,17 @@ int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4]
         }
         double *r = rows + 6 * it;
         r[0] = it * dt; r[1] = nrj; r[2] = ekin; r[3] = i0; r[4] = i1n; r[5] = i2n;
-        if (jac_rows) { jac_rows[2 * it] = jac_max; jac_rows[2 * it + 1] = nrj_jac; }
+        if (thdiag) {
+            double *t = thdiag + 13 * it;
+            const double mass0 = (xmax[0] - xmin[0]) * (xmax[1] - xmin[1]);
+            const double nrj0 = (0.5 * eps * ORC_PI) * (0.5 * eps * ORC_PI) / (kx1 * kx2) * (1.0 / (kx1 * kx1) + 1.0 / (kx2 * kx2));
+            double l20 = (2.0 * ORC_PI / kx1) * (2.0 * ORC_PI / kx2) * 0.25;
+            l20 = l20 * (1.0 + 0.25 * (eps * eps)) / ORC_PI;
+            t[0] = it * dt; t[1] = nrj; t[2] = (it == 0) ? mass0 : ekin; t[3] = nrj0; t[4] = mass0; t[5] = jac_max; t[6] = nrj_jac;
+            if (it == 0) { t[7] = mass0; t[8] = mass0; t[9] = l20; }
+            else { t[7] = i0; t[8] = i1n; t[9] = i2n; }
+            t[10] = mass0; t[11] = mass0; t[12] = l20;
+        }
     }
     if (f_out) memcpy(f_out, f, sizeof(double) * ntot);
     free(f); free(rho);

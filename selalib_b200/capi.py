@@ -35,7 +35,7 @@ class DispT(C.Structure):
 class Sim4dParams(C.Structure):
     _fields_ = [("nc", C.c_int * 4), ("xmin", C.c_double * 4), ("xmax", C.c_double * 4),
                 ("kx1", C.c_double), ("kx2", C.c_double), ("eps", C.c_double), ("dt", C.c_double),
-                ("split", C.c_int), ("method", C.c_int), ("order", C.c_int)]
+                ("split", C.c_int), ("method", C.c_int), ("order", C.c_int), ("stencil_r", C.c_int), ("stencil_s", C.c_int)]
 
 
 class Sim6dParams(C.Structure):
@@ -439,12 +439,37 @@ class Dist4d:
 # ---------------------------------------------------------------------------------------------
 # simulations
 # ---------------------------------------------------------------------------------------------
+def splitting_case(name):
+    """namelist split_case string -> SLLB_SPLIT_* number"""
+    k = C.c_int(-1)
+    _ck(lib().sllb_splitting_case_from_name(name.encode(), C.byref(k)))
+    return k.value
+
+
+def splitting_coeff(split, dt):
+    """(split_step array, split_begin_T, dim_split_V, nb_split_step) of sll_f_new_time_splitting_coeff"""
+    if isinstance(split, str):
+        split = splitting_case(split)
+    steps = np.zeros(32); n = C.c_int(); nb = C.c_int(); bt = C.c_int(); dv = C.c_int()
+    _ck(lib().sllb_splitting_coeff(C.c_int(split), C.c_double(dt), _p(steps), C.byref(n), C.byref(nb), C.byref(bt), C.byref(dv)))
+    return steps[:n.value].copy(), bool(bt.value), dv.value, nb.value
+
+
+def compute_w_hermite(r, s):
+    w = np.zeros(s - r + 1)
+    _ck(lib().sllb_compute_w_hermite(C.c_int(r), C.c_int(s), _p(w)))
+    return w
+
+
 class Sim4d:
-    def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None):
+    def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None, stencil=(0, 0)):
+        if isinstance(split, str):
+            split = splitting_case(split)
         p = Sim4dParams()
         p.nc[:] = nc; p.xmin[:] = xmin; p.xmax[:] = xmax
         p.kx1, p.kx2, p.eps, p.dt = kx1, kx2, eps, dt
         p.split, p.method, p.order = split, method, order
+        p.stencil_r, p.stencil_s = stencil
         self.h = vp()
         _ck(lib().sllb_sim4d_create(C.byref(p), comm.h if comm is not None else None, C.byref(self.h)))
 
@@ -452,6 +477,11 @@ class Sim4d:
         rows = np.zeros((nsteps, 6))
         _ck(lib().sllb_sim4d_run(self.h, C.c_int(nsteps), C.c_int(1 if diagnostics else 0), _p(rows) if diagnostics else None))
         return rows
+
+    def thdiag(self):
+        row = np.zeros(13)
+        _ck(lib().sllb_sim4d_thdiag(self.h, _p(row)))
+        return row
 
     def diagnostics(self):
         row = np.zeros(6)

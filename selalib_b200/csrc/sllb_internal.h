@@ -101,5 +101,8 @@ int field_alloc(int ndim, const int *ext, sllb_field **F);
 int field_wrap(int ndim, const int *ext, double *d, sllb_field **F);
 int to_dispdesc(const sllb_disp_t *disp, DevBuf &scratch, DispDesc *dd);
 int upload_shift(sllb_field *F, const int32_t *shift, long long n, const int **d_shift);
+cudaError_t launch_jacobian2d(const double *e1, const double *e2, int n1, int n2, int r, int s, const double *d_w,
+                              double factor, double *jac, cudaStream_t st);
+cudaError_t launch_lincomb2(const double *x, const double *y, double a, double b, long long n, double *out, cudaStream_t st);
 int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out);
 } // namespace sllb

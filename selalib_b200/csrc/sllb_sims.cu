@@ -368,6 +368,13 @@ struct sllb_sim4d {
     double delta[4];
     int bx[8], bv[8];  // my boxes in the two layouts
     DevBuf rho_tile, rho_gather, rho_full, E1, E2, E1loc, E2loc, small, linesum;
+    // splitting schedule (sll_t_splitting_coeff) and, for dim_split_V = 2, the modified-potential fields
+    double steps[SLLB_SPLIT_MAX_STEPS];
+    int nb_split_step = 3, dim_split_V = 1;
+    bool begin_T = false;
+    int stencil_r = -2, stencil_s = 2;
+    DevBuf jacE, K1, K2, C1, C2, fdw;
+    double jac_max = 0.0, nrj_jac = 0.0;
     // where the charge density of the current f can be had without another sweep over f:
     // 0 nothing (reduce f), 1 rho_full already holds it (T stage plane kernel), 2 line sums of the last x4 pass
     int rho_state = 0;
@@ -440,6 +447,44 @@ static int sim4d_fields(sllb_sim4d *S) {
         }
     }
     SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho_full.p, nullptr, S->E1.p, S->E2.p, nullptr));
+    if (S->dim_split_V == 2) {
+        // field_x{1,2}(:,:,2) = E of the Poisson problem with jacobian_E as right-hand side (:1113-1126)
+        SLLB_CUDA(launch_jacobian2d(S->E1.p, S->E2.p, N1, N2, S->stencil_r, S->stencil_s, S->fdw.p,
+                                    4.0 / (S->delta[0] * S->delta[1]), S->jacE.p, 0));
+        SLLB_TRY(sllb_poisson_solve(S->poisson, S->jacE.p, nullptr, S->K1.p, S->K2.p, nullptr));
+    }
+    return SLLB_OK;
+}
+
+// sum over the (N1+1)(N2+1) nodes INCLUDING the periodic duplicates of a(i,j)^2 + (squared ? b^2 : 2 b)
+static double dup_sum(const std::vector<double> &a, const std::vector<double> &b, int N1, int N2, bool squared) {
+    double s = 0;
+    for (int j = 0; j <= N2; ++j) for (int i = 0; i <= N1; ++i) {
+        const size_t k = (size_t)(i % N1) + (size_t)N1 * (j % N2);
+        s += a[k] * a[k] + (squared ? b[k] * b[k] : b[k] + b[k]);
+    }
+    return s;
+}
+// thdiag columns 6 and 7: max|jacobian_E| (always computed by the reference, :1113) and nrj_jac (:1124-1126; the t = 0
+// row sums field_x2 unsquared, :905)
+static int sim4d_jac_diag(sllb_sim4d *S) {
+    const int N1 = S->p.nc[0], N2 = S->p.nc[1];
+    const size_t n12 = (size_t)N1 * N2;
+    if (S->dim_split_V != 2)
+        SLLB_CUDA(launch_jacobian2d(S->E1.p, S->E2.p, N1, N2, S->stencil_r, S->stencil_s, S->fdw.p,
+                                    4.0 / (S->delta[0] * S->delta[1]), S->jacE.p, 0));
+    std::vector<double> j(n12);
+    SLLB_CUDA(cudaMemcpy(j.data(), S->jacE.p, n12 * 8, cudaMemcpyDeviceToHost));
+    double m = 0;
+    for (double v : j) if (fabs(v) > m) m = fabs(v);
+    S->jac_max = m;
+    S->nrj_jac = 0.0;
+    if (S->dim_split_V == 2) {
+        std::vector<double> k1(n12), k2(n12);
+        SLLB_CUDA(cudaMemcpy(k1.data(), S->K1.p, n12 * 8, cudaMemcpyDeviceToHost));
+        SLLB_CUDA(cudaMemcpy(k2.data(), S->K2.p, n12 * 8, cudaMemcpyDeviceToHost));
+        S->nrj_jac = dup_sum(k1, k2, N1, N2, S->istep > 0) * S->delta[0] * S->delta[1];
+    }
     return SLLB_OK;
 }
 
@@ -504,17 +549,25 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     }
     return SLLB_OK;
 }
-static int sim4d_V(sllb_sim4d *S, double step, bool fuse) {
+static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
     sllb_field *Fv = S->D->F[1];
     const sllb_sim4d_params_t &p = S->p;
     const double *e1 = S->E1.p, *e2 = S->E2.p;
+    if (S->dim_split_V == 2) {
+        // alpha = field(:,:,1) step(k+1) + field(:,:,2) step(k+2) (:1137-1141,1153-1157): one combined field, unit step
+        const long long n12 = (long long)p.nc[0] * p.nc[1];
+        SLLB_CUDA(launch_lincomb2(S->E1.p, S->K1.p, step, step2, n12, S->C1.p, 0));
+        SLLB_CUDA(launch_lincomb2(S->E2.p, S->K2.p, step, step2, n12, S->C2.p, 0));
+        e1 = S->C1.p; e2 = S->C2.p;
+        step = 1.0;
+    }
     if (S->D->nranks > 1) { // my (x1,x2) tile of the replicated field
         const int ext[4] = {p.nc[0], p.nc[1], 1, 1};
         Box4 b;
         b.lo[0] = S->bv[0]; b.n[0] = S->bv[1] - S->bv[0] + 1; b.lo[1] = S->bv[2]; b.n[1] = S->bv[3] - S->bv[2] + 1;
         b.lo[2] = b.lo[3] = 0; b.n[2] = b.n[3] = 1;
-        SLLB_CUDA(launch_pack4d(S->E1.p, ext, b, S->E1loc.p, 0));
-        SLLB_CUDA(launch_pack4d(S->E2.p, ext, b, S->E2loc.p, 0));
+        SLLB_CUDA(launch_pack4d(e1, ext, b, S->E1loc.p, 0));
+        SLLB_CUDA(launch_pack4d(e2, ext, b, S->E2loc.p, 0));
         e1 = S->E1loc.p; e2 = S->E2loc.p;
     }
     // out(v) = in(v - E*step*dt)  (:1137-1166), displacement computed from E inside the kernel (K5)
@@ -544,11 +597,18 @@ extern "C" {
 
 int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d_t *Sout) {
     if (!p || !Sout) return fail(SLLB_ERR_INVALID, "sim4d_create: null");
-    if (p->split < 0 || p->split > 2) return fail(SLLB_ERR_UNSUPPORTED, "sim4d_create: split must be Strang VTV (0), Strang TVT (1) or Lie TV (2)");
     SLLB_TRY(require_device());
     sllb_sim4d *S = new sllb_sim4d();
     S->p = *p;
     S->comm = comm;
+    {
+        int bt = 0;
+        int rcs = sllb_splitting_coeff(p->split, p->dt, S->steps, nullptr, &S->nb_split_step, &bt, &S->dim_split_V);
+        if (rcs) { delete S; return rcs; }
+        S->begin_T = bt != 0;
+        if (p->stencil_r != 0 || p->stencil_s != 0) { S->stencil_r = p->stencil_r; S->stencil_s = p->stencil_s; }
+        if (S->stencil_r >= 0 || S->stencil_s <= 0 || S->stencil_s - S->stencil_r > 16) { delete S; return fail(SLLB_ERR_INVALID, "sim4d_create: need stencil_r < 0 < stencil_s"); }
+    }
     for (int d = 0; d < 4; ++d) S->delta[d] = (p->xmax[d] - p->xmin[d]) / (double)p->nc[d];
     int rc = sllb_dist4d_create(comm, p->nc, &S->D);
     if (!rc) rc = sllb_poisson2d_create(p->nc[0], p->nc[1], p->xmin[0], p->xmax[0], p->xmin[1], p->xmax[1], &S->poisson);
@@ -566,6 +626,19 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
     if (!rc) rc = S->E1loc.ensure(tile);
     if (!rc) rc = S->E2loc.ensure(tile);
     if (!rc) rc = S->small.ensure(16);
+    if (!rc) rc = S->jacE.ensure(n12);
+    if (!rc) rc = S->fdw.ensure(32);
+    if (!rc && S->dim_split_V == 2) {
+        rc = S->K1.ensure(n12);
+        if (!rc) rc = S->K2.ensure(n12);
+        if (!rc) rc = S->C1.ensure(n12);
+        if (!rc) rc = S->C2.ensure(n12);
+    }
+    if (!rc) {
+        double w[32];
+        rc = sllb_compute_w_hermite(S->stencil_r, S->stencil_s, w);
+        if (!rc) rc = check_cuda(cudaMemcpy(S->fdw.p, w, sizeof(double) * (S->stencil_s - S->stencil_r + 1), cudaMemcpyHostToDevice), "fd weights");
+    }
     if (rc) { sllb_sim4d_destroy(S); return rc; }
     // initial data in the x-sequential layout (sll_f_landau_mode_initializer_4d)
     sllb_field *Fx = S->D->F[0];
@@ -630,14 +703,33 @@ int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6) {
     row6[3] = loc[0] * vol; row6[4] = loc[1] * vol; row6[5] = loc[2] * vol;
     return SLLB_OK;
 }
+int sllb_sim4d_thdiag(sllb_sim4d_t S, double *row13) {
+    if (!S || !row13) return fail(SLLB_ERR_INVALID, "sim4d_thdiag: null");
+    const sllb_sim4d_params_t &p = S->p;
+    double r6[6];
+    SLLB_TRY(sllb_sim4d_diagnostics(S, r6));
+    SLLB_TRY(sim4d_nrj(S));
+    SLLB_TRY(sim4d_jac_diag(S));
+    const double pi = 3.14159265358979323846;
+    const double mass0 = (p.xmax[0] - p.xmin[0]) * (p.xmax[1] - p.xmin[1]); // analytic (:913-918)
+    const double nrj0 = (0.5 * p.eps * pi) * (0.5 * p.eps * pi) / (p.kx1 * p.kx2) * (1.0 / (p.kx1 * p.kx1) + 1.0 / (p.kx2 * p.kx2)); // :449-450
+    double l20 = (2.0 * pi / p.kx1) * (2.0 * pi / p.kx2) * 0.25;                                                                       // :451-452
+    l20 = l20 * (1.0 + 0.25 * (p.eps * p.eps)) / pi;
+    const bool t0 = S->istep == 0;
+    row13[0] = S->istep * p.dt; row13[1] = S->nrj; row13[2] = t0 ? mass0 : r6[2]; row13[3] = nrj0; row13[4] = mass0;
+    row13[5] = S->jac_max; row13[6] = S->nrj_jac;
+    row13[7] = t0 ? mass0 : r6[3]; row13[8] = t0 ? mass0 : r6[4]; row13[9] = t0 ? l20 : r6[5];
+    row13[10] = mass0; row13[11] = mass0; row13[12] = l20;
+    return SLLB_OK;
+}
 int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows) {
     if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim4d_run: bad arguments");
     const sllb_sim4d_params_t &p = S->p;
-    // splitting tables: sll_m_time_splitting_coeff.F90:168-195
-    double steps[3]; int nsub; bool beginT;
-    if (p.split == 0) { steps[0] = 0.5; steps[1] = 1.0; steps[2] = 0.5; nsub = 3; beginT = false; }
-    else if (p.split == 1) { steps[0] = 0.5; steps[1] = 1.0; steps[2] = 0.5; nsub = 3; beginT = true; }
-    else { steps[0] = 1.0; steps[1] = 1.0; nsub = 2; beginT = true; }
+    // splitting schedule: sll_m_time_splitting_coeff.F90:157-594 (sllb_splitting_coeff), loop :1030-1180
+    const double *steps = S->steps;
+    const int nsub = S->nb_split_step, dimV = S->dim_split_V;
+    const bool beginT = S->begin_T;
+    (void)p;
     S->timer.begin();
     S->timer.mark(-1);
     const bool can_fuse = S->D->p2p && g_fused_remap && S->D->nranks > 1;
@@ -660,9 +752,9 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
                 S->timer.mark(2);
                 SLLB_TRY(sim4d_fields(S));
                 S->timer.mark(1);
-                SLLB_TRY(sim4d_V(S, steps[isub], fuse));
+                SLLB_TRY(sim4d_V(S, steps[isub], dimV == 2 ? steps[isub + 1] : 0.0, fuse));
                 S->timer.mark(0);
-                isub += 1;
+                isub += dimV;
             }
             T = !T;
         }

@@ -146,3 +146,36 @@ def test_spline_dd_blocks_host_plan():
     assert box[16] == sb.SHIFT_SKIP and box[0] == 1 and box[-1] == -2
     with pytest.raises(sb.SllbError):
         sb.lagrange_dd_blocks(-v * 0.3, 2)          # displacement leaves [-stencil/2, stencil/2)
+
+
+def test_splitting_tables_match_independent_transcription():
+    """sllb_splitting_coeff (half-palindromes + dt polynomials) against the oracle's literal transcription of
+    sll_m_time_splitting_coeff.F90:157-594, every split_case, several dt; plus structural checks."""
+    from oracle import orc
+    for k, name in enumerate(orc.SPLIT_CASES):
+        assert sb.splitting_case(name) == k
+        for dt in (0.0, 0.05, 0.1, 0.25):
+            steps, bt, dv, nb = sb.splitting_coeff(name, dt)
+            osteps, obt, odv = orc.splitting_coeff(name, dt)
+            assert bt == obt and dv == odv and steps.size == osteps.size
+            assert np.abs(steps - osteps).max() <= 4e-16, name
+        # consistency of the schemes at dt = 0: T weights and V weights each sum to one
+        steps, bt, dv, nb = sb.splitting_coeff(name, 0.0)
+        T, V, idx, isT = [], [], 0, bt
+        for _ in range(nb):
+            if isT:
+                T.append(steps[idx]); idx += 1
+            else:
+                V.append(steps[idx]); idx += dv
+            isT = not isT
+        assert idx == steps.size
+        assert abs(sum(T) - 1) < 1e-14 and abs(sum(V) - 1) < 1e-14, name
+    with pytest.raises(sb.SllbError):
+        sb.splitting_case("SLL_NOT_A_CASE")
+    # finite-difference weights of compute_jacobian (sll_s_compute_w_hermite)
+    assert np.allclose(sb.compute_w_hermite(-2, 2), [1 / 12, -2 / 3, 0, 2 / 3, -1 / 12], atol=1e-16)
+    for r, s in ((-1, 1), (-2, 2), (-3, 3), (-2, 3)):
+        assert np.abs(sb.compute_w_hermite(r, s) - orc.compute_w_hermite(r, s)).max() < 1e-15
+        k = np.arange(r, s + 1)
+        w = sb.compute_w_hermite(r, s)
+        assert abs(w.sum()) < 1e-15 and abs((w * k).sum() - 1) < 1e-14      # exact on constants and on x
