@@ -148,6 +148,53 @@ module sll_m_b200_bindings
          real(c_double), intent(inout) :: rho(*)
          integer(c_int) :: ierr
       end function
+      ! ---- local cubic splines with halo cells (sll_t_advection_6d_spline_dd_slim) ----
+      function sllb_spline_dd_blocks(n, disp, shift, alpha, nblocks) bind(C, name="sllb_spline_dd_blocks") result(ierr)
+         import :: c_int, c_int32_t, c_double
+         integer(c_int), value :: n
+         real(c_double), intent(in) :: disp(*)
+         integer(c_int32_t), intent(out) :: shift(*)
+         real(c_double), intent(out) :: alpha(*)
+         integer(c_int), intent(out) :: nblocks
+         integer(c_int) :: ierr
+      end function
+      function sllb_dd6d_create(comm, global, procs, d) bind(C, name="sllb_dd6d_create") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: comm
+         integer(c_int), intent(in) :: global(6), procs(6)
+         type(c_ptr), intent(out) :: d
+         integer(c_int) :: ierr
+      end function
+      function sllb_dd6d_field(d, f) bind(C, name="sllb_dd6d_field") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: d
+         type(c_ptr), intent(out) :: f
+         integer(c_int) :: ierr
+      end function
+      !> disp: type(sllb_disp_t) by reference; shift: the table of sllb_spline_dd_blocks or c_null_ptr
+      function sllb_dd6d_advect_axis_spline(d, axis, disp, shift, hw_left, hw_right) &
+         bind(C, name="sllb_dd6d_advect_axis_spline") result(ierr)
+         import :: c_int, c_ptr
+         type(c_ptr), value :: d, disp, shift
+         integer(c_int), value :: axis, hw_left, hw_right
+         integer(c_int) :: ierr
+      end function
+      ! ---- splitting schedules (sll_f_new_time_splitting_coeff) ----
+      function sllb_splitting_case_from_name(name, split_case) bind(C, name="sllb_splitting_case_from_name") result(ierr)
+         import :: c_int, c_char
+         character(kind=c_char), intent(in) :: name(*)
+         integer(c_int), intent(out) :: split_case
+         integer(c_int) :: ierr
+      end function
+      function sllb_splitting_coeff(split_case, dt, steps, nsteps, nb_split_step, split_begin_t, dim_split_v) &
+         bind(C, name="sllb_splitting_coeff") result(ierr)
+         import :: c_int, c_double
+         integer(c_int), value :: split_case
+         real(c_double), value :: dt
+         real(c_double), intent(out) :: steps(32)
+         integer(c_int), intent(out) :: nsteps, nb_split_step, split_begin_t, dim_split_v
+         integer(c_int) :: ierr
+      end function
    end interface
 
 contains
