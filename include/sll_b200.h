@@ -67,7 +67,9 @@ void sllb_launch_count_reset(void);
 #define SLLB_INTERP_PERIODIC_SPLINE 3   /* sll_t_periodic_interpolator_1d, sll_p_spline */
 #define SLLB_INTERP_PERIODIC_LAGRANGE 4 /* sll_t_periodic_interpolator_1d, sll_p_lagrange */
 
-#define SLLB_BC_PERIODIC 0 /* sll_p_periodic; other boundary types -> SLLB_ERR_UNSUPPORTED */
+#define SLLB_BC_PERIODIC 0 /* sll_p_periodic */
+#define SLLB_BC_HERMITE 1  /* sll_p_hermite (cubic-spline interpolator only, fast algorithm, num_points >= 27);
+                              other boundary types -> SLLB_ERR_UNSUPPORTED */
 
 /* batched per-axis methods */
 #define SLLB_METHOD_SPLINE 0            /* periodic cubic spline (order 4) */
@@ -102,6 +104,12 @@ int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int
 int sllb_interp1d_array_disp(sllb_interp1d_t h, int n, const double *data, double alpha, double *out);
 int sllb_interp1d_array_disp_inplace(sllb_interp1d_t h, int n, double *data, double alpha);
 int sllb_interp1d_delete(sllb_interp1d_t h);
+/* (f)3: sll_p_hermite (src/splines/splines_basic/sll_m_cubic_splines.F90:325-369,583-652,692-748).  num_points grid
+ * points on [xmin, xmax], no periodic duplicate; end slopes from 5-point one-sided differences of the data (:176-181)
+ * unless set here (the optional slope_left / slope_right of init).  interpolate_array_disp follows
+ * sll_s_cubic_spline_1d_eval_disp (:2616-2682), the in-place call clamps the feet to [xmin, xmax] and evaluates like
+ * sll_s_cubic_spline_1d_eval_array (sll_m_cubic_spline_interpolator_1d.F90:165-178). */
+int sllb_interp1d_set_slopes(sllb_interp1d_t h, double slope_left, double slope_right);
 
 /* ---- device-resident distribution function ------------------------------ */
 typedef struct sllb_field *sllb_field_t;
@@ -144,6 +152,11 @@ int sllb_advect_axis_affine(sllb_field_t F, int axis, int method, int order, int
  * `nfield_axes` axes of F (v-advection; K5) */
 int sllb_advect_axis_field(sllb_field_t F, int axis, int method, int order, const double *d_field,
                            int nfield_axes, double scale);
+/* K10, batched Hermite-BC spline: every line of F along `axis` (extents[axis] grid points on [xmin, xmax], NOT
+ * periodic) is replaced by S(x_i + alpha), alpha = displacement of the line in PHYSICAL units, as the velocity
+ * passes of simulations/parallel/bsl_vp_2d2v_cart/sll_m_sim_bsl_vp_2d2v_cart.F90:520-545 do line by line.
+ * inplace_semantics: 1 = interpolate_array_disp_inplace (what that simulation calls), 0 = interpolate_array_disp. */
+int sllb_advect_axis_hermite(sllb_field_t F, int axis, double xmin, double xmax, const sllb_disp_t *disp, int inplace_semantics);
 /* K1c: the x1 and the x2 pass of a T stage in ONE sweep over f: every contiguous (axis 0, axis 1) plane is
  * staged in shared memory, both periodic cubic-spline advections are applied there and the plane is written
  * once (the two displacements must be constant over a plane, as alpha = v3*step, alpha = v4*step of

@@ -18,7 +18,7 @@ ip = C.POINTER(C.c_int)
 
 def build(force=False):
     so = os.path.join(_HERE, "liborc.so")
-    srcs = [os.path.join(_HERE, n) for n in ("sll_oracle.c", "sll_oracle_halo.c", "sll_oracle_split.c", "Makefile")]
+    srcs = [os.path.join(_HERE, n) for n in ("sll_oracle.c", "sll_oracle_halo.c", "sll_oracle_split.c", "sll_oracle_hermite.c", "Makefile")]
     if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return so
@@ -340,4 +340,48 @@ def spline_dd_advect_axis(f, axis, nblk, disp, dsel, shifts=None):
     if rc != 0:
         raise ValueError("local spline: too few points per piece for the 15-term boundary series (np > 15, np >= 16 - si, "
                          "np >= 17 + si)")
+    return f
+
+
+# ---- cubic splines with Hermite boundary conditions (sll_m_cubic_splines, sll_p_hermite) ----
+def hermite_coeffs(data, xmin, xmax, fast=1, slopes=None):
+    data = _f(data); c = np.zeros(data.size + 4)
+    hs = slopes is not None
+    lib().orc_spline_hermite_compute_interpolant(_p(data), C.c_int(data.size), C.c_double(xmin), C.c_double(xmax), C.c_int(fast),
+                                                 C.c_int(hs), C.c_double(slopes[0] if hs else 0.0), C.c_int(hs),
+                                                 C.c_double(slopes[1] if hs else 0.0), _p(c))
+    return c[:data.size + 3]
+
+
+def spline_eval_array(coeffs, npts, xmin, xmax, x):
+    x = _f(np.atleast_1d(x)); out = np.zeros(x.size); coeffs = _f(coeffs)
+    lib().orc_spline_eval_array(_p(coeffs), C.c_int(npts), C.c_double(xmin), C.c_double(xmax), _p(x), C.c_int(x.size), _p(out))
+    return out
+
+
+def hermite_interpolate_array_disp(data, xmin, xmax, alpha, fast=1, slopes=None, inplace=False):
+    """sll_t_cubic_spline_interpolator_1d with sll_p_hermite: interpolate_array_disp / _inplace"""
+    data = _f(data).copy(); out = np.zeros_like(data)
+    hs = slopes is not None
+    sl, sr = (slopes if hs else (0.0, 0.0))
+    if inplace:
+        lib().orc_hermite_interpolate_array_disp_inplace(C.c_int(data.size), C.c_double(xmin), C.c_double(xmax), C.c_int(fast),
+                                                         C.c_int(hs), C.c_double(sl), C.c_int(hs), C.c_double(sr), _p(data),
+                                                         C.c_double(alpha))
+        return data
+    lib().orc_hermite_interpolate_array_disp(C.c_int(data.size), C.c_double(xmin), C.c_double(xmax), C.c_int(fast), C.c_int(hs),
+                                             C.c_double(sl), C.c_int(hs), C.c_double(sr), _p(data), C.c_double(alpha), _p(out))
+    return out
+
+
+def hermite_advect_axis(f, axis, xmin, xmax, disp, dsel, fast=1, inplace=True):
+    """every line of the Fortran-ordered f along `axis`: Hermite-spline interpolation at x_i + disp (physical units)"""
+    assert f.flags.f_contiguous
+    shape = f.shape
+    inner = int(np.prod(shape[:axis], dtype=np.int64))
+    outer = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    disp = _f(disp)
+    L = C.c_long
+    lib().orc_hermite_advect_axis(_p(f), L(outer), C.c_int(shape[axis]), L(inner), C.c_double(xmin), C.c_double(xmax),
+                                  C.c_int(fast), C.c_int(1 if inplace else 0), _p(disp), *[L(int(v)) for v in dsel])
     return f

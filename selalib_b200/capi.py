@@ -14,6 +14,7 @@ ADV_PERIODIC_SPLINE, ADV_PERIODIC_LAGRANGE, ADV_BSL = 0, 1, 2
 (INTERP_CUBIC_SPLINE, INTERP_LAGRANGE_CENTERED, INTERP_LAGRANGE_FIXED, INTERP_PERIODIC_SPLINE,
  INTERP_PERIODIC_LAGRANGE) = range(5)
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 1, 2, 3, 4
+BC_PERIODIC, BC_HERMITE = 0, 1
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -162,6 +163,9 @@ class Interpolator1d:
                                        C.c_int(bc), C.c_int(d_or_order), C.c_int(periodic_last),
                                        C.c_int(fast_algorithm), C.byref(self.h)))
 
+    def set_slopes(self, slope_left, slope_right):
+        _ck(lib().sllb_interp1d_set_slopes(self.h, C.c_double(slope_left), C.c_double(slope_right)))
+
     def interpolate_array_disp(self, num_pts, data, alpha):
         data = np.ascontiguousarray(data, dtype=np.float64)
         out = np.empty(num_pts)
@@ -266,6 +270,11 @@ class Field:
             sh = np.ascontiguousarray(shift, dtype=np.int32)
             assert sh.size == d.nvalues
         _ck(lib().sllb_advect_axis_spline_dd(self.h, C.c_int(axis), C.byref(d), sh.ctypes.data_as(C.POINTER(C.c_int32)) if sh is not None else None))
+
+    def advect_axis_hermite(self, axis, xmin, xmax, values, dsel=(1, 1, 0, 1, 1, 0), scale=1.0, inplace=True):
+        """Hermite-BC cubic spline along a non-periodic axis; values = displacements in physical units"""
+        d = _disp(self, values, scale, dsel)
+        _ck(lib().sllb_advect_axis_hermite(self.h, C.c_int(axis), C.c_double(xmin), C.c_double(xmax), C.byref(d), C.c_int(1 if inplace else 0)))
 
     def advect_plane(self, values0, dsel0, scale0, values1, dsel1, scale1, rho_scale=None):
         """K1c: spline passes along axes 0 and 1 in one sweep; returns rho (host) when rho_scale is given."""

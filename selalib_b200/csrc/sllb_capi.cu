@@ -686,7 +686,22 @@ struct sllb_interp1d {
     double xmin, xmax, delta;
     int method, stencil;
     sllb_field *line = nullptr;
+    int bc = SLLB_BC_PERIODIC;
+    int have_slopes = 0;
+    double slope_left = 0.0, slope_right = 0.0;
 };
+static int hermite_line(sllb_interp1d *h, const double *in, double *out, double alpha, int inplace) {
+    const int N = h->num_points;
+    SLLB_CUDA(cudaMemcpy(h->line->d, in, (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+    SLLB_TRY(h->line->disp_scratch.ensure(1));
+    SLLB_CUDA(cudaMemcpy(h->line->disp_scratch.p, &alpha, sizeof(double), cudaMemcpyHostToDevice));
+    DispDesc dd;
+    dd.v = h->line->disp_scratch.p; dd.scale = 1.0;
+    dd.odiv = dd.omod = dd.idiv = dd.imod = 1; dd.ostr = dd.istr = 0;
+    SLLB_CUDA(launch_hermite(h->line->d, 1, N, 1, dd, h->delta, inplace, h->have_slopes, h->slope_left, h->slope_right, g_staging, 0));
+    SLLB_CUDA(cudaMemcpy(out, h->line->d, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost));
+    return SLLB_OK;
+}
 
 static int line_shift(sllb_field *line, int method, int stencil, double disp_cells, const double *in, double *out, int n) {
     const int N = line->ext[0];
@@ -748,9 +763,24 @@ int sllb_adv1d_delete(sllb_adv1d_t h) {
 
 int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int bc, int d_or_order, int periodic_last,
                          int fast_algorithm, sllb_interp1d_t *h) {
-    (void)fast_algorithm;
     if (!h || !(xmax > xmin)) return fail(SLLB_ERR_INVALID, "interp1d_create: bad arguments");
-    if (bc != SLLB_BC_PERIODIC) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: only sll_p_periodic is implemented");
+    if (bc == SLLB_BC_HERMITE) {
+        // sll_t_cubic_spline_interpolator_1d with sll_p_hermite: num_points grid points, no periodic duplicate
+        if (kind != SLLB_INTERP_CUBIC_SPLINE) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: sll_p_hermite is a cubic-spline boundary condition");
+        if (num_points < 27 || !fast_algorithm)
+            return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: Hermite splines are implemented with the fast algorithm only "
+                                              "(num_points >= 27, sll_m_cubic_splines.F90:266-272)");
+        SLLB_TRY(require_device());
+        sllb_interp1d *p = new sllb_interp1d();
+        p->kind = kind; p->num_points = num_points; p->num_cells = num_points - 1; p->periodic_last = 0;
+        p->xmin = xmin; p->xmax = xmax; p->delta = (xmax - xmin) / (double)(num_points - 1);
+        p->method = -1; p->stencil = 4; p->bc = bc;
+        int rc = field_alloc(1, &num_points, &p->line);
+        if (rc) { delete p; return rc; }
+        *h = p;
+        return SLLB_OK;
+    }
+    if (bc != SLLB_BC_PERIODIC) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: boundary condition not implemented (sll_p_periodic, sll_p_hermite)");
     int method, stencil, ncell;
     switch (kind) {
     case SLLB_INTERP_CUBIC_SPLINE: method = SLLB_METHOD_SPLINE; stencil = 4; periodic_last = 1; break;
@@ -782,12 +812,48 @@ int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int
 }
 int sllb_interp1d_array_disp(sllb_interp1d_t h, int n, const double *data, double alpha, double *out) {
     if (!h || !data || !out) return fail(SLLB_ERR_INVALID, "interpolate_array_disp: null");
+    if (h->bc == SLLB_BC_HERMITE) {
+        if (n != h->num_points) return fail(SLLB_ERR_INVALID, "interpolate_array_disp: bad num_pts");
+        SLLB_TRY(require_device());
+        return hermite_line(h, data, out, alpha, 0);
+    }
     if (n != h->num_cells && n != h->num_cells + 1) return fail(SLLB_ERR_INVALID, "interpolate_array_disp: bad num_pts");
     SLLB_TRY(require_device());
     return line_shift(h->line, h->method, h->stencil, alpha / h->delta, data, out, n);
 }
 int sllb_interp1d_array_disp_inplace(sllb_interp1d_t h, int n, double *data, double alpha) {
+    if (h && data && h->bc == SLLB_BC_HERMITE) { // clamped feet + eval_array (sll_m_cubic_spline_interpolator_1d.F90:165-178)
+        if (n != h->num_points) return fail(SLLB_ERR_INVALID, "interpolate_array_disp_inplace: bad num_pts");
+        SLLB_TRY(require_device());
+        return hermite_line(h, data, data, alpha, 1);
+    }
     return sllb_interp1d_array_disp(h, n, data, alpha, data);
+}
+/* the optional slope_left / slope_right of sll_t_cubic_spline_interpolator_1d%init (:323-366); without them the
+ * slopes come from 5-point one-sided differences of the data (sll_m_cubic_splines.F90:720-730) */
+int sllb_interp1d_set_slopes(sllb_interp1d_t h, double slope_left, double slope_right) {
+    if (!h || h->bc != SLLB_BC_HERMITE) return fail(SLLB_ERR_INVALID, "interp1d_set_slopes: not a Hermite spline interpolator");
+    h->have_slopes = 1; h->slope_left = slope_left; h->slope_right = slope_right;
+    return SLLB_OK;
+}
+/* batched: every line of F along `axis` (np = extents[axis] grid points on [xmin, xmax], NOT periodic) becomes
+ * S(x_i + alpha), alpha = the displacement of the line in physical units */
+int sllb_advect_axis_hermite(sllb_field_t F, int axis, double xmin, double xmax, const sllb_disp_t *disp, int inplace_semantics) {
+    if (!F || axis < 0 || axis >= F->ndim || !(xmax > xmin)) return fail(SLLB_ERR_INVALID, "advect_axis_hermite: bad arguments");
+    SLLB_TRY(require_device());
+    DispDesc dd;
+    SLLB_TRY(to_dispdesc(disp, F->disp_scratch, &dd));
+    long long inner = 1, outer = 1;
+    for (int d = 0; d < axis; ++d) inner *= F->ext[d];
+    for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
+    const int np = F->ext[axis];
+    cudaError_t e = launch_hermite(F->d, outer, np, inner, dd, (xmax - xmin) / (double)(np - 1), inplace_semantics ? 1 : 0, 0, 0.0, 0.0,
+                                   g_staging, 0);
+    if (e == cudaErrorInvalidValue) {
+        cudaGetLastError();
+        return fail(SLLB_ERR_UNSUPPORTED, "advect_axis_hermite: Hermite splines need >= 27 points per line (fast algorithm)");
+    }
+    return check_cuda(e, "k_hermite launch");
 }
 int sllb_interp1d_delete(sllb_interp1d_t h) {
     if (!h) return SLLB_OK;

@@ -61,6 +61,10 @@ cudaError_t launch_spline_dd(double *f, long long outer, int np, long long inner
 cudaError_t launch_spline_dd_prepare(const double *f, long long outer, int np, long long inner, const DispDesc &dd,
                                      const int *d_shift, int hwl, int hwr, double *for_right, double *for_left,
                                      cudaStream_t st);
+// K10: cubic spline with Hermite boundary conditions (fast algorithm, np >= 27) on every line of f viewed as
+// [outer][np][inner]; displacement in PHYSICAL units (the alpha of interpolate_array_disp[_inplace]), delta = cell size.
+cudaError_t launch_hermite(double *f, long long outer, int np, long long inner, const DispDesc &dd, double delta, int inplace,
+                           int have_slopes, double sl, double sr, int staging, cudaStream_t st);
 // K7: buf[o][j][in] = f[o][j0+j][in], j < hw
 cudaError_t launch_halo_pack(const double *f, long long outer, int n, long long inner, int j0, int hw, double *buf,
                              cudaStream_t st);

@@ -4,6 +4,7 @@
 // against the oracle in the CPU test suite.  The GPU parity tests check the kernels themselves.
 #define SLLB_HOST_EMULATION 1
 #include "../../selalib_b200/csrc/sllb_spline15.cuh"
+#include "../../selalib_b200/csrc/sllb_hermite.cuh"
 
 #include <climits>
 #include <cstring>
@@ -19,7 +20,27 @@ static void init_consts() {
     ready = true;
 }
 
+static void init_hermite_consts() {
+    static bool ready = false;
+    if (ready) return;
+    const double a = sqrt((2.0 + sqrt(3.0)) / 6.0), b = sqrt((2.0 - sqrt(3.0)) / 6.0);
+    double ct = 1.0;
+    for (int i = 0; i < SLLB_HERMITE_TERMS; ++i) { c_hq[i] = ct; ct *= -(b / a); }
+    ready = true;
+}
+
 extern "C" {
+// one line through hermite_coeffs_line + hermite_eval_point as k_hermite_strided runs them (pitch 1)
+int emu_hermite_line(const double *lin, double *lout, int np, double delta, double alpha, int inplace, int have_slopes,
+                     double sl, double sr) {
+    init_hermite_consts();
+    if (np < SLLB_HERMITE_TERMS) return -1;
+    std::vector<double> tile(lin, lin + np);
+    double g0, gnp1;
+    hermite_coeffs_line<1>(tile.data(), np, delta, have_slopes, sl, sr, &g0, &gnp1);
+    for (int i = 1; i <= np; ++i) lout[i - 1] = hermite_eval_point<1>(tile.data(), np, i, alpha / delta, inplace, g0, gnp1);
+    return 0;
+}
 // line of n = nblk*np points; mode 0: strided kernel (TO_GLOBAL), 1: contiguous kernel (parked results + rotation).
 // nblk == 1 -> WRAP kernels; nblk > 1 -> prepare + halo rows + non-WRAP kernel per piece.
 int emu_spline_dd_line(const double *lin, double *lout, int n, int nblk, int si, double alpha, int hwl, int hwr, int mode) {
