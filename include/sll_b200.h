@@ -363,6 +363,9 @@ typedef struct {
     int split;
     int method, order;
     int stencil_r, stencil_s; /* finite-difference stencil of compute_jacobian; 0, 0 = the namelist default -2, 2 (:366-367) */
+    /* advector_x1..x4 / order_x1..x4 of the namelist (:556-624): per-axis method and order; order_axis[d] = 0 means
+     * "use method / order above" */
+    int method_axis[4], order_axis[4];
 } sllb_sim4d_params_t;
 int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm /* NULL = single GPU */, sllb_sim4d_t *S);
 int sllb_sim4d_destroy(sllb_sim4d_t S);
@@ -371,6 +374,18 @@ int sllb_sim4d_destroy(sllb_sim4d_t S);
 int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows);
 /* row for the current state (time 0 row before any step) */
 int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6);
+/* Namelist front-end: reads the file sim_bsl_vp_2d2v_cart_poisson_serial takes (&geometry, &initial_function,
+ * &time_iterations, &advector, &poisson; defaults and mesh cases as sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:300-440;
+ * `filename` with or without the ".nml" the reference appends, :375), builds the simulation and returns
+ * number_iterations / freq_diag_time.  SLL_SPLINES -> cubic splines (order 4), SLL_LAGRANGE -> centred Lagrange of the
+ * given order; SLL_LANDAU initial function.  Anything else: SLLB_ERR_UNSUPPORTED with the reference's message. */
+int sllb_sim4d_create_from_namelist(const char *filename, sllb_comm_t comm, sllb_sim4d_t *S, int *number_iterations,
+                                    int *freq_diag_time);
+/* the whole program: create from the namelist, run number_iterations steps and write `thdiag_path` (rank 0) in the
+ * reference's format, one '(13g20.12)' row at t = 0 and after every freq_diag_time steps (:998-1010,1262-1275) */
+int sllb_sim4d_run_namelist(const char *filename, sllb_comm_t comm, const char *thdiag_path);
+/* Fortran G20.12 edit descriptor (host helper of the writer): buf receives exactly 20 characters + NUL */
+int sllb_format_g20_12(double x, char *buf21);
 /* the 13 columns of the reference's thdiag file for the current state (:998-1010 at t = 0, :1262-1275 later):
  * time, nrj, ekin, nrj0, ekin0, max|jacobian_E|, nrj_jac, int f, int |f|, int f^2, mass0, mass0, l20 */
 int sllb_sim4d_thdiag(sllb_sim4d_t S, double *row13);

@@ -36,7 +36,8 @@ class DispT(C.Structure):
 class Sim4dParams(C.Structure):
     _fields_ = [("nc", C.c_int * 4), ("xmin", C.c_double * 4), ("xmax", C.c_double * 4),
                 ("kx1", C.c_double), ("kx2", C.c_double), ("eps", C.c_double), ("dt", C.c_double),
-                ("split", C.c_int), ("method", C.c_int), ("order", C.c_int), ("stencil_r", C.c_int), ("stencil_s", C.c_int)]
+                ("split", C.c_int), ("method", C.c_int), ("order", C.c_int), ("stencil_r", C.c_int), ("stencil_s", C.c_int),
+                ("method_axis", C.c_int * 4), ("order_axis", C.c_int * 4)]
 
 
 class Sim6dParams(C.Structure):
@@ -470,6 +471,17 @@ def compute_w_hermite(r, s):
     return w
 
 
+def format_g20_12(x):
+    buf = C.create_string_buffer(24)
+    _ck(lib().sllb_format_g20_12(C.c_double(x), buf))
+    return buf.value.decode()
+
+
+def sim4d_run_namelist(filename, thdiag_path, comm=None):
+    """sim_bsl_vp_2d2v_cart_poisson_serial <filename>: run the namelist, write the thdiag file"""
+    _ck(lib().sllb_sim4d_run_namelist(filename.encode(), comm.h if comm is not None else None, thdiag_path.encode()))
+
+
 class Sim4d:
     def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None, stencil=(0, 0)):
         if isinstance(split, str):
@@ -479,6 +491,10 @@ class Sim4d:
         p.kx1, p.kx2, p.eps, p.dt = kx1, kx2, eps, dt
         p.split, p.method, p.order = split, method, order
         p.stencil_r, p.stencil_s = stencil
+        if isinstance(method, (tuple, list)):      # per-axis advectors (advector_x1..x4 / order_x1..x4)
+            orders = order if isinstance(order, (tuple, list)) else [order] * 4
+            p.method_axis[:] = list(method); p.order_axis[:] = list(orders)
+            p.method, p.order = method[0], orders[0]
         self.h = vp()
         _ck(lib().sllb_sim4d_create(C.byref(p), comm.h if comm is not None else None, C.byref(self.h)))
 

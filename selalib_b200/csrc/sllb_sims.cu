@@ -375,6 +375,7 @@ struct sllb_sim4d {
     int stencil_r = -2, stencil_s = 2;
     DevBuf jacE, K1, K2, C1, C2, fdw;
     double jac_max = 0.0, nrj_jac = 0.0;
+    int m[4], o[4];   // interpolation method / order per axis (advector_x1..x4, order_x1..x4 of the namelist)
     // where the charge density of the current f can be had without another sweep over f:
     // 0 nothing (reduce f), 1 rho_full already holds it (T stage plane kernel), 2 line sums of the last x4 pass
     int rho_state = 0;
@@ -510,7 +511,7 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     S->rho_state = 0;
     // cubic splines: both passes and the charge density in one sweep (K1c); on several GPUs the same kernel also
     // stores into the v-sequential layout of the owning ranks when the next stage is a V stage (`fuse`)
-    if (p.method == SLLB_METHOD_SPLINE && g_plane_kernel) {
+    if (S->m[0] == SLLB_METHOD_SPLINE && S->m[1] == SLLB_METHOD_SPLINE && g_plane_kernel) {
         DispDesc d0, d1;
         SLLB_TRY(Fx->disp_scratch2.ensure((size_t)Fx->ext[3]));
         SLLB_TRY(make_affine_disp(Fx, 0, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2], -step * p.dt / S->delta[0], &d0));
@@ -537,15 +538,15 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
         if (rc != SLLB_ERR_UNSUPPORTED) return rc;
     }
     // out(x) = in(x - v*step*dt): displacement in cells = -v*step*dt/delta_x  (:1037-1064)
-    SLLB_TRY(sllb_advect_axis_affine(Fx, 0, p.method, p.order, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2],
+    SLLB_TRY(sllb_advect_axis_affine(Fx, 0, S->m[0], S->o[0], 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2],
                                      -step * p.dt / S->delta[0]));
     DispDesc dd;
     SLLB_TRY(make_affine_disp(Fx, 1, 3, p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3], -step * p.dt / S->delta[1], &dd));
     if (fuse) {
-        SLLB_TRY(dist4d_advect_remap_dev(S->D, 0, 1, p.method, p.order, dd, &S->timer));
+        SLLB_TRY(dist4d_advect_remap_dev(S->D, 0, 1, S->m[1], S->o[1], dd, &S->timer));
         S->layout = 1;
     } else {
-        SLLB_TRY(advect_axis_dev(Fx, 1, p.method, p.order, dd));
+        SLLB_TRY(advect_axis_dev(Fx, 1, S->m[1], S->o[1], dd));
     }
     return SLLB_OK;
 }
@@ -571,23 +572,23 @@ static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
         e1 = S->E1loc.p; e2 = S->E2loc.p;
     }
     // out(v) = in(v - E*step*dt)  (:1137-1166), displacement computed from E inside the kernel (K5)
-    SLLB_TRY(sllb_advect_axis_field(Fv, 2, p.method, p.order, e1, 2, -step * p.dt / S->delta[2]));
+    SLLB_TRY(sllb_advect_axis_field(Fv, 2, S->m[2], S->o[2], e1, 2, -step * p.dt / S->delta[2]));
     DispDesc dd;
     SLLB_TRY(make_field_disp(Fv, 3, e2, 2, -step * p.dt / S->delta[3], &dd));
     S->rho_state = 0;
     if (fuse) {
-        SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, p.method, p.order, dd, &S->timer));
+        SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, S->m[3], S->o[3], dd, &S->timer));
         S->layout = 0;
     } else {
         // f stays in this layout, so the next thing that happens to it is another V stage: hand its charge
         // density over as line sums of this pass (sum over x4 per (x1,x2,x3) line) instead of re-reading f
         int rc = SLLB_ERR_UNSUPPORTED;
-        if (p.method == SLLB_METHOD_SPLINE && g_plane_kernel) {
+        if (S->m[3] == SLLB_METHOD_SPLINE && g_plane_kernel) {
             rc = S->linesum.ensure((size_t)Fv->ext[0] * Fv->ext[1] * Fv->ext[2]);
-            if (!rc) rc = advect_axis_dev(Fv, 3, p.method, p.order, dd, nullptr, S->linesum.p);
+            if (!rc) rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], dd, nullptr, S->linesum.p);
             if (rc == SLLB_OK) S->rho_state = 2;
         }
-        if (rc == SLLB_ERR_UNSUPPORTED) rc = advect_axis_dev(Fv, 3, p.method, p.order, dd);
+        if (rc == SLLB_ERR_UNSUPPORTED) rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], dd);
         if (rc) return rc;
     }
     return SLLB_OK;
@@ -606,6 +607,11 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
         int rcs = sllb_splitting_coeff(p->split, p->dt, S->steps, nullptr, &S->nb_split_step, &bt, &S->dim_split_V);
         if (rcs) { delete S; return rcs; }
         S->begin_T = bt != 0;
+        for (int d = 0; d < 4; ++d) {
+            const bool per_axis = p->order_axis[d] != 0;
+            S->m[d] = per_axis ? p->method_axis[d] : p->method;
+            S->o[d] = per_axis ? p->order_axis[d] : p->order;
+        }
         if (p->stencil_r != 0 || p->stencil_s != 0) { S->stencil_r = p->stencil_r; S->stencil_s = p->stencil_s; }
         if (S->stencil_r >= 0 || S->stencil_s <= 0 || S->stencil_s - S->stencil_r > 16) { delete S; return fail(SLLB_ERR_INVALID, "sim4d_create: need stencil_r < 0 < stencil_s"); }
     }

@@ -179,3 +179,15 @@ def test_splitting_tables_match_independent_transcription():
         k = np.arange(r, s + 1)
         w = sb.compute_w_hermite(r, s)
         assert abs(w.sum()) < 1e-15 and abs((w * k).sum() - 1) < 1e-14      # exact on constants and on x
+
+
+def test_fortran_g20_12_formatter():
+    """the '(13g20.12)' rows of thdiag.dat (sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:998-1010): Fortran G editing,
+    checked on values as they appear in the reference's own vpsim4d_cartesian_ref.dat columns"""
+    cases = {0.0: "   0.00000000000    ", 1.00003947842: "   1.00003947842    ", 157.913693328: "   157.913693328    ",
+             0.789568343347E-04: "  0.789568343347E-04", -0.5: " -0.500000000000    ", 0.1: "  0.100000000000    ",
+             123456789012.4: "   123456789012.    ", 1e12: "  0.100000000000E+13", -3.25e-7: " -0.325000000000E-06",
+             0.0999999999999: "  0.999999999999E-01"}
+    for x, s in cases.items():
+        assert sb.format_g20_12(x) == s, (x, sb.format_g20_12(x))
+        assert len(sb.format_g20_12(x)) == 20

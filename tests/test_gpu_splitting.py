@@ -70,3 +70,80 @@ def test_sim4d_modified_potential_changes_the_result(sb):
         out.append(S.field().download())
         S.destroy()
     assert 1e-9 < relerr(out[1], out[0]) < 1e-2
+
+
+NML = """
+&geometry
+  mesh_case_x1="SLL_LANDAU_MESH"
+  num_cells_x1 = 16
+  x1_min = 0.0
+  nbox_x1 = 1
+  mesh_case_x2="SLL_LANDAU_MESH"
+  num_cells_x2 = 16
+  x2_min = 0.0
+  nbox_x2 = 1
+  mesh_case_x3="SLL_CARTESIAN_MESH"
+  num_cells_x3 = 32
+  x3_min = -6.
+  x3_max = 6.
+  mesh_case_x4="SLL_CARTESIAN_MESH"
+  num_cells_x4 = 32
+  x4_min = -6.
+  x4_max = 6.
+/
+
+&initial_function
+  initial_function_case="SLL_LANDAU"
+  kmode_x1 = 0.5
+  kmode_x2 = 0.5
+  eps = 1e-3
+/
+
+&time_iterations
+  dt = %(dt)s
+  number_iterations = 4
+  freq_diag = 20
+  freq_diag_time = 2
+  !split_case = "SLL_STRANG_VTV"
+  split_case = "SLL_ORDER6VPnew1_VTV"
+/
+
+&advector
+ advector_x1 = "%(adv)s"
+ order_x1 = 4
+ advector_x2 = "%(adv)s"
+ order_x2 = 4
+ advector_x3 = "%(adv)s"
+ order_x3 = 4
+ advector_x4 = "%(adv)s"
+ order_x4 = 4
+/
+&poisson
+ stencil_r=-3
+ stencil_s=3
+/
+"""
+
+
+@pytest.mark.parametrize("adv,method", [("SLL_LAGRANGE", 2), ("SLL_SPLINES", 0)])
+def test_namelist_front_end_writes_thdiag(sb, orc, tmp_path, adv, method):
+    """the shipped vpsim4d_cartesian_input.nml (simulations/parallel/bsl_vp_2d2v_cart_poisson_serial; Lagrange order 4,
+    SLL_ORDER6VPnew1_VTV, stencil -3..3) with a smaller dt drives the GPU build; the thdiag file has the reference's
+    format and its rows match the oracle's time loop with the reference-algorithm advectors (FFT sll_p_lagrange /
+    sll_p_spline of sll_s_periodic_interp)"""
+    nml = tmp_path / "vpsim4d_cartesian_input.nml"
+    nml.write_text(NML % {"dt": "0.1", "adv": adv})
+    out = tmp_path / "thdiag.dat"
+    sb.sim4d_run_namelist(str(tmp_path / "vpsim4d_cartesian_input"), str(out))     # extension appended like the reference
+    lines = out.read_text().splitlines()
+    assert len(lines) == 3 and all(len(l) == 13 * 20 for l in lines)
+    rows = np.array([[float(l[20 * k:20 * k + 20]) for k in range(13)] for l in lines])
+    nc = [16, 16, 32, 32]
+    xmin, xmax = [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6]
+    _, othd = orc.sim4d(nc, xmin, xmax, 0.5, 0.5, 1e-3, 0.1, 4, split="SLL_ORDER6VPnew1_VTV", method=1 if method == 0 else 2,
+                        order=4, stencil=(-3, 3), want_thdiag=True)
+    ref = othd[[0, 2, 4]]
+    assert np.abs(rows[:, 0] - ref[:, 0]).max() < 1e-12
+    assert np.abs(rows[:, [2, 7, 8, 9]] / ref[:, [2, 7, 8, 9]] - 1).max() < 1e-8
+    assert np.abs(rows[:, 1] / ref[:, 1] - 1).max() < 1e-6 and np.abs(rows[:, 5] / ref[:, 5] - 1).max() < 1e-5
+    assert np.abs(rows[:, [3, 4, 10, 11, 12]] / ref[:, [3, 4, 10, 11, 12]] - 1).max() < 1e-11
