@@ -374,6 +374,13 @@ int sllb_sim4d_destroy(sllb_sim4d_t S);
 int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows);
 /* row for the current state (time 0 row before any step) */
 int sllb_sim4d_diagnostics(sllb_sim4d_t S, double *row6);
+/* Ensemble streaming on ONE GPU (parameter scans: many independent states through the same time step).  Every call
+ * (1) starts the download of the state stepped by the PREVIOUS call into host_prev_out, (2) starts the upload of
+ * host_next_in, (3) advances the state uploaded by the previous call by one time step while both copies run (PCIe
+ * is full duplex; three device copies of f rotate), (4) waits for all three.  Both host arrays hold the periodic
+ * cells (column-major), should be pinned, and may be NULL: N states take N + 2 calls, the first only uploads, the
+ * last only downloads.  The states are independent: each one's fields are recomputed from its own f. */
+int sllb_sim4d_stream_step(sllb_sim4d_t S, const double *host_next_in, double *host_prev_out);
 /* Namelist front-end: reads the file sim_bsl_vp_2d2v_cart_poisson_serial takes (&geometry, &initial_function,
  * &time_iterations, &advector, &poisson; defaults and mesh cases as sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:300-440;
  * `filename` with or without the ".nml" the reference appends, :375), builds the simulation and returns

@@ -503,6 +503,11 @@ class Sim4d:
         _ck(lib().sllb_sim4d_run(self.h, C.c_int(nsteps), C.c_int(1 if diagnostics else 0), _p(rows) if diagnostics else None))
         return rows
 
+    def stream_step(self, host_next_in=None, host_prev_out=None):
+        """ensemble streaming: arguments are raw host pointers (ints) or None"""
+        _ck(lib().sllb_sim4d_stream_step(self.h, C.cast(vp(host_next_in), dp) if host_next_in else None,
+                                         C.cast(vp(host_prev_out), dp) if host_prev_out else None))
+
     def thdiag(self):
         row = np.zeros(13)
         _ck(lib().sllb_sim4d_thdiag(self.h, _p(row)))

@@ -375,6 +375,11 @@ struct sllb_sim4d {
     int stencil_r = -2, stencil_s = 2;
     DevBuf jacE, K1, K2, C1, C2, fdw;
     double jac_max = 0.0, nrj_jac = 0.0;
+    // ensemble streaming (sllb_sim4d_stream_step): two more copies of f and two copy streams, so that the upload of the
+    // next member and the download of the previous one overlap this member's step (PCIe is full duplex)
+    DevBuf ring[2];
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    bool have_incoming = false, have_outgoing = false;
     int m[4], o[4];   // interpolation method / order per axis (advector_x1..x4, order_x1..x4 of the namelist)
     // where the charge density of the current f can be had without another sweep over f:
     // 0 nothing (reduce f), 1 rho_full already holds it (T stage plane kernel), 2 line sums of the last x4 pass
@@ -662,6 +667,8 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
 }
 int sllb_sim4d_destroy(sllb_sim4d_t S) {
     if (!S) return SLLB_OK;
+    if (S->s_up) cudaStreamDestroy(S->s_up);
+    if (S->s_down) cudaStreamDestroy(S->s_down);
     sllb_poisson_destroy(S->poisson);
     sllb_dist4d_destroy(S->D);
     delete S;
@@ -672,6 +679,47 @@ int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F) {
     S->rho_state = 0; // the caller may overwrite f through the handle
     SLLB_TRY(sim4d_to_layout(S, 0));
     *F = S->D->F[0];
+    return SLLB_OK;
+}
+/* Ensemble streaming on one GPU: every call (1) starts the download of the member stepped by the PREVIOUS call to
+ * host_prev_out, (2) starts the upload of host_next_in (both pinned host arrays of the periodic cells, either may be
+ * NULL), (3) advances the member uploaded by the previous call by one time step while those copies run, (4) waits for
+ * all three and rotates the three device copies of f.  N members take N + 2 calls: the first call only uploads, the
+ * last only downloads.  Every member is an independent state: its fields are recomputed from its f. */
+int sllb_sim4d_stream_step(sllb_sim4d_t S, const double *host_next_in, double *host_prev_out) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim4d_stream_step: null");
+    if (S->D->nranks != 1) return fail(SLLB_ERR_UNSUPPORTED, "sim4d_stream_step: single GPU only");
+    sllb_field *F = S->D->F[0];
+    const size_t n = (size_t)F->total;
+    if (!S->s_up) {
+        SLLB_TRY(S->ring[0].ensure(n));
+        SLLB_TRY(S->ring[1].ensure(n));
+        SLLB_CUDA(cudaStreamCreateWithFlags(&S->s_up, cudaStreamNonBlocking));
+        SLLB_CUDA(cudaStreamCreateWithFlags(&S->s_down, cudaStreamNonBlocking));
+    }
+    auto swap_cur = [&](DevBuf &other) { // exchange the compute copy with a ring copy (both layouts alias it on one GPU)
+        double *t = F->d; F->d = other.p; other.p = t;
+        S->D->F[1]->d = F->d;
+    };
+    DevBuf &rin = S->ring[0], &rout = S->ring[1];
+    SLLB_CUDA(cudaDeviceSynchronize());
+    if (S->have_outgoing && host_prev_out)
+        SLLB_CUDA(cudaMemcpyAsync(host_prev_out, rout.p, n * sizeof(double), cudaMemcpyDeviceToHost, S->s_down));
+    const bool step_now = S->have_incoming;
+    if (step_now) swap_cur(rin); // the member uploaded by the previous call becomes the compute copy; rin is free again
+    if (host_next_in)
+        SLLB_CUDA(cudaMemcpyAsync(rin.p, host_next_in, n * sizeof(double), cudaMemcpyHostToDevice, S->s_up));
+    int rc = SLLB_OK;
+    if (step_now) {
+        S->rho_state = 0; S->layout = 0; // a fresh, independent state: fields are recomputed from this f
+        rc = sllb_sim4d_run(S, 1, 0, nullptr);
+    }
+    SLLB_CUDA(cudaStreamSynchronize(S->s_up));
+    SLLB_CUDA(cudaStreamSynchronize(S->s_down));
+    if (rc) return rc;
+    if (step_now) swap_cur(rout); // the stepped member waits in rout for the next call's download
+    S->have_outgoing = step_now;
+    S->have_incoming = host_next_in != nullptr;
     return SLLB_OK;
 }
 int sllb_sim4d_box(sllb_sim4d_t S, int which, int box[8]) {
