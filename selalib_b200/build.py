@@ -14,7 +14,7 @@ SOURCES = ["sllb_kernels.cu", "sllb_capi.cu", "sllb_sims.cu", "sllb_dd6d.cu", "s
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-ccbin", HOST_CXX, "--use_fast_math=false" if False else "-fmad=true"]
+         "-ccbin", HOST_CXX, "-fmad=true"]
 
 
 def _stale():

@@ -917,7 +917,9 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
 // K2b: Lagrange, contiguous axis.  Tile = LT whole lines in natural layout (one bulk TMA copy),
 // thread per output point, per-line weights in shared memory.
 // ------------------------------------------------------------------------------------------------
-template <int S>
+// POW2: N is a power of two (the usual case): line / point indices and the periodic wrap are shifts and masks instead
+// of an integer division and seven compare-selects per point (the kernel is issue-bound on 32-point lines otherwise).
+template <int S, bool POW2>
 __global__ void __launch_bounds__(256) k_lagrange_contig(double *__restrict__ f, const long long nlines, const int N,
                                                          const DispDesc dd, const int LT, const int use_tma) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -949,19 +951,33 @@ __global__ void __launch_bounds__(256) k_lagrange_contig(double *__restrict__ f,
     if (use_tma) mbar_wait(bar, 0);
     else cp_async_wait_all();
     __syncthreads();
-    for (int idx = tid; idx < npts; idx += 256) {
-        const int ln = idx / N, i = idx - ln * N;
-        int j = i + offs[ln];
-        if (j >= N) j -= N;
-        const double *row = tile + (size_t)ln * N;
-        const double *w = wts + ln * S;
-        double acc = w[0] * row[j];
+    if constexpr (POW2) {
+        const int mask = N - 1, sh = 31 - __clz(N);
+        for (int idx = tid; idx < npts; idx += 256) {
+            const int ln = idx >> sh, i = idx & mask;
+            const int j0 = i + offs[ln];
+            const double *row = tile + ((size_t)ln << sh);
+            const double *w = wts + ln * S;
+            double acc = w[0] * row[j0 & mask];
 #pragma unroll
-        for (int k = 1; k < S; ++k) {
-            j = (j == N - 1) ? 0 : j + 1;
-            acc = fma(w[k], row[j], acc);
+            for (int k = 1; k < S; ++k) acc = fma(w[k], row[(j0 + k) & mask], acc);
+            st_stream(g + idx, acc);
         }
-        st_stream(g + idx, acc);
+    } else {
+        for (int idx = tid; idx < npts; idx += 256) {
+            const int ln = idx / N, i = idx - ln * N;
+            int j = i + offs[ln];
+            if (j >= N) j -= N;
+            const double *row = tile + (size_t)ln * N;
+            const double *w = wts + ln * S;
+            double acc = w[0] * row[j];
+#pragma unroll
+            for (int k = 1; k < S; ++k) {
+                j = (j == N - 1) ? 0 : j + 1;
+                acc = fma(w[k], row[j], acc);
+            }
+            st_stream(g + idx, acc);
+        }
     }
 }
 
@@ -1135,7 +1151,8 @@ static cudaError_t launch_lagrange_contig(double *f, long long nlines, int N, co
     if (LT > nlines) LT = (int)nlines;
     size_t smem = 128 + (size_t)LT * N * 8 + (size_t)LT * S * 8 + (size_t)LT * 4 + 16;
     if (smem > SMEM_MAX) return cudaErrorInvalidValue;
-    auto kern = k_lagrange_contig<S>;
+    const bool pow2 = (N & (N - 1)) == 0;
+    auto kern = pow2 ? k_lagrange_contig<S, true> : k_lagrange_contig<S, false>;
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
     bool tma_ok = (((long long)LT * N) % 2 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && (nlines % LT == 0) &&

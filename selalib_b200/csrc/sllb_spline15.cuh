@@ -46,18 +46,29 @@ SLLB_DEV void spline15_sums(const double *x0, const int np, const int si, const 
                                               const double rem_c, double *sum_d, double *sum_c) {
     double sd = WRAP ? 0.0 : rem_d, sc = WRAP ? 0.0 : rem_c;
     if (WRAP) {
+        // two / four independent partial sums: the 16- and 31-term chains are latency, not throughput
+        double sd1 = 0.0, sc1 = 0.0, sc2 = 0.0, sc3 = 0.0;
         int idx = wrap_idx(si - 1, np);
 #pragma unroll
         for (int i = 0; i <= SLLB_HALO_TERMS; ++i) {
-            sd = fma(c_hpw[i], x0[idx * PITCH], sd);
+            if (i & 1) sd1 = fma(c_hpw[i], x0[idx * PITCH], sd1);
+            else sd = fma(c_hpw[i], x0[idx * PITCH], sd);
             idx = (idx == 0) ? np - 1 : idx - 1;
         }
+        sd += sd1;
         idx = wrap_idx(si + 1 - SLLB_HALO_TERMS, np); // k = si+np+1+m, m = -15
 #pragma unroll
         for (int m = -SLLB_HALO_TERMS; m <= SLLB_HALO_TERMS; ++m) {
-            sc = fma(c_hpw[m < 0 ? -m : m], x0[idx * PITCH], sc);
+            const double t = c_hpw[m < 0 ? -m : m], v = x0[idx * PITCH];
+            switch ((m + SLLB_HALO_TERMS) & 3) {
+            case 0: sc = fma(t, v, sc); break;
+            case 1: sc1 = fma(t, v, sc1); break;
+            case 2: sc2 = fma(t, v, sc2); break;
+            default: sc3 = fma(t, v, sc3); break;
+            }
             idx = (idx == np - 1) ? 0 : idx + 1;
         }
+        sc = (sc + sc1) + (sc2 + sc3);
     } else {
 #pragma unroll
         for (int i = 0; i <= SLLB_HALO_TERMS; ++i) {
