@@ -409,8 +409,11 @@ def run_ours(args, rank, world, local_rank):
 
 def main():
     # the image exports NCCL_DEBUG=VERSION, which makes NCCL print a banner on stdout; rank 0 must print ONE JSON line
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL prints its version banner on stdout at debug levels VERSION *and* WARN: drop the level the image exports and
+    # send whatever else NCCL logs to stderr, so that stdout stays the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

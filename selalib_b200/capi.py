@@ -551,9 +551,9 @@ class Sim2d:
                                     C.c_double(x2_min), C.c_double(x2_max), C.c_int(init), C.c_double(kmode),
                                     C.c_double(eps), C.c_double(dt), C.c_int(method), C.c_int(order), C.byref(self.h)))
 
-    def run(self, nsteps):
+    def run(self, nsteps, diagnostics=True):
         rows = np.zeros((nsteps, 8))
-        _ck(lib().sllb_sim2d_run(self.h, C.c_int(nsteps), _p(rows)))
+        _ck(lib().sllb_sim2d_run(self.h, C.c_int(nsteps), _p(rows) if diagnostics else None))
         return rows
 
     def field(self):

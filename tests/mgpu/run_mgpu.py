@@ -20,8 +20,11 @@ import selalib_b200 as sb  # noqa: E402
 
 
 def main():
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+    # NCCL prints its version banner on stdout at debug levels VERSION *and* WARN: drop the level the image exports and
+    # send whatever else NCCL logs to stderr, so that stdout stays the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     sb.init(local)
