@@ -412,6 +412,9 @@ typedef struct sllb_sim2d *sllb_sim2d_t;
 int sllb_sim2d_create(int nc_x1, int nc_x2, double x1_min, double x1_max, double x2_min, double x2_max,
                       int init, double kmode, double eps, double dt, int method, int order, sllb_sim2d_t *S);
 int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows);
+/* the 1D1V step is a dozen kernels on a few MB (launch-bound): by default sllb_sim2d_run records one time step as a CUDA
+ * graph after the first step and replays it; 0 = one launch per kernel (same values) */
+int sllb_set_cuda_graphs(int on);
 int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F);
 int sllb_sim2d_destroy(sllb_sim2d_t S);
 

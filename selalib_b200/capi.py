@@ -124,6 +124,10 @@ def set_remap_rotation(on):
     _ck(lib().sllb_set_remap_rotation(C.c_int(1 if on else 0)))
 
 
+def set_cuda_graphs(on):
+    _ck(lib().sllb_set_cuda_graphs(C.c_int(1 if on else 0)))
+
+
 def set_spline_split(chunks):
     _ck(lib().sllb_set_spline_split(C.c_int(chunks)))
 

@@ -12,6 +12,9 @@ namespace sllb {
 
 static thread_local std::string t_error;
 int g_staging = STAGING_AUTO;
+// the stream every launch of this thread goes to: the legacy default stream, except while sllb_sim2d_run records one
+// time step into a CUDA graph (stream capture needs a stream of its own)
+thread_local cudaStream_t g_stream = 0;
 static int g_device = 0;
 static bool g_device_ok = false;
 
@@ -176,7 +179,7 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
     long long inner = 1, outer = 1;
     for (int d = 0; d < axis; ++d) inner *= F->ext[d];
     for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
-    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, 0, remap, linesum);
+    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, g_stream, remap, linesum);
     if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: line sums are produced by the chunked strided spline kernel only"); }
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
@@ -203,10 +206,10 @@ int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, do
         SLLB_TRY(F->red_scratch.ensure((size_t)nparts * n1 * n2));
         partial = F->red_scratch.p;
     }
-    cudaError_t e = launch_spline_plane(F->d, n1, n2, nplanes, dd0, dd1, partial, 0, remap);
+    cudaError_t e = launch_spline_plane(F->d, n1, n2, nplanes, dd0, dd1, partial, g_stream, remap);
     if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: plane shape or displacement pattern not supported"); }
     SLLB_TRY(check_cuda(e, "k_spline_plane launch"));
-    if (d_rho) SLLB_CUDA(launch_sum_partials(partial, (long long)n1 * n2, nparts, rho_scale, d_rho, 0));
+    if (d_rho) SLLB_CUDA(launch_sum_partials(partial, (long long)n1 * n2, nparts, rho_scale, d_rho, g_stream));
     return SLLB_OK;
 }
 
@@ -216,7 +219,7 @@ int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, dou
     for (int d = 0; d < F->ndim - nv; ++d) nx *= F->ext[d];
     for (int d = F->ndim - nv; d < F->ndim; ++d) nvt *= F->ext[d];
     SLLB_TRY(F->rows.ensure((size_t)nvt * 3));
-    SLLB_CUDA(launch_row_sums(F->d, nx, nvt, F->rows.p, 0));
+    SLLB_CUDA(launch_row_sums(F->d, nx, nvt, F->rows.p, g_stream));
     std::vector<double> h((size_t)nvt * 3);
     SLLB_CUDA(cudaMemcpy(h.data(), F->rows.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 3 + 2 * nv; ++k) out[k] = 0.0;
@@ -371,7 +374,7 @@ int sllb_advect_axis(sllb_field_t F, int axis, int method, int order, const sllb
         if (disp->nvalues < 1) return fail(SLLB_ERR_INVALID, "advect_axis: nvalues < 1");
         SLLB_TRY(F->disp_scratch.ensure((size_t)disp->nvalues));
         SLLB_CUDA(cudaMemcpyAsync(F->disp_scratch.p, disp->values, (size_t)disp->nvalues * sizeof(double),
-                                  cudaMemcpyHostToDevice, 0));
+                                  cudaMemcpyHostToDevice, g_stream));
         dd.v = F->disp_scratch.p;
     }
     dd.scale = disp->scale;
@@ -387,7 +390,7 @@ int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv
     SLLB_TRY(require_device());
     const int nvv = F->ext[v_axis];
     SLLB_TRY(F->disp_scratch.ensure((size_t)nvv));
-    SLLB_CUDA(launch_affine(F->disp_scratch.p, nvv, vmin, dv, 0));
+    SLLB_CUDA(launch_affine(F->disp_scratch.p, nvv, vmin, dv, g_stream));
     dd->v = F->disp_scratch.p; dd->scale = scale;
     dd->odiv = dd->omod = dd->idiv = dd->imod = 1; dd->ostr = dd->istr = 0;
     long long stride = 1;
@@ -434,7 +437,7 @@ int to_dispdesc(const sllb_disp_t *disp, DevBuf &scratch, DispDesc *dd) {
     else {
         if (disp->nvalues < 1) return fail(SLLB_ERR_INVALID, "displacement: nvalues < 1");
         SLLB_TRY(scratch.ensure((size_t)disp->nvalues));
-        SLLB_CUDA(cudaMemcpyAsync(scratch.p, disp->values, (size_t)disp->nvalues * sizeof(double), cudaMemcpyHostToDevice, 0));
+        SLLB_CUDA(cudaMemcpyAsync(scratch.p, disp->values, (size_t)disp->nvalues * sizeof(double), cudaMemcpyHostToDevice, g_stream));
         dd->v = scratch.p;
     }
     dd->scale = disp->scale;
@@ -448,7 +451,7 @@ int upload_shift(sllb_field *F, const int32_t *shift, long long n, const int **d
     if (!shift) return SLLB_OK;
     if (n < 1) return fail(SLLB_ERR_INVALID, "shift table: nvalues < 1");
     SLLB_TRY(F->shift_scratch.ensure((size_t)(n + 1) / 2));
-    SLLB_CUDA(cudaMemcpyAsync(F->shift_scratch.p, shift, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+    SLLB_CUDA(cudaMemcpyAsync(F->shift_scratch.p, shift, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, g_stream));
     *d_shift = reinterpret_cast<const int *>(F->shift_scratch.p);
     return SLLB_OK;
 }
@@ -515,7 +518,7 @@ int sllb_advect_axis_spline_dd(sllb_field_t F, int axis, const sllb_disp_t *disp
     for (int d = 0; d < axis; ++d) inner *= F->ext[d];
     for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
     cudaError_t e = launch_spline_dd(F->d, outer, F->ext[axis], inner, dd, d_shift, nullptr, 0, nullptr, 0, nullptr, nullptr,
-                                     g_staging, 0);
+                                     g_staging, g_stream);
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(SLLB_ERR_UNSUPPORTED, "advect_axis_spline_dd: the local spline needs more than 15 points per line "
@@ -542,7 +545,7 @@ int sllb_reduce_velocity(sllb_field_t F, int nx_axes, double scale, double *d_rh
     for (int d = 0; d < nx_axes; ++d) nx *= F->ext[d];
     for (int d = nx_axes; d < F->ndim; ++d) nv *= F->ext[d];
     SLLB_TRY(F->red_scratch.ensure(reduce_scratch_doubles(nx, nv)));
-    SLLB_CUDA(launch_reduce_velocity(F->d, nx, nv, scale, d_rho, F->red_scratch.p, 0));
+    SLLB_CUDA(launch_reduce_velocity(F->d, nx, nv, scale, d_rho, F->red_scratch.p, g_stream));
     return SLLB_OK;
 }
 int sllb_reduce_velocity_host(sllb_field_t F, int nx_axes, double scale, double *h_rho) {
@@ -625,18 +628,23 @@ int sllb_poisson_destroy(sllb_poisson_t P) {
 int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, double *d_e1, double *d_e2, double *d_e3) {
     if (!P || !d_rho) return fail(SLLB_ERR_INVALID, "poisson_solve: null");
     SLLB_TRY(require_device());
+    if (P->stream != g_stream) {
+        SLLB_CUFFT(cufftSetStream(P->fwd, g_stream));
+        SLLB_CUFFT(cufftSetStream(P->bwd, g_stream));
+        P->stream = g_stream;
+    }
     SLLB_CUFFT(cufftExecD2Z(P->fwd, const_cast<double *>(d_rho), P->rho_hat));
     cufftDoubleComplex *ph = d_phi ? P->spec[0] : nullptr, *e1 = d_e1 ? P->spec[1] : nullptr;
     cufftDoubleComplex *e2 = d_e2 ? P->spec[2] : nullptr, *e3 = d_e3 ? P->spec[3] : nullptr;
     if (P->dim == 1) {
         if (d_phi) return fail(SLLB_ERR_UNSUPPORTED, "poisson1d: potential output not implemented (the reference returns E only)");
-        if (e1) SLLB_CUDA(launch_poisson1d_mult(P->rho_hat, P->n[0], P->L[0], e1, 0));
+        if (e1) SLLB_CUDA(launch_poisson1d_mult(P->rho_hat, P->n[0], P->L[0], e1, g_stream));
         e2 = e3 = nullptr;
     } else if (P->dim == 2) {
-        SLLB_CUDA(launch_poisson2d_mult(P->rho_hat, P->n[0], P->n[1], P->L[0], P->L[1], ph, e1, e2, 0));
+        SLLB_CUDA(launch_poisson2d_mult(P->rho_hat, P->n[0], P->n[1], P->L[0], P->L[1], ph, e1, e2, g_stream));
         e3 = nullptr;
     } else {
-        SLLB_CUDA(launch_poisson3d_mult(P->rho_hat, P->n[0], P->n[1], P->n[2], P->L[0], P->L[1], P->L[2], ph, e1, e2, e3, 0));
+        SLLB_CUDA(launch_poisson3d_mult(P->rho_hat, P->n[0], P->n[1], P->n[2], P->L[0], P->L[1], P->L[2], ph, e1, e2, e3, g_stream));
     }
     if (ph) SLLB_CUFFT(cufftExecZ2D(P->bwd, ph, d_phi));
     if (e1) SLLB_CUFFT(cufftExecZ2D(P->bwd, e1, d_e1));
@@ -848,7 +856,7 @@ int sllb_advect_axis_hermite(sllb_field_t F, int axis, double xmin, double xmax,
     for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
     const int np = F->ext[axis];
     cudaError_t e = launch_hermite(F->d, outer, np, inner, dd, (xmax - xmin) / (double)(np - 1), inplace_semantics ? 1 : 0, 0, 0.0, 0.0,
-                                   g_staging, 0);
+                                   g_staging, g_stream);
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(SLLB_ERR_UNSUPPORTED, "advect_axis_hermite: Hermite splines need >= 27 points per line (fast algorithm)");

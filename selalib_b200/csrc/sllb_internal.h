@@ -17,6 +17,7 @@ int check_cuda(cudaError_t e, const char *what);
 int check_cufft(cufftResult r, const char *what);
 int require_device();
 extern int g_staging;
+extern thread_local cudaStream_t g_stream;
 
 #define SLLB_CUDA(call)                                  \
     do {                                                 \
@@ -84,6 +85,7 @@ struct sllb_poisson {
     cufftDoubleComplex *rho_hat = nullptr, *spec[4] = {nullptr, nullptr, nullptr, nullptr};
     sllb::DevBuf rho_in, out[4];
     long long nreal = 0, ncplx = 0;
+    cudaStream_t stream = 0;   // the stream the two plans are currently bound to
 };
 
 namespace sllb {

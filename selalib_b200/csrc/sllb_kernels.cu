@@ -22,6 +22,7 @@ static long long g_launches = 0;
 long long launch_count() { return g_launches; }
 void launch_count_reset() { g_launches = 0; }
 void count_launch() { ++g_launches; }
+void count_launches(long long n) { g_launches += n; }
 #define COUNT_LAUNCH() (++g_launches)
 
 // ------------------------------------------------------------------------------------------------
@@ -310,6 +311,63 @@ __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, c
     OutMap om = make_outmap(rd, o, in, N, inner);
     if constexpr (METHOD == 0) spline_line<BW, true>(s + tid, N, disp, &om);
     else lagrange_line<S, BW>(s + tid, N, disp, &om);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a (split): Lagrange on a strided axis with every line cut into P chunks, one group of BW lanes per chunk
+// (block = BW lines x P chunks).  Same tile and arithmetic as k_advect_strided; used when one thread per line would
+// leave the GPU mostly idle (few lines, long lines: the 1D1V problems) -- the stencil needs no sweep, so the chunks
+// are independent once the whole lines sit in shared memory (in-place update: nobody reads global memory after that).
+// ------------------------------------------------------------------------------------------------
+template <int BW, int S>
+__global__ void __launch_bounds__(1024) k_lagrange_strided_split(double *__restrict__ f, const long long nlines, const int N,
+                                                                  const long long inner, const DispDesc dd, const int use_tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s = reinterpret_cast<double *>(smem_raw + 128);
+    const int tid = threadIdx.x, lane = tid % BW, chunk = tid / BW, P = blockDim.x / BW;
+    const long long l = (long long)blockIdx.x * BW + lane;
+    const bool active = l < nlines;
+    const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    double *base = f + o * (long long)N * inner + in;
+    if (use_tma) {
+        if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(N * BW * 8));
+        const double *src0 = base - lane;
+        for (int j = tid; j < N; j += blockDim.x) bulk_g2s(s + (size_t)j * BW, src0 + (long long)j * inner, BW * 8, bar);
+        mbar_wait(bar, 0);
+    } else {
+        if (active)
+            for (int j = chunk; j < N; j += P) cp_async8(s + (size_t)j * BW + lane, base + (long long)j * inner);
+        cp_async_wait_all();
+        __syncthreads();
+    }
+    if (!active) return;
+    const int C = (N + P - 1) / P, i0 = chunk * C, i1 = (i0 + C < N) ? i0 + C : N;
+    if (i0 >= i1) return;
+    double pp[S], w[S];
+    int idx = lagr_setup<S>(disp_of(dd, o, in), N, pp) + i0;
+    idx %= N;
+    const double *sc = s + lane;
+#pragma unroll
+    for (int k = 1; k < S; ++k) {
+        w[k] = sc[idx * BW];
+        idx = (idx == N - 1) ? 0 : idx + 1;
+    }
+    double *p = base + (long long)i0 * inner;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+#pragma unroll
+        for (int k = 0; k < S - 1; ++k) w[k] = w[k + 1];
+        w[S - 1] = sc[idx * BW];
+        idx = (idx == N - 1) ? 0 : idx + 1;
+        double acc = pp[0] * w[0];
+#pragma unroll
+        for (int k = 1; k < S; ++k) acc = fma(pp[k], w[k], acc);
+        st_stream(p, acc);
+        p += inner;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1131,9 +1189,42 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
     return cudaGetLastError();
 }
 
+template <int BW, int S>
+static cudaError_t launch_lagrange_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
+                                           int staging, cudaStream_t st, int P) {
+    const size_t smem = 128 + (size_t)N * BW * 8;
+    auto kern = k_lagrange_strided_split<BW, S>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    const bool tma_ok = (inner % BW == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * BW * 8 < (1u << 20));
+    const int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
+    const long long nblk = (nlines + BW - 1) / BW;
+    kern<<<(unsigned)nblk, BW * P, smem, st>>>(f, nlines, N, inner, dd, use_tma);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 template <int METHOD, int S>
 static cudaError_t launch_strided(double *f, long long nlines, int N, long long inner, const DispDesc &dd, int staging,
                                   cudaStream_t st, const RemapDst &rd) {
+    if constexpr (METHOD == 1) {
+        // few, long lines (the 1D1V problems): one thread per line leaves most SMs idle -- cut the lines into chunks
+        const long long blocks32 = (nlines + 31) / 32;
+        if (!rd.on && blocks32 < 2 * 148 && N >= 128) {
+            int P = 1;
+            while (P < 32 && N / (2 * P) >= 16 && blocks32 * P < 8 * 148) P *= 2;
+            if (P > 1) {
+                // narrowest group of lanes that still gives every SM a block, widest that fits otherwise
+                int bw = 32;
+                while (bw > 8 && ((size_t)N * bw * 8 + 128 > SMEM_MAX || (nlines + bw - 1) / bw < 148)) bw /= 2;
+                if ((size_t)N * bw * 8 + 128 <= SMEM_MAX && bw * P <= 1024) {
+                    if (bw == 32) return launch_lagrange_split_t<32, S>(f, nlines, N, inner, dd, staging, st, P);
+                    if (bw == 16) return launch_lagrange_split_t<16, S>(f, nlines, N, inner, dd, staging, st, P);
+                    return launch_lagrange_split_t<8, S>(f, nlines, N, inner, dd, staging, st, P);
+                }
+            }
+        }
+    }
     // widest tile that fits: BW lanes x N points x 8 B (+128 B header)
     if ((size_t)N * 32 * 8 + 128 <= SMEM_MAX && (inner >= 32 || nlines >= 32))
         return launch_strided_t<32, METHOD, S>(f, nlines, N, inner, dd, staging, st, rd);

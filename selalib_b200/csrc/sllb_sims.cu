@@ -855,7 +855,13 @@ struct sllb_sim2d {
     sllb_poisson *poisson = nullptr;
     DevBuf rho, E;
     int istep = 0;
+    // one time step recorded as a CUDA graph (the 1D1V problems are a few MB: the step is bound by its ~10 kernel
+    // launches, not by memory traffic)
+    cudaStream_t gstream = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    long long glaunches = 0;   // kernels in the recorded step (launch bookkeeping of the replays)
 };
+static int g_cuda_graphs = 1;
 __global__ void k_init2d(double *f, int n0, int n1, double x0min, double x1min, double d0, double d1, int init,
                          double kmode, double eps) {
     const long long ntot = (long long)n0 * n1;
@@ -870,7 +876,7 @@ __global__ void k_init2d(double *f, int n0, int n1, double x0min, double x1min, 
 static int sim2d_field(sllb_sim2d *S) {
     // rho = 1 - sum_j f w_j, trapezoid weights over the duplicated v end points == delta_v * plain sum (:937-943,1590-1604)
     SLLB_TRY(sllb_reduce_velocity(S->F, 1, S->delta[1], S->rho.p));
-    SLLB_CUDA(launch_rho_1d1v(S->rho.p, S->nc[0], 1.0, 1.0, 0));
+    SLLB_CUDA(launch_rho_1d1v(S->rho.p, S->nc[0], 1.0, 1.0, g_stream));
     SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, nullptr, S->E.p, nullptr, nullptr));
     return SLLB_OK;
 }
@@ -898,6 +904,8 @@ int sllb_sim2d_create(int nc_x1, int nc_x2, double x1_min, double x1_max, double
 }
 int sllb_sim2d_destroy(sllb_sim2d_t S) {
     if (!S) return SLLB_OK;
+    if (S->gexec) cudaGraphExecDestroy(S->gexec);
+    if (S->gstream) cudaStreamDestroy(S->gstream);
     sllb_poisson_destroy(S->poisson);
     sllb_field_destroy(S->F);
     delete S;
@@ -920,7 +928,8 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
     w1[0] = 0.5 * (S->xmin[1] + S->xmax[1]);
     w2[0] = 0.5 * (S->xmin[1] * S->xmin[1] + S->xmax[1] * S->xmax[1]);
     std::vector<double> hE(S->nc[0]);
-    for (int it = 0; it < nsteps; ++it) {
+    if (S->gexec) SLLB_CUDA(cudaDeviceSynchronize()); // the replays run on their own stream: nothing of the caller's may be in flight
+    auto one_step = [&]() -> int {
         bool T = false;
         for (int ss = 0; ss < 3; ++ss) {
             if (T) { // out(x) = in(x - v*step*dt)  (:1570-1585)
@@ -931,6 +940,39 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
                 SLLB_TRY(sllb_advect_axis_field(S->F, 1, S->method, S->order, S->E.p, 1, steps[ss] * S->dt / S->delta[1]));
             }
             T = !T;
+        }
+        return SLLB_OK;
+    };
+    for (int it = 0; it < nsteps; ++it) {
+        if (g_cuda_graphs && !S->gexec && S->istep >= 1) {
+            // every buffer the step needs exists after the first step: record the next one (it is executed by the
+            // launch below, not while recording)
+            if (!S->gstream) SLLB_CUDA(cudaStreamCreateWithFlags(&S->gstream, cudaStreamNonBlocking));
+            SLLB_CUDA(cudaDeviceSynchronize());
+            cudaGraph_t graph = nullptr;
+            const long long l0 = launch_count();
+            g_stream = S->gstream;
+            cudaError_t ce = cudaStreamBeginCapture(S->gstream, cudaStreamCaptureModeThreadLocal);
+            int rc = ce == cudaSuccess ? one_step() : SLLB_ERR_CUDA;
+            cudaError_t ee = cudaStreamEndCapture(S->gstream, &graph);
+            g_stream = 0;
+            S->glaunches = launch_count() - l0;
+            count_launches(-S->glaunches); // recorded, not executed
+            if (rc == SLLB_OK && ee == cudaSuccess && graph) ee = cudaGraphInstantiate(&S->gexec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != SLLB_OK || ce != cudaSuccess || ee != cudaSuccess) { // fall back to plain launches, loudly recorded
+                cudaGetLastError();
+                S->gexec = nullptr;
+                g_cuda_graphs = 0;
+                set_error("sim2d_run: CUDA graph capture failed, continuing with stream launches");
+            }
+        }
+        if (S->gexec) {
+            SLLB_CUDA(cudaGraphLaunch(S->gexec, S->gstream));
+            count_launches(S->glaunches);
+            if (rows) SLLB_CUDA(cudaStreamSynchronize(S->gstream)); // the diagnostics below read f and E on the default stream
+        } else {
+            SLLB_TRY(one_step());
         }
         S->istep += 1;
         if (rows) {
@@ -947,6 +989,11 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
         }
     }
     SLLB_CUDA(cudaDeviceSynchronize());
+    return SLLB_OK;
+}
+/* 1 (default): sllb_sim2d_run replays one recorded time step as a CUDA graph; 0: one launch per kernel */
+int sllb_set_cuda_graphs(int on) {
+    g_cuda_graphs = on ? 1 : 0;
     return SLLB_OK;
 }
 } // extern "C"
