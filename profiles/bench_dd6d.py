@@ -57,6 +57,8 @@ def main():
         return float(t.item())
 
     n = a.n
+    if os.environ.get("SLLB_PLANE") == "0":
+        sb.set_plane_kernel(False)   # A/B: eta1 and eta2 as two passes instead of the fused plane kernel
     S = sb.Sim6d([n] * 6, 6.0, [4 * np.pi] * 3, a.stencil, a.stencil, 0.01, 0.01, [0.5] * 3, comm=comm)
     lay = S.layout()
     S.run(a.warmup, first=True)

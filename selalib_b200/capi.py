@@ -281,7 +281,7 @@ class Field:
         d = _disp(self, values, scale, dsel)
         _ck(lib().sllb_advect_axis_hermite(self.h, C.c_int(axis), C.c_double(xmin), C.c_double(xmax), C.byref(d), C.c_int(1 if inplace else 0)))
 
-    def advect_plane(self, values0, dsel0, scale0, values1, dsel1, scale1, rho_scale=None):
+    def advect_plane(self, values0, dsel0, scale0, values1, dsel1, scale1, rho_scale=None, method=METHOD_SPLINE, order=4):
         """K1c: spline passes along axes 0 and 1 in one sweep; returns rho (host) when rho_scale is given."""
         ds = []
         keep = []
@@ -296,7 +296,7 @@ class Field:
         if rho_scale is not None:
             import torch
             rho_dev = torch.empty(self.extents[0] * self.extents[1], dtype=torch.float64, device="cuda")
-        _ck(lib().sllb_advect_plane(self.h, C.c_int(METHOD_SPLINE), C.c_int(4), C.byref(ds[0]), C.byref(ds[1]),
+        _ck(lib().sllb_advect_plane(self.h, C.c_int(method), C.c_int(order), C.byref(ds[0]), C.byref(ds[1]),
                                     C.c_double(rho_scale if rho_scale is not None else 0.0),
                                     C.cast(vp(rho_dev.data_ptr()), dp) if rho_dev is not None else None))
         if rho_dev is not None:

@@ -213,6 +213,17 @@ int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, do
     return SLLB_OK;
 }
 
+// K2d: Lagrange passes along axes 0 and 1 on every plane in one sweep
+int advect_lagrange_plane_dev(sllb_field *F, int method, int order, const DispDesc &dd0, const DispDesc &dd1) {
+    if (!F || F->ndim < 2) return fail(SLLB_ERR_INVALID, "advect_plane: bad field");
+    if (!g_plane_kernel) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: disabled (sllb_set_plane_kernel)");
+    long long nplanes = 1;
+    for (int d = 2; d < F->ndim; ++d) nplanes *= F->ext[d];
+    cudaError_t e = launch_lagrange_plane(F->d, F->ext[0], F->ext[1], nplanes, method, order, dd0, dd1, g_stream);
+    if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: plane shape, stencil or displacement pattern not supported"); }
+    return check_cuda(e, "k_lagrange_plane launch");
+}
+
 int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out) {
     if (!F || nv < 0 || nv >= F->ndim || !out) return fail(SLLB_ERR_INVALID, "moments: bad arguments");
     long long nx = 1, nvt = 1;
@@ -529,11 +540,15 @@ int sllb_advect_axis_spline_dd(sllb_field_t F, int axis, const sllb_disp_t *disp
 int sllb_advect_plane(sllb_field_t F, int method, int order, const sllb_disp_t *disp0, const sllb_disp_t *disp1,
                       double rho_scale, double *d_rho) {
     if (!F) return fail(SLLB_ERR_INVALID, "advect_plane: null field");
-    if (method != SLLB_METHOD_SPLINE || order != 4) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: cubic splines only");
     SLLB_TRY(require_device());
     DispDesc d0, d1;
     SLLB_TRY(to_dispdesc(disp0, F->disp_scratch, &d0));
     SLLB_TRY(to_dispdesc(disp1, F->disp_scratch2, &d1));
+    if (method == SLLB_METHOD_LAGRANGE_FIXED || method == SLLB_METHOD_LAGRANGE_CENTERED) {
+        if (d_rho) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: the charge density comes with the spline plane kernel only");
+        return advect_lagrange_plane_dev(F, method, order, d0, d1);
+    }
+    if (method != SLLB_METHOD_SPLINE || order != 4) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: cubic splines (order 4) or Lagrange stencils");
     return advect_plane_dev(F, d0, d1, rho_scale, d_rho);
 }
 

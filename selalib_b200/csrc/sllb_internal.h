@@ -96,6 +96,7 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
                     double *linesum = nullptr);
 int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
                      const RemapDst *remap = nullptr);
+int advect_lagrange_plane_dev(sllb_field *F, int method, int order, const DispDesc &dd0, const DispDesc &dd1);
 extern int g_plane_kernel;
 int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv, double scale, DispDesc *dd);
 int make_field_disp(sllb_field *F, int axis, const double *d_field, int nfield_axes, double scale, DispDesc *dd);

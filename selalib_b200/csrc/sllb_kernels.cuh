@@ -42,6 +42,10 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
                                 double *rho_partial, cudaStream_t st, const RemapDst *remap = nullptr);
 cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts, double scale, double *rho, cudaStream_t st);
 
+// K2d: the axis-0 and the axis-1 Lagrange pass on every contiguous n0 x n1 plane in one sweep (displacements constant
+// over a plane).  cudaErrorNotSupported when the plane / displacement pattern / stencil does not fit.
+cudaError_t launch_lagrange_plane(double *f, int n0, int n1, long long nplanes, int method, int order, const DispDesc &dd0,
+                                  const DispDesc &dd1, cudaStream_t st);
 // K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]
 cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
                                  long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st);
