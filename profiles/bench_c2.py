@@ -14,13 +14,18 @@ import selalib_b200 as sb  # noqa: E402
 
 n = int(os.environ.get("SLLB_C2_N", "1024"))
 steps = int(os.environ.get("SLLB_C2_STEPS", "2000"))
+spline = os.environ.get("SLLB_C2_METHOD", "lagrange7") == "spline"   # C1: 128 x 128 Landau damping with cubic splines
 sb.init(0)
-res = {"workload": f"1D1V two-stream {n}x{n} fp64, Lagrange fixed 7-point, Strang VTV, dt=0.002, k=0.5, eps=0.01, v in [-6,6]",
+res = {"workload": (f"1D1V Landau damping {n}x{n} fp64, periodic cubic splines, Strang VTV, dt=0.1, k=0.5, eps=1e-3, v in [-6,6]" if spline else
+                    f"1D1V two-stream {n}x{n} fp64, Lagrange fixed 7-point, Strang VTV, dt=0.002, k=0.5, eps=0.01, v in [-6,6]"),
        "passes_per_step": 3, "points": n * n}
 for graphs in ([0, 1] if hasattr(sb, "set_cuda_graphs") else [None]):
     if graphs is not None:
         sb.set_cuda_graphs(graphs)
-    S = sb.Sim2d(n, n, 0.0, 4 * np.pi, -6.0, 6.0, 1, 0.5, 0.01, 0.002, method=sb.METHOD_LAGRANGE_FIXED, order=7)
+    if spline:
+        S = sb.Sim2d(n, n, 0.0, 4 * np.pi, -6.0, 6.0, 0, 0.5, 1e-3, 0.1, method=sb.METHOD_SPLINE, order=4)
+    else:
+        S = sb.Sim2d(n, n, 0.0, 4 * np.pi, -6.0, 6.0, 1, 0.5, 0.01, 0.002, method=sb.METHOD_LAGRANGE_FIXED, order=7)
     S.run(200, diagnostics=False) if "diagnostics" in S.run.__code__.co_varnames else S.run(200)
     torch.cuda.synchronize()
     sb.launch_count_reset()
