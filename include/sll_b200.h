@@ -317,6 +317,10 @@ int sllb_dd6d_set_force_halo(int on);
  * edge planes straight into the neighbour's halo buffer over NVLink; 0: pack + ncclSend/ncclRecv */
 int sllb_dd6d_set_halo_p2p(int on);
 int sllb_dd6d_p2p(sllb_dd6d_t D, int *enabled);
+/* a split-axis pass over peer memory is pipelined: the lines are cut into `chunks` pieces, the exchange of piece c+1
+ * (edge planes stored into the neighbours' halo buffers + barrier) overlaps the stencil kernel of piece c on a second
+ * stream.  Default 4 (or SLLB_HALO_CHUNKS); 1 = exchange everything, then advect.  Same values either way. */
+int sllb_dd6d_set_halo_chunks(int chunks);
 
 /* ---- a17 / (f)3: operator-splitting schedules ------------------------------
  * sll_f_new_time_splitting_coeff (src/time_integration/splitting_methods/sll_m_time_splitting_coeff.F90:86-594):

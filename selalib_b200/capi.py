@@ -647,6 +647,10 @@ def dd6d_set_halo_p2p(on):
     _ck(lib().sllb_dd6d_set_halo_p2p(C.c_int(1 if on else 0)))
 
 
+def dd6d_set_halo_chunks(chunks):
+    _ck(lib().sllb_dd6d_set_halo_chunks(C.c_int(chunks)))
+
+
 def dd6d_set_force_halo(on):
     _ck(lib().sllb_dd6d_set_force_halo(C.c_int(1 if on else 0)))
 

@@ -38,7 +38,13 @@ struct sllb_dd6d {
     DevBuf flag;
     int parity = 0;
     double exch_ms = 0.0;      // device time of the last halo exchange (pack + send/recv)
+    // pipelined split-axis pass: the lines are cut into chunks, the exchange of chunk c+1 (peer stores + barrier, on
+    // s_comm) overlaps the stencil kernel of chunk c (on s_comp)
+    cudaStream_t s_comm = nullptr, s_comp = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_comm0 = nullptr, ev_comm1 = nullptr, ev_chunk[16] = {};
+    bool exch_pending = false; // exch_ms of the last pipelined pass still to be read from ev_comm0/1
 };
+static int g_halo_chunks = -1; // -1: SLLB_HALO_CHUNKS or 4; 1 = exchange everything, then one kernel
 
 static int g_force_halo = 0;
 static int g_halo_p2p = 1;   // 1: peer stores when available, 0: pack + ncclSend/ncclRecv
@@ -147,8 +153,18 @@ int sllb_dd6d_set_force_halo(int on) {
     g_force_halo = on ? 1 : 0;
     return SLLB_OK;
 }
+int sllb_dd6d_set_halo_chunks(int chunks) {
+    if (chunks < 1 || chunks > 16) return fail(SLLB_ERR_INVALID, "dd6d_set_halo_chunks: 1..16");
+    g_halo_chunks = chunks;
+    return SLLB_OK;
+}
 int sllb_dd6d_destroy(sllb_dd6d_t D) {
     if (!D) return SLLB_OK;
+    if (D->s_comm) {
+        cudaStreamDestroy(D->s_comm); cudaStreamDestroy(D->s_comp);
+        cudaEventDestroy(D->ev_start); cudaEventDestroy(D->ev_end); cudaEventDestroy(D->ev_comm0); cudaEventDestroy(D->ev_comm1);
+        for (cudaEvent_t e : D->ev_chunk) if (e) cudaEventDestroy(e);
+    }
     for (void *ptr : D->ipc_opened) cudaIpcCloseMemHandle(ptr);
     sllb_field_destroy(D->F);
     delete D;
@@ -241,10 +257,85 @@ int sllb_dd6d_halo_download(sllb_dd6d_t D, int side, double *host) {
 }
 int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms) {
     if (!D || !ms) return fail(SLLB_ERR_INVALID, "dd6d_exchange_ms: null");
+    if (D->exch_pending) { // pipelined pass: first pack to last barrier on the communication stream (overlapped with compute)
+        float t = 0;
+        cudaEventSynchronize(D->ev_comm1);
+        cudaEventElapsedTime(&t, D->ev_comm0, D->ev_comm1);
+        D->exch_ms = t;
+        D->exch_pending = false;
+    }
     *ms = D->exch_ms;
     return SLLB_OK;
 }
 
+} // extern "C"
+/* Split-axis pass with the exchange pipelined against the stencil: chunk c of the lines is exchanged (edge planes stored
+ * straight into the neighbours' halo buffers, all-reduce as barrier) on the communication stream while the halo-cells
+ * kernel works on chunk c-1 on the compute stream.  Same kernels, same values as exchange-then-advect. */
+static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const DispDesc &dd, int nchunks) {
+    const int h = (stencil - 1) / 2, n = D->nw[axis];
+    const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
+    if (!D->s_comm) {
+        // the stencil kernel fills every SM up to the resident-block limit with its one-warp blocks; the communication
+        // stream gets the higher priority so that the few pack blocks of the next chunk are placed as soon as slots free up
+        int prio_lo = 0, prio_hi = 0;
+        SLLB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_comm, cudaStreamNonBlocking, prio_hi));
+        SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_comp, cudaStreamNonBlocking, prio_lo));
+        SLLB_CUDA(cudaEventCreateWithFlags(&D->ev_start, cudaEventDisableTiming));
+        SLLB_CUDA(cudaEventCreateWithFlags(&D->ev_end, cudaEventDisableTiming));
+        SLLB_CUDA(cudaEventCreate(&D->ev_comm0));
+        SLLB_CUDA(cudaEventCreate(&D->ev_comm1));
+        for (cudaEvent_t &e : D->ev_chunk) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // chunks of whole `o` slabs when there are enough of them, else ranges of `in` in multiples of 32 lines (TMA rows)
+    std::vector<LineBox> boxes;
+    if (outer >= nchunks) {
+        for (int c = 0; c < nchunks; ++c) {
+            const long long a = outer * c / nchunks, b = outer * (c + 1) / nchunks;
+            if (b > a) boxes.push_back(LineBox{a, b - a, 0, inner});
+        }
+    } else {
+        const long long units = inner / 32;
+        if (outer != 1 || inner % 32 != 0 || units < nchunks) boxes.push_back(LineBox{0, outer, 0, inner});
+        else
+            for (int c = 0; c < nchunks; ++c) {
+                const long long a = units * c / nchunks * 32, b = units * (c + 1) / nchunks * 32;
+                if (b > a) boxes.push_back(LineBox{0, 1, a, b - a});
+            }
+    }
+    // two pack blocks per SM: enough stores in flight for NVLink, and the stencil kernel of the previous chunk keeps most of
+    // every SM
+    static const int pack_blocks = [] { const char *e = getenv("SLLB_PACK_BLOCKS"); return (e && atoi(e) > 0) ? atoi(e) : 148 * 2; }();
+    const int par = D->parity;
+    double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 8 + par * 2 + 1]);
+    double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + par * 2 + 0]);
+    D->cur_l = D->pbuf[par * 2 + 0].p; D->cur_r = D->pbuf[par * 2 + 1].p;
+    SLLB_CUDA(cudaEventRecord(D->ev_start, 0));
+    SLLB_CUDA(cudaStreamWaitEvent(D->s_comm, D->ev_start, 0));
+    SLLB_CUDA(cudaStreamWaitEvent(D->s_comp, D->ev_start, 0));
+    SLLB_CUDA(cudaEventRecord(D->ev_comm0, D->s_comm));
+    for (size_t c = 0; c < boxes.size(); ++c) {
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, h, dst_r, D->s_comm, &boxes[c], pack_blocks));
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - h, h, dst_l, D->s_comm, &boxes[c], pack_blocks));
+        SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, D->s_comm));
+        SLLB_CUDA(cudaEventRecord(D->ev_chunk[c], D->s_comm));
+    }
+    SLLB_CUDA(cudaEventRecord(D->ev_comm1, D->s_comm));
+    for (size_t c = 0; c < boxes.size(); ++c) {
+        SLLB_CUDA(cudaStreamWaitEvent(D->s_comp, D->ev_chunk[c], 0));
+        cudaError_t e = launch_lagrange_halo(D->F->d, D->cur_l, D->cur_r, outer, n, inner, stencil, dd, g_staging, D->s_comp, &boxes[c]);
+        if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: stencil / block size not implemented"); }
+        SLLB_TRY(check_cuda(e, "k_lagrange_halo launch"));
+    }
+    SLLB_CUDA(cudaEventRecord(D->ev_end, D->s_comp));
+    SLLB_CUDA(cudaStreamWaitEvent(0, D->ev_end, 0));
+    D->parity ^= 1;
+    D->hw_l = h; D->hw_r = h; D->halo_axis = axis;
+    D->exch_pending = true;
+    return SLLB_OK;
+}
+extern "C" {
 /* halo exchange + sll_s_advection_6d_lagrange_dd_slim_advect_eta{axis+1}: fixed odd stencil, in place.
  * procs(axis) == 1 uses the periodic kernel directly (same arithmetic as the reference's local periodic
  * halo copy followed by the halo-cells stencil). */
@@ -256,6 +347,19 @@ int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_
     if (axis == 0) return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: a split contiguous axis (eta1) is not implemented "
                                                      "(sll_f_set_process_grid splits eta1 only from 64 ranks on)");
     const int h = (stencil - 1) / 2;
+    if (g_halo_chunks < 0) { const char *e = getenv("SLLB_HALO_CHUNKS"); g_halo_chunks = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 4; }
+    {
+        const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
+        const size_t cl = (size_t)(outer * h * inner);
+        if (D->p2p && g_halo_p2p && D->procs[axis] > 1 && cl <= D->pcap && g_halo_chunks > 1 && disp->values_on_device && h <= D->nw[axis]) {
+            DispDesc ddp;
+            ddp.v = disp->values; ddp.scale = disp->scale;
+            ddp.odiv = disp->odiv > 0 ? disp->odiv : 1; ddp.omod = disp->omod > 0 ? disp->omod : 1; ddp.ostr = disp->ostr;
+            ddp.idiv = disp->idiv > 0 ? disp->idiv : 1; ddp.imod = disp->imod > 0 ? disp->imod : 1; ddp.istr = disp->istr;
+            return dd6d_advect_axis_pipelined(D, axis, stencil, ddp, g_halo_chunks);
+        }
+    }
+    D->exch_pending = false;
     SLLB_TRY(sllb_dd6d_halo_exchange(D, axis, h, h));
     DispDesc dd;
     if (disp->values_on_device) dd.v = disp->values;
@@ -546,7 +650,7 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
         // splines: halo of one plane on both sides, shifts 0 and -1 (:1082-1087); else fixed Lagrange
         if (S->p.advector == SLLB_ADVECTOR_SPLINE) SLLB_TRY(sllb_dd6d_advect_axis_spline(S->D, 3 + d, &ds, nullptr, 1, 1));
         else SLLB_TRY(sllb_dd6d_advect_axis(S->D, 3 + d, S->p.stencil_v, &ds));
-        if (S->D->procs[3 + d] > 1) S->halo_ms += S->D->exch_ms;
+        if (S->D->procs[3 + d] > 1) { double ms = 0; SLLB_TRY(sllb_dd6d_exchange_ms(S->D, &ms)); S->halo_ms += ms; }
     }
     return SLLB_OK;
 }

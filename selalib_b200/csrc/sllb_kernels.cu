@@ -964,15 +964,17 @@ template <int BW, int S>
 __global__ void __launch_bounds__(BW) k_lagrange_halo(double *__restrict__ f, const double *__restrict__ hl,
                                                        const double *__restrict__ hr, const long long nlines,
                                                        const int N, const long long inner, const DispDesc dd,
-                                                       const int use_tma) {
+                                                       const int use_tma, const LineBox lbx) {
     constexpr int H = (S - 1) / 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *s = reinterpret_cast<double *>(smem_raw + 128);
     const int tid = threadIdx.x;
+    // the lines of the sub-box lbx (all of them when it spans the block): o in [o0, o0+ocount), in in [i0, i0+icount)
     const long long l = (long long)blockIdx.x * BW + tid;
     const bool active = l < nlines;
-    const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    const long long osub = active ? l / lbx.icount : 0;
+    const long long o = lbx.o0 + osub, in = lbx.i0 + (active ? l - osub * lbx.icount : 0);
     double *base = f + o * (long long)N * inner + in;
     const double *lb = hl + o * (long long)H * inner + in;
     const double *rb = hr + o * (long long)H * inner + in;
@@ -1015,16 +1017,31 @@ __global__ void __launch_bounds__(BW) k_lagrange_halo(double *__restrict__ f, co
 }
 
 // K7: halo pack, buf[o][j][in] = f[o][j0 + j][in] for j < hw; f viewed as [outer][n][inner]
-__global__ void __launch_bounds__(256) k_halo_pack(const double *__restrict__ f, const long long outer, const int n,
-                                                   const long long inner, const int j0, const int hw,
-                                                   double *__restrict__ buf) {
-    const long long chunk = (long long)hw * inner;
-    for (long long o = blockIdx.y; o < outer; o += gridDim.y) {
-        const double *src = f + (o * n + j0) * inner;
-        double *dst = buf + o * chunk;
-        for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < chunk; t += (long long)gridDim.x * 256)
-            dst[t] = __ldcs(src + t);
-    }
+// VEC: 16-byte loads/stores (rows 16-byte aligned and of even length), four in flight per thread: the stores may cross
+// NVLink (peer halo buffers), where latency, not issue rate, limits a thread
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_halo_pack(const double *__restrict__ f, const int n, const long long inner,
+                                                   const int j0, const int hw, double *__restrict__ buf, const LineBox lbx) {
+    const long long stride = (long long)gridDim.x * 256, t0 = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (long long o = lbx.o0 + blockIdx.y; o < lbx.o0 + lbx.ocount; o += gridDim.y)
+        for (int j = 0; j < hw; ++j) {
+            const double *src = f + (o * n + j0 + j) * inner + lbx.i0;
+            double *dst = buf + (o * hw + j) * inner + lbx.i0;
+            if (VEC) {
+                const double2 *s2 = reinterpret_cast<const double2 *>(src);
+                double2 *d2 = reinterpret_cast<double2 *>(dst);
+                const long long n2 = lbx.icount / 2;
+                long long t = t0;
+                for (; t + 3 * stride < n2; t += 4 * stride) {
+                    const double2 a = __ldcs(s2 + t), b = __ldcs(s2 + t + stride), c = __ldcs(s2 + t + 2 * stride),
+                                  d = __ldcs(s2 + t + 3 * stride);
+                    d2[t] = a; d2[t + stride] = b; d2[t + 2 * stride] = c; d2[t + 3 * stride] = d;
+                }
+                for (; t < n2; t += stride) d2[t] = __ldcs(s2 + t);
+            } else {
+                for (long long t = t0; t < lbx.icount; t += stride) dst[t] = __ldcs(src + t);
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1343,7 +1360,7 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
 
 template <int S>
 static cudaError_t launch_lagrange_halo_t(double *f, const double *hl, const double *hr, long long nlines, int n,
-                                          long long inner, const DispDesc &dd, int staging, cudaStream_t st) {
+                                          long long inner, const DispDesc &dd, int staging, cudaStream_t st, const LineBox &lbx) {
     constexpr int BW = 32;
     const int R = n + (S - 1);
     size_t smem = 128 + (size_t)R * BW * 8;
@@ -1352,35 +1369,51 @@ static cudaError_t launch_lagrange_halo_t(double *f, const double *hl, const dou
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
     auto al16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-    bool tma_ok = (inner % BW == 0) && al16(f) && al16(hl) && al16(hr);
+    bool tma_ok = (inner % BW == 0) && (lbx.i0 % BW == 0) && (lbx.icount % BW == 0) && al16(f) && al16(hl) && al16(hr);
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + BW - 1) / BW;
-    kern<<<(unsigned)nblk, BW, smem, st>>>(f, hl, hr, nlines, n, inner, dd, use_tma);
+    kern<<<(unsigned)nblk, BW, smem, st>>>(f, hl, hr, nlines, n, inner, dd, use_tma, lbx);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
 cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
-                                 long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st) {
+                                 long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st,
+                                 const LineBox *box) {
     if (n < 1 || outer < 1 || inner < 2) return cudaErrorInvalidValue;
-    const long long nlines = outer * inner;
+    LineBox lbx;
+    if (box) lbx = *box;
+    else { lbx.o0 = 0; lbx.ocount = outer; lbx.i0 = 0; lbx.icount = inner; }
+    if (lbx.o0 < 0 || lbx.i0 < 0 || lbx.ocount < 1 || lbx.icount < 1 || lbx.o0 + lbx.ocount > outer || lbx.i0 + lbx.icount > inner)
+        return cudaErrorInvalidValue;
+    const long long nlines = lbx.ocount * lbx.icount;
     switch (order) {
-    case 3: return launch_lagrange_halo_t<3>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
-    case 5: return launch_lagrange_halo_t<5>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
-    case 7: return launch_lagrange_halo_t<7>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
-    case 9: return launch_lagrange_halo_t<9>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
-    case 11: return launch_lagrange_halo_t<11>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st);
+    case 3: return launch_lagrange_halo_t<3>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st, lbx);
+    case 5: return launch_lagrange_halo_t<5>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st, lbx);
+    case 7: return launch_lagrange_halo_t<7>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st, lbx);
+    case 9: return launch_lagrange_halo_t<9>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st, lbx);
+    case 11: return launch_lagrange_halo_t<11>(f, halo_left, halo_right, nlines, n, inner, dd, staging, st, lbx);
     default: return cudaErrorInvalidValue;
     }
 }
+// max_blocks > 0 caps the grid (pipelined exchange: the pack kernel must leave room on every SM for the stencil kernel
+// that runs beside it)
 cudaError_t launch_halo_pack(const double *f, long long outer, int n, long long inner, int j0, int hw, double *buf,
-                             cudaStream_t st) {
+                             cudaStream_t st, const LineBox *box, int max_blocks) {
     if (hw <= 0) return cudaSuccess;
-    const long long chunk = (long long)hw * inner;
-    long long gx = (chunk + 1023) / 1024;
+    LineBox lbx;
+    if (box) lbx = *box;
+    else { lbx.o0 = 0; lbx.ocount = outer; lbx.i0 = 0; lbx.icount = inner; }
+    const bool vec = inner % 2 == 0 && lbx.i0 % 2 == 0 && lbx.icount % 2 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(buf) & 15) == 0;
+    const long long cap = max_blocks > 0 ? max_blocks : 148LL * 64;
+    long long gx = (lbx.icount / (vec ? 2 : 1) + 1023) / 1024;
     if (gx > 148 * 8) gx = 148 * 8;
-    long long gy = outer < 65535 ? outer : 65535;
-    while (gx * gy > 148LL * 64 && gx > 1) gx = (gx + 1) / 2;
-    k_halo_pack<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(f, outer, n, inner, j0, hw, buf);
+    if (gx < 1) gx = 1;
+    long long gy = lbx.ocount < 65535 ? lbx.ocount : 65535;
+    while (gx * gy > cap && gx > 1) gx = (gx + 1) / 2;
+    while (gx * gy > cap && gy > 1) gy = (gy + 1) / 2;
+    if (vec) k_halo_pack<true><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(f, n, inner, j0, hw, buf, lbx);
+    else k_halo_pack<false><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(f, n, inner, j0, hw, buf, lbx);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }

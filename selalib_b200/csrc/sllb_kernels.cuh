@@ -46,9 +46,13 @@ cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts,
 // over a plane).  cudaErrorNotSupported when the plane / displacement pattern / stencil does not fit.
 cudaError_t launch_lagrange_plane(double *f, int n0, int n1, long long nplanes, int method, int order, const DispDesc &dd0,
                                   const DispDesc &dd1, cudaStream_t st);
-// K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner]
+// a sub-box of the lines of an axis pass: o in [o0, o0+ocount), in in [i0, i0+icount) (pipelined halo exchange)
+struct LineBox { long long o0, ocount, i0, icount; };
+// K2c: fixed odd Lagrange with halo planes (domain-decomposed axis): halo_left/right are [outer][(order-1)/2][inner];
+// box != nullptr: only the lines of that sub-box
 cudaError_t launch_lagrange_halo(double *f, const double *halo_left, const double *halo_right, long long outer, int n,
-                                 long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st);
+                                 long long inner, int order, const DispDesc &dd, int staging, cudaStream_t st,
+                                 const LineBox *box = nullptr);
 // K9: local cubic spline with halo cells (sll_m_cubic_spline_halo_1d, NUM_TERMS = 15) on every line of f viewed as
 // [outer][np][inner], in place.  halo_l == nullptr: the axis is not split, the ring neighbour is the line itself
 // (periodic wrap, one kernel).  Otherwise halo_l / halo_r are [outer][hwl|hwr][inner] planes of the neighbours and
@@ -71,7 +75,7 @@ cudaError_t launch_hermite(double *f, long long outer, int np, long long inner, 
                            int have_slopes, double sl, double sr, int staging, cudaStream_t st);
 // K7: buf[o][j][in] = f[o][j0+j][in], j < hw
 cudaError_t launch_halo_pack(const double *f, long long outer, int n, long long inner, int j0, int hw, double *buf,
-                             cudaStream_t st);
+                             cudaStream_t st, const LineBox *box = nullptr, int max_blocks = 0);
 
 // K3: rho[x] = scale * sum_v f[x + nx*v]; partial = scratch of reduce_scratch_doubles(nx, nv)
 size_t reduce_scratch_doubles(long long nx, long long nv);
