@@ -191,3 +191,37 @@ def test_fortran_g20_12_formatter():
     for x, s in cases.items():
         assert sb.format_g20_12(x) == s, (x, sb.format_g20_12(x))
         assert len(sb.format_g20_12(x)) == 20
+
+
+def test_namelist_front_end_host_logic(tmp_path):
+    """sllb_sim4d_create_from_namelist: parsing, defaults and the reference's error messages happen on the host, before a
+    device is needed (sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:300-624)"""
+    import ctypes as C
+    lib = sb.lib()
+
+    def create(text, name="in"):
+        path = tmp_path / (name + ".nml")
+        path.write_text(text)
+        S = C.c_void_p()
+        nit, fdt = C.c_int(-1), C.c_int(-1)
+        rc = lib.sllb_sim4d_create_from_namelist(str(tmp_path / name).encode(), None, C.byref(S), C.byref(nit), C.byref(fdt))
+        if rc == 0:
+            lib.sllb_sim4d_destroy(S)
+        return rc, sb.last_error(), nit.value, fdt.value
+
+    ok = "&geometry\n num_cells_x1 = 16\n/\n&time_iterations\n dt = 0.1\n number_iterations = 7\n freq_diag_time = 2\n/\n"
+    rc, msg, nit, fdt = create(ok)
+    assert rc in (0, sb.ERR_NO_DEVICE), msg          # parsed; only the device may be missing
+    if rc == 0:
+        assert (nit, fdt) == (7, 2)
+    rc, msg, _, _ = create(ok + "&advector\n advector_x3 = \"SLL_FOO\"\n/\n", "bad_adv")
+    assert rc == sb.ERR_UNSUPPORTED and "advector in x3" in msg and "not implemented" in msg
+    rc, msg, _, _ = create("&time_iterations\n split_case = \"SLL_NOPE\"\n/\n", "bad_split")
+    assert rc == sb.ERR_INVALID and "split_case not defined" in msg
+    rc, msg, _, _ = create("&geometry\n mesh_case_x3 = \"SLL_LANDAU_MESH\"\n/\n", "bad_mesh")
+    assert rc == sb.ERR_UNSUPPORTED and "mesh_case_x3" in msg
+    rc, msg, _, _ = create("&initial_function\n initial_function_case = \"SLL_BEAM\"\n/\n", "bad_init")
+    assert rc == sb.ERR_UNSUPPORTED
+    S = C.c_void_p()
+    rc = lib.sllb_sim4d_create_from_namelist(str(tmp_path / "does_not_exist").encode(), None, C.byref(S), None, None)
+    assert rc == sb.ERR_INVALID and "failed to open file" in sb.last_error()
