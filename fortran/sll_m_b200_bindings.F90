@@ -22,6 +22,7 @@ module sll_m_b200_bindings
    integer(c_int), parameter :: sllb_interp_periodic_spline = 3
    integer(c_int), parameter :: sllb_interp_periodic_lagrange = 4
    integer(c_int), parameter :: sllb_bc_periodic = 0
+   integer(c_int), parameter :: sllb_bc_hermite = 1   ! sll_p_hermite, cubic-spline interpolator only
    integer(c_int), parameter :: sllb_method_spline = 0
    integer(c_int), parameter :: sllb_method_lagrange_fixed = 1
    integer(c_int), parameter :: sllb_method_lagrange_centered = 2
@@ -146,6 +147,21 @@ module sll_m_b200_bindings
          integer(c_int), value :: nx_axes
          real(c_double), value :: scale
          real(c_double), intent(inout) :: rho(*)
+         integer(c_int) :: ierr
+      end function
+      function sllb_interp1d_set_slopes(h, slope_left, slope_right) bind(C, name="sllb_interp1d_set_slopes") result(ierr)
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: h
+         real(c_double), value :: slope_left, slope_right
+         integer(c_int) :: ierr
+      end function
+      !> Hermite-BC spline on every line of a device field along `axis` (disp: type(sllb_disp_t) by reference)
+      function sllb_advect_axis_hermite(f, axis, xmin, xmax, disp, inplace_semantics) &
+         bind(C, name="sllb_advect_axis_hermite") result(ierr)
+         import :: c_int, c_double, c_ptr
+         type(c_ptr), value :: f, disp
+         integer(c_int), value :: axis, inplace_semantics
+         real(c_double), value :: xmin, xmax
          integer(c_int) :: ierr
       end function
       ! ---- local cubic splines with halo cells (sll_t_advection_6d_spline_dd_slim) ----

@@ -40,21 +40,31 @@ module sll_m_interpolator_1d_b200
 
 contains
 
-   subroutine b200_interp_init(interpolator, kind, num_points, xmin, xmax, d_or_order, periodic_last, fast_algorithm)
+   !> bc_type = sllb_bc_hermite with optional slope_left / slope_right mirrors
+   !> sll_t_cubic_spline_interpolator_1d%init(num_points, xmin, xmax, sll_p_hermite [, slope_left, slope_right])
+   !> (sll_m_cubic_spline_interpolator_1d.F90:317-381)
+   subroutine b200_interp_init(interpolator, kind, num_points, xmin, xmax, d_or_order, periodic_last, fast_algorithm, &
+                               bc_type, slope_left, slope_right)
       class(sll_t_interpolator_1d_b200), intent(inout) :: interpolator
       sll_int32, intent(in) :: kind, num_points
       sll_real64, intent(in) :: xmin, xmax
-      sll_int32, intent(in), optional :: d_or_order, periodic_last
+      sll_int32, intent(in), optional :: d_or_order, periodic_last, bc_type
       logical, intent(in), optional :: fast_algorithm
-      integer(c_int) :: d, pl, fa
-      d = 4; pl = 1; fa = 1
+      sll_real64, intent(in), optional :: slope_left, slope_right
+      integer(c_int) :: d, pl, fa, bc
+      d = 4; pl = 1; fa = 1; bc = sllb_bc_periodic
+      if (present(bc_type)) bc = int(bc_type, c_int)
       if (present(d_or_order)) d = int(d_or_order, c_int)
       if (present(periodic_last)) pl = int(periodic_last, c_int)
       if (present(fast_algorithm)) fa = merge(1_c_int, 0_c_int, fast_algorithm)
       interpolator%num_points = num_points
       call sll_s_b200_check(sllb_interp1d_create(int(kind, c_int), int(num_points, c_int), real(xmin, c_double), &
-                                                 real(xmax, c_double), sllb_bc_periodic, d, pl, fa, &
+                                                 real(xmax, c_double), bc, d, pl, fa, &
                                                  interpolator%handle), 'b200_interp_init')
+      if (present(slope_left) .and. present(slope_right)) then
+         call sll_s_b200_check(sllb_interp1d_set_slopes(interpolator%handle, real(slope_left, c_double), &
+                                                        real(slope_right, c_double)), 'b200_interp_init')
+      end if
    end subroutine b200_interp_init
 
    subroutine b200_array_disp(this, num_pts, data, alpha, output_array)
