@@ -106,3 +106,18 @@ def test_lagrange_plane_kernel_equals_two_passes(sb, shape):
             F.advect_plane(v0, ds0, 1.0, v1, ds1, 1.0, method=mcode, order=order)
             assert np.array_equal(F.download(), ref), (mcode, order)
     F.destroy()
+
+
+def test_sim2d_reproduces_the_shipped_1d1v_trace(sb):
+    """G4 on the GPU: vpsim2d_cartesian_input.nml (Landau damping 32 x 64, cubic splines, Strang VTV, dt = 0.1, 600 steps)
+    against the L2-norm and potential-energy columns of the reference's shipped vpsim2d_cartesian_ref.dat
+    (tests/golden/vpsim2d_cartesian_ref_l2_epot.dat): L2 to the printed 12 digits, field energy to 1e-8 of its maximum at every step"""
+    import os
+    gold = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vpsim2d_cartesian_ref_l2_epot.dat"))
+    S = sb.Sim2d(32, 64, 0.0, 4 * np.pi, -6.0, 6.0, 0, 0.5, 0.001, 0.1, method=sb.METHOD_SPLINE, order=4)
+    rows = S.run(600)
+    S.destroy()
+    assert np.abs(rows[:, 0] - gold[:, 0]).max() < 1e-9
+    assert np.abs(rows[:, 4] / gold[:, 1] - 1).max() < 1e-11
+    # the field energy oscillates through near-zero minima: compare on the scale of its maximum
+    assert np.abs(rows[:, 6] - gold[:, 2]).max() < 1e-8 * gold[:, 2].max()

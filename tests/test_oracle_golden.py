@@ -45,3 +45,15 @@ def test_oracle_matches_committed_traces():
     assert np.allclose(rows4, t["rows4"], rtol=1e-11, atol=1e-18)
     rows2 = orc.sim2d(64, 64, 0.0, 4 * np.pi, -6.0, 6.0, 0, 0.5, 1e-3, 0.1, 20)
     assert np.allclose(rows2, t["rows2"], rtol=1e-11, atol=1e-18)
+
+
+def test_g4_1d1v_trace_l2_and_field_energy():
+    """simulations/parallel/bsl_vp_1d1v_cart/vpsim2d_cartesian_ref.dat (600 steps of vpsim2d_cartesian_input.nml, 12
+    printed digits): the L2 norm of f is reproduced over the whole run to the printed precision and the potential energy
+    to 1e-8 of its maximum at every step (observed 2.2e-9, the printed precision of the smallest values).  Fixture: tests/golden/vpsim2d_cartesian_ref_l2_epot.dat (make_vpsim2d_fixture.py)."""
+    gold = np.loadtxt(os.path.join(G, "vpsim2d_cartesian_ref_l2_epot.dat"))
+    rows = orc.sim2d(32, 64, 0.0, 4 * np.pi, -6.0, 6.0, 0, 0.5, 0.001, 0.1, 600, method=0, order=4)
+    assert np.abs(rows[:, 0] - gold[:, 0]).max() < 1e-9
+    assert np.abs(rows[:, 4] / gold[:, 1] - 1).max() < 1e-11
+    # the field energy oscillates through near-zero minima: compare on the scale of its maximum
+    assert np.abs(rows[:, 6] - gold[:, 2]).max() < 1e-8 * gold[:, 2].max()
