@@ -30,12 +30,17 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
-    objs = []
-    for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+    objs = [os.path.join(LIBDIR, src.replace(".cu", ".o")) for src in SOURCES]
+
+    def compile_one(pair):
+        src, obj = pair
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         subprocess.check_call(cmd)
-        objs.append(obj)
+
+    # the translation units are independent: compile them side by side
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1 if verbose else min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        list(pool.map(compile_one, zip(SOURCES, objs)))
     cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-o", SO] + objs + ["-lcufft", "-lnccl", "-lcudart"]
     subprocess.check_call(cmd)
     return SO
