@@ -74,14 +74,16 @@ void sllb_launch_count_reset(void);
 /* batched per-axis methods */
 #define SLLB_METHOD_SPLINE 0            /* periodic cubic spline (order 4) */
 #define SLLB_METHOD_LAGRANGE_FIXED 1    /* odd stencil 3,5,7,9,11 centred on the grid point */
-#define SLLB_METHOD_LAGRANGE_CENTERED 2 /* even stencil 4,6,8 centred on the foot cell */
+#define SLLB_METHOD_LAGRANGE_CENTERED 2 /* even stencil 4..18 centred on the foot cell (closed forms up to 8 as in the
+                                           reference's fast module, product form beyond) */
 
 /* ---- a1/a2: sll_c_advector_1d%advect_1d_constant -------------------------
  * replaces sll_f_new_periodic_1d_advector / periodic_advect_1d_constant
  * (sll_m_advection_1d_periodic.F90:57-130) and the abstract interface
  * (sll_m_advection_1d_base.F90:53-68).  out(x_i) = in(x_i - A*dt); `in` may alias
  * `out`; n = num_cells or num_cells+1 (the duplicate is filled when n > num_cells).
- * kind PERIODIC_SPLINE supports order 4; PERIODIC_LAGRANGE supports order 4,6,8; BSL: n = num_cells+1 points as the
+ * kind PERIODIC_SPLINE supports order 4; PERIODIC_LAGRANGE supports even orders 4..18 (the shipped two-stream
+ * namelist of the 1D1V simulation uses 18); BSL: n = num_cells+1 points as the
  * reference object is built on npts grid points (n = num_cells also accepted). */
 typedef struct sllb_adv1d *sllb_adv1d_t;
 int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int order, sllb_adv1d_t *h);

@@ -184,7 +184,7 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
         return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: method/order/line length not implemented (spline: order 4; "
-                                          "Lagrange fixed: 3,5,7,9,11; centred: 4,6,8; 8 <= n, line must fit shared memory)");
+                                          "Lagrange fixed: 3,5,7,9,11; centred: even 4..18; 8 <= n, line must fit shared memory)");
     }
     return check_cuda(e, "advect kernel launch");
 }
@@ -748,8 +748,8 @@ int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int ord
         if (order != 4) return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_spline implemented for order 4 (cubic) only");
         method = SLLB_METHOD_SPLINE; stencil = 4;
     } else if (kind == SLLB_ADV_PERIODIC_LAGRANGE) {
-        if (order != 4 && order != 6 && order != 8)
-            return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_lagrange implemented for order 4, 6, 8");
+        if (order < 4 || order > 18 || order % 2 != 0)
+            return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_lagrange implemented for even orders 4 .. 18");
         method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = order;
     } else if (kind == SLLB_ADV_BSL) {
         method = SLLB_METHOD_SPLINE; stencil = 4;
@@ -815,8 +815,8 @@ int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int
     case SLLB_INTERP_LAGRANGE_FIXED: method = SLLB_METHOD_LAGRANGE_FIXED; stencil = 2 * d_or_order + 1; break;
     default: return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: interpolator kind not implemented");
     }
-    if (method == SLLB_METHOD_LAGRANGE_CENTERED && stencil != 4 && stencil != 6 && stencil != 8)
-        return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: centred Lagrange implemented for stencils 4, 6, 8");
+    if (method == SLLB_METHOD_LAGRANGE_CENTERED && (stencil < 4 || stencil > 18 || stencil % 2 != 0))
+        return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: centred Lagrange implemented for even stencils 4 .. 18");
     if (method == SLLB_METHOD_LAGRANGE_FIXED && (stencil < 3 || stencil > 11))
         return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: fixed Lagrange implemented for stencils 3..11");
     /* both interpolators define the cell size from num_points-1 cells

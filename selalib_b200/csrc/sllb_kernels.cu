@@ -1139,7 +1139,7 @@ static cudaError_t launch_lagrange_split_t(double *f, long long nlines, int N, l
 template <int METHOD, int S>
 static cudaError_t launch_strided(double *f, long long nlines, int N, long long inner, const DispDesc &dd, int staging,
                                   cudaStream_t st, const RemapDst &rd) {
-    if constexpr (METHOD == 1) {
+    if constexpr (METHOD == 1 && S <= 11) { // the chunked kernel is bounded to 1024 threads (64 registers): short stencils only
         // few, long lines (the 1D1V problems): one thread per line leaves most SMs idle -- cut the lines into chunks
         const long long blocks32 = (nlines + 31) / 32;
         if (!rd.on && blocks32 < 2 * 148 && N >= 128) {
@@ -1351,7 +1351,7 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
     }
     if (method == METHOD_LAGRANGE_CENTERED) {
         switch (order) {
-            LAGR_CASE(4) LAGR_CASE(6) LAGR_CASE(8)
+            LAGR_CASE(4) LAGR_CASE(6) LAGR_CASE(8) LAGR_CASE(10) LAGR_CASE(12) LAGR_CASE(14) LAGR_CASE(16) LAGR_CASE(18)
         default: return cudaErrorInvalidValue;
         }
     }

@@ -8,6 +8,15 @@ namespace sllb {
 // Lagrange weights: closed-form polynomials of sll_m_lagrange_interpolation_1d_fast.F90
 // (:59-67,110-121,170-182 even; :239-246,286-295,341-352,405-419,478-494 odd)
 // ------------------------------------------------------------------------------------------------
+// 1 / prod_{j != k} (k - j) of the S-point Lagrange basis on consecutive integers, at compile time
+template <int S>
+__host__ __device__ constexpr double lagr_inv_den(int k) {
+    double den = 1.0;
+    for (int j = 0; j < S; ++j)
+        if (j != k) den *= (double)(k - j);
+    return 1.0 / den;
+}
+
 template <int S>
 __device__ __forceinline__ void lagr_coeff(double p, double *pp) {
     const double p2 = p * p;
@@ -70,6 +79,18 @@ __device__ __forceinline__ void lagr_coeff(double p, double *pp) {
         pp[5] = (p + 2.) * p * (p - 4.) * (p2 - 9.) * (p2 - 1.) * (1. / 240.);
         pp[6] = -(p + 3.) * p * (p - 4.) * (p2 - 4.) * (p2 - 1.) * (1. / 720.);
         pp[7] = p * (p2 - 9.) * (p2 - 4.) * (p2 - 1.) * (1. / 5040.);
+    } else {
+        // even stencils beyond the reference's closed forms (sll_p_lagrange of sll_s_periodic_interp takes any order,
+        // sll_m_periodic_interp.F90:290-366): the same basis in product form, nodes -(S/2-1) .. S/2 around the foot cell
+        static_assert((S & 1) == 0 && S >= 10 && S <= 18, "Lagrange stencil not implemented");
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+            double num = 1.0;
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (j != k) num *= p - (double)(j - (S / 2 - 1));
+            pp[k] = num * lagr_inv_den<S>(k);
+        }
     }
 }
 

@@ -102,7 +102,7 @@ int sllb_sim4d_create_from_namelist(const char *filename, sllb_comm_t comm, sllb
             if (order != 4) return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector ") + av[d] + ": periodic splines are implemented for order 4");
             p.method_axis[d] = SLLB_METHOD_SPLINE;
         } else if (a == "SLL_LAGRANGE") {
-            if (order != 4 && order != 6 && order != 8) return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector ") + av[d] + ": periodic Lagrange is implemented for orders 4, 6, 8");
+            if (order < 4 || order > 18 || order % 2 != 0) return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector ") + av[d] + ": periodic Lagrange is implemented for even orders 4 .. 18");
             p.method_axis[d] = SLLB_METHOD_LAGRANGE_CENTERED;
         } else
             return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector in x") + char('1' + d) + " " + a + " not implemented");

@@ -16,7 +16,8 @@ def lib():
         so = os.path.join(_HERE, "libspline15_host.so")
         deps = [os.path.join(_HERE, "spline15_host.cpp"),
                 os.path.join(_HERE, "..", "..", "selalib_b200", "csrc", "sllb_spline15.cuh"),
-                os.path.join(_HERE, "..", "..", "selalib_b200", "csrc", "sllb_hermite.cuh")]
+                os.path.join(_HERE, "..", "..", "selalib_b200", "csrc", "sllb_hermite.cuh"),
+                os.path.join(_HERE, "..", "..", "selalib_b200", "csrc", "sllb_lagrange.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, deps[0]])
         _LIB = C.CDLL(so)
@@ -43,5 +44,15 @@ def hermite_line(line, delta, alpha, inplace=True, slopes=None):
     rc = lib().emu_hermite_line(line.ctypes.data_as(dp), out.ctypes.data_as(dp), C.c_int(line.size), C.c_double(delta),
                                 C.c_double(alpha), C.c_int(1 if inplace else 0), C.c_int(hs),
                                 C.c_double(slopes[0] if hs else 0.0), C.c_double(slopes[1] if hs else 0.0))
+    assert rc == 0, rc
+    return out
+
+
+def lagrange_line(line, disp, stencil):
+    line = np.ascontiguousarray(line, dtype=np.float64)
+    out = np.empty_like(line)
+    dp = C.POINTER(C.c_double)
+    lib().emu_lagrange_line.restype = C.c_int
+    rc = lib().emu_lagrange_line(line.ctypes.data_as(dp), out.ctypes.data_as(dp), C.c_int(line.size), C.c_double(disp), C.c_int(stencil))
     assert rc == 0, rc
     return out

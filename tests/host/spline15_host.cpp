@@ -5,6 +5,10 @@
 #define SLLB_HOST_EMULATION 1
 #include "../../selalib_b200/csrc/sllb_spline15.cuh"
 #include "../../selalib_b200/csrc/sllb_hermite.cuh"
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#include "../../selalib_b200/csrc/sllb_lagrange.cuh"
 
 #include <climits>
 #include <cstring>
@@ -27,6 +31,20 @@ static void init_hermite_consts() {
     double ct = 1.0;
     for (int i = 0; i < SLLB_HERMITE_TERMS; ++i) { c_hq[i] = ct; ct *= -(b / a); }
     ready = true;
+}
+
+// periodic Lagrange line exactly as the kernels form it: lagr_setup<S> (weights + first stencil offset), then the
+// left-to-right sum of lagrange_line / k_lagrange_contig
+template <int S>
+static void lagr_line_t(const double *lin, double *lout, int n, double disp) {
+    double pp[S];
+    const int off = lagr_setup<S>(disp, n, pp);
+    for (int i = 0; i < n; ++i) {
+        int j = (i + off) % n;
+        double acc = pp[0] * lin[j];
+        for (int k = 1; k < S; ++k) { j = (j == n - 1) ? 0 : j + 1; acc = fma(pp[k], lin[j], acc); }
+        lout[i] = acc;
+    }
 }
 
 extern "C" {
@@ -74,5 +92,24 @@ int emu_spline_dd_line(const double *lin, double *lout, int n, int nblk, int si,
         spline15_line<1, false, true>(x0, np, si, alpha, sd, sc, lout + (long)r * np, 1);
     }
     return 0;
+}
+
+int emu_lagrange_line(const double *lin, double *lout, int n, double disp, int stencil) {
+    switch (stencil) {
+    case 3: lagr_line_t<3>(lin, lout, n, disp); return 0;
+    case 5: lagr_line_t<5>(lin, lout, n, disp); return 0;
+    case 7: lagr_line_t<7>(lin, lout, n, disp); return 0;
+    case 9: lagr_line_t<9>(lin, lout, n, disp); return 0;
+    case 11: lagr_line_t<11>(lin, lout, n, disp); return 0;
+    case 4: lagr_line_t<4>(lin, lout, n, disp); return 0;
+    case 6: lagr_line_t<6>(lin, lout, n, disp); return 0;
+    case 8: lagr_line_t<8>(lin, lout, n, disp); return 0;
+    case 10: lagr_line_t<10>(lin, lout, n, disp); return 0;
+    case 12: lagr_line_t<12>(lin, lout, n, disp); return 0;
+    case 14: lagr_line_t<14>(lin, lout, n, disp); return 0;
+    case 16: lagr_line_t<16>(lin, lout, n, disp); return 0;
+    case 18: lagr_line_t<18>(lin, lout, n, disp); return 0;
+    default: return -1;
+    }
 }
 }

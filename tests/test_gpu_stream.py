@@ -121,3 +121,35 @@ def test_sim2d_reproduces_the_shipped_1d1v_trace(sb):
     assert np.abs(rows[:, 4] / gold[:, 1] - 1).max() < 1e-11
     # the field energy oscillates through near-zero minima: compare on the scale of its maximum
     assert np.abs(rows[:, 6] - gold[:, 2]).max() < 1e-8 * gold[:, 2].max()
+
+
+@pytest.mark.parametrize("order", [10, 12, 14, 16, 18])
+def test_high_order_periodic_lagrange_vs_oracle(sb, order):
+    """sll_p_lagrange of sll_s_periodic_interp takes any even order (the shipped two-stream namelist uses 18): orders
+    beyond the closed forms, batched on a contiguous axis, two strided axes (TMA rows and the cp.async fallback) and through
+    the line object sll_t_advector_1d_periodic"""
+    from oracle import orc
+    rng = np.random.default_rng(20261017 + order)
+    for shape in ((64, 32, 40), (36, 24, 30)):
+        f0 = np.asfortranarray(rng.standard_normal(shape))
+        F = sb.Field(shape)
+        for axis in range(3):
+            v_axis = (axis + 1) % 3
+            disp = rng.uniform(-2.5, 2.5, shape[v_axis])
+            if v_axis > axis:
+                dsel = (1, shape[v_axis], 1, 1, 1, 0)
+            else:
+                dsel = (1, 1, 0, 1, shape[v_axis], 1)
+            ref = orc.advect_axis(f0.copy(order="F"), axis, "fft_lagrange", order, disp, dsel)
+            F.upload(f0)
+            F.advect_axis(axis, sb.METHOD_LAGRANGE_CENTERED, order, disp, 1.0, dsel)
+            err = np.abs(F.download() - ref).max() / np.abs(ref).max()
+            assert err <= 1e-12, (shape, axis, err)
+        F.destroy()
+    nc = 48
+    A = sb.Advector1dPeriodic(nc, 0.0, 2.0, kind=sb.ADV_PERIODIC_LAGRANGE, order=order)
+    inp = rng.standard_normal(nc + 1); inp[-1] = inp[0]
+    out = A.advect_1d_constant(0.37, 0.21, inp)
+    ref = orc.advect_1d_periodic_constant("lagrange", nc, 0.0, 2.0, order, 0.37, 0.21, inp)
+    assert np.abs(out - ref).max() <= 1e-12 * np.abs(inp).max()
+    A.delete()

@@ -211,3 +211,30 @@ def test_bsl_advector_kat():
         b = orc.spline_interpolate_array_disp(f, 0.0, 1.0, -A * dt)
         c = orc.advect_1d_periodic_constant("spline", n, 0.0, 1.0, 4, A, dt, f)
         assert np.abs(a - b).max() < 1e-13 and np.abs(a - c).max() < 1e-13
+
+
+@pytest.mark.parametrize("stencil", [4, 6, 8, 10, 12, 14, 16, 18])
+def test_device_lagrange_weights_any_even_order(stencil):
+    """lagr_setup / lagr_coeff of the Lagrange kernels (sllb_lagrange.cuh compiled for the host) against the reference's
+    sll_p_lagrange periodic interpolation of that order (FFT formulation, sll_m_periodic_interp.F90:290-366): closed forms
+    up to 8 points, product form beyond; 1e-12 max|f|"""
+    from host import emu
+    n = 64
+    for disp in (0.0, 0.31, -0.77, 1.0, 2.45, -3.6):
+        u = RNG.standard_normal(n)
+        f = np.asfortranarray(u.reshape(1, n, 1).copy())
+        ref = orc.advect_axis(f, 1, "fft_lagrange", stencil, np.array([disp]), (1, 1, 0, 1, 1, 0))[0, :, 0]
+        got = emu.lagrange_line(u, disp, stencil)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(u).max(), (stencil, disp)
+
+
+@pytest.mark.parametrize("stencil", [3, 5, 7, 9, 11])
+def test_device_lagrange_weights_fixed(stencil):
+    from host import emu
+    n = 50
+    for disp in (0.0, 0.31, -0.77):
+        u = RNG.standard_normal(n)
+        f = np.asfortranarray(u.reshape(1, n, 1).copy())
+        ref = orc.advect_axis(f, 1, "lagrange_fixed", stencil, np.array([disp]), (1, 1, 0, 1, 1, 0))[0, :, 0]
+        got = emu.lagrange_line(u, disp, stencil)
+        assert np.abs(got - ref).max() <= 1e-13 * np.abs(u).max()
