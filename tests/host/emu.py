@@ -56,3 +56,23 @@ def lagrange_line(line, disp, stencil):
     rc = lib().emu_lagrange_line(line.ctypes.data_as(dp), out.ctypes.data_as(dp), C.c_int(line.size), C.c_double(disp), C.c_int(stencil))
     assert rc == 0, rc
     return out
+
+
+def spline_dd_prepare(local, si):
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    a, b = C.c_double(), C.c_double()
+    lib().emu_spline_dd_prepare(local.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(local.size), C.c_int(si), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def spline_dd_piece(local, halo_l, halo_r, si, alpha, rem_d, rem_c):
+    dp = C.POINTER(C.c_double)
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    hl = np.ascontiguousarray(halo_l, dtype=np.float64); hr = np.ascontiguousarray(halo_r, dtype=np.float64)
+    out = np.empty_like(local)
+    lib().emu_spline_dd_piece.restype = C.c_int
+    rc = lib().emu_spline_dd_piece(local.ctypes.data_as(dp), hl.ctypes.data_as(dp), C.c_int(hl.size), hr.ctypes.data_as(dp),
+                                   C.c_int(hr.size), C.c_int(local.size), C.c_int(si), C.c_double(alpha), C.c_double(rem_d),
+                                   C.c_double(rem_c), out.ctypes.data_as(dp))
+    assert rc == 0, rc
+    return out

@@ -112,4 +112,26 @@ int emu_lagrange_line(const double *lin, double *lout, int n, double disp, int s
     default: return -1;
     }
 }
+
+// the two halves of a split-axis pass as separate calls, for the multi-process (gloo) test of the exchange protocol:
+// what k_spline_dd_prepare computes for the neighbours from MY piece ...
+int emu_spline_dd_prepare(const double *local, int np, int si, double *for_right, double *for_left) {
+    init_consts();
+    spline15_prepare(local, 1, np, si, for_right, for_left);
+    return 0;
+}
+// ... and what k_spline_dd_strided<false> does with my piece, the received halo cells and the received sums
+int emu_spline_dd_piece(const double *local, const double *halo_l, int hwl, const double *halo_r, int hwr, int np, int si,
+                        double alpha, double rem_d, double rem_c, double *out) {
+    init_consts();
+    if (si < -hwl || si > hwr - 1) return -2;
+    std::vector<double> tile(hwl + np + hwr);
+    for (int j = 0; j < hwl; ++j) tile[j] = halo_l[j];
+    for (int j = 0; j < np; ++j) tile[hwl + j] = local[j];
+    for (int j = 0; j < hwr; ++j) tile[hwl + np + j] = halo_r[j];
+    double sd, sc;
+    spline15_sums<1, false>(tile.data() + hwl, np, si, rem_d, rem_c, &sd, &sc);
+    spline15_line<1, false, true>(tile.data() + hwl, np, si, alpha, sd, sc, out, 1);
+    return 0;
+}
 }
