@@ -238,3 +238,23 @@ def test_device_lagrange_weights_fixed(stencil):
         ref = orc.advect_axis(f, 1, "lagrange_fixed", stencil, np.array([disp]), (1, 1, 0, 1, 1, 0))[0, :, 0]
         got = emu.lagrange_line(u, disp, stencil)
         assert np.abs(got - ref).max() <= 1e-13 * np.abs(u).max()
+
+
+def test_periodic_interp_order_of_accuracy():
+    """test_periodic_interpolation.F90:17-56: sll_p_spline of order 8 on u = 1/(2 + sin(3 * 2 pi i / N)), alpha = 0.05, N = 32,
+    64, 128, 256; the program prints the observed order (no threshold): restated here as order > 7 between successive N."""
+    errs = []
+    for N in (32, 64, 128, 256):
+        i = np.arange(N)
+        u = 1.0 / (2.0 + np.sin(3 * 2 * np.pi * i / N))
+        exact = 1.0 / (2.0 + np.sin(3 * 2 * np.pi * (i - 0.05) / N))
+        errs.append(np.abs(orc.periodic_interp(u, 0.05, kind="spline", order=8) - exact).max())
+    orders = [np.log2(errs[k] / errs[k + 1]) for k in range(2)]
+    assert all(o > 7.0 for o in orders), (errs, orders)
+    # order 4 == the cubic spline of sll_m_cubic_splines (a3 == a5/a6), cf. SURVEY.md section 8a
+    N = 64
+    u = RNG.standard_normal(N)
+    a = orc.periodic_interp(u, 0.3, kind="spline", order=4)
+    f = np.asfortranarray(u.reshape(1, N, 1).copy())
+    b = orc.advect_axis(f, 1, "spline", 4, np.array([-0.3]), (1, 1, 0, 1, 1, 0))[0, :, 0]
+    assert np.abs(a - b).max() < 1e-13
