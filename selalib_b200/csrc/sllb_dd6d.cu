@@ -46,9 +46,9 @@ struct sllb_dd6d {
 };
 static int g_halo_chunks = -1; // -1: SLLB_HALO_CHUNKS or 4; 1 = exchange everything, then one kernel
 
-static int g_force_halo = 0;
+static int g_force_halo = 0; // 1: take the halo-exchange + halo-cells kernel path even when procs(axis) == 1
 static int g_halo_p2p = 1;   // 1: peer stores when available, 0: pack + ncclSend/ncclRecv
-static const int HALO_P2P_HW_MAX = 5; // widest halo (stencil 11) the peer buffers are sized for // 1: take the halo-exchange + halo-cells kernel path even when procs(axis) == 1
+static const int HALO_P2P_HW_MAX = 5; // widest halo (stencil 11) the peer buffers are sized for
 
 namespace {
 // MPI_Cart_create ordering (row-major: the LAST dimension varies fastest), sll_m_decomposition.F90:379-555
