@@ -225,3 +225,13 @@ def test_namelist_front_end_host_logic(tmp_path):
     S = C.c_void_p()
     rc = lib.sllb_sim4d_create_from_namelist(str(tmp_path / "does_not_exist").encode(), None, C.byref(S), None, None)
     assert rc == sb.ERR_INVALID and "failed to open file" in sb.last_error()
+
+
+def test_public_headers_compile_as_c_and_cpp(tmp_path):
+    """include/*.h are the drop-in boundary: plain C (what a cgo / iso_c_binding / ctypes binding reads) and C++"""
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "sll_b200.h"\n#include "sll_b200_sim6d_compat.h"\nint main(void) { return SLLB_SHIFT_SKIP == INT32_MIN ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)])
