@@ -323,6 +323,9 @@ int sllb_dd6d_p2p(sllb_dd6d_t D, int *enabled);
  * (edge planes stored into the neighbours' halo buffers + barrier) overlaps the stencil kernel of piece c on a second
  * stream.  Default 4 (or SLLB_HALO_CHUNKS); 1 = exchange everything, then advect.  Same values either way. */
 int sllb_dd6d_set_halo_chunks(int chunks);
+/* host only: the pieces (o0, ocount, i0, icount) x *nboxes the lines [outer][inner] of a pass are cut into; boxes4 holds
+ * up to 4 * 16 values */
+int sllb_dd6d_chunk_boxes(long long outer, long long inner, int nchunks, long long *boxes4, int *nboxes);
 
 /* ---- a17 / (f)3: operator-splitting schedules ------------------------------
  * sll_f_new_time_splitting_coeff (src/time_integration/splitting_methods/sll_m_time_splitting_coeff.F90:86-594):

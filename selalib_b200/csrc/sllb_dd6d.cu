@@ -269,6 +269,34 @@ int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms) {
 }
 
 } // extern "C"
+// The lines of a split-axis pass cut into at most `nchunks` pieces for the pipelined exchange: whole `o` slabs when there
+// are enough of them, else ranges of `in` in multiples of 32 lines (the TMA rows of the stencil kernel); one piece when
+// neither works.  The pieces tile the line space exactly.
+static std::vector<LineBox> chunk_boxes(long long outer, long long inner, int nchunks) {
+    std::vector<LineBox> boxes;
+    if (outer >= nchunks) {
+        for (int c = 0; c < nchunks; ++c) {
+            const long long a = outer * c / nchunks, b = outer * (c + 1) / nchunks;
+            if (b > a) boxes.push_back(LineBox{a, b - a, 0, inner});
+        }
+    } else {
+        const long long units = inner / 32;
+        if (outer != 1 || inner % 32 != 0 || units < nchunks) boxes.push_back(LineBox{0, outer, 0, inner});
+        else
+            for (int c = 0; c < nchunks; ++c) {
+                const long long a = units * c / nchunks * 32, b = units * (c + 1) / nchunks * 32;
+                if (b > a) boxes.push_back(LineBox{0, 1, a, b - a});
+            }
+    }
+    return boxes;
+}
+extern "C" int sllb_dd6d_chunk_boxes(long long outer, long long inner, int nchunks, long long *boxes4, int *nboxes) {
+    if (outer < 1 || inner < 1 || nchunks < 1 || nchunks > 16 || !boxes4 || !nboxes) return fail(SLLB_ERR_INVALID, "dd6d_chunk_boxes: bad arguments");
+    const std::vector<LineBox> b = chunk_boxes(outer, inner, nchunks);
+    for (size_t k = 0; k < b.size(); ++k) { boxes4[4 * k] = b[k].o0; boxes4[4 * k + 1] = b[k].ocount; boxes4[4 * k + 2] = b[k].i0; boxes4[4 * k + 3] = b[k].icount; }
+    *nboxes = (int)b.size();
+    return SLLB_OK;
+}
 /* Split-axis pass with the exchange pipelined against the stencil: chunk c of the lines is exchanged (edge planes stored
  * straight into the neighbours' halo buffers, all-reduce as barrier) on the communication stream while the halo-cells
  * kernel works on chunk c-1 on the compute stream.  Same kernels, same values as exchange-then-advect. */
@@ -288,22 +316,7 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
         SLLB_CUDA(cudaEventCreate(&D->ev_comm1));
         for (cudaEvent_t &e : D->ev_chunk) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    // chunks of whole `o` slabs when there are enough of them, else ranges of `in` in multiples of 32 lines (TMA rows)
-    std::vector<LineBox> boxes;
-    if (outer >= nchunks) {
-        for (int c = 0; c < nchunks; ++c) {
-            const long long a = outer * c / nchunks, b = outer * (c + 1) / nchunks;
-            if (b > a) boxes.push_back(LineBox{a, b - a, 0, inner});
-        }
-    } else {
-        const long long units = inner / 32;
-        if (outer != 1 || inner % 32 != 0 || units < nchunks) boxes.push_back(LineBox{0, outer, 0, inner});
-        else
-            for (int c = 0; c < nchunks; ++c) {
-                const long long a = units * c / nchunks * 32, b = units * (c + 1) / nchunks * 32;
-                if (b > a) boxes.push_back(LineBox{0, 1, a, b - a});
-            }
-    }
+    const std::vector<LineBox> boxes = chunk_boxes(outer, inner, nchunks);
     // two pack blocks per SM: enough stores in flight for NVLink, and the stencil kernel of the previous chunk keeps most of
     // every SM
     static const int pack_blocks = [] { const char *e = getenv("SLLB_PACK_BLOCKS"); return (e && atoi(e) > 0) ? atoi(e) : 148 * 2; }();

@@ -235,3 +235,24 @@ def test_public_headers_compile_as_c_and_cpp(tmp_path):
     inc = os.path.join(ROOT, "include")
     subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c++", str(src)])
+
+
+def test_pipelined_exchange_chunks_tile_the_lines():
+    """sllb_dd6d_chunk_boxes: the pieces of a pipelined split-axis pass cover every line exactly once, inner ranges are
+    multiples of 32 lines (TMA rows), and shapes that cannot be cut stay in one piece"""
+    import ctypes as C
+    lib = sb.lib()
+    for outer, inner, nch in ((256, 1024, 4), (16, 4096, 4), (1, 32 * 32 * 32 * 16 * 16, 4), (1, 8388608, 8), (3, 100, 4), (1, 96, 4),
+                              (1, 50, 4), (5, 64, 16)):
+        buf = (C.c_longlong * 64)(); nb = C.c_int(0)
+        assert lib.sllb_dd6d_chunk_boxes(C.c_longlong(outer), C.c_longlong(inner), C.c_int(nch), buf, C.byref(nb)) == 0
+        boxes = np.array(buf[:4 * nb.value]).reshape(-1, 4)
+        cover = np.zeros((outer, min(inner, 4096)), dtype=int)
+        for o0, oc, i0, ic in boxes:
+            assert oc >= 1 and ic >= 1 and o0 >= 0 and i0 >= 0 and o0 + oc <= outer and i0 + ic <= inner
+            if ic != inner:
+                assert i0 % 32 == 0 and ic % 32 == 0
+            cover[o0:o0 + oc, min(i0, cover.shape[1]):min(i0 + ic, cover.shape[1])] += 1
+        assert (cover == 1).all()
+        assert sum(oc * ic for _, oc, _, ic in boxes) == outer * inner
+        assert 1 <= nb.value <= nch
