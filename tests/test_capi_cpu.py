@@ -256,3 +256,17 @@ def test_pipelined_exchange_chunks_tile_the_lines():
         assert (cover == 1).all()
         assert sum(oc * ic for _, oc, _, ic in boxes) == outer * inner
         assert 1 <= nb.value <= nch
+
+
+def test_new_entry_points_fail_loudly_without_a_device():
+    """no CPU fallback behind the (f) entry points either: without a CUDA device they return SLLB_ERR_NO_DEVICE"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    for ctor in (lambda: sb.Interpolator1d(sb.INTERP_CUBIC_SPLINE, 33, -6.0, 6.0, bc=sb.BC_HERMITE),
+                 lambda: sb.Sim4d([16, 16, 32, 32], [0, 0, -6, -6], [12.5, 12.5, 6, 6], 0.5, 0.5, 1e-3, 0.1, split="SLL_ORDER6VPOT_VTV"),
+                 lambda: sb.Sim6d([16] * 6, 6.0, [12.5] * 3, 3, 3, 0.01, 0.01, [0.5] * 3, advector=sb.ADVECTOR_SPLINE),
+                 lambda: sb.Dd6d(None, [16] * 6)):
+        with pytest.raises(sb.SllbError) as e:
+            ctor()
+        assert e.value.code == sb.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
