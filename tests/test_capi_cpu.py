@@ -270,3 +270,25 @@ def test_new_entry_points_fail_loudly_without_a_device():
         with pytest.raises(sb.SllbError) as e:
             ctor()
         assert e.value.code == sb.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def _build_c_driver(tmp_path):
+    import subprocess
+    libdir = os.path.join(ROOT, "selalib_b200", "lib")
+    exe = str(tmp_path / "sim_bsl_vp_2d2v_cart_poisson_serial_b200")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-O2", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "sim_bsl_vp_2d2v_cart_poisson_serial_b200.c"), "-o", exe,
+                           "-L" + libdir, "-lsllb200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_driver_builds_and_fails_loudly_without_a_device(tmp_path):
+    """tests/c/sim_bsl_vp_2d2v_cart_poisson_serial_b200.c: a plain-C host of the drop-in boundary links against the
+    library; without a GPU it stops with the library's message instead of computing anything"""
+    import subprocess
+    import torch
+    exe = _build_c_driver(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (covered by tests/test_gpu_splitting.py)")
+    out = subprocess.run([exe, str(tmp_path / "whatever")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 1 and "no usable CUDA device" in out.stderr

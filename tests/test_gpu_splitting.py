@@ -147,3 +147,27 @@ def test_namelist_front_end_writes_thdiag(sb, orc, tmp_path, adv, method):
     assert np.abs(rows[:, [2, 7, 8, 9]] / ref[:, [2, 7, 8, 9]] - 1).max() < 1e-8
     assert np.abs(rows[:, 1] / ref[:, 1] - 1).max() < 1e-6 and np.abs(rows[:, 5] / ref[:, 5] - 1).max() < 1e-5
     assert np.abs(rows[:, [3, 4, 10, 11, 12]] / ref[:, [3, 4, 10, 11, 12]] - 1).max() < 1e-11
+
+
+def test_c_driver_runs_the_namelist(sb, orc, tmp_path):
+    """the plain-C counterpart of the reference executable (tests/c/): namelist in, thdiag.dat out, rows as sllb_sim4d_thdiag"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "selalib_b200", "lib")
+    exe = str(tmp_path / "sim_bsl_vp_2d2v_cart_poisson_serial_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-O2", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c", "sim_bsl_vp_2d2v_cart_poisson_serial_b200.c"), "-o", exe,
+                           "-L" + libdir, "-lsllb200", "-Wl,-rpath," + libdir])
+    (tmp_path / "in.nml").write_text(NML % {"dt": "0.1", "adv": "SLL_SPLINES"})
+    out = subprocess.run([exe, str(tmp_path / "in")], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = (tmp_path / "thdiag.dat").read_text().splitlines()
+    assert len(lines) == 3 and all(len(l) == 260 for l in lines)
+    rows = np.array([[float(l[20 * k:20 * k + 20]) for k in range(13)] for l in lines])
+    S = sb.Sim4d([16, 16, 32, 32], [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1, split="SLL_ORDER6VPnew1_VTV",
+                 stencil=(-3, 3))
+    S.run(4, diagnostics=False)
+    ref = S.thdiag()
+    S.destroy()
+    assert (np.abs(rows[2] - ref) <= 1e-9 * np.abs(ref) + 1e-30).all(), (rows[2], ref)   # 12 printed digits; nrj_jac is 0
