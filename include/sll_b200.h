@@ -414,6 +414,8 @@ int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]);
 /* finest: [local passes, reduce+poisson, NCCL remap, diag, fused V-stage pass (x4 + remap), barrier after it,
  *          fused T-stage plane kernel (x1 + x2 + rho + remap), all-reduce (rho + barrier) after it] */
 int sllb_sim4d_phase_ms8(sllb_sim4d_t S, double out[8]);
+/* phase timing is opt-in: 1 = sllb_sim4d_run records one CUDA event per phase (pooled, reused), 0 (default) = none */
+int sllb_set_phase_timers(int on);
 
 /* 1D1V sim_bsl_vp_1d1v_cart (single GPU). init 0 Landau, 1 two-stream. rows: nsteps x 8
  * (time, mass, l1, momentum, l2, ekin, epot, etot; sll_m_sim_bsl_vp_1d1v_cart.F90:1783) */
@@ -428,8 +430,12 @@ int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F);
 int sllb_sim2d_destroy(sllb_sim2d_t S);
 
 /* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (fixed / centred Lagrange or local splines) on 1..P GPUs (velocity axes split,
- * halo exchange per v-advection, rho all-reduced). rows: (nsteps+1) x 14 as the reference's
- * <prefix>.dat (sll_m_sim_6d_utilities.F90:357-364,632-633); every rank gets the global row. */
+ * halo exchange per v-advection, rho all-reduced). rows: R x 14 as the reference's <prefix>.dat
+ * (sll_m_sim_6d_utilities.F90:357-364,632-633), R = nsteps + 1 for the FIRST call on a handle (it also writes the
+ * t = 0 row) and nsteps for every later call (sllb_sim6d_run_rows tells which); every rank gets the global row.
+ * time_in_phase: the reference ends its single loop with a half V step (:735-741).  A handle may be run in several
+ * calls: a call that follows such an ending first applies the other half of that V step, so that run(a) followed by
+ * run(b) advances f exactly as far as one run(a+b); the rows of the two variants agree, f to rounding. */
 typedef struct sllb_sim6d *sllb_sim6d_t;
 typedef struct {
     int n[6];
@@ -452,6 +458,7 @@ int sllb_sim6d_create(const sllb_sim6d_params_t *p, sllb_sim6d_t *S);
 /* process_grid: NULL / zeros = sll_f_set_process_grid(nranks) */
 int sllb_sim6d_create_dist(const sllb_sim6d_params_t *p, sllb_comm_t comm, const int process_grid[6], sllb_sim6d_t *S);
 int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows);
+int sllb_sim6d_run_rows(sllb_sim6d_t S, int nsteps, int *nrows); /* rows the next sllb_sim6d_run(S, nsteps, rows) writes */
 int sllb_sim6d_field(sllb_sim6d_t S, sllb_field_t *F); /* local block */
 int sllb_sim6d_decomposition(sllb_sim6d_t S, sllb_dd6d_t *D);
 int sllb_sim6d_advect_x(sllb_sim6d_t S);

@@ -47,6 +47,19 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP team size of the oracle's loops over lines (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def spline_interpolate_array_disp(data, xmin, xmax, alpha, fast=-1):
     data = _f(data); out = np.empty_like(data)
     lib().orc_cubic_spline_interpolate_array_disp(C.c_int(data.size), C.c_double(xmin), C.c_double(xmax),

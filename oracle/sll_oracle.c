@@ -41,6 +41,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm of bench.py asks for the host's cores explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------- */
 /* FFT helpers (unnormalised DFT, sign = -1 forward / +1 backward).           */
 /* Semantics of FFTPACK zfftf/zfftb (external/fftpack) and FFTW c2c: a DFT is  */

@@ -124,6 +124,11 @@ def set_remap_rotation(on):
     _ck(lib().sllb_set_remap_rotation(C.c_int(1 if on else 0)))
 
 
+def set_phase_timers(on):
+    """opt-in per-phase CUDA events inside sllb_sim4d_run (Sim4d.phase_ms8)"""
+    _ck(lib().sllb_set_phase_timers(C.c_int(1 if on else 0)))
+
+
 def set_cuda_graphs(on):
     _ck(lib().sllb_set_cuda_graphs(C.c_int(1 if on else 0)))
 
@@ -668,8 +673,12 @@ class Sim6d:
         _ck(lib().sllb_sim6d_create_dist(C.byref(p), comm.h if comm is not None else None,
                                          _ints(process_grid) if process_grid is not None else None, C.byref(self.h)))
 
-    def run(self, nsteps, first=True):
-        rows = np.zeros((nsteps + (1 if first else 0), 14))
+    def run(self, nsteps, first=None):
+        """rows written by this call: the first call on a handle includes the t = 0 row (the library knows which call
+        this is; `first` is kept for old callers and ignored)."""
+        nrows = C.c_int(0)
+        _ck(lib().sllb_sim6d_run_rows(self.h, C.c_int(nsteps), C.byref(nrows)))
+        rows = np.zeros((nrows.value, 14))
         _ck(lib().sllb_sim6d_run(self.h, C.c_int(nsteps), _p(rows)))
         return rows
 

@@ -43,6 +43,8 @@ struct sllb_dd6d {
     cudaStream_t s_comm = nullptr, s_comp = nullptr;
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_comm0 = nullptr, ev_comm1 = nullptr, ev_chunk[16] = {};
     bool exch_pending = false; // exch_ms of the last pipelined pass still to be read from ev_comm0/1
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr; // around the last plain exchange (read lazily by sllb_dd6d_exchange_ms)
+    bool xch_pending = false;
 };
 static int g_halo_chunks = -1; // -1: SLLB_HALO_CHUNKS or 4; 1 = exchange everything, then one kernel
 
@@ -165,6 +167,7 @@ int sllb_dd6d_destroy(sllb_dd6d_t D) {
         cudaEventDestroy(D->ev_start); cudaEventDestroy(D->ev_end); cudaEventDestroy(D->ev_comm0); cudaEventDestroy(D->ev_comm1);
         for (cudaEvent_t e : D->ev_chunk) if (e) cudaEventDestroy(e);
     }
+    if (D->ev_x0) { cudaEventDestroy(D->ev_x0); cudaEventDestroy(D->ev_x1); }
     for (void *ptr : D->ipc_opened) cudaIpcCloseMemHandle(ptr);
     sllb_field_destroy(D->F);
     delete D;
@@ -204,9 +207,11 @@ int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) 
         SLLB_TRY(D->halo_r.ensure(cr > 0 ? cr : 1));
         D->cur_l = D->halo_l.p; D->cur_r = D->halo_r.p;
     }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, 0);
+    // two events owned by the decomposition, recorded around the exchange and read only if somebody asks for the time:
+    // no event creation, no host synchronisation per exchange
+    if (!D->ev_x0) { SLLB_CUDA(cudaEventCreate(&D->ev_x0)); SLLB_CUDA(cudaEventCreate(&D->ev_x1)); }
+    SLLB_CUDA(cudaEventRecord(D->ev_x0, 0));
+    D->xch_pending = false;
     if (D->procs[axis] == 1) {
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, D->halo_r.p, 0));
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, D->halo_l.p, 0));
@@ -239,12 +244,9 @@ int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) 
         }
         SLLB_NCCL(ncclGroupEnd());
     }
-    cudaEventRecord(e1, 0);
-    cudaEventSynchronize(e1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    D->exch_ms = ms;
+    SLLB_CUDA(cudaEventRecord(D->ev_x1, 0));
+    D->xch_pending = true;
+    D->exch_pending = false;
     D->hw_l = hw_left; D->hw_r = hw_right; D->halo_axis = axis;
     return SLLB_OK;
 }
@@ -263,6 +265,12 @@ int sllb_dd6d_exchange_ms(sllb_dd6d_t D, double *ms) {
         cudaEventElapsedTime(&t, D->ev_comm0, D->ev_comm1);
         D->exch_ms = t;
         D->exch_pending = false;
+    } else if (D->xch_pending) {
+        float t = 0;
+        cudaEventSynchronize(D->ev_x1);
+        cudaEventElapsedTime(&t, D->ev_x0, D->ev_x1);
+        D->exch_ms = t;
+        D->xch_pending = false;
     }
     *ms = D->exch_ms;
     return SLLB_OK;
@@ -346,6 +354,7 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
     D->parity ^= 1;
     D->hw_l = h; D->hw_r = h; D->halo_axis = axis;
     D->exch_pending = true;
+    D->xch_pending = false;
     return SLLB_OK;
 }
 extern "C" {
@@ -463,6 +472,7 @@ struct sllb_sim6d {
     sllb_poisson *poisson = nullptr;
     DevBuf rho, phi, ex, ey, ez, small;
     bool started = false;
+    bool half_kick_pending = false; // the previous sllb_sim6d_run ended with the closing half kick of time_in_phase
     int itime = 0;
     double halo_ms = 0.0, advect_ms = 0.0;
     // spline / centred advectors: per x axis the displacement -v dt/dx of the local velocity indices, as the reference
@@ -667,6 +677,16 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
     }
     return SLLB_OK;
 }
+/* Rows sllb_sim6d_run(S, nsteps, rows) will write: the first call on a handle also writes the t = 0 row. */
+int sllb_sim6d_run_rows(sllb_sim6d_t S, int nsteps, int *nrows) {
+    if (!S || !nrows || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run_rows: bad arguments");
+    *nrows = nsteps + (S->started ? 0 : 1);
+    return SLLB_OK;
+}
+/* Time loop (:643-760).  With time_in_phase the reference closes its one loop with a half V step so that x and v are
+ * known at the same time; here a handle may be run in several calls, so a call that follows such an ending opens with
+ * the other half of that V step (E has not changed in between: a V step leaves rho untouched), i.e.
+ * run(a) + run(b) advances f exactly as far as run(a + b). */
 int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
     if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run: bad arguments");
     int row = 0;
@@ -675,14 +695,19 @@ int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
         row = 1;
         SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
         S->started = true;
+    } else if (S->half_kick_pending && nsteps > 0) {
+        SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
+        S->half_kick_pending = false;
     }
     for (int it = 1; it <= nsteps; ++it) {
         SLLB_TRY(sllb_sim6d_advect_x(S));
         SLLB_TRY(sllb_sim6d_fields(S));
         S->itime += 1;
         if (rows) SLLB_TRY(sllb_sim6d_diagnostics(S, (double)S->itime * S->p.delta_t, rows + 14 * (row++)));
-        if (S->p.time_in_phase && it == nsteps) SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
-        else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
+        if (S->p.time_in_phase && it == nsteps) {
+            SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
+            S->half_kick_pending = true;
+        } else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
     }
     SLLB_CUDA(cudaDeviceSynchronize());
     return SLLB_OK;

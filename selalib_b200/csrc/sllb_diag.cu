@@ -1,0 +1,133 @@
+// sllb_diag.cu -- the per-step diagnostics of the 2D2V time loop (sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:1112,
+// 1183-1260: field energy, mass, L1/L2 norms, kinetic energy) computed on the device, so that a run with diagnostics
+// every step (what the reference does) never waits for the host: every kernel below is a deterministic fixed-shape
+// reduction launched on the time loop's stream, and the rows stay in HBM until the run is over.
+#include "sllb_internal.h"
+#include "sllb_device.cuh"
+
+namespace sllb {
+
+namespace {
+constexpr int RT = 1024;
+// fixed-order block sum of NV values per thread (warp shuffles, then the 32 warp results by thread 0)
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *out, bool do_max = false) {
+    __shared__ double sh[NV][32];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, v[k], o);
+            v[k] = do_max ? fmax(v[k], t) : v[k] + t;
+        }
+    }
+    const int w = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (ln == 0)
+        for (int k = 0; k < NV; ++k) sh[k][w] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NV; ++k) {
+            double t = sh[k][0];
+            for (int i = 1; i < nw; ++i) t = do_max ? fmax(t, sh[k][i]) : t + sh[k][i];
+            out[k] = t;
+        }
+}
+} // namespace
+
+__global__ void __launch_bounds__(RT) k_moments_from_rows(const double *__restrict__ rows3, const int n3, const int n4,
+                                                          const double *__restrict__ w3, const double *__restrict__ w4,
+                                                          double *__restrict__ out4) {
+    double v[4] = {0, 0, 0, 0};
+    const long long nv = (long long)n3 * n4;
+    for (long long r = threadIdx.x; r < nv; r += RT) {
+        const double s0 = rows3[3 * r];
+        v[0] += s0; v[1] += rows3[3 * r + 1]; v[2] += rows3[3 * r + 2];
+        v[3] = fma(w3[r % n3] + w4[r / n3], s0, v[3]);
+    }
+    block_sum<4>(v, out4);
+}
+cudaError_t launch_moments_from_rows(const double *rows3, int n3, int n4, const double *w3, const double *w4, double *out4,
+                                     cudaStream_t st) {
+    k_moments_from_rows<<<1, RT, 0, st>>>(rows3, n3, n4, w3, w4, out4);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static const int ML_BLOCKS = 148;
+size_t moments_from_lines_scratch() { return (size_t)ML_BLOCKS * 4; }
+__global__ void __launch_bounds__(RT) k_moments_from_lines1(const double *__restrict__ sum_, const double *__restrict__ l1,
+                                                            const double *__restrict__ l2, const double *__restrict__ kin,
+                                                            const long long nx, const int n3, const double *__restrict__ w3,
+                                                            double *__restrict__ partial) {
+    double v[4] = {0, 0, 0, 0};
+    const long long n = nx * n3;
+    for (long long l = (long long)blockIdx.x * RT + threadIdx.x; l < n; l += (long long)gridDim.x * RT) {
+        const double s0 = sum_[l];
+        v[0] += s0; v[1] += l1[l]; v[2] += l2[l];
+        v[3] += fma(w3[l / nx], s0, kin[l]);
+    }
+    block_sum<4>(v, partial + 4 * blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_moments_from_lines2(const double *__restrict__ partial, const int nb,
+                                                             double *__restrict__ out4) {
+    double v[4] = {0, 0, 0, 0};
+    for (int b = threadIdx.x; b < nb; b += 256)
+        for (int k = 0; k < 4; ++k) v[k] += partial[4 * b + k];
+    block_sum<4>(v, out4);
+}
+cudaError_t launch_moments_from_lines(const double *sum_, const double *l1, const double *l2, const double *kin, long long nx,
+                                      int n3, const double *w3, double *scratch, double *out4, cudaStream_t st) {
+    k_moments_from_lines1<<<ML_BLOCKS, RT, 0, st>>>(sum_, l1, l2, kin, nx, n3, w3, scratch);
+    count_launch();
+    k_moments_from_lines2<<<1, 256, 0, st>>>(scratch, ML_BLOCKS, out4);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(RT) k_dup_energy2d(const double *__restrict__ a, const double *__restrict__ b, const int n1,
+                                                     const int n2, const double scale, const int squared,
+                                                     double *__restrict__ out1) {
+    double v[1] = {0};
+    const long long n = (long long)n1 * n2;
+    for (long long k = threadIdx.x; k < n; k += RT) {
+        const int i = (int)(k % n1), j = (int)(k / n1);
+        // node (0, .) is also node (n1, .), node (., 0) also (., n2)
+        const double w = (i == 0 ? 2.0 : 1.0) * (j == 0 ? 2.0 : 1.0);
+        const double bb = squared ? b[k] * b[k] : b[k] + b[k];
+        v[0] = fma(w, fma(a[k], a[k], bb), v[0]);
+    }
+    block_sum<1>(v, out1);
+    if (threadIdx.x == 0) out1[0] *= scale;
+}
+cudaError_t launch_dup_energy2d(const double *a, const double *b, int n1, int n2, double scale, int squared, double *out1,
+                                cudaStream_t st) {
+    k_dup_energy2d<<<1, RT, 0, st>>>(a, b, n1, n2, scale, squared, out1);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(RT) k_absmax(const double *__restrict__ a, const long long n, double *__restrict__ out1) {
+    double v[1] = {0};
+    for (long long k = threadIdx.x; k < n; k += RT) v[0] = fmax(v[0], fabs(a[k]));
+    block_sum<1>(v, out1, true);
+}
+cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream_t st) {
+    k_absmax<<<1, RT, 0, st>>>(a, n, out1);
+    count_launch();
+    return cudaGetLastError();
+}
+
+__global__ void k_sim4d_row(const double *__restrict__ m4, const double *__restrict__ nrj, const double time, const double vol,
+                            double *__restrict__ row6) {
+    if (threadIdx.x != 0) return;
+    row6[0] = time; row6[1] = nrj[0];
+    row6[2] = 0.5 * m4[3] * vol;
+    row6[3] = m4[0] * vol; row6[4] = m4[1] * vol; row6[5] = m4[2] * vol;
+}
+cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, double *row6, cudaStream_t st) {
+    k_sim4d_row<<<1, 32, 0, st>>>(m4, nrj, time, vol, row6);
+    count_launch();
+    return cudaGetLastError();
+}
+
+} // namespace sllb

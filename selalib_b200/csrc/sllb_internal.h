@@ -93,7 +93,7 @@ int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<
                      std::vector<void *> &opened, bool *ok);
 // internal (device-pointer) entry points used by the simulations
 int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr,
-                    double *linesum = nullptr);
+                    double *linesum = nullptr, const LineDiag *diag = nullptr);
 int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
                      const RemapDst *remap = nullptr);
 int advect_lagrange_plane_dev(sllb_field *F, int method, int order, const DispDesc &dd0, const DispDesc &dd1);
@@ -108,4 +108,19 @@ cudaError_t launch_jacobian2d(const double *e1, const double *e2, int n1, int n2
                               double factor, double *jac, cudaStream_t st);
 cudaError_t launch_lincomb2(const double *x, const double *y, double a, double b, long long n, double *out, cudaStream_t st);
 int moments_local(sllb_field *F, int nv, const double *w1, const double *w2, double *out);
+// sllb_diag.cu: time-loop diagnostics of the 2D2V simulation without leaving the device
+// out4 = (sum f, sum |f|, sum f^2, sum (w3[i3] + w4[i4]) f) from the per-row sums of K8 (rows3 = [n3*n4][3])
+cudaError_t launch_moments_from_rows(const double *rows3, int n3, int n4, const double *w3, const double *w4, double *out4,
+                                     cudaStream_t st);
+// the same four numbers from the per-line arrays the last x4 pass of a step leaves behind (lines = [nx][n3], x fastest):
+// sum f = sum sum_, ..., kinetic = sum_l (w3[i3(l)] sum_[l] + kin[l])
+cudaError_t launch_moments_from_lines(const double *sum_, const double *l1, const double *l2, const double *kin, long long nx,
+                                      int n3, const double *w3, double *scratch, double *out4, cudaStream_t st);
+size_t moments_from_lines_scratch();
+// nrj = scale * sum over the (n1+1)(n2+1) nodes including the periodic duplicates of a^2 + (squared ? b^2 : 2 b)
+cudaError_t launch_dup_energy2d(const double *a, const double *b, int n1, int n2, double scale, int squared, double *out1,
+                                cudaStream_t st);
+cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream_t st);
+// row6 = (time, nrj[0], 0.5 vol m4[3], vol m4[0], vol m4[1], vol m4[2])
+cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, double *row6, cudaStream_t st);
 } // namespace sllb

@@ -293,17 +293,19 @@ __global__ void __launch_bounds__(1024) k_lagrange_strided_split(double *__restr
 // tile is C instead of N steps and P times more warps are resident to hide latency.
 // Chunk [k0,k1) computes g[k] for k = k1+2 .. k0 and emits cells k0+1 .. k1 (mod N).
 // ------------------------------------------------------------------------------------------------
-template <int P, bool REMAP>
+template <int P, bool REMAP, bool DIAG = false>
 __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restrict__ f, const int N,
                                                                   const long long inner, const DispDesc dd,
                                                                   const int use_tma, const long long nlines,
                                                                   double *__restrict__ linesum,
-                                                                  const __grid_constant__ RemapDst rd) {
+                                                                  const __grid_constant__ RemapDst rd,
+                                                                  const LineDiag dg) {
     constexpr int BW = 32;
+    constexpr int NPART = DIAG ? 4 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *part = reinterpret_cast<double *>(smem_raw + 128);          // [P][32] chunk sums (linesum only)
-    double *s = reinterpret_cast<double *>(smem_raw + 128 + P * 32 * 8);
+    double *part = reinterpret_cast<double *>(smem_raw + 128);          // [NPART][P][32] chunk sums (linesum only)
+    double *s = reinterpret_cast<double *>(smem_raw + 128 + NPART * P * 32 * 8);
     const int tid = threadIdx.x, lane = tid & 31, chunk = tid >> 5;
     unsigned bid = blockIdx.x;
     if constexpr (REMAP) { bid += (unsigned)rd.block_rot; if (bid >= gridDim.x) bid -= gridDim.x; }
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
         sc[k * BW] = e;
     }
     __syncthreads();
-    double total = 0.0;
+    double total = 0.0, t1 = 0.0, t2 = 0.0, tk = 0.0;
     if (active) {
         // per-line weights (see spline_line)
         const double disp = disp_of(dd, o, in);
@@ -398,6 +400,7 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
                 const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
                 st_stream(p, val);
                 total += val;
+                if constexpr (DIAG) { t1 += fabs(val); t2 = fma(val, val, t2); tk = fma(__ldg(dg.w2 + iout), val, tk); }
                 p = (iout == 0) ? ptop : p - inner;
                 iout = (iout == 0) ? N - 1 : iout - 1;
                 a3 = a2; a2 = a1; a1 = a0;
@@ -407,12 +410,20 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     // optional: sum of every advected line (charge-density reduction fused into the pass, see K3b)
     if (linesum != nullptr) {
         part[chunk * 32 + lane] = total;
+        if constexpr (DIAG) {
+            part[(P + chunk) * 32 + lane] = t1;
+            part[(2 * P + chunk) * 32 + lane] = t2;
+            part[(3 * P + chunk) * 32 + lane] = tk;
+        }
         __syncthreads();
-        if (chunk == 0 && active) {
-            double t = part[lane];
+        if (chunk < NPART && active) { // warp m folds moment m of the block's 32 lines over the P chunks
+            const double *pm = part + (size_t)chunk * P * 32;
+            double t = pm[lane];
 #pragma unroll
-            for (int c = 1; c < P; ++c) t += part[c * 32 + lane];
-            linesum[l] = t;
+            for (int c = 1; c < P; ++c) t += pm[c * 32 + lane];
+            double *dst = linesum;
+            if constexpr (DIAG) dst = (chunk == 0) ? linesum : (chunk == 1 ? dg.l1 : (chunk == 2 ? dg.l2 : dg.kin));
+            dst[l] = t;
         }
     }
 }
@@ -1098,8 +1109,13 @@ static int remap_block_rotation(const RemapDst &rd, long long nblk) {
 }
 template <int P>
 static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
-                                         int staging, cudaStream_t st, const RemapDst &rd, double *linesum) {
-    size_t smem = 128 + (size_t)P * 32 * 8 + (size_t)N * 32 * 8;
+                                         int staging, cudaStream_t st, const RemapDst &rd, double *linesum,
+                                         const LineDiag *diag) {
+    const bool with_diag = diag != nullptr && linesum != nullptr && !rd.on && P >= 4;
+    if (diag != nullptr && !with_diag) return cudaErrorNotSupported;
+    LineDiag dg = {nullptr, nullptr, nullptr, nullptr};
+    if (with_diag) dg = *diag;
+    size_t smem = 128 + (size_t)(with_diag ? 4 : 1) * P * 32 * 8 + (size_t)N * 32 * 8;
     bool tma_ok = (inner % 32 == 0) && ((reinterpret_cast<uintptr_t>(f) & 15) == 0) && ((size_t)N * 32 * 8 < (1u << 20));
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + 31) / 32;
@@ -1110,12 +1126,19 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
         if (e != cudaSuccess) return e;
         RemapDst rr = rd;
         rr.block_rot = remap_block_rotation(rd, nblk);
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr);
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg);
+    } else if (with_diag) {
+        if constexpr (P >= 4) {
+            auto kern = k_spline_strided_split<P, false, true>;
+            e = set_smem(kern, smem);
+            if (e != cudaSuccess) return e;
+            kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg);
+        }
     } else {
         auto kern = k_spline_strided_split<P, false>;
         e = set_smem(kern, smem);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd);
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg);
     }
     COUNT_LAUNCH();
     return cudaGetLastError();
@@ -1294,7 +1317,8 @@ cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts,
 }
 
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
-                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap, double *linesum) {
+                          const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap, double *linesum,
+                          const LineDiag *diag) {
     if (n < 8 || outer < 1 || inner < 1) return cudaErrorInvalidValue;
     RemapDst rd;
     if (remap && remap->on) {
@@ -1310,7 +1334,7 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
     if (nlines > 0x7fffffffLL * 8) return cudaErrorInvalidValue;
     if (method == METHOD_SPLINE) {
         if (order != 4) return cudaErrorInvalidValue;
-        if (inner == 1 && linesum) return cudaErrorNotSupported;
+        if (inner == 1 && (linesum || diag)) return cudaErrorNotSupported;
         if (inner == 1) {
             // split kernel: one bulk TMA copy per 32-line tile (16-byte granularity) and P chunks per line
             const bool tile_ok = (size_t)n * 32 * 8 + 256 <= SMEM_MAX && (size_t)n * 32 * 8 < (1u << 20) &&
@@ -1331,14 +1355,14 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
         if ((size_t)n * 32 * 8 + 128 + 8 * 32 * 8 <= SMEM_MAX) {
             int P = g_spline_split;
             if (P < 0) P = (n % 4 == 0 && n / 4 >= 32) ? 4 : ((n % 2 == 0 && n / 2 >= 32) ? 2 : 1);
-            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd, linesum);
-            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd, linesum);
-            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd, linesum);
+            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag);
+            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag);
+            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag);
         }
-        if (linesum) return cudaErrorNotSupported; // line sums come from the chunked kernel only
+        if (linesum || diag) return cudaErrorNotSupported; // line sums come from the chunked kernel only
         return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st, rd);
     }
-    if (linesum) return cudaErrorNotSupported;
+    if (linesum || diag) return cudaErrorNotSupported;
 #define LAGR_CASE(SS)                                                                            \
     case SS:                                                                                     \
         if (inner == 1) return launch_lagrange_contig<SS>(f, nlines, n, dd, staging, st);       \

@@ -29,10 +29,14 @@ struct RemapDst {
 
 // K1/K2: one 1D periodic advection on every line of f viewed as [outer][n][inner], in place.
 // Returns cudaSuccess, cudaErrorInvalidValue (bad n / order) or a launch error.
+// Per-line moments of the advected line next to its sum (time-loop diagnostics fused into the last pass of a step):
+// l1[line] = sum |out|, l2[line] = sum out^2, kin[line] = sum_i w2[i] out(i) with w2 indexed by the OUTPUT point.
+struct LineDiag { double *l1, *l2, *kin; const double *w2; };
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
                           const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap = nullptr,
-                          double *linesum = nullptr);
-// linesum (strided spline passes only, else cudaErrorNotSupported): linesum[line] = sum of the advected line
+                          double *linesum = nullptr, const LineDiag *diag = nullptr);
+// linesum (strided spline passes only, else cudaErrorNotSupported): linesum[line] = sum of the advected line;
+// diag needs linesum
 
 // K1c: both passes of a T stage (axes 0 and 1) on every contiguous n1 x n2 plane in one sweep, optionally
 // accumulating per-CTA partial sums over the planes: rho_partial[plane_grid(...)][n1*n2].

@@ -81,8 +81,14 @@ int sllb_sim4d_create_from_namelist(const char *filename, sllb_comm_t comm, sllb
         p.xmin[d] = get_real(nml, "geometry", mn[d], d < 2 ? 0.0 : -6.0);
         if (mesh == "SLL_LANDAU_MESH" && d < 2)
             p.xmax[d] = (double)get_int(nml, "geometry", nb[d], 1) * 2.0 * pi / (d == 0 ? p.kx1 : p.kx2);
-        else if (mesh == "SLL_CARTESIAN_MESH")
+        else if (mesh == "SLL_CARTESIAN_MESH") {
+            // x3_max / x4_max default to 6 (:323,327); x1_max / x2_max have no default in the reference (:314-321: the
+            // variable is read before it is ever set), so a namelist that leaves them out is refused here
+            if (d < 2 && !find(nml, "geometry", mx[d]))
+                return fail(SLLB_ERR_INVALID, std::string("#") + mx[d] + " must be given with " + mc[d] + " = SLL_CARTESIAN_MESH "
+                                              "(the reference has no default for it)");
             p.xmax[d] = get_real(nml, "geometry", mx[d], 6.0);
+        }
         else
             return fail(SLLB_ERR_UNSUPPORTED, std::string("#") + mc[d] + " " + mesh + " not implemented");
     }
@@ -131,26 +137,44 @@ static int write_row13(FILE *fp, const double *row) {
 int sllb_sim4d_run_namelist(const char *filename, sllb_comm_t comm, const char *thdiag_path) {
     sllb_sim4d_t S = nullptr;
     int nit = 0, fdt = 1;
-    SLLB_TRY(sllb_sim4d_create_from_namelist(filename, comm, &S, &nit, &fdt));
+    SLLB_TRY(require_device());
+    // Only rank 0 touches the file, but every rank takes part in the collectives of the time loop: the outcome of the
+    // rank-0-only fopen is shared BEFORE anything collective starts, so that all ranks give up together; a failed write
+    // later on is remembered and reported at the end without leaving the loop (no rank is left alone in a collective).
     const bool writer = !comm || comm->rank == 0;
     FILE *fp = nullptr;
+    int open_failed = 0;
     if (writer) {
         fp = fopen(thdiag_path ? thdiag_path : "thdiag.dat", "w");
-        if (!fp) { sllb_sim4d_destroy(S); return fail(SLLB_ERR_INVALID, "sim4d_run_namelist: cannot create the thdiag file"); }
+        open_failed = fp ? 0 : 1;
     }
+    if (comm && comm->nranks > 1) {
+        DevBuf flag;
+        SLLB_TRY(flag.ensure(1));
+        const double mine = (double)open_failed;
+        double all = 0.0;
+        SLLB_CUDA(cudaMemcpy(flag.p, &mine, sizeof(double), cudaMemcpyHostToDevice));
+        SLLB_TRY(sllb_comm_allreduce_sum(comm, flag.p, 1));
+        SLLB_CUDA(cudaMemcpy(&all, flag.p, sizeof(double), cudaMemcpyDeviceToHost));
+        open_failed = all > 0.0 ? 1 : 0;
+    }
+    if (open_failed) { if (fp) fclose(fp); return fail(SLLB_ERR_INVALID, "sim4d_run_namelist: cannot create the thdiag file"); }
+    int rc = sllb_sim4d_create_from_namelist(filename, comm, &S, &nit, &fdt);   // same namelist, same verdict on every rank
+    if (rc) { if (fp) fclose(fp); return rc; }
     double row[13];
-    int rc = sllb_sim4d_thdiag(S, row);
-    if (!rc && fp) rc = write_row13(fp, row);
+    int wrc = SLLB_OK;
+    rc = sllb_sim4d_thdiag(S, row);
+    if (!rc && fp) wrc = write_row13(fp, row);
     for (int it = 1; it <= nit && !rc; ++it) {
         rc = sllb_sim4d_run(S, 1, 0, nullptr);
         if (!rc && it % fdt == 0) {
             rc = sllb_sim4d_thdiag(S, row);
-            if (!rc && fp) rc = write_row13(fp, row);
+            if (!rc && fp && !wrc) wrc = write_row13(fp, row);
         }
     }
     if (fp) fclose(fp);
     sllb_sim4d_destroy(S);
-    return rc;
+    return rc ? rc : wrc;
 }
 
 } // extern "C"

@@ -132,32 +132,49 @@ int sllb_comm_allgather(sllb_comm_t c, const double *d_send, double *d_recv, int
 /* phase timers (CUDA events on the launch stream)                                              */
 /* ------------------------------------------------------------------------------------------ */
 namespace {
+// Opt-in (sllb_set_phase_timers): a mark is one cudaEventRecord on the launch stream; the events come from a pool that
+// lives as long as the simulation, so a long run neither creates nor destroys events per stage.
 struct PhaseTimer {
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev;   // pool
     std::vector<int> tag;
+    size_t used = 0;
     bool on = false;
-    void begin() { reset(); on = true; }
+    void begin(bool enable) { used = 0; tag.clear(); on = enable; }
     void mark(int phase_just_finished) {
         if (!on) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, 0);
-        ev.push_back(e); tag.push_back(phase_just_finished);
+        if (used == ev.size()) {
+            if (ev.size() >= 4096) { // bounded: fold what has been recorded so far, keep the last event as the new origin
+                fold();
+                std::swap(ev[0], ev[used - 1]);
+                used = 1; tag.assign(1, -1);
+            } else {
+                cudaEvent_t e;
+                if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+                ev.push_back(e);
+            }
+        }
+        cudaEventRecord(ev[used], 0);
+        ++used; tag.push_back(phase_just_finished);
     }
-    void collect(double out[8]) {
-        for (int k = 0; k < 8; ++k) out[k] = 0;
-        if (ev.size() < 2) return;
-        cudaEventSynchronize(ev.back());
-        for (size_t i = 1; i < ev.size(); ++i) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void fold() {
+        if (used < 2) return;
+        cudaEventSynchronize(ev[used - 1]);
+        for (size_t i = 1; i < used; ++i) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
-            if (tag[i] >= 0 && tag[i] < 8) out[tag[i]] += ms;
+            if (tag[i] >= 0 && tag[i] < 8) acc[tag[i]] += ms;
         }
     }
-    void reset() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); tag.clear(); on = false; }
-    ~PhaseTimer() { reset(); }
+    void collect(double out[8]) {
+        fold();
+        for (int k = 0; k < 8; ++k) { out[k] = acc[k]; acc[k] = 0; }
+        used = 0; tag.clear(); on = false;
+    }
+    ~PhaseTimer() { for (auto e : ev) cudaEventDestroy(e); }
 };
 } // namespace
+static int g_phase_timers = 0;
 static void phase_mark(PhaseTimer *t, int tag) { if (t) t->mark(tag); }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -387,6 +404,11 @@ struct sllb_sim4d {
     double nrj = 0.0;
     int istep = 0;
     int layout = 0;    // which copy of f is current: 0 x-sequential, 1 v-sequential
+    // per-step diagnostics on the device (sllb_diag.cu): second-moment weights of the two velocity axes per layout,
+    // the per-line moments the last x4 pass of a step leaves behind, the four global moments, the field energy, the rows
+    DevBuf w2dev[2], dl1, dl2, dkin, dscratch, m4, nrjd, rows_dev;
+    bool want_line_diag = false;  // set by the time loop for the last stage of a step when diagnostics are on
+    bool line_diag_valid = false; // dl1/dl2/dkin/linesum describe the current f
     PhaseTimer timer;
     // local passes, rho+poisson, NCCL remap, diagnostics, fused V-stage pass, barrier after it, fused T-stage plane
     // kernel, all-reduce (rho + barrier) after it
@@ -509,11 +531,55 @@ static int sim4d_nrj(sllb_sim4d *S) {
     return SLLB_OK;
 }
 
+// second-moment weights of the local velocity indices of a layout; the trapezoid rule over the duplicated end points
+// averages v^2 at both ends, which for the periodic pair (vmin, vmax) is 0.5 (vmin^2 + vmax^2)
+static int sim4d_w2_tables(sllb_sim4d *S) {
+    const sllb_sim4d_params_t &p = S->p;
+    for (int lay = 0; lay < 2; ++lay) {
+        sllb_field *F = S->D->F[lay];
+        const int *bx = lay == 0 ? S->bx : S->bv;
+        std::vector<double> w2;
+        for (int a = 2; a < 4; ++a)
+            for (int i = 0; i < F->ext[a]; ++i) {
+                const int ig = i + bx[2 * a];
+                const double v = p.xmin[a] + ig * S->delta[a];
+                w2.push_back(ig == 0 ? 0.5 * (p.xmin[a] * p.xmin[a] + p.xmax[a] * p.xmax[a]) : v * v);
+            }
+        SLLB_TRY(S->w2dev[lay].ensure(w2.size()));
+        SLLB_CUDA(cudaMemcpy(S->w2dev[lay].p, w2.data(), w2.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    return SLLB_OK;
+}
+// One diagnostics row (time, field energy, kinetic energy, mass, L1, L2: :1112,1183-1260) written to DEVICE memory: no
+// host synchronisation, so a run with diagnostics every step keeps the GPU busy.
+static int sim4d_diag_device(sllb_sim4d *S, double *d_row6) {
+    sllb_field *F = S->D->F[S->layout];
+    const sllb_sim4d_params_t &p = S->p;
+    SLLB_TRY(S->m4.ensure(4));
+    SLLB_TRY(S->nrjd.ensure(1));
+    SLLB_CUDA(launch_dup_energy2d(S->E1.p, S->E2.p, p.nc[0], p.nc[1], S->delta[0] * S->delta[1], 1, S->nrjd.p, 0));
+    const double *w3 = S->w2dev[S->layout].p, *w4 = w3 + F->ext[2];
+    if (S->line_diag_valid && S->layout == 1) {
+        SLLB_TRY(S->dscratch.ensure(moments_from_lines_scratch()));
+        SLLB_CUDA(launch_moments_from_lines(S->linesum.p, S->dl1.p, S->dl2.p, S->dkin.p, (long long)F->ext[0] * F->ext[1],
+                                            F->ext[2], w3, S->dscratch.p, S->m4.p, 0));
+    } else {
+        const long long nx = (long long)F->ext[0] * F->ext[1], nv = (long long)F->ext[2] * F->ext[3];
+        SLLB_TRY(F->rows.ensure((size_t)nv * 3));
+        SLLB_CUDA(launch_row_sums(F->d, nx, nv, F->rows.p, 0));
+        SLLB_CUDA(launch_moments_from_rows(F->rows.p, F->ext[2], F->ext[3], w3, w4, S->m4.p, 0));
+    }
+    if (S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->m4.p, 4));
+    SLLB_CUDA(launch_sim4d_row(S->m4.p, S->nrjd.p, S->istep * p.dt, S->delta[0] * S->delta[1] * S->delta[2] * S->delta[3], d_row6, 0));
+    return SLLB_OK;
+}
+
 // `fuse`: the stage's last pass writes straight into the other layout (advect + remap in one kernel)
 static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     sllb_field *Fx = S->D->F[0];
     const sllb_sim4d_params_t &p = S->p;
     S->rho_state = 0;
+    S->line_diag_valid = false;
     // cubic splines: both passes and the charge density in one sweep (K1c); on several GPUs the same kernel also
     // stores into the v-sequential layout of the owning ranks when the next stage is a V stage (`fuse`)
     if (S->m[0] == SLLB_METHOD_SPLINE && S->m[1] == SLLB_METHOD_SPLINE && g_plane_kernel) {
@@ -557,6 +623,7 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
 }
 static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
     sllb_field *Fv = S->D->F[1];
+    S->line_diag_valid = false;
     const sllb_sim4d_params_t &p = S->p;
     const double *e1 = S->E1.p, *e2 = S->E2.p;
     if (S->dim_split_V == 2) {
@@ -589,8 +656,20 @@ static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
         // density over as line sums of this pass (sum over x4 per (x1,x2,x3) line) instead of re-reading f
         int rc = SLLB_ERR_UNSUPPORTED;
         if (S->m[3] == SLLB_METHOD_SPLINE && g_plane_kernel) {
-            rc = S->linesum.ensure((size_t)Fv->ext[0] * Fv->ext[1] * Fv->ext[2]);
-            if (!rc) rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], dd, nullptr, S->linesum.p);
+            const size_t nl = (size_t)Fv->ext[0] * Fv->ext[1] * Fv->ext[2];
+            rc = S->linesum.ensure(nl);
+            if (!rc && S->want_line_diag) {
+                // the moments of the diagnostics row come out of this pass too (no extra sweep over f)
+                rc = S->dl1.ensure(nl);
+                if (!rc) rc = S->dl2.ensure(nl);
+                if (!rc) rc = S->dkin.ensure(nl);
+                if (!rc) {
+                    LineDiag dg = {S->dl1.p, S->dl2.p, S->dkin.p, S->w2dev[1].p + Fv->ext[2]};
+                    rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], dd, nullptr, S->linesum.p, &dg);
+                    if (rc == SLLB_OK) S->line_diag_valid = true;
+                }
+            }
+            if (!rc && !S->line_diag_valid) rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], dd, nullptr, S->linesum.p);
             if (rc == SLLB_OK) S->rho_state = 2;
         }
         if (rc == SLLB_ERR_UNSUPPORTED) rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], dd);
@@ -626,6 +705,8 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
     if (rc) { sllb_sim4d_destroy(S); return rc; }
     sllb_dist4d_box(S->D, 0, S->bx);
     sllb_dist4d_box(S->D, 1, S->bv);
+    rc = sim4d_w2_tables(S);
+    if (rc) { sllb_sim4d_destroy(S); return rc; }
     const size_t n12 = (size_t)p->nc[0] * p->nc[1];
     sllb_field *Fv = S->D->F[1];
     const size_t tile = (size_t)Fv->ext[0] * Fv->ext[1];
@@ -677,6 +758,7 @@ int sllb_sim4d_destroy(sllb_sim4d_t S) {
 int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F) {
     if (!S || !F) return fail(SLLB_ERR_INVALID, "sim4d_field: null");
     S->rho_state = 0; // the caller may overwrite f through the handle
+    S->line_diag_valid = false;
     SLLB_TRY(sim4d_to_layout(S, 0));
     *F = S->D->F[0];
     return SLLB_OK;
@@ -784,9 +866,10 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
     const int nsub = S->nb_split_step, dimV = S->dim_split_V;
     const bool beginT = S->begin_T;
     (void)p;
-    S->timer.begin();
+    S->timer.begin(g_phase_timers != 0);
     S->timer.mark(-1);
     const bool can_fuse = S->D->p2p && g_fused_remap && S->D->nranks > 1;
+    if (with_diagnostics && nsteps > 0) SLLB_TRY(S->rows_dev.ensure((size_t)6 * nsteps));
     for (int it = 0; it < nsteps; ++it) {
         int isub = 0; bool T = beginT;
         for (int ss = 0; ss < nsub; ++ss) {
@@ -795,6 +878,7 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
             const bool last_stage = (it == nsteps - 1 && ss == nsub - 1);
             const bool nextT = (ss == nsub - 1) ? beginT : !T;
             const bool fuse = can_fuse && !last_stage && (nextT != T);
+            S->want_line_diag = with_diagnostics && ss == nsub - 1;
             if (T) {
                 isub += 1;
                 SLLB_TRY(sim4d_to_layout(S, 0));
@@ -813,15 +897,25 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
             T = !T;
         }
         S->istep += 1;
+        S->want_line_diag = false;
         if (with_diagnostics) {
-            SLLB_TRY(sim4d_nrj(S));
-            if (rows) SLLB_TRY(sllb_sim4d_diagnostics(S, rows + 6 * it));
+            SLLB_TRY(sim4d_diag_device(S, S->rows_dev.p + 6 * it));
             S->timer.mark(3);
         }
     }
     SLLB_CUDA(cudaDeviceSynchronize());
+    if (with_diagnostics && nsteps > 0) {
+        std::vector<double> h((size_t)6 * nsteps);
+        SLLB_CUDA(cudaMemcpy(h.data(), S->rows_dev.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        S->nrj = h[6 * (size_t)(nsteps - 1) + 1];
+        if (rows) memcpy(rows, h.data(), h.size() * sizeof(double));
+    }
     S->timer.collect(S->phase_ms);
-    S->timer.reset();
+    return SLLB_OK;
+}
+/* 1: sllb_sim4d_run records a CUDA event per phase (sllb_sim4d_phase_ms*); 0 (default): no events on the hot path */
+int sllb_set_phase_timers(int on) {
+    g_phase_timers = on ? 1 : 0;
     return SLLB_OK;
 }
 int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]) {

@@ -119,6 +119,29 @@ def test_sim6d_golden_through_halo_path(sb):
     assert np.array_equal(rows, r0) and np.array_equal(f, f0)   # identical arithmetic, bit for bit
 
 
+@pytest.mark.parametrize("in_phase", [False, True])
+def test_sim6d_run_in_two_calls_equals_one_call(sb, in_phase):
+    """run(a) + run(b) == run(a + b): with time_in_phase the first call ends with the closing half V step and the second
+    one opens with the other half (no half step lost at the call boundary); rows written = nsteps (+1 on the first call)."""
+    args = ([8, 8, 8, 16, 16, 16], 6.0, [12.5663706144] * 3, 5, 5, 0.01, 0.01, [0.5] * 3)
+    S1 = sb.Sim6d(*args, time_in_phase=in_phase)
+    r1 = S1.run(3)
+    f1 = S1.field().download()
+    S1.destroy()
+    S2 = sb.Sim6d(*args, time_in_phase=in_phase)
+    ra = S2.run(1)
+    rb = S2.run(2)
+    f2 = S2.field().download()
+    S2.destroy()
+    assert r1.shape == (4, 14) and ra.shape == (2, 14) and rb.shape == (2, 14)
+    r2 = np.vstack([ra, rb])
+    if in_phase:   # two half V steps instead of one whole at the call boundary: equal to rounding
+        assert np.abs(r2 - r1).max() <= 1e-12 * np.abs(r1).max()
+        assert np.abs(f2 - f1).max() <= 1e-12 * np.abs(f1).max()
+    else:          # identical sequence of kernels
+        assert np.array_equal(r2, r1) and np.array_equal(f2, f1)
+
+
 def test_cpp_interface_of_the_reference_simulation(sb, tmp_path):
     """Our restatement of simulations/parallel/bsl_vp_3d3v_cart_dd/test_cpp_interface.cpp: a C++ host drives the
     simulation through the reference's own C symbols (namelist in, <prefix>.dat out) and the result is checked
