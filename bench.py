@@ -138,7 +138,8 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from oracle import orc
-    cores = orc.num_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: ask for the host's cores explicitly
+    cores = orc.set_num_threads(env_int("SLLB_REF_THREADS", 0) or orc.host_cores())
     n = NSIDE
     f = cpu_field(n)
     # size the per-step sample so that the whole run ends within a few minutes whatever K is
@@ -158,7 +159,7 @@ def run_reference(args, rank):
     value = done / dtm
     sample = (f"per step: the 6 advection passes of one Strang step over 1/{frac} of the lines (full {n}-point lines, all four "
               f"axes) of the {n}^4 field + 2 Poisson solves; direct cubic-spline algorithm (sll_m_cubic_splines fast path), "
-              "line copy-in/out, OpenMP static over lines; rho reduction excluded")
+              f"line copy-in/out, OpenMP static over lines on {cores} threads; rho reduction excluded")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dtm / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -167,6 +168,87 @@ def run_reference(args, rank):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def c5_block(sb, torch, dist, comm, rank, world, peak):
+    """C5 (BASELINE config 5): 3D3V Landau damping 32^6 fp64, domain-decomposed 7-point Lagrange advection with halo
+    exchange over NVLink (sim_bsl_vp_3d3v_cart_dd_slim semantics), timed like the headline: CUDA events, max over ranks."""
+    n = env_int("SLLB_C5_N", 32)
+    steps, warmup = env_int("SLLB_C5_STEPS", 5), 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    args6 = ([n] * 6, 6.0, [4 * np.pi] * 3, 7, 7, 0.01, 0.01, [0.5] * 3)
+    S = sb.Sim6d(*args6, comm=comm, time_in_phase=False)
+    lay = S.layout()
+    r_w = S.run(warmup)
+    S.halo_ms()
+    barrier()
+    sb.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r_t = S.run(steps)
+    e1.record()
+    barrier()
+    ms = maxr(e0.elapsed_time(e1))
+    launches = sb.launch_count()
+    rows = np.vstack([r_w, r_t])
+    reps = 3
+    S.halo_ms()
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for _ in range(reps):
+        S.advect_x()
+    x1.record()
+    barrier()
+    x_ms = maxr(x0.elapsed_time(x1)) / (3 * reps)
+    S.halo_ms()
+    v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    v0.record()
+    for _ in range(reps):
+        S.advect_v(0.01)
+    v1.record()
+    barrier()
+    v_ms = maxr(v0.elapsed_time(v1)) / (3 * reps)
+    nsplit = sum(1 for p in lay["procs"][3:] if p > 1)
+    halo_ms = maxr(S.halo_ms()) / max(1, nsplit * reps)
+    S.destroy()
+    local_pts = float(np.prod(lay["nw"]))
+    npts = float(n) ** 6
+    # cross-N exactness: rank 0 repeats the same steps on ONE GPU (8.6 GB) and compares the 14-column rows
+    rows_vs_1gpu = None
+    if world > 1 and rank == 0 and not os.environ.get("SLLB_SKIP_1GPU_CHECK"):
+        S1 = sb.Sim6d(*args6, time_in_phase=False)
+        r1 = S1.run(warmup + steps)
+        S1.destroy()
+        scale = np.maximum(np.abs(r1).max(axis=0), 1e-300)
+        rows_vs_1gpu = float((np.abs(rows - r1) / scale).max())
+    barrier()
+    hw = 3
+    halo_bytes = 2 * hw * local_pts / lay["nw"][5] * 8 if world > 1 else 0
+    return {"workload": f"3D3V Landau damping {n}^6 fp64, Lagrange fixed 7-point in all six directions, dt=0.01, landau_prod "
+                        "alpha=0.01 k=0.5, L=4pi, v_max=6 (sim_bsl_vp_3d3v_cart_dd_slim semantics), strong scaling",
+            "metric": "6D phase-space point-updates/s per advection pass", "value": 6 * npts * steps / (ms * 1e-3),
+            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "process_grid": lay["procs"], "local_block": lay["nw"],
+            "x_pass_ms": x_ms, "x_pass_gbs": 16 * local_pts / (x_ms * 1e-3) / 1e9,
+            "x_pass_frac_of_measured_hbm": 16 * local_pts / (x_ms * 1e-3) / 1e9 / peak,
+            "v_pass_ms": v_ms, "v_pass_gbs": 16 * local_pts / (v_ms * 1e-3) / 1e9,
+            "halo_ms_per_split_pass": halo_ms, "halo_bytes_sent_per_split_pass": halo_bytes,
+            "halo_gbs_per_direction": (halo_bytes / 2) / (halo_ms * 1e-3) / 1e9 if halo_ms > 0 else None,
+            "frac_of_aggregate_hbm_roofline_whole_step": 16.0 * 6 * npts * steps / (ms * 1e-3) / 1e9 / (peak * world),
+            "gpu_launches": int(launches),
+            "check": {"mass": float(rows[-1, 1]), "l2": float(rows[-1, 2]), "rows_vs_1gpu_rel": rows_vs_1gpu}}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -180,6 +262,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     sb.init(local_rank)
     comm = None
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -205,22 +288,43 @@ def run_ours(args, rank, world, local_rank):
     if os.environ.get("SLLB_REMAP_ROTATION") is not None:
         sb.set_remap_rotation(env_int("SLLB_REMAP_ROTATION", 1))
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    S = sb.Sim4d([n] * 4, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, split=0, method=sb.METHOD_SPLINE, order=4, comm=comm)
+    sim_args = ([n] * 4, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1)
+    sim_kw = dict(split=0, method=sb.METHOD_SPLINE, order=4)
+    S = sb.Sim4d(*sim_args, comm=comm, **sim_kw)
     npts = float(n) ** 4
 
-    # ---- kernel-resident timing: inputs already in HBM -------------------------------------------
-    S.run(args.warmup, diagnostics=False)
+    # ---- kernel-resident timing: inputs already in HBM; the diagnostics row of every step (field energy, mass, L1, L2,
+    # kinetic energy -- the reference computes them every step) is inside the timed region ---------------------------
+    sb.set_phase_timers(False)
+    S.run(args.warmup, diagnostics=True)
     barrier()
     sb.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    S.run(args.steps, diagnostics=False)
+    rows_t = S.run(args.steps, diagnostics=True)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = sb.launch_count()
-    phase = S.phase_ms8().tolist()
     value = PASSES_PER_STEP * npts * args.steps / (ms * 1e-3)
+    # cross-N exactness signal: the state after exactly warmup + steps steps from the initial data, before anything else
+    # touches f -- identical (to rounding) whatever the number of GPUs
+    csum = S.checksum()
+    check = {"steps_from_initial_data": args.warmup + args.steps, "mass": float(rows_t[-1, 3]), "field_energy": float(rows_t[-1, 1]),
+             "l2": float(rows_t[-1, 5]), "checksum_wf": float(csum[0]), "checksum_wf2": float(csum[1]),
+             "what": "after the timed region; checksum = sum w f and sum w f^2 with w a function of the GLOBAL index of every point"}
+    # the same region without the diagnostics rows, and the per-phase breakdown (pooled CUDA events, opt-in)
+    barrier()
+    e0.record()
+    S.run(args.steps, diagnostics=False)
+    e1.record()
+    barrier()
+    ms_nodiag = max_over_ranks(e0.elapsed_time(e1))
+    sb.set_phase_timers(True)
+    ph_steps = min(args.steps, 10)
+    S.run(ph_steps, diagnostics=True)
+    phase = (S.phase_ms8() / ph_steps).tolist()
+    sb.set_phase_timers(False)
 
     # ---- per-kernel timing for the roofline (CUDA events on the launch stream, local field) ------
     F = S.field()
@@ -275,31 +379,37 @@ def run_ours(args, rank, world, local_rank):
         a1.record()
         torch.cuda.synchronize()
         plane_ms = a0.elapsed_time(a1) / reps
-    # dominant kernel: the strided spline pass (x3 and x4 passes of both V stages = 4 of the 6 passes of a step
-    # on one GPU; x2, x3, x4 passes on several GPUs)
-    strided = [kernel_ms[a] for a in axes if a >= 2] or [kernel_ms[a] for a in axes if a != 0]
+    # dominant kernel: the strided spline pass.  One GPU: the x3 and x4 passes of both V stages (4 of the 6 passes of a
+    # step), timed on axes 2 and 3.  Several GPUs: the field handed out here is the x-sequential box, so the same kernel is
+    # timed on its strided x2 axis (the x3/x4 passes run it in the other layout, x4 with the remap stores fused in).
+    if world == 1:
+        strided, timed_on = [kernel_ms[2], kernel_ms[3]], "x3 and x4 passes (4 of the 6 passes of a step; the other two are the single k_spline_plane_r launch of the T stage)"
+    else:
+        strided, timed_on = [kernel_ms[1]], "timed in place on the strided x2 axis of the local x-sequential box (in the step it runs the x3 pass and, with the remap stores fused in, the x4 pass)"
     t_dom = sum(strided) / len(strided)
     peak, peak_src = measured_peak()
     achieved = 16.0 * local_pts / (t_dom * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("k_advect_strided_bytes_per_launch")
-            if traffic is not None:
-                traffic = traffic * local_pts / float(NSIDE) ** 4   # captured on the 128^4 field
+            tj = json.load(open(tpath))
+            traffic = tj["kernels"]["k_spline_strided_split<4, 0>"]["dram_bytes_per_launch"] * local_pts / float(128) ** 4
+            traffic_src = tj.get("source")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_spline_strided_split<4> (x3 and x4 passes: 4 of the 6 passes of a step; the other two "
-                                          "are the single k_spline_plane_r launch of the T stage)",
+    roofline = {"bound": "hbm", "kernel": f"k_spline_strided_split<4>: {timed_on}",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * local_pts,
                 "ms_per_launch": t_dom, "ms_per_launch_by_axis": {f"x{a + 1}": kernel_ms[a] for a in axes},
                 "gbs_by_axis": {f"x{a + 1}": 16.0 * local_pts / (kernel_ms[a] * 1e-3) / 1e9 for a in axes},
                 "t_stage_plane_kernel": None if plane_ms is None else {
-                    "kernel": "k_spline_plane_r<rho> (x1 pass + x2 pass + charge density in one sweep)", "ms_per_launch": plane_ms,
+                    "kernel": "k_spline_plane_r<rho> (x1 pass + x2 pass + charge density in one sweep) + the sum of its per-CTA partial densities", "ms_per_launch": plane_ms,
                     "algorithmic_bytes_per_launch": 32.0 * local_pts, "achieved_gbs_at_16B_per_point_per_pass": 32.0 * local_pts / (plane_ms * 1e-3) / 1e9,
-                    "hbm_bytes_moved_per_launch": 16.0 * local_pts, "hbm_gbs": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9},
+                    "hbm_bytes_moved_per_launch": 16.0 * local_pts, "hbm_gbs": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9,
+                    "frac_of_measured_hbm": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9 / peak},
+                "whole_step_frac_of_aggregate_hbm_roofline": 16.0 * value / 1e9 / (peak * world),
                 "timing": f"CUDA events on the launch stream, {reps} launches after 3 warm-ups, field {ext} "
                           f"({local_pts * 8 / 1e9:.2f} GB > L2)"}
 
@@ -309,25 +419,17 @@ def run_ours(args, rank, world, local_rank):
     hp = C.cast(C.c_void_p(host.data_ptr()), C.POINTER(C.c_double))
     assert lib.sllb_field_download(F.h, hp, None) == 0
     F = S.field()
-    row = np.zeros(6)
     e2e_steps = max(1, min(args.steps, env_int("SLLB_E2E_STEPS", 10)))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         assert lib.sllb_field_upload(F.h, hp, None) == 0          # H2D of the step's input state (pinned)
-        r = S.run(1, diagnostics=True)                             # one Strang step + diagnostics row (D2H)
+        S.run(1, diagnostics=True)                                 # one Strang step + diagnostics row (D2H)
         F = S.field()                                              # x-sequential layout (remap back when N > 1)
         assert lib.sllb_field_download(F.h, hp, None) == 0         # D2H of the step's result
-        row = r[0]
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = PASSES_PER_STEP * npts * e2e_steps / e2e_s
-    # resident mode (how the simulation is meant to run: f never leaves HBM, only the diagnostics row does)
-    barrier()
-    t0 = time.perf_counter()
-    S.run(e2e_steps, diagnostics=True)
-    barrier()
-    res_s = max_over_ranks(time.perf_counter() - t0)
     # ensemble streaming (single GPU): the same per-step traffic, but the upload of the next state and the download of the
     # previous one overlap the current state's step (sllb_sim4d_stream_step; PCIe is full duplex).  Fill and drain
     # calls are inside the timed region: every counted state is uploaded, stepped and downloaded within it.
@@ -362,14 +464,38 @@ def run_ours(args, rank, world, local_rank):
            "serial_value": e2e_value, "note": stream_note,
            "serial_what": "per step, one after the other: sllb_field_upload (pinned host f -> HBM) + sllb_sim4d_run(1 step, "
                           "diagnostics) + sllb_field_download (HBM -> pinned host f); per-rank local box",
-           "resident_value": PASSES_PER_STEP * npts * e2e_steps / res_s,
-           "resident_what": "sllb_sim4d_run with f resident in HBM, one 6-double diagnostics row to the host per step"}
+           "resident_value": value,
+           "resident_what": "the headline value: sllb_sim4d_run with f resident in HBM, one 6-double diagnostics row per step"}
+    S.destroy()
+
+    # ---- cross-N exactness of the headline run: rank 0 repeats the same steps on ONE GPU and compares -------------
+    if world > 1 and not os.environ.get("SLLB_SKIP_1GPU_CHECK"):
+        if rank == 0:
+            S1 = sb.Sim4d(*sim_args, comm=None, **sim_kw)
+            S1.run(args.warmup, diagnostics=True)
+            r1 = S1.run(args.steps, diagnostics=True)
+            c1 = S1.checksum()
+            S1.destroy()
+            ref = {"mass": float(r1[-1, 3]), "field_energy": float(r1[-1, 1]), "l2": float(r1[-1, 5]),
+                   "checksum_wf": float(c1[0]), "checksum_wf2": float(c1[1])}
+            check["vs_1gpu_rel"] = {k: abs(check[k] - v) / max(abs(v), 1e-300) for k, v in ref.items()}
+            check["vs_1gpu_max_rel"] = max(check["vs_1gpu_rel"].values())
+        barrier()
+
+    # ---- C5: the 3D3V domain-decomposed Lagrange path on the same GPUs (BASELINE config 5) -------
+    c5 = None
+    if not os.environ.get("SLLB_SKIP_C5"):
+        try:
+            c5 = c5_block(sb, torch, dist, comm, rank, world, peak)
+        except (RuntimeError, sb.SllbError) as exc:
+            c5 = {"error": str(exc)}
     clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not os.environ.get("SLLB_SKIP_CPU"):
         from oracle import orc
+        orc.set_num_threads(orc.host_cores())
         frac = env_int("SLLB_REF_FRAC", 4)
         fc = cpu_field(n)
         cpu_sample_step(orc, fc, n, frac * 8)
@@ -393,20 +519,23 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "passes_per_step": PASSES_PER_STEP, "points": int(npts),
+                           "timed_region": "sllb_sim4d_run(steps, diagnostics every step): 6 advection passes + 2 charge densities + 2 Poisson solves + the diagnostics row per step",
                            "l2": f"inputs larger than L2: f is {npts * 8 / 1e9:.2f} GB ({local_pts * 8 / 1e9:.2f} GB per GPU) vs 126 MB L2",
-                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap fused into the last advection pass of each stage (peer stores over NVLink, CUDA IPC) + all-reduce barrier; 2 remaps per Strang step",
+                           "parallelism": "single GPU" if world == 1 else f"{world} GPUs, x<->v remap fused into the last advection pass of each stage (peer stores over NVLink, CUDA IPC); 2 remaps per Strang step",
                            "staging": "TMA bulk copies (cp.async.bulk, UBLKCP): 256 B rows of 32-line tiles (V stage), whole 128x128 planes (T stage)"},
-                "phase_ms_per_step": {"advect_local_passes": phase[0] / args.steps, "rho+poisson": phase[1] / args.steps,
-                                      "nccl_remap": phase[2] / args.steps, "diagnostics": phase[3] / args.steps,
-                                      "advect_fused_remap_passes": (phase[4] + phase[6]) / args.steps,
-                                      "barrier_after_fused_pass": (phase[5] + phase[7]) / args.steps,
-                                      "fused_V_pass_x4+remap": phase[4] / args.steps, "barrier_after_V": phase[5] / args.steps,
-                                      "fused_T_plane_x1+x2+rho+remap": phase[6] / args.steps,
-                                      "allreduce_rho_after_T": phase[7] / args.steps},
+                "ms_per_step_without_diagnostics": ms_nodiag / args.steps,
+                "value_without_diagnostics": PASSES_PER_STEP * npts * args.steps / (ms_nodiag * 1e-3),
+                "phase_ms_per_step": {"advect_local_passes": phase[0], "rho+poisson": phase[1],
+                                      "nccl_remap": phase[2], "diagnostics": phase[3],
+                                      "advect_fused_remap_passes": phase[4] + phase[6],
+                                      "barrier_after_fused_pass": phase[5] + phase[7],
+                                      "fused_V_pass_x4+remap": phase[4], "barrier_after_V": phase[5],
+                                      "fused_T_plane_x1+x2+rho+remap": phase[6],
+                                      "allreduce_rho_after_T": phase[7],
+                                      "how": f"separate {ph_steps}-step run with pooled CUDA events (sllb_set_phase_timers), not the timed region"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu_baseline, "check": {"mass": float(row[3]), "field_energy": float(row[1])}}
+                "cpu_baseline": cpu_baseline, "check": check, "extra": {"c5_3d3v": c5}}
         print(json.dumps(line), flush=True)
-    S.destroy()
     if comm is not None:
         comm.destroy()
         dist.destroy_process_group()

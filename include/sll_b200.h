@@ -222,6 +222,9 @@ int sllb_poisson_destroy(sllb_poisson_t P);
  * outputs may be NULL.  1D: e2,e3 ignored. 2D: e3 ignored.  E = -grad phi, -lap phi = rho. */
 int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, double *d_e1, double *d_e2,
                        double *d_e3);
+/* 2D solves on grids up to 256 x 256 run as three dense-DFT kernels written for this path (sllb_poisson_direct.cu:
+ * a 128 x 128 problem is bound by the ~10 launches of the library FFT route); 0 = always cuFFT.  Same values to ~1e-15. */
+int sllb_set_poisson_direct(int on);
 /* HOST arrays with leading dimensions ld (= nc or nc+1, duplicates filled like
  * sll_m_poisson_2d_periodic.F90:370-374 / sll_m_poisson_1d_periodic.F90:170) */
 int sllb_poisson_solve_host(sllb_poisson_t P, const double *rho, const int *ld, double *phi, double *e1,
@@ -414,6 +417,11 @@ int sllb_sim4d_phase_ms6(sllb_sim4d_t S, double out[6]);
 /* finest: [local passes, reduce+poisson, NCCL remap, diag, fused V-stage pass (x4 + remap), barrier after it,
  *          fused T-stage plane kernel (x1 + x2 + rho + remap), all-reduce (rho + barrier) after it] */
 int sllb_sim4d_phase_ms8(sllb_sim4d_t S, double out[8]);
+/* rho, E1, E2 of the last field solve of the time loop (N1 x N2 periodic cells, column-major); NULL = skip */
+int sllb_sim4d_fields_host(sllb_sim4d_t S, double *rho, double *e1, double *e2);
+/* (sum w f, sum w f^2) over the GLOBAL field with a weight that depends on the global index of every point: equal (to
+ * rounding) on any number of ranks, sensitive to misplaced elements (cross-rank exactness signal of bench.py) */
+int sllb_sim4d_checksum(sllb_sim4d_t S, double out[2]);
 /* phase timing is opt-in: 1 = sllb_sim4d_run records one CUDA event per phase (pooled, reused), 0 (default) = none */
 int sllb_set_phase_timers(int on);
 

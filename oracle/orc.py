@@ -256,24 +256,29 @@ def compute_jacobian(E1, E2, factor, r=-2, s=2):
 
 
 def sim4d(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split=0, method=0, order=4, want_f=False, stencil=(-2, 2),
-          want_thdiag=False):
-    """split: case number (0 Strang VTV, 1 Strang TVT, 2 Lie TV, ... see SPLIT_CASES) or the namelist's name"""
+          want_thdiag=False, cells_only=False, want_fields=False):
+    """split: case number (0 Strang VTV, 1 Strang TVT, 2 Lie TV, ... see SPLIT_CASES) or the namelist's name;
+    cells_only: the v_max planes are reset to the v_min planes after every T stage (see orc_sim4d_run_ex2)"""
     if isinstance(split, str):
         split = SPLIT_CASES.index(split)
     rows = np.zeros((nsteps + 1, 6))
     thd = np.zeros((nsteps + 1, 13))
     f = np.zeros(tuple(c + 1 for c in nc), order="F") if want_f else None
-    lib().orc_sim4d_run_ex.restype = C.c_int
-    rc = lib().orc_sim4d_run_ex((C.c_int * 4)(*nc), (C.c_double * 4)(*xmin), (C.c_double * 4)(*xmax), C.c_double(kx1),
-                                C.c_double(kx2), C.c_double(eps), C.c_double(dt), C.c_int(nsteps), C.c_int(split),
-                                C.c_int(method), C.c_int(order), _p(rows), _p(f) if want_f else None,
-                                C.c_int(stencil[0]), C.c_int(stencil[1]), _p(thd))
+    fields = np.zeros((nc[0] + 1, nc[1] + 1, 3), order="F") if want_fields else None
+    lib().orc_sim4d_run_ex2.restype = C.c_int
+    rc = lib().orc_sim4d_run_ex2((C.c_int * 4)(*nc), (C.c_double * 4)(*xmin), (C.c_double * 4)(*xmax), C.c_double(kx1),
+                                 C.c_double(kx2), C.c_double(eps), C.c_double(dt), C.c_int(nsteps), C.c_int(split),
+                                 C.c_int(method), C.c_int(order), _p(rows), _p(f) if want_f else None,
+                                 C.c_int(stencil[0]), C.c_int(stencil[1]), _p(thd), C.c_int(1 if cells_only else 0),
+                                 _p(fields) if want_fields else None)
     assert rc == 0, rc
     out = (rows,)
     if want_f:
         out += (f,)
     if want_thdiag:
         out += (thd,)
+    if want_fields:   # rho, E1, E2 of the last field solve, duplicated end points included
+        out += (fields,)
     return out if len(out) > 1 else rows
 
 

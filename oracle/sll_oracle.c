@@ -1126,9 +1126,25 @@ int orc_sim4d_run(const int nc[4], const double xmin[4], const double xmax[4], d
 /* split: case numbering of sll_oracle_split.c (0 Strang VTV ... 17); stencil_r/s: finite-difference stencil of
  * compute_jacobian (namelist defaults -2, 2, :366-367); thdiag (may be NULL): (nsteps+1) x 13, the rows of the
  * reference's thdiag file (:998-1010 at t = 0 with the analytic mass0 / l20 of SLL_LANDAU :449-452, :1262-1275 later) */
+int orc_sim4d_run_ex2(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
+                      double eps, double dt, int nsteps, int split, int method, int order, double *rows,
+                      double *f_out, int stencil_r, int stencil_s, double *thdiag, int cells_only, double *fields_out);
 int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
                      double eps, double dt, int nsteps, int split, int method, int order, double *rows,
                      double *f_out, int stencil_r, int stencil_s, double *thdiag) {
+    return orc_sim4d_run_ex2(nc, xmin, xmax, kx1, kx2, eps, dt, nsteps, split, method, order, rows, f_out, stencil_r, stencil_s,
+                             thdiag, 0, NULL);
+}
+/* cells_only = 0: the reference as it is.  The arrays carry the duplicated end point nc+1 in every direction; in a T
+ * stage the planes v = v_min and v = v_max (the same periodic cell) are moved with OPPOSITE velocities (:1037-1064) and
+ * both enter the trapezoid rho with weight 1/2 (sll_m_reduction.F90:229-272); the next V stage overwrites the v_max plane
+ * with the v_min one again (out(N+1) = out(1), sll_m_advection_1d_periodic.F90:126-128).
+ * cells_only = 1: the SAME code, but after every T stage the v_max planes are reset to copies of the v_min planes, i.e.
+ * the state is a function of the periodic cells alone -- what a code that stores N points per direction computes.  The
+ * difference between the two modes is that end-plane term and nothing else (tests/test_gpu_baseline_sizes.py). */
+int orc_sim4d_run_ex2(const int nc[4], const double xmin[4], const double xmax[4], double kx1, double kx2,
+                      double eps, double dt, int nsteps, int split, int method, int order, double *rows,
+                      double *f_out, int stencil_r, int stencil_s, double *thdiag, int cells_only, double *fields_out) {
     int np[4]; long ntot = 1;
     double delta[4];
     for (int d = 0; d < 4; ++d) { np[d] = nc[d] + 1; ntot *= np[d]; delta[d] = (xmax[d] - xmin[d]) / (double)nc[d]; }
@@ -1195,6 +1211,16 @@ int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4]
                         }
                         free(line);
                     }
+                    if (cells_only) {
+#pragma omp parallel for schedule(static)
+                        for (int i4 = 0; i4 < np[3]; ++i4) {
+                            for (long k = 0; k < n12; ++k) f[k + n12 * ((long)nc[2] + (long)np[2] * i4)] = f[k + n12 * ((long)np[2] * i4)];
+                        }
+#pragma omp parallel for schedule(static)
+                        for (int i3 = 0; i3 < np[2]; ++i3) {
+                            for (long k = 0; k < n12; ++k) f[k + n12 * (i3 + (long)np[2] * nc[3])] = f[k + n12 * i3];
+                        }
+                    }
                 } else {
                     FIELD4();
                     double st = steps[isub], st2 = (dimV == 2) ? steps[isub + 1] : 0.0;
@@ -1260,6 +1286,8 @@ int orc_sim4d_run_ex(const int nc[4], const double xmin[4], const double xmax[4]
         }
     }
     if (f_out) memcpy(f_out, f, sizeof(double) * ntot);
+    /* rho, E1, E2 of the last field solve ((nc1+1) x (nc2+1) each, duplicated end points included) */
+    if (fields_out) memcpy(fields_out, rho, sizeof(double) * 3 * n12);
     free(f); free(rho);
     return 0;
 }

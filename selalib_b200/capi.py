@@ -124,6 +124,11 @@ def set_remap_rotation(on):
     _ck(lib().sllb_set_remap_rotation(C.c_int(1 if on else 0)))
 
 
+def set_poisson_direct(on):
+    """2D Poisson on small grids: 1 = three dense-DFT kernels (default), 0 = cuFFT"""
+    _ck(lib().sllb_set_poisson_direct(C.c_int(1 if on else 0)))
+
+
 def set_phase_timers(on):
     """opt-in per-phase CUDA events inside sllb_sim4d_run (Sim4d.phase_ms8)"""
     _ck(lib().sllb_set_phase_timers(C.c_int(1 if on else 0)))
@@ -505,6 +510,7 @@ class Sim4d:
             p.method_axis[:] = list(method); p.order_axis[:] = list(orders)
             p.method, p.order = method[0], orders[0]
         self.h = vp()
+        self.nc = tuple(int(c) for c in nc)
         _ck(lib().sllb_sim4d_create(C.byref(p), comm.h if comm is not None else None, C.byref(self.h)))
 
     def run(self, nsteps, diagnostics=True):
@@ -540,6 +546,19 @@ class Sim4d:
     def phase_ms(self):
         out = np.zeros(6)
         _ck(lib().sllb_sim4d_phase_ms6(self.h, _p(out)))
+        return out
+
+    def fields(self):
+        """rho, E1, E2 of the last field solve (N1 x N2 periodic cells each)"""
+        n1, n2 = self.nc[0], self.nc[1]
+        out = [np.zeros((n1, n2), order="F") for _ in range(3)]
+        _ck(lib().sllb_sim4d_fields_host(self.h, _p(out[0]), _p(out[1]), _p(out[2])))
+        return out
+
+    def checksum(self):
+        """(sum w f, sum w f^2) over the global field, w from the global index: equal on any number of ranks"""
+        out = np.zeros(2)
+        _ck(lib().sllb_sim4d_checksum(self.h, _p(out)))
         return out
 
     def phase_ms8(self):

@@ -192,6 +192,7 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
 // K1c: spline passes along axes 0 and 1 on every plane in one sweep (+ optional rho = scale * sum over the
 // other axes of the result).  SLLB_ERR_UNSUPPORTED when the shape / displacement pattern does not fit.
 int g_plane_kernel = 1;
+int g_poisson_direct = [] { const char *e = getenv("SLLB_POISSON_DIRECT"); return (e && e[0] == '0') ? 0 : 1; }();
 int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
                      const RemapDst *remap) {
     if (!F || F->ndim < 2) return fail(SLLB_ERR_INVALID, "advect_plane: bad field");
@@ -579,6 +580,10 @@ int sllb_moments(sllb_field_t F, int nv, const double *w1, const double *w2, dou
 }
 
 /* ---------------- Poisson ---------------- */
+int sllb_set_poisson_direct(int on) {
+    g_poisson_direct = on ? 1 : 0;
+    return SLLB_OK;
+}
 static int poisson_common(sllb_poisson *p) {
     p->nreal = (long long)p->n[0] * p->n[1] * p->n[2];
     p->ncplx = (long long)(p->n[0] / 2 + 1) * p->n[1] * p->n[2];
@@ -617,6 +622,8 @@ int sllb_poisson2d_create(int nc_x, int nc_y, double x_min, double x_max, double
     sllb_poisson *p = new sllb_poisson();
     p->dim = 2; p->n[0] = nc_x; p->n[1] = nc_y; p->L[0] = x_max - x_min; p->L[1] = y_max - y_min;
     int rc = poisson_common(p);
+    // small grids: the three-kernel dense-DFT solve (a 128 x 128 problem is launch-bound as library FFT calls)
+    if (!rc && poisson2d_direct_supported(nc_x, nc_y)) rc = poisson2d_direct_create(nc_x, nc_y, p->L[0], p->L[1], &p->direct);
     if (rc) { sllb_poisson_destroy(p); return rc; }
     *P = p;
     return SLLB_OK;
@@ -635,6 +642,7 @@ int sllb_poisson3d_create(int nx, int ny, int nz, double Lx, double Ly, double L
 int sllb_poisson_destroy(sllb_poisson_t P) {
     if (!P) return SLLB_OK;
     if (P->plans) { cufftDestroy(P->fwd); cufftDestroy(P->bwd); }
+    poisson2d_direct_destroy(P->direct);
     if (P->rho_hat) cudaFree(P->rho_hat);
     for (int k = 0; k < 4; ++k) if (P->spec[k]) cudaFree(P->spec[k]);
     delete P;
@@ -643,6 +651,11 @@ int sllb_poisson_destroy(sllb_poisson_t P) {
 int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, double *d_e1, double *d_e2, double *d_e3) {
     if (!P || !d_rho) return fail(SLLB_ERR_INVALID, "poisson_solve: null");
     SLLB_TRY(require_device());
+    if (P->dim == 2 && P->direct && g_poisson_direct) {
+        SLLB_CUDA(poisson2d_direct_solve(P->direct, d_rho, 1, 0, 1.0, nullptr, 0, d_phi, d_e1, d_e2, nullptr, nullptr, nullptr,
+                                         nullptr, g_stream));
+        return SLLB_OK;
+    }
     if (P->stream != g_stream) {
         SLLB_CUFFT(cufftSetStream(P->fwd, g_stream));
         SLLB_CUFFT(cufftSetStream(P->bwd, g_stream));

@@ -117,15 +117,48 @@ cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream
     return cudaGetLastError();
 }
 
+// position-weighted checksums of a local box of the 4D field: out2 = (sum w f, sum w f^2) with a weight that depends on the
+// GLOBAL index of the point, w = 1 + ((3 g0 + 5 g1 + 7 g2 + 11 g3) mod 64) / 64, so that any misplaced element shows
+__global__ void __launch_bounds__(RT) k_checksum4d1(const double *__restrict__ f, const int n0, const int n1, const int n2,
+                                                    const int n3, const int lo0, const int lo1, const int lo2, const int lo3,
+                                                    double *__restrict__ partial) {
+    double v[2] = {0, 0};
+    const long long n = (long long)n0 * n1 * n2 * n3;
+    for (long long t = (long long)blockIdx.x * RT + threadIdx.x; t < n; t += (long long)gridDim.x * RT) {
+        long long r = t;
+        const int i0 = (int)(r % n0); r /= n0;
+        const int i1 = (int)(r % n1); r /= n1;
+        const int i2 = (int)(r % n2); r /= n2;
+        const int i3 = (int)r;
+        const int h = (3 * (i0 + lo0) + 5 * (i1 + lo1) + 7 * (i2 + lo2) + 11 * (i3 + lo3)) & 63;
+        const double w = 1.0 + (double)h * (1.0 / 64.0), x = f[t];
+        v[0] = fma(w, x, v[0]);
+        v[1] = fma(w * x, x, v[1]);
+    }
+    block_sum<2>(v, partial + 2 * blockIdx.x);
+}
+__global__ void __launch_bounds__(256) k_checksum4d2(const double *__restrict__ partial, const int nb, double *__restrict__ out2) {
+    double v[2] = {0, 0};
+    for (int b = threadIdx.x; b < nb; b += 256) { v[0] += partial[2 * b]; v[1] += partial[2 * b + 1]; }
+    block_sum<2>(v, out2);
+}
+cudaError_t launch_checksum4d(const double *f, const int ext[4], const int lo[4], double *scratch, double *out2, cudaStream_t st) {
+    k_checksum4d1<<<ML_BLOCKS, RT, 0, st>>>(f, ext[0], ext[1], ext[2], ext[3], lo[0], lo[1], lo[2], lo[3], scratch);
+    count_launch();
+    k_checksum4d2<<<1, 256, 0, st>>>(scratch, ML_BLOCKS, out2);
+    count_launch();
+    return cudaGetLastError();
+}
+
 __global__ void k_sim4d_row(const double *__restrict__ m4, const double *__restrict__ nrj, const double time, const double vol,
-                            double *__restrict__ row6) {
+                            const int root, double *__restrict__ row6) {
     if (threadIdx.x != 0) return;
-    row6[0] = time; row6[1] = nrj[0];
+    row6[0] = root ? time : 0.0; row6[1] = root ? nrj[0] : 0.0;
     row6[2] = 0.5 * m4[3] * vol;
     row6[3] = m4[0] * vol; row6[4] = m4[1] * vol; row6[5] = m4[2] * vol;
 }
-cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, double *row6, cudaStream_t st) {
-    k_sim4d_row<<<1, 32, 0, st>>>(m4, nrj, time, vol, row6);
+cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, int root, double *row6, cudaStream_t st) {
+    k_sim4d_row<<<1, 32, 0, st>>>(m4, nrj, time, vol, root, row6);
     count_launch();
     return cudaGetLastError();
 }

@@ -75,7 +75,9 @@ struct sllb_comm {
     int nranks = 1, rank = 0;
 };
 
+namespace sllb { struct Poisson2dDirect; }
 struct sllb_poisson {
+    sllb::Poisson2dDirect *direct = nullptr;   // 2D, small grids: three-kernel dense-DFT solve (sllb_poisson_direct.cu)
     int dim = 0;
     int n[3] = {1, 1, 1};
     double L[3] = {1, 1, 1};
@@ -89,6 +91,17 @@ struct sllb_poisson {
 };
 
 namespace sllb {
+// sllb_poisson_direct.cu: 2D periodic Poisson for N1, N2 <= 256 as three dense-DFT kernels (no library FFT).
+// rho = scale * sum of `nslots` arrays spaced by slot_stride (rho_sum != NULL: the summed density is also written there);
+// mode 0: sll_t_poisson_2d_periodic (phi, E1, E2), mode 1: sll_s_poisson_2d_periodic_par_solve (Delta phi = rho, phi only);
+// tile_box = {lo0, n0, lo1, n1}: E1/E2 of that sub-box additionally go to the dense arrays tile_e1 / tile_e2.
+int poisson2d_direct_supported(int n1, int n2);
+int poisson2d_direct_create(int n1, int n2, double L1, double L2, Poisson2dDirect **out);
+void poisson2d_direct_destroy(Poisson2dDirect *P);
+cudaError_t poisson2d_direct_solve(Poisson2dDirect *P, const double *rho, int nslots, long long slot_stride, double scale,
+                                   double *rho_sum, int mode, double *phi, double *e1, double *e2, const double *unused,
+                                   double *tile_e1, double *tile_e2, const int tile_box[4], cudaStream_t st);
+extern int g_poisson_direct;   // 1 (default): 2D solves on small grids take the direct path; 0: always cuFFT
 int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<void *> &peers,
                      std::vector<void *> &opened, bool *ok);
 // internal (device-pointer) entry points used by the simulations
@@ -120,7 +133,10 @@ size_t moments_from_lines_scratch();
 // nrj = scale * sum over the (n1+1)(n2+1) nodes including the periodic duplicates of a^2 + (squared ? b^2 : 2 b)
 cudaError_t launch_dup_energy2d(const double *a, const double *b, int n1, int n2, double scale, int squared, double *out1,
                                 cudaStream_t st);
+// (sum w f, sum w f^2), w from the global index of every point; scratch: moments_from_lines_scratch() doubles
+cudaError_t launch_checksum4d(const double *f, const int ext[4], const int lo[4], double *scratch, double *out2, cudaStream_t st);
 cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream_t st);
-// row6 = (time, nrj[0], 0.5 vol m4[3], vol m4[0], vol m4[1], vol m4[2])
-cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, double *row6, cudaStream_t st);
+// row6 = (time, nrj[0], 0.5 vol m4[3], vol m4[0], vol m4[1], vol m4[2]); root = 0: time and nrj are written as 0 (the
+// rows of several ranks are summed afterwards)
+cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, int root, double *row6, cudaStream_t st);
 } // namespace sllb

@@ -112,6 +112,7 @@ extern int g_plane_ept;    // plane kernel: 0 auto, 16 or 32 points per thread
 extern int g_remap_rotation; // fused remap: rank-dependent start tile
 extern int g_spline_split; // -1 auto, else lines are cut into this many chunks (1,2,4,8)
 long long launch_count();
+void count_launch();
 void count_launches(long long n);
 void launch_count_reset();
 
