@@ -72,7 +72,7 @@ void sllb_launch_count_reset(void);
                               other boundary types -> SLLB_ERR_UNSUPPORTED */
 
 /* batched per-axis methods */
-#define SLLB_METHOD_SPLINE 0            /* periodic cubic spline (order 4) */
+#define SLLB_METHOD_SPLINE 0            /* periodic spline: order 4 (cubic), 6 (quintic), 8 (septic) */
 #define SLLB_METHOD_LAGRANGE_FIXED 1    /* odd stencil 3,5,7,9,11 centred on the grid point */
 #define SLLB_METHOD_LAGRANGE_CENTERED 2 /* even stencil 4..18 centred on the foot cell (closed forms up to 8 as in the
                                            reference's fast module, product form beyond) */
@@ -82,7 +82,7 @@ void sllb_launch_count_reset(void);
  * (sll_m_advection_1d_periodic.F90:57-130) and the abstract interface
  * (sll_m_advection_1d_base.F90:53-68).  out(x_i) = in(x_i - A*dt); `in` may alias
  * `out`; n = num_cells or num_cells+1 (the duplicate is filled when n > num_cells).
- * kind PERIODIC_SPLINE supports order 4; PERIODIC_LAGRANGE supports even orders 4..18 (the shipped two-stream
+ * kind PERIODIC_SPLINE supports orders 4, 6 and 8; PERIODIC_LAGRANGE supports even orders 4..18 (the shipped two-stream
  * namelist of the 1D1V simulation uses 18); BSL: n = num_cells+1 points as the
  * reference object is built on npts grid points (n = num_cells also accepted). */
 typedef struct sllb_adv1d *sllb_adv1d_t;
@@ -396,7 +396,7 @@ int sllb_sim4d_stream_step(sllb_sim4d_t S, const double *host_next_in, double *h
 /* Namelist front-end: reads the file sim_bsl_vp_2d2v_cart_poisson_serial takes (&geometry, &initial_function,
  * &time_iterations, &advector, &poisson; defaults and mesh cases as sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:300-440;
  * `filename` with or without the ".nml" the reference appends, :375), builds the simulation and returns
- * number_iterations / freq_diag_time.  SLL_SPLINES -> cubic splines (order 4), SLL_LAGRANGE -> centred Lagrange of the
+ * number_iterations / freq_diag_time.  SLL_SPLINES -> periodic splines of order 4, 6 or 8, SLL_LAGRANGE -> centred Lagrange of the
  * given order; SLL_LANDAU initial function.  Anything else: SLLB_ERR_UNSUPPORTED with the reference's message. */
 int sllb_sim4d_create_from_namelist(const char *filename, sllb_comm_t comm, sllb_sim4d_t *S, int *number_iterations,
                                     int *freq_diag_time);
@@ -443,7 +443,8 @@ int sllb_sim2d_destroy(sllb_sim2d_t S);
  * t = 0 row) and nsteps for every later call (sllb_sim6d_run_rows tells which); every rank gets the global row.
  * time_in_phase: the reference ends its single loop with a half V step (:735-741).  A handle may be run in several
  * calls: a call that follows such an ending first applies the other half of that V step, so that run(a) followed by
- * run(b) advances f exactly as far as one run(a+b); the rows of the two variants agree, f to rounding. */
+ * run(b) advances f exactly as far as one run(a+b).  The two differ only by the interpolation error of applying that V
+ * step as two halves (not by a lost half step); with time_in_phase = 0 they are bit-identical. */
 typedef struct sllb_sim6d *sllb_sim6d_t;
 typedef struct {
     int n[6];

@@ -183,7 +183,7 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
     if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: line sums are produced by the chunked strided spline kernel only"); }
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();
-        return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: method/order/line length not implemented (spline: order 4; "
+        return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: method/order/line length not implemented (spline: orders 4, 6, 8; "
                                           "Lagrange fixed: 3,5,7,9,11; centred: even 4..18; 8 <= n, line must fit shared memory)");
     }
     return check_cuda(e, "advect kernel launch");
@@ -758,8 +758,8 @@ int sllb_adv1d_create(int kind, int num_cells, double xmin, double xmax, int ord
     if (!h || num_cells < 8 || !(xmax > xmin)) return fail(SLLB_ERR_INVALID, "adv1d_create: bad arguments");
     int method, stencil;
     if (kind == SLLB_ADV_PERIODIC_SPLINE) {
-        if (order != 4) return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_spline implemented for order 4 (cubic) only");
-        method = SLLB_METHOD_SPLINE; stencil = 4;
+        if (order != 4 && order != 6 && order != 8) return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_spline implemented for orders 4, 6 and 8");
+        method = SLLB_METHOD_SPLINE; stencil = order;
     } else if (kind == SLLB_ADV_PERIODIC_LAGRANGE) {
         if (order < 4 || order > 18 || order % 2 != 0)
             return fail(SLLB_ERR_UNSUPPORTED, "adv1d_create: sll_p_lagrange implemented for even orders 4 .. 18");
@@ -821,8 +821,8 @@ int sllb_interp1d_create(int kind, int num_points, double xmin, double xmax, int
     switch (kind) {
     case SLLB_INTERP_CUBIC_SPLINE: method = SLLB_METHOD_SPLINE; stencil = 4; periodic_last = 1; break;
     case SLLB_INTERP_PERIODIC_SPLINE:
-        if (d_or_order != 4) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: periodic spline implemented for order 4 only");
-        method = SLLB_METHOD_SPLINE; stencil = 4; periodic_last = 1; break;
+        if (d_or_order != 4 && d_or_order != 6 && d_or_order != 8) return fail(SLLB_ERR_UNSUPPORTED, "interp1d_create: periodic spline implemented for orders 4, 6 and 8");
+        method = SLLB_METHOD_SPLINE; stencil = d_or_order; periodic_last = 1; break;
     case SLLB_INTERP_PERIODIC_LAGRANGE: method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = d_or_order; periodic_last = 1; break;
     case SLLB_INTERP_LAGRANGE_CENTERED: method = SLLB_METHOD_LAGRANGE_CENTERED; stencil = 2 * d_or_order; break;
     case SLLB_INTERP_LAGRANGE_FIXED: method = SLLB_METHOD_LAGRANGE_FIXED; stencil = 2 * d_or_order + 1; break;

@@ -686,7 +686,8 @@ int sllb_sim6d_run_rows(sllb_sim6d_t S, int nsteps, int *nrows) {
 /* Time loop (:643-760).  With time_in_phase the reference closes its one loop with a half V step so that x and v are
  * known at the same time; here a handle may be run in several calls, so a call that follows such an ending opens with
  * the other half of that V step (E has not changed in between: a V step leaves rho untouched), i.e.
- * run(a) + run(b) advances f exactly as far as run(a + b). */
+ * run(a) + run(b) advances f exactly as far as run(a + b); the results differ by the interpolation error of doing that
+ * V step in two halves, not by a lost half step. */
 int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
     if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run: bad arguments");
     int row = 0;

@@ -192,6 +192,101 @@ __device__ __forceinline__ void lagrange_line(const double *sc, const int N, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// K1d: periodic spline of order 6 / 8 (degree 5 / 7) on one line held in shared memory: sll_s_periodic_interp with
+// sll_p_spline (sll_m_periodic_interp.F90:108-119,202-229).  The reference divides the spectrum by the eigenvalues of the
+// circulant collocation matrix M (B-spline values at the nodes: (1,26,66,26,1)/120, (1,120,1191,2416,1191,120,1)/5040)
+// and multiplies by those of the shifted evaluation.  Here M^-1 is applied in place as the exact factorisation of M into
+// first-order recursive filters, one causal + one anticausal sweep per root z of its symbol inside the unit circle
+//     1/m(z) = p! prod_i  -z_i / ((1 - z_i/z)(1 - z_i z)),
+// each started from the periodic sum of the line (|z|^72 < 3e-20: truncated for long lines, closed with 1/(1 - z^N) for
+// short ones) -- the same scheme as the cubic kernels, where the single root is sqrt(3) - 2.  Then
+// out(k) = sum_j b_j(beta) c(k + floor(disp) + j), j = -(p-1)/2 .. (p+1)/2, b = sll_s_uniform_bsplines_eval_basis(p, beta)
+// (sll_m_low_level_bsplines.F90:880-915), as a register window sliding along the line.
+// ------------------------------------------------------------------------------------------------
+template <int ORDER>
+__device__ __forceinline__ void bspline_basis(const double off, double *bspl) {
+    bspl[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= ORDER - 1; ++j) {
+        double xx = -off;
+        const double j_real = (double)j, inv_j = 1.0 / j_real;
+        double saved = 0.0;
+#pragma unroll
+        for (int r = 0; r <= j - 1; ++r) {
+            xx += 1.0;
+            const double temp = bspl[r] * inv_j;
+            bspl[r] = saved + xx * temp;
+            saved = (j_real - xx) * temp;
+        }
+        bspl[j] = saved;
+    }
+}
+template <int ORDER, int PITCH>
+__device__ __forceinline__ void bspline_line(double *sc, const int N, const double disp, OutMap *om) {
+    static_assert(ORDER == 6 || ORDER == 8, "periodic splines of order 6 and 8");
+    constexpr int NP = (ORDER - 2) / 2;
+    // roots of z^2 + 26 z + 66 + 26/z + 1/z^2 and of z^3 + 120 z^2 + 1191 z + 2416 + ... inside the unit circle
+    const double poles[3] = {ORDER == 6 ? -0.43057534709997379185 : -0.53528043079643816554,
+                             ORDER == 6 ? -0.043096288203264654247 : -0.12255461519232669052, -0.0091486948096082769286};
+    const double gain = ORDER == 6 ? 120.0 : 5040.0;
+    const int K = N < 72 ? N : 72;
+#pragma unroll
+    for (int ip = 0; ip < NP; ++ip) {
+        const double z = poles[ip];
+        double zp = 1.0, acc = 0.0;
+        int idx = 0;
+        for (int m = 0; m < K; ++m) {          // c+(0) = sum_m z^m s(-m)
+            acc = fma(zp, sc[idx * PITCH], acc);
+            zp *= z;
+            idx = (idx == 0) ? N - 1 : idx - 1;
+        }
+        const double closing = (K == N) ? 1.0 / (1.0 - zp) : 1.0;   // zp = z^N when the whole line was summed
+        double e = acc * closing;
+        sc[0] = e;
+        for (int k = 1; k < N; ++k) {
+            e = fma(z, e, sc[k * PITCH]);
+            sc[k * PITCH] = e;
+        }
+        zp = z; acc = 0.0; idx = N - 1;
+        for (int m = 0; m < K; ++m) {          // c(N-1) = -sum_m z^(m+1) c+(N-1+m)
+            acc = fma(zp, sc[idx * PITCH], acc);
+            zp *= z;
+            idx = (idx == N - 1) ? 0 : idx + 1;
+        }
+        double c = -acc * closing;
+        sc[(N - 1) * PITCH] = c;
+        for (int k = N - 2; k >= 0; --k) {
+            c = z * (c - sc[k * PITCH]);
+            sc[k * PITCH] = c;
+        }
+    }
+    const double fl = floor(disp);
+    double pp[ORDER], w[ORDER];
+    bspline_basis<ORDER>(disp - fl, pp);
+#pragma unroll
+    for (int k = 0; k < ORDER; ++k) pp[k] *= gain;
+    int idx = (int)(((long long)fl - (ORDER - 2) / 2) % N);
+    if (idx < 0) idx += N;
+#pragma unroll
+    for (int k = 1; k < ORDER; ++k) {
+        w[k] = sc[idx * PITCH];
+        idx = (idx == N - 1) ? 0 : idx + 1;
+    }
+    om->seek(0);
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int k = 0; k < ORDER - 1; ++k) w[k] = w[k + 1];
+        w[ORDER - 1] = sc[idx * PITCH];
+        idx = (idx == N - 1) ? 0 : idx + 1;
+        double a = pp[0] * w[0];
+#pragma unroll
+        for (int k = 1; k < ORDER; ++k) a = fma(pp[k], w[k], a);
+        st_stream(om->p, a);
+        om->next();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1a/K2a: strided axis (inner > 1).  Block = BW adjacent lines (adjacent in the flattened faster
 // axes, i.e. contiguous in memory row by row); shared tile s[k*BW + t] = f(line t, point k).
 // METHOD 0 = spline, 1 = Lagrange with stencil S.
@@ -225,6 +320,7 @@ __global__ void __launch_bounds__(BW) k_advect_strided(double *__restrict__ f, c
     const double disp = disp_of(dd, o, in);
     OutMap om = make_outmap(rd, o, in, N, inner);
     if constexpr (METHOD == 0) spline_line<BW, true>(s + tid, N, disp, &om);
+    else if constexpr (METHOD == 2) bspline_line<S, BW>(s + tid, N, disp, &om);
     else lagrange_line<S, BW>(s + tid, N, disp, &om);
 }
 
@@ -1332,6 +1428,13 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
     if (e != cudaSuccess) return e;
     const long long nlines = outer * inner;
     if (nlines > 0x7fffffffLL * 8) return cudaErrorInvalidValue;
+    if (method == METHOD_SPLINE && (order == 6 || order == 8)) {
+        // quintic / septic periodic splines (sll_p_spline of order 6 / 8): thread per line on the strided tiles, for the
+        // contiguous axis too (there the rows of the tile are gathered element by element)
+        if (linesum || diag) return cudaErrorNotSupported;
+        return order == 6 ? launch_strided<2, 6>(f, nlines, n, inner, dd, staging, st, rd)
+                          : launch_strided<2, 8>(f, nlines, n, inner, dd, staging, st, rd);
+    }
     if (method == METHOD_SPLINE) {
         if (order != 4) return cudaErrorInvalidValue;
         if (inner == 1 && (linesum || diag)) return cudaErrorNotSupported;

@@ -105,7 +105,7 @@ int sllb_sim4d_create_from_namelist(const char *filename, sllb_comm_t comm, sllb
         const std::string a = get_str(nml, "advector", av[d], "SLL_LAGRANGE");
         const int order = get_int(nml, "advector", od[d], 4);
         if (a == "SLL_SPLINES") {
-            if (order != 4) return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector ") + av[d] + ": periodic splines are implemented for order 4");
+            if (order != 4 && order != 6 && order != 8) return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector ") + av[d] + ": periodic splines are implemented for orders 4, 6 and 8");
             p.method_axis[d] = SLLB_METHOD_SPLINE;
         } else if (a == "SLL_LAGRANGE") {
             if (order < 4 || order > 18 || order % 2 != 0) return fail(SLLB_ERR_UNSUPPORTED, std::string("#advector ") + av[d] + ": periodic Lagrange is implemented for even orders 4 .. 18");

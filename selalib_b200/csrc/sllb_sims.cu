@@ -703,7 +703,7 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     S->line_diag_valid = false;
     // cubic splines: both passes and the charge density in one sweep (K1c); on several GPUs the same kernel also
     // stores into the v-sequential layout of the owning ranks when the next stage is a V stage (`fuse`)
-    if (S->m[0] == SLLB_METHOD_SPLINE && S->m[1] == SLLB_METHOD_SPLINE && g_plane_kernel) {
+    if (S->m[0] == SLLB_METHOD_SPLINE && S->m[1] == SLLB_METHOD_SPLINE && S->o[0] == 4 && S->o[1] == 4 && g_plane_kernel) {
         DispDesc d0, d1;
         SLLB_TRY(Fx->disp_scratch2.ensure((size_t)Fx->ext[3]));
         SLLB_TRY(make_affine_disp(Fx, 0, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2], -step * p.dt / S->delta[0], &d0));
@@ -789,7 +789,7 @@ static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
         // f stays in this layout, so the next thing that happens to it is another V stage: hand its charge
         // density over as line sums of this pass (sum over x4 per (x1,x2,x3) line) instead of re-reading f
         int rc = SLLB_ERR_UNSUPPORTED;
-        if (S->m[3] == SLLB_METHOD_SPLINE && g_plane_kernel) {
+        if (S->m[3] == SLLB_METHOD_SPLINE && S->o[3] == 4 && g_plane_kernel) {
             const size_t nl = (size_t)Fv->ext[0] * Fv->ext[1] * Fv->ext[2];
             rc = S->linesum.ensure(nl);
             if (!rc && S->want_line_diag) {

@@ -90,9 +90,52 @@ def test_advector_bsl(sb, orc, n):
     adv.delete()
 
 
+@pytest.mark.parametrize("order", [6, 8])
+@pytest.mark.parametrize("n", [8, 20, 64, 100, 128, 512])
+def test_advector_periodic_spline_order_6_8(sb, orc, n, order):
+    """a3: sll_s_periodic_interp with sll_p_spline of order 6 / 8 (the reference's test_periodic_interpolation.F90 runs
+    order 8): in-block recursive-filter solve == the reference's FFT diagonalisation, short lines included (the periodic
+    sums close with 1/(1 - z^N) there)."""
+    rng = np.random.default_rng(SEED + 31 * n + order)
+    xmin, xmax = 0.0, 4 * np.pi
+    adv = sb.Advector1dPeriodic(n, xmin, xmax, sb.ADV_PERIODIC_SPLINE, order)
+    for A, dt in [(0.73, 0.1), (-5.9, 0.1), (0.0, 0.1), (37.3, 0.5), (-1e-9, 1.0)]:
+        f = rng.standard_normal(n)
+        fin = np.append(f, f[0])
+        ref = orc.advect_1d_periodic_constant("spline", n, xmin, xmax, order, A, dt, fin)
+        out = adv.advect_1d_constant(A, dt, fin)
+        assert out.shape == (n + 1,) and out[-1] == out[0]
+        assert relerr(out, ref) < TOL, (A, dt, relerr(out, ref))
+    ones = np.ones(n + 1)
+    assert np.abs(adv.advect_1d_constant(0.3, 0.1, ones) - 1.0).max() < 1e-14
+    adv.delete()
+
+
+@pytest.mark.parametrize("order", [6, 8])
+def test_periodic_spline_order_6_8_whole_array_passes(sb, orc, order):
+    """the same splines as whole-array passes on every axis of a 4D field (strided tiles and the contiguous axis)"""
+    rng = np.random.default_rng(SEED + order)
+    shape = (32, 16, 24, 40)
+    f0 = np.asfortranarray(rng.standard_normal(shape))
+    F = sb.Field(shape)
+    for axis in range(4):
+        v_axis = (axis + 2) % 4
+        disp = rng.uniform(-2.5, 2.5, shape[v_axis])
+        if v_axis > axis:
+            stride = int(np.prod(shape[axis + 1:v_axis], dtype=np.int64))
+            dsel = (stride, shape[v_axis], 1, 1, 1, 0)
+        else:
+            dsel = (1, 1, 0, int(np.prod(shape[:v_axis], dtype=np.int64)), shape[v_axis], 1)
+        ref = orc.advect_axis(f0.copy(order="F"), axis, "fft_spline", order, disp, dsel)
+        F.upload(f0)
+        F.advect_axis(axis, sb.METHOD_SPLINE, order, disp, 1.0, dsel)
+        assert relerr(F.download(), ref) < TOL, axis
+    F.destroy()
+
+
 def test_advector_unsupported(sb):
     with pytest.raises(sb.SllbError) as e:
-        sb.Advector1dPeriodic(64, 0.0, 1.0, sb.ADV_PERIODIC_SPLINE, 8)
+        sb.Advector1dPeriodic(64, 0.0, 1.0, sb.ADV_PERIODIC_SPLINE, 10)
     assert e.value.code == 2
     with pytest.raises(sb.SllbError):
         sb.Advector1dPeriodic(64, 0.0, 1.0, sb.ADV_PERIODIC_LAGRANGE, 5)

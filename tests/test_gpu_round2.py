@@ -89,9 +89,9 @@ def test_checksum_detects_misplaced_elements(sb):
     w = 1.0 + ((3 * i0 + 5 * i1 + 7 * i2 + 11 * i3) & 63) / 64.0
     assert abs(c0[0] / (w * f).sum() - 1) < 1e-13 and abs(c0[1] / (w * f * f).sum() - 1) < 1e-13
     g = f.copy(order="F")
-    g[3, 5, 7, 9], g[4, 5, 7, 9] = f[4, 5, 7, 9], f[3, 5, 7, 9]      # swap two neighbours: the mass does not notice
+    g[3, 5, 7, 9], g[3, 5, 15, 16] = f[3, 5, 15, 16], f[3, 5, 7, 9]    # swap two elements: the mass does not notice
     F.upload(g)
     c1 = S.checksum()
     assert abs(g.sum() - f.sum()) < 1e-18 + 1e-15 * abs(f.sum())
-    assert abs(c1[0] - c0[0]) > 1e-12 * abs(c0[0]) or abs(c1[1] - c0[1]) > 1e-12 * abs(c0[1])
+    assert abs(c1[0] - c0[0]) > 1e-9 * abs(c0[0]) or abs(c1[1] - c0[1]) > 1e-9 * abs(c0[1])
     S.destroy()
