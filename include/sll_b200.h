@@ -215,6 +215,11 @@ int sllb_poisson1d_create(int nc, double xmin, double xmax, sllb_poisson_t *P);
 /* sll_t_poisson_2d_periodic_fft (sll_m_poisson_2d_periodic.F90:250-383) */
 int sllb_poisson2d_create(int nc_x, int nc_y, double x_min, double x_max, double y_min, double y_max,
                           sllb_poisson_t *P);
+/* sll_t_poisson_2d_periodic_par (sll_m_poisson_2d_periodic_par.F90:120-338, the solver of sim_bsl_vp_2d2v_cart): solves
+ * Delta phi = rho on [0,Lx] x [0,Ly] (the caller gives the source its sign), zero-mean potential, potential only
+ * (sllb_poisson_solve[_host] with e1 = e2 = NULL); the reference distributes the two 1D transforms over the ranks of a
+ * 2D layout, here the nc_x x nc_y problem is solved on the device that holds rho */
+int sllb_poisson2d_par_create(int ncx, int ncy, double Lx, double Ly, sllb_poisson_t *P);
 /* sll_t_poisson_3d_periodic_par (sll_m_poisson_3d_periodic_par.F90:297-470,981-1158), replicated */
 int sllb_poisson3d_create(int nx, int ny, int nz, double Lx, double Ly, double Lz, sllb_poisson_t *P);
 int sllb_poisson_destroy(sllb_poisson_t P);
@@ -405,6 +410,7 @@ int sllb_sim4d_create_from_namelist(const char *filename, sllb_comm_t comm, sllb
 int sllb_sim4d_run_namelist(const char *filename, sllb_comm_t comm, const char *thdiag_path);
 /* Fortran G20.12 edit descriptor (host helper of the writer): buf receives exactly 20 characters + NUL */
 int sllb_format_g20_12(double x, char *buf21);
+int sllb_format_g(double x, int w, int d, char *buf /* w + 1 chars */); /* Fortran Gw.d */
 /* the 13 columns of the reference's thdiag file for the current state (:998-1010 at t = 0, :1262-1275 later):
  * time, nrj, ekin, nrj0, ekin0, max|jacobian_E|, nrj_jac, int f, int |f|, int f^2, mass0, mass0, l20 */
 int sllb_sim4d_thdiag(sllb_sim4d_t S, double *row13);
@@ -436,6 +442,29 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows);
 int sllb_set_cuda_graphs(int on);
 int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F);
 int sllb_sim2d_destroy(sllb_sim2d_t S);
+/* init also takes 2 = SLL_BUMP_ON_TAIL.  The knobs the namelist of sim_bsl_vp_1d1v_cart sets
+ * (sll_m_sim_bsl_vp_1d1v_cart.F90:431-494): split_case (numbering of sllb_splitting_case_from_name; the 1D1V loop walks
+ * split_step(1..nb_split_step) alternating T and V, :1462-1696, so only schemes with dim_split_V = 1 apply),
+ * advector_x1 / advector_x2 with their orders, time_init. */
+int sllb_sim2d_set_splitting(sllb_sim2d_t S, int split_case);
+int sllb_sim2d_set_advectors(sllb_sim2d_t S, int method_x1, int order_x1, int method_x2, int order_x2);
+int sllb_sim2d_set_time(sllb_sim2d_t S, double time_init);
+int sllb_sim2d_geometry(sllb_sim2d_t S, double lim[4]); /* x1_min, x1_max, x2_min, x2_max */
+int sllb_sim2d_fields_host(sllb_sim2d_t S, double *rho, double *efield); /* N1 cells each, NULL = skip */
+/* one row of the reference's thdiag.dat (:1703-1801): time, mass, l1norm, momentum, l2norm, kinetic_energy,
+ * potential_energy, total, Re/Im rho^_k (k = 0..nb_mode), f_hat_x2(k) = sum_v w_v |f^_k(v)|^2 (k = 0..nb_mode):
+ * 8 + 3 (nb_mode + 1) doubles; transforms normalised by 1/N like the reference's r2r plan (:1195) */
+int sllb_sim2d_thdiag(sllb_sim2d_t S, int nb_mode, double *row);
+/* the reference's restart stream (:1281-1307 read, :1762-1770 write): time, then f with the duplicated end points,
+ * (N1+1) x (N2+1) doubles column-major; a file written by either code is read by the other */
+int sllb_sim2d_write_restart(sllb_sim2d_t S, const char *path);
+int sllb_sim2d_read_restart(sllb_sim2d_t S, const char *path, double *time);
+/* namelist front-end (:431-565 with the reference's defaults and error messages) and the whole program: thdiag.dat in
+ * '(8g25.15)' + modes, x/v/f0/deltaf/rhotot/efield/t .bdat, f_plot_<iplot>_proc_0000.rst every freq_diag_restart steps,
+ * restart_file / time_init_from_restart_file on the way in; files go to `outdir` (NULL = current directory) */
+int sllb_sim2d_create_from_namelist(const char *filename, sllb_sim2d_t *S, int *number_iterations, int *freq_diag_time,
+                                    int *nb_mode);
+int sllb_sim2d_run_namelist(const char *filename, const char *outdir);
 
 /* 3D3V sim_bsl_vp_3d3v_cart_dd_slim (fixed / centred Lagrange or local splines) on 1..P GPUs (velocity axes split,
  * halo exchange per v-advection, rho all-reduced). rows: R x 14 as the reference's <prefix>.dat

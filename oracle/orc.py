@@ -146,6 +146,15 @@ def poisson_2d(rho, nc_x, nc_y, x_min, x_max, y_min, y_max, want_phi=False):
     return (ex, ey, phi) if want_phi else (ex, ey)
 
 
+def poisson_2d_par(rho, ncx, ncy, Lx, Ly):
+    """sll_s_poisson_2d_periodic_par_solve (Delta phi = rho); rho: Fortran-ordered (ncx+1, ncy+1) array"""
+    rho = np.asfortranarray(rho, dtype=np.float64)
+    assert rho.shape == (ncx + 1, ncy + 1)
+    phi = np.zeros_like(rho, order="F")
+    lib().orc_poisson_2d_periodic_par_solve(C.c_int(ncx), C.c_int(ncy), C.c_double(Lx), C.c_double(Ly), _p(rho), _p(phi))
+    return phi
+
+
 def poisson_3d(rho, Lx, Ly, Lz):
     rho = np.asfortranarray(rho, dtype=np.float64)
     nx, ny, nz = rho.shape

@@ -707,6 +707,34 @@ static void c2r_2d(const cplx *in, int n1, int n2, double *out) {
 /* initialize + solve_e_fields_poisson_2d_periodic_fft,
  * src/field_solvers/poisson_solvers/sll_m_poisson_2d_periodic.F90:250-310,342-383.
  * rho, ex, ey: (ld1 x ld2) with ld = nc or nc+1 (duplicates filled when nc+1). */
+/* sll_s_poisson_2d_periodic_par_solve, src/field_solvers/poisson_solvers_parallel/sll_m_poisson_2d_periodic_par.F90:214-338,
+ * on one process (the remaps between the two sequential layouts are the identity): complex transforms along x then y of
+ * rho(1:ncx, 1:ncy), phi^ = -rho^ / (((kx/Lx)^2 + (ky/Ly)^2) 4 pi^2) with both mode numbers folded to -n/2 .. n/2-1 and
+ * the (1,1) mode set to zero, inverse transforms along y then x, periodic point copied in both directions (:316,329),
+ * real part times 1/(ncx ncy).  rho and phi are (ncx+1) x (ncy+1), column-major. */
+void orc_poisson_2d_periodic_par_solve(int ncx, int ncy, double Lx, double Ly, const double *rho, double *phi) {
+    const int ld = ncx + 1;
+    cplx *a = (cplx *)malloc(sizeof(cplx) * (size_t)ncx * ncy);
+    cplx *work = (cplx *)malloc(sizeof(cplx) * (size_t)(ncx > ncy ? ncx : ncy));
+    for (int j = 0; j < ncy; ++j) for (int i = 0; i < ncx; ++i) a[i + (size_t)ncx * j] = rho[i + (size_t)ld * j];
+    for (int j = 0; j < ncy; ++j) fft_lines(a + (size_t)ncx * j, ncx, 1, -1, work);
+    for (int i = 0; i < ncx; ++i) fft_lines(a + i, ncy, ncx, -1, work);
+    const double r_Lx = 1.0 / Lx, r_Ly = 1.0 / Ly;
+    for (int j = 0; j < ncy; ++j) for (int i = 0; i < ncx; ++i) {
+        if (i == 0 && j == 0) { a[0] = 0; continue; }
+        double kx = (double)i, ky = (double)j;
+        if (kx >= ncx / 2) kx = kx - ncx;
+        if (ky >= ncy / 2) ky = ky - ncy;
+        a[i + (size_t)ncx * j] = -a[i + (size_t)ncx * j] / ((pow(kx * r_Lx, 2) + pow(ky * r_Ly, 2)) * 4.0 * ORC_PI * ORC_PI);
+    }
+    for (int i = 0; i < ncx; ++i) fft_lines(a + i, ncy, ncx, +1, work);
+    for (int j = 0; j < ncy; ++j) fft_lines(a + (size_t)ncx * j, ncx, 1, +1, work);
+    const double normalization = 1.0 / ((double)ncx * (double)ncy);
+    for (int j = 0; j <= ncy; ++j) for (int i = 0; i <= ncx; ++i)
+        phi[i + (size_t)ld * j] = creal(a[(i % ncx) + (size_t)ncx * (j % ncy)]) * normalization;
+    free(a); free(work);
+}
+
 void orc_poisson_2d_periodic_solve_e(int nc_x, int nc_y, double x_min, double x_max, double y_min,
                                      double y_max, const double *rho, int ld1, int ld2,
                                      double *e_x, double *e_y, double *phi) {

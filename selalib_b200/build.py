@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libsllb200.so")
-SOURCES = ["sllb_kernels.cu", "sllb_capi.cu", "sllb_sims.cu", "sllb_dd6d.cu", "sllb_compat6d.cu", "sllb_spline_dd.cu", "sllb_splitting.cu", "sllb_hermite.cu", "sllb_sim4d_nml.cu", "sllb_lagrange_plane.cu", "sllb_diag.cu", "sllb_poisson_direct.cu"]
+SOURCES = ["sllb_kernels.cu", "sllb_capi.cu", "sllb_sims.cu", "sllb_dd6d.cu", "sllb_compat6d.cu", "sllb_spline_dd.cu", "sllb_splitting.cu", "sllb_hermite.cu", "sllb_sim4d_nml.cu", "sllb_lagrange_plane.cu", "sllb_diag.cu", "sllb_poisson_direct.cu", "sllb_sim2d_nml.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -341,10 +341,16 @@ class Field:
 
 
 class Poisson:
-    def __init__(self, n, xmin, xmax):
+    def __init__(self, n, xmin, xmax, par=False):
+        """par=True (2D): sll_t_poisson_2d_periodic_par, Delta phi = rho, potential only"""
         self.h = vp()
         self.n = tuple(int(v) for v in n)
-        if len(n) == 1:
+        self.par = bool(par)
+        if par:
+            assert len(n) == 2
+            _ck(lib().sllb_poisson2d_par_create(C.c_int(n[0]), C.c_int(n[1]), C.c_double(xmax[0] - xmin[0]),
+                                                C.c_double(xmax[1] - xmin[1]), C.byref(self.h)))
+        elif len(n) == 1:
             _ck(lib().sllb_poisson1d_create(C.c_int(n[0]), C.c_double(xmin[0]), C.c_double(xmax[0]), C.byref(self.h)))
         elif len(n) == 2:
             _ck(lib().sllb_poisson2d_create(C.c_int(n[0]), C.c_int(n[1]), C.c_double(xmin[0]), C.c_double(xmax[0]),
@@ -364,8 +370,10 @@ class Poisson:
             ptrs[0] = None
         for k in range(dim + 1, 4):
             ptrs[k] = None
+        if self.par:
+            ptrs[1] = ptrs[2] = None
         _ck(lib().sllb_poisson_solve_host(self.h, _p(rho), ld, *ptrs))
-        return tuple(outs[: dim + 1])
+        return outs[0] if self.par else tuple(outs[: dim + 1])
 
     def destroy(self):
         if self.h:
@@ -496,6 +504,17 @@ def sim4d_run_namelist(filename, thdiag_path, comm=None):
     _ck(lib().sllb_sim4d_run_namelist(filename.encode(), comm.h if comm is not None else None, thdiag_path.encode()))
 
 
+def sim2d_run_namelist(filename, outdir=None):
+    """sim_bsl_vp_1d1v_cart <filename>: run the namelist, write thdiag.dat, the .bdat files and the restart files"""
+    _ck(lib().sllb_sim2d_run_namelist(filename.encode(), outdir.encode() if outdir else None))
+
+
+def format_g(x, w, d):
+    buf = C.create_string_buffer(w + 1)
+    _ck(lib().sllb_format_g(C.c_double(x), C.c_int(w), C.c_int(d), buf))
+    return buf.value.decode()
+
+
 class Sim4d:
     def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None, stencil=(0, 0)):
         if isinstance(split, str):
@@ -579,6 +598,15 @@ class Sim2d:
                                     C.c_double(x2_min), C.c_double(x2_max), C.c_int(init), C.c_double(kmode),
                                     C.c_double(eps), C.c_double(dt), C.c_int(method), C.c_int(order), C.byref(self.h)))
 
+    @classmethod
+    def from_namelist(cls, filename):
+        """the namelist of sim_bsl_vp_1d1v_cart; returns (sim, number_iterations, freq_diag_time, nb_mode)"""
+        self = cls.__new__(cls)
+        self.h = vp()
+        nit, fdt, nbm = C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(lib().sllb_sim2d_create_from_namelist(filename.encode(), C.byref(self.h), C.byref(nit), C.byref(fdt), C.byref(nbm)))
+        return self, nit.value, fdt.value, nbm.value
+
     def run(self, nsteps, diagnostics=True):
         rows = np.zeros((nsteps, 8))
         _ck(lib().sllb_sim2d_run(self.h, C.c_int(nsteps), _p(rows) if diagnostics else None))
@@ -588,6 +616,38 @@ class Sim2d:
         f = vp()
         _ck(lib().sllb_sim2d_field(self.h, C.byref(f)))
         return Field(handle=f)
+
+    def set_splitting(self, split):
+        if isinstance(split, str):
+            split = splitting_case(split)
+        _ck(lib().sllb_sim2d_set_splitting(self.h, C.c_int(split)))
+
+    def set_advectors(self, method_x1, order_x1, method_x2, order_x2):
+        _ck(lib().sllb_sim2d_set_advectors(self.h, C.c_int(method_x1), C.c_int(order_x1), C.c_int(method_x2), C.c_int(order_x2)))
+
+    def set_time(self, t):
+        _ck(lib().sllb_sim2d_set_time(self.h, C.c_double(t)))
+
+    def fields(self):
+        """rho and E of the current state (N1 periodic cells each)"""
+        n1 = self.field().extents[0]
+        rho, e = np.zeros(n1), np.zeros(n1)
+        _ck(lib().sllb_sim2d_fields_host(self.h, _p(rho), _p(e)))
+        return rho, e
+
+    def thdiag(self, nb_mode):
+        """one row of the reference's thdiag.dat: 8 integrals, Re/Im of rho^_k, f_hat_x2(k), k = 0..nb_mode"""
+        row = np.zeros(8 + 3 * (nb_mode + 1))
+        _ck(lib().sllb_sim2d_thdiag(self.h, C.c_int(nb_mode), _p(row)))
+        return row
+
+    def write_restart(self, path):
+        _ck(lib().sllb_sim2d_write_restart(self.h, path.encode()))
+
+    def read_restart(self, path):
+        t = C.c_double(0.0)
+        _ck(lib().sllb_sim2d_read_restart(self.h, path.encode(), C.byref(t)))
+        return t.value
 
     def destroy(self):
         if self.h:

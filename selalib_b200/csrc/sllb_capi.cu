@@ -194,7 +194,7 @@ int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDe
 int g_plane_kernel = 1;
 int g_poisson_direct = [] { const char *e = getenv("SLLB_POISSON_DIRECT"); return (e && e[0] == '0') ? 0 : 1; }();
 int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
-                     const RemapDst *remap) {
+                     const RemapDst *remap, const double **partials_out, int *nparts_out) {
     if (!F || F->ndim < 2) return fail(SLLB_ERR_INVALID, "advect_plane: bad field");
     if (!g_plane_kernel) return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: disabled (sllb_set_plane_kernel)");
     const int n1 = F->ext[0], n2 = F->ext[1];
@@ -202,7 +202,7 @@ int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, do
     for (int d = 2; d < F->ndim; ++d) nplanes *= F->ext[d];
     double *partial = nullptr;
     int nparts = 0;
-    if (d_rho) {
+    if (d_rho || partials_out) {
         nparts = plane_grid(n1, n2, nplanes);
         SLLB_TRY(F->red_scratch.ensure((size_t)nparts * n1 * n2));
         partial = F->red_scratch.p;
@@ -210,7 +210,8 @@ int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, do
     cudaError_t e = launch_spline_plane(F->d, n1, n2, nplanes, dd0, dd1, partial, g_stream, remap);
     if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_plane: plane shape or displacement pattern not supported"); }
     SLLB_TRY(check_cuda(e, "k_spline_plane launch"));
-    if (d_rho) SLLB_CUDA(launch_sum_partials(partial, (long long)n1 * n2, nparts, rho_scale, d_rho, g_stream));
+    if (partials_out) { *partials_out = partial; *nparts_out = nparts; }   // the caller sums (and scales) them
+    else if (d_rho) SLLB_CUDA(launch_sum_partials(partial, (long long)n1 * n2, nparts, rho_scale, d_rho, g_stream));
     return SLLB_OK;
 }
 
@@ -628,6 +629,13 @@ int sllb_poisson2d_create(int nc_x, int nc_y, double x_min, double x_max, double
     *P = p;
     return SLLB_OK;
 }
+/* sll_t_poisson_2d_periodic_par (sll_m_poisson_2d_periodic_par.F90:120-338): solves Delta phi = rho (the caller gives the
+ * source its sign) on [0,Lx] x [0,Ly], zero-mean phi, no field outputs; replicated on one device */
+int sllb_poisson2d_par_create(int ncx, int ncy, double Lx, double Ly, sllb_poisson_t *P) {
+    SLLB_TRY(sllb_poisson2d_create(ncx, ncy, 0.0, Lx, 0.0, Ly, P));
+    (*P)->par_variant = 1;
+    return SLLB_OK;
+}
 int sllb_poisson3d_create(int nx, int ny, int nz, double Lx, double Ly, double Lz, sllb_poisson_t *P) {
     if (!P || nx < 4 || ny < 4 || nz < 4 || !(Lx > 0) || !(Ly > 0) || !(Lz > 0))
         return fail(SLLB_ERR_INVALID, "poisson3d_create: bad arguments");
@@ -651,9 +659,11 @@ int sllb_poisson_destroy(sllb_poisson_t P) {
 int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, double *d_e1, double *d_e2, double *d_e3) {
     if (!P || !d_rho) return fail(SLLB_ERR_INVALID, "poisson_solve: null");
     SLLB_TRY(require_device());
+    if (P->dim == 2 && P->par_variant && (d_e1 || d_e2 || !d_phi))
+        return fail(SLLB_ERR_INVALID, "poisson_solve: sll_t_poisson_2d_periodic_par returns the potential only (phi must be given, e1/e2 NULL)");
     if (P->dim == 2 && P->direct && g_poisson_direct) {
-        SLLB_CUDA(poisson2d_direct_solve(P->direct, d_rho, 1, 0, 1.0, nullptr, 0, d_phi, d_e1, d_e2, nullptr, nullptr, nullptr,
-                                         nullptr, g_stream));
+        SLLB_CUDA(poisson2d_direct_solve(P->direct, d_rho, 1, 0, 1.0, nullptr, P->par_variant, d_phi, d_e1, d_e2, nullptr, nullptr,
+                                         nullptr, nullptr, g_stream));
         return SLLB_OK;
     }
     if (P->stream != g_stream) {
@@ -668,6 +678,9 @@ int sllb_poisson_solve(sllb_poisson_t P, const double *d_rho, double *d_phi, dou
         if (d_phi) return fail(SLLB_ERR_UNSUPPORTED, "poisson1d: potential output not implemented (the reference returns E only)");
         if (e1) SLLB_CUDA(launch_poisson1d_mult(P->rho_hat, P->n[0], P->L[0], e1, g_stream));
         e2 = e3 = nullptr;
+    } else if (P->dim == 2 && P->par_variant) {
+        SLLB_CUDA(launch_poisson2d_par_mult(P->rho_hat, P->n[0], P->n[1], P->L[0], P->L[1], ph, g_stream));
+        e1 = e2 = e3 = nullptr;
     } else if (P->dim == 2) {
         SLLB_CUDA(launch_poisson2d_mult(P->rho_hat, P->n[0], P->n[1], P->L[0], P->L[1], ph, e1, e2, g_stream));
         e3 = nullptr;

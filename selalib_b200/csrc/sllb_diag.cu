@@ -75,6 +75,13 @@ __global__ void __launch_bounds__(256) k_moments_from_lines2(const double *__res
         for (int k = 0; k < 4; ++k) v[k] += partial[4 * b + k];
     block_sum<4>(v, out4);
 }
+cudaError_t launch_moments_from_lines_partials(const double *sum_, const double *l1, const double *l2, const double *kin, long long nx,
+                                               int n3, const double *w3, double *partial, int *nb_out, cudaStream_t st) {
+    k_moments_from_lines1<<<ML_BLOCKS, RT, 0, st>>>(sum_, l1, l2, kin, nx, n3, w3, partial);
+    count_launch();
+    *nb_out = ML_BLOCKS;
+    return cudaGetLastError();
+}
 cudaError_t launch_moments_from_lines(const double *sum_, const double *l1, const double *l2, const double *kin, long long nx,
                                       int n3, const double *w3, double *scratch, double *out4, cudaStream_t st) {
     k_moments_from_lines1<<<ML_BLOCKS, RT, 0, st>>>(sum_, l1, l2, kin, nx, n3, w3, scratch);
@@ -150,15 +157,86 @@ cudaError_t launch_checksum4d(const double *f, const int ext[4], const int lo[4]
     return cudaGetLastError();
 }
 
-__global__ void k_sim4d_row(const double *__restrict__ m4, const double *__restrict__ nrj, const double time, const double vol,
-                            const int root, double *__restrict__ row6) {
-    if (threadIdx.x != 0) return;
-    row6[0] = root ? time : 0.0; row6[1] = root ? nrj[0] : 0.0;
-    row6[2] = 0.5 * m4[3] * vol;
-    row6[3] = m4[0] * vol; row6[4] = m4[1] * vol; row6[5] = m4[2] * vol;
+// |f^_k(v)|^2 for the first modes k < nmodes of every row f(:, v), f^_k = (1/n1) sum_x f(x, v) e^{-2 pi i k x / n1}
+// (the normalised r2r transform + sll_f_fft_get_mode_r2c_1d of sll_m_sim_bsl_vp_1d1v_cart.F90:1745-1754)
+__global__ void __launch_bounds__(128) k_row_modes(const double *__restrict__ f, const int n1, const int nmodes,
+                                                   double *__restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *row = reinterpret_cast<double *>(smem_raw);
+    double2 *tw = reinterpret_cast<double2 *>(row + n1);
+    const long long v = blockIdx.x;
+    for (int x = threadIdx.x; x < n1; x += blockDim.x) {
+        row[x] = f[v * n1 + x];
+        double sn, cs;
+        sincospi(2.0 * (double)x / (double)n1, &sn, &cs);
+        tw[x] = make_double2(cs, sn);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nmodes; k += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        int idx = 0;
+        const int kk = k % n1;
+        for (int x = 0; x < n1; ++x) {
+            re = fma(row[x], tw[idx].x, re);
+            im = fma(-row[x], tw[idx].y, im);
+            idx += kk; if (idx >= n1) idx -= n1;
+        }
+        re /= (double)n1; im /= (double)n1;
+        part[v * nmodes + k] = re * re + im * im;
+    }
 }
-cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, int root, double *row6, cudaStream_t st) {
-    k_sim4d_row<<<1, 32, 0, st>>>(m4, nrj, time, vol, root, row6);
+// out[k] = sum_v w * part[v][k], fixed order
+__global__ void k_modes_reduce(const double *__restrict__ part, const long long nv, const int nmodes, const double w,
+                               double *__restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nmodes) return;
+    double a = 0.0;
+    for (long long v = 0; v < nv; ++v) a = fma(part[v * nmodes + k], w, a);
+    out[k] = a;
+}
+cudaError_t launch_row_modes(const double *f, int n1, long long nv, int nmodes, double w, double *part, double *out,
+                             cudaStream_t st) {
+    k_row_modes<<<(unsigned)nv, 128, (size_t)n1 * 24, st>>>(f, n1, nmodes, part);
+    count_launch();
+    k_modes_reduce<<<(nmodes + 63) / 64, 64, 0, st>>>(part, nv, nmodes, w, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// The diagnostics row of a time step: folds the last stage of the two reductions that feed it (the nb partial quadruples of
+// the moments, the nn partial sums of the field energy) in a fixed order.  counters == NULL: time and destination as
+// given.  Otherwise (time loop, possibly a CUDA-graph replay whose arguments are frozen): counters[0] = index of the row
+// inside rows_base, counters[1] = number of the time step that has just been completed minus one; both are advanced
+// here, so every launch writes the next row.
+__global__ void k_sim4d_row(const double *__restrict__ m4p, const int nb, const double *__restrict__ nrjp, const int nn,
+                            const double nrj_scale, const double time, const double dt, const double vol, const int root,
+                            double *__restrict__ row6, double *__restrict__ rows_base, double *__restrict__ counters) {
+    __shared__ double sh[5];
+    const int t = threadIdx.x;
+    if (t < 4) {
+        double a = 0.0;
+        for (int b = 0; b < nb; ++b) a += m4p[4 * b + t];
+        sh[t] = a;
+    } else if (t == 4) {
+        double a = 0.0;
+        for (int i = 0; i < nn; ++i) a += nrjp[i];
+        sh[4] = a * nrj_scale;
+    }
+    __syncthreads();
+    if (t != 0) return;
+    double tm = time;
+    if (counters) {
+        row6 = rows_base + 6 * (long long)counters[0];
+        tm = (counters[1] + 1.0) * dt;
+        counters[0] += 1.0; counters[1] += 1.0;
+    }
+    row6[0] = root ? tm : 0.0; row6[1] = root ? sh[4] : 0.0;
+    row6[2] = 0.5 * sh[3] * vol;
+    row6[3] = sh[0] * vol; row6[4] = sh[1] * vol; row6[5] = sh[2] * vol;
+}
+cudaError_t launch_sim4d_row(const double *m4_partials, int nb, const double *nrj_parts, int nn, double nrj_scale, double time,
+                             double dt, double vol, int root, double *row6, double *rows_base, double *counters, cudaStream_t st) {
+    k_sim4d_row<<<1, 32, 0, st>>>(m4_partials, nb, nrj_parts, nn, nrj_scale, time, dt, vol, root, row6, rows_base, counters);
     count_launch();
     return cudaGetLastError();
 }

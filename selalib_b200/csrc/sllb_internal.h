@@ -77,6 +77,7 @@ struct sllb_comm {
 
 namespace sllb { struct Poisson2dDirect; }
 struct sllb_poisson {
+    int par_variant = 0;                       // 2D: 1 = sll_t_poisson_2d_periodic_par (Delta phi = rho, phi only)
     sllb::Poisson2dDirect *direct = nullptr;   // 2D, small grids: three-kernel dense-DFT solve (sllb_poisson_direct.cu)
     int dim = 0;
     int n[3] = {1, 1, 1};
@@ -98,8 +99,10 @@ namespace sllb {
 int poisson2d_direct_supported(int n1, int n2);
 int poisson2d_direct_create(int n1, int n2, double L1, double L2, Poisson2dDirect **out);
 void poisson2d_direct_destroy(Poisson2dDirect *P);
+// nrj_rows != NULL (needs e1 and e2): nrj_rows[x2] = sum over x1 of w (E1^2 + E2^2), w = 2 on the x1 = 0 / x2 = 0 lines
+// (each counts twice in the reference's sum over the (N1+1)(N2+1) nodes with the periodic duplicates)
 cudaError_t poisson2d_direct_solve(Poisson2dDirect *P, const double *rho, int nslots, long long slot_stride, double scale,
-                                   double *rho_sum, int mode, double *phi, double *e1, double *e2, const double *unused,
+                                   double *rho_sum, int mode, double *phi, double *e1, double *e2, double *nrj_rows,
                                    double *tile_e1, double *tile_e2, const int tile_box[4], cudaStream_t st);
 extern int g_poisson_direct;   // 1 (default): 2D solves on small grids take the direct path; 0: always cuFFT
 int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<void *> &peers,
@@ -107,8 +110,9 @@ int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<
 // internal (device-pointer) entry points used by the simulations
 int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr,
                     double *linesum = nullptr, const LineDiag *diag = nullptr);
+// partials_out != NULL: the per-CTA partial densities are left unsummed ([nparts][n1*n2], unscaled) for the caller
 int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
-                     const RemapDst *remap = nullptr);
+                     const RemapDst *remap = nullptr, const double **partials_out = nullptr, int *nparts_out = nullptr);
 int advect_lagrange_plane_dev(sllb_field *F, int method, int order, const DispDesc &dd0, const DispDesc &dd1);
 extern int g_plane_kernel;
 int make_affine_disp(sllb_field *F, int axis, int v_axis, double vmin, double dv, double scale, DispDesc *dd);
@@ -135,8 +139,17 @@ cudaError_t launch_dup_energy2d(const double *a, const double *b, int n1, int n2
                                 cudaStream_t st);
 // (sum w f, sum w f^2), w from the global index of every point; scratch: moments_from_lines_scratch() doubles
 cudaError_t launch_checksum4d(const double *f, const int ext[4], const int lo[4], double *scratch, double *out2, cudaStream_t st);
+// out[k] = w * sum_v |f^_k(v)|^2, k < nmodes (f is [nv][n1], x fastest); part: scratch of nv * nmodes doubles
+cudaError_t launch_row_modes(const double *f, int n1, long long nv, int nmodes, double w, double *part, double *out,
+                             cudaStream_t st);
 cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream_t st);
 // row6 = (time, nrj[0], 0.5 vol m4[3], vol m4[0], vol m4[1], vol m4[2]); root = 0: time and nrj are written as 0 (the
 // rows of several ranks are summed afterwards)
-cudaError_t launch_sim4d_row(const double *m4, const double *nrj, double time, double vol, int root, double *row6, cudaStream_t st);
+// m4 = sum of nb partial quadruples (fixed order); nrj = nrj_scale * sum of nn values (fixed order);
+// counters != NULL: the row goes to rows_base + 6 * counters[0] with time (counters[1] + 1) dt, and both counters advance
+cudaError_t launch_sim4d_row(const double *m4_partials, int nb, const double *nrj_parts, int nn, double nrj_scale, double time,
+                             double dt, double vol, int root, double *row6, double *rows_base, double *counters, cudaStream_t st);
+// first stage of launch_moments_from_lines only: partial[148][4] (moments_from_lines_scratch() doubles)
+cudaError_t launch_moments_from_lines_partials(const double *sum_, const double *l1, const double *l2, const double *kin, long long nx,
+                                               int n3, const double *w3, double *partial, int *nb_out, cudaStream_t st);
 } // namespace sllb

@@ -1578,6 +1578,17 @@ __global__ void k_reduce_stage2(const double *__restrict__ partial, long long nx
     for (int c = 0; c < nchunks; ++c) a += partial[(long long)c * nx + x];
     rho[x] = a * scale;
 }
+// first stage only: scratch[c][x] = sum over the c-th chunk of v; returns the number of chunks (the consumer sums them:
+// the direct Poisson solve folds that sum into its first kernel)
+cudaError_t launch_reduce_velocity_partials(const double *f, long long nx, long long nv, double *scratch, int *nchunks_out,
+                                            cudaStream_t st) {
+    int nchunks = (int)(nv < RED_CHUNKS ? nv : RED_CHUNKS);
+    dim3 grid((unsigned)((nx + 127) / 128), nchunks);
+    k_reduce_stage1<<<grid, 128, 0, st>>>(f, nx, nv, nchunks, scratch);
+    COUNT_LAUNCH();
+    *nchunks_out = nchunks;
+    return cudaGetLastError();
+}
 cudaError_t launch_reduce_velocity(const double *f, long long nx, long long nv, double scale, double *rho,
                                    double *scratch, cudaStream_t st) {
     int nchunks = (int)(nv < RED_CHUNKS ? nv : RED_CHUNKS);
@@ -1694,6 +1705,33 @@ cudaError_t launch_poisson2d_mult(const cufftDoubleComplex *rho_hat, int n1, int
     const double tp = 2.0 * 3.14159265358979323846;
     dim3 grid((n1 / 2 + 1 + 63) / 64, n2);
     k_poisson2d<<<grid, 64, 0, st>>>(rho_hat, n1, n2, tp / L1, tp / L2, phi_hat, e1_hat, e2_hat);
+    COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+// 2D, parallel variant (sll_s_poisson_2d_periodic_par_solve, sll_m_poisson_2d_periodic_par.F90:214-338): Delta phi = rho,
+// phi^ = -rho^ / (4 pi^2 ((kx/Lx)^2 + (ky/Ly)^2)) with both indices folded to -n/2 .. n/2-1 (:300-306), phi^(0,0) = 0.
+// The reference transforms complex-to-complex and keeps the real part; the multiplier is real and even, so the half
+// spectrum of a real-to-complex transform gives the same field.
+__global__ void k_poisson2d_par(const cufftDoubleComplex *__restrict__ r, int n1, int n2, double kx0, double ky0,
+                                cufftDoubleComplex *__restrict__ ph) {
+    const int nh = n1 / 2 + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nh) return;
+    const size_t idx = i + (size_t)j * nh;
+    cufftDoubleComplex out = {0.0, 0.0};
+    if (i + j != 0) {
+        const double kx = (double)i * kx0, ky = (double)((j < n2 / 2) ? j : j - n2) * ky0;
+        const double d = -(kx * kx + ky * ky) * ((double)n1 * (double)n2);
+        out.x = r[idx].x / d; out.y = r[idx].y / d;
+    }
+    ph[idx] = out;
+}
+cudaError_t launch_poisson2d_par_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, double L1, double L2,
+                                      cufftDoubleComplex *phi_hat, cudaStream_t st) {
+    const double tp = 2.0 * 3.14159265358979323846;
+    dim3 grid((n1 / 2 + 1 + 63) / 64, n2);
+    k_poisson2d_par<<<grid, 64, 0, st>>>(rho_hat, n1, n2, tp / L1, tp / L2, phi_hat);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -86,6 +86,9 @@ size_t reduce_scratch_doubles(long long nx, long long nv);
 cudaError_t launch_reduce_velocity(const double *f, long long nx, long long nv, double scale, double *rho,
                                    double *scratch, cudaStream_t st);
 
+cudaError_t launch_reduce_velocity_partials(const double *f, long long nx, long long nv, double *scratch, int *nchunks_out,
+                                            cudaStream_t st);
+
 // K8: per velocity index v: s[v] = (sum_x f, sum_x |f|, sum_x f^2)   -> out[3*nv]
 cudaError_t launch_row_sums(const double *f, long long nx, long long nv, double *out3, cudaStream_t st);
 
@@ -95,6 +98,8 @@ cudaError_t launch_poisson1d_mult(const cufftDoubleComplex *rho_hat, int nc, dou
 cudaError_t launch_poisson2d_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, double L1, double L2,
                                   cufftDoubleComplex *phi_hat, cufftDoubleComplex *e1_hat, cufftDoubleComplex *e2_hat,
                                   cudaStream_t st);
+cudaError_t launch_poisson2d_par_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, double L1, double L2,
+                                      cufftDoubleComplex *phi_hat, cudaStream_t st);
 cudaError_t launch_poisson3d_mult(const cufftDoubleComplex *rho_hat, int n1, int n2, int n3, double L1, double L2,
                                   double L3, cufftDoubleComplex *phi_hat, cufftDoubleComplex *e1_hat,
                                   cufftDoubleComplex *e2_hat, cufftDoubleComplex *e3_hat, cudaStream_t st);

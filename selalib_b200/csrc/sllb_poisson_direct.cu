@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) k_pd_cols(const double2 *__restrict__ A, 
 
 // K_C: block = row x2; thread x1.  out(x1) = [Z(0).re + (-1)^x1 Z(N1/2).re + 2 sum_{0<k<N1/2} Re(Z(k) w1^(-k x1))] / (N1 N2).
 // Optionally also writes the (x1, x2) sub-box [lo0, lo0+t0) x [lo1, lo1+t1) of E1, E2 into dense tile arrays.
-struct PdTile { double *e1, *e2; int lo0, t0, lo1, t1; };
+struct PdTile { double *e1, *e2; int lo0, t0, lo1, t1; double *nrj_rows; };
 __global__ void __launch_bounds__(256) k_pd_rows_inv(const double2 *__restrict__ Z, const int n1, const int n2,
                                                      const double2 *__restrict__ tw1, double *__restrict__ phi,
                                                      double *__restrict__ e1, double *__restrict__ e2, const PdTile tile) {
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) k_pd_rows_inv(const double2 *__restrict__
     for (int x = threadIdx.x; x < n1; x += blockDim.x) tw[x] = tw1[x];
     __syncthreads();
     const double nrm = 1.0 / ((double)n1 * (double)n2);
+    double esq = 0.0;   // this thread's part of sum_x1 w (E1^2 + E2^2) on the row
     for (int x1 = threadIdx.x; x1 < n1; x1 += blockDim.x) {
         for (int q = 0; q < 3; ++q) {
             if (!outs[q]) continue;
@@ -161,10 +162,23 @@ __global__ void __launch_bounds__(256) k_pd_rows_inv(const double2 *__restrict__
             }
             const double v = (zq[0].x + ((x1 & 1) ? -zq[n1 / 2].x : zq[n1 / 2].x) + 2.0 * acc) * nrm;
             outs[q][(size_t)x2 * n1 + x1] = v;
+            if (q > 0) esq = fma((x1 == 0 ? 2.0 : 1.0) * (x2 == 0 ? 2.0 : 1.0) * v, v, esq);
             if (q > 0 && tile.e1) {
                 const int a0 = x1 - tile.lo0, a1 = x2 - tile.lo1;
                 if (a0 >= 0 && a0 < tile.t0 && a1 >= 0 && a1 < tile.t1) (q == 1 ? tile.e1 : tile.e2)[(size_t)a1 * tile.t0 + a0] = v;
             }
+        }
+    }
+    if (tile.nrj_rows) {   // fixed-shape block sum: warp shuffles, then the warp results in order
+        __shared__ double wsum[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) esq += __shfl_xor_sync(0xffffffffu, esq, o);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = esq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double a = wsum[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a += wsum[w];
+            tile.nrj_rows[x2] = a;
         }
     }
 }
@@ -196,9 +210,8 @@ void poisson2d_direct_destroy(Poisson2dDirect *P) {
     delete P;
 }
 cudaError_t poisson2d_direct_solve(Poisson2dDirect *P, const double *rho, int nslots, long long slot_stride, double scale,
-                                   double *rho_sum, int mode, double *phi, double *e1, double *e2, const double *unused,
+                                   double *rho_sum, int mode, double *phi, double *e1, double *e2, double *nrj_rows,
                                    double *tile_e1, double *tile_e2, const int tile_box[4], cudaStream_t st) {
-    (void)unused;
     const int n1 = P->n1, n2 = P->n2, h1 = n1 / 2 + 1;
     const double tp = 2.0 * 3.14159265358979323846;
     const int ta = h1 < 256 ? ((h1 + 31) / 32) * 32 : 256;
@@ -212,6 +225,7 @@ cudaError_t poisson2d_direct_solve(Poisson2dDirect *P, const double *rho, int ns
     tile.e1 = tile_e1; tile.e2 = tile_e2;
     tile.lo0 = tile_box ? tile_box[0] : 0; tile.t0 = tile_box ? tile_box[1] : 0;
     tile.lo1 = tile_box ? tile_box[2] : 0; tile.t1 = tile_box ? tile_box[3] : 0;
+    tile.nrj_rows = (e1 && e2) ? nrj_rows : nullptr;
     const int tc = n1 < 256 ? ((n1 + 31) / 32) * 32 : 256;
     k_pd_rows_inv<<<n2, tc, (size_t)h1 * 16 * 3 + (size_t)n1 * 16, st>>>(P->Z, n1, n2, P->tw1, phi, e1, e2, tile);
     count_launch();

@@ -19,9 +19,10 @@ extern "C" {
 
 /* Fortran G20.12: F(16).(12-s) followed by four blanks when the value rounded to 12 significant digits lies in
  * [0.1, 10^12), E20.12 otherwise, zero as F16.11 (Fortran 2003, 10.6.4.1.2) */
-int sllb_format_g20_12(double x, char *buf21) {
-    if (!buf21) return fail(SLLB_ERR_INVALID, "format_g20_12: null");
-    const int w = 20, d = 12;
+int sllb_format_g20_12(double x, char *buf21) { return sllb_format_g(x, 20, 12, buf21); }
+/* Fortran Gw.d (no exponent width): used as g20.12 by the 2D2V thdiag file and as g25.15 by the 1D1V one */
+int sllb_format_g(double x, int w, int d, char *buf) {
+    if (!buf || w < d + 7 || w > 60 || d < 1) return fail(SLLB_ERR_INVALID, "format_g: need d >= 1 and d + 7 <= w <= 60");
     char body[160];
     if (x == 0.0) snprintf(body, sizeof(body), "%*.*f    ", w - 4, d - 1, 0.0);
     else if (!std::isfinite(x)) snprintf(body, sizeof(body), "%*s", w, std::isnan(x) ? "NaN" : (x > 0 ? "Infinity" : "-Infinity"));
@@ -47,7 +48,7 @@ int sllb_format_g20_12(double x, char *buf21) {
     if ((int)strlen(body) != w) { // does not fit: Fortran prints asterisks
         memset(body, '*', w); body[w] = 0;
     }
-    memcpy(buf21, body, w + 1);
+    memcpy(buf, body, w + 1);
     return SLLB_OK;
 }
 

@@ -118,12 +118,12 @@ int sllb_comm_destroy(sllb_comm_t c) {
 }
 int sllb_comm_allreduce_sum(sllb_comm_t c, double *d_buf, int64_t count) {
     if (!c || !d_buf) return fail(SLLB_ERR_INVALID, "allreduce: null");
-    SLLB_NCCL(ncclAllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, c->comm, 0));
+    SLLB_NCCL(ncclAllReduce(d_buf, d_buf, (size_t)count, ncclDouble, ncclSum, c->comm, g_stream));
     return SLLB_OK;
 }
 int sllb_comm_allgather(sllb_comm_t c, const double *d_send, double *d_recv, int64_t count_per_rank) {
     if (!c || !d_send || !d_recv) return fail(SLLB_ERR_INVALID, "allgather: null");
-    SLLB_NCCL(ncclAllGather(d_send, d_recv, (size_t)count_per_rank, ncclDouble, c->comm, 0));
+    SLLB_NCCL(ncclAllGather(d_send, d_recv, (size_t)count_per_rank, ncclDouble, c->comm, g_stream));
     return SLLB_OK;
 }
 } // extern "C"
@@ -153,7 +153,7 @@ struct PhaseTimer {
                 ev.push_back(e);
             }
         }
-        cudaEventRecord(ev[used], 0);
+        cudaEventRecord(ev[used], g_stream);
         ++used; tag.push_back(phase_just_finished);
     }
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -271,13 +271,13 @@ __global__ void __launch_bounds__(32) k_flag_barrier(const PeerSig sig, const in
 static int dist4d_barrier(sllb_dist4d *D) {
     if (D->nranks < 2) return SLLB_OK;
     if (!D->flag_barrier) {
-        SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
+        SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, g_stream));
         return SLLB_OK;
     }
     PeerSig sig;
     for (int r = 0; r < 8; ++r) sig.p[r] = r < D->nranks ? D->peer_sig[r] : nullptr;
     D->epoch += 1;
-    k_flag_barrier<<<1, 32, 0, 0>>>(sig, D->nranks, D->rank, D->epoch, D->errflag.p);
+    k_flag_barrier<<<1, 32, 0, g_stream>>>(sig, D->nranks, D->rank, D->epoch, D->errflag.p);
     count_launch();
     return check_cuda(cudaGetLastError(), "k_flag_barrier");
 }
@@ -437,21 +437,21 @@ int sllb_dist4d_remap(sllb_dist4d_t D, int direction) {
         if (cs > 0) {
             Box4 b;
             for (int d = 0; d < 4; ++d) { b.lo[d] = sb[r * 8 + 2 * d] - slo[d]; b.n[d] = sb[r * 8 + 2 * d + 1] - sb[r * 8 + 2 * d] + 1; }
-            SLLB_CUDA(launch_pack4d(src->d, sn, b, D->sendbuf.p + soff[r], 0));
+            SLLB_CUDA(launch_pack4d(src->d, sn, b, D->sendbuf.p + soff[r], g_stream));
         }
     }
     SLLB_NCCL(ncclGroupStart());
     for (int r = 0; r < D->nranks; ++r) {
         const long long cs = soff[r + 1] - soff[r], cr = roff[r + 1] - roff[r];
-        if (cs > 0) SLLB_NCCL(ncclSend(D->sendbuf.p + soff[r], (size_t)cs, ncclDouble, r, D->comm->comm, 0));
-        if (cr > 0) SLLB_NCCL(ncclRecv(D->recvbuf.p + roff[r], (size_t)cr, ncclDouble, r, D->comm->comm, 0));
+        if (cs > 0) SLLB_NCCL(ncclSend(D->sendbuf.p + soff[r], (size_t)cs, ncclDouble, r, D->comm->comm, g_stream));
+        if (cr > 0) SLLB_NCCL(ncclRecv(D->recvbuf.p + roff[r], (size_t)cr, ncclDouble, r, D->comm->comm, g_stream));
     }
     SLLB_NCCL(ncclGroupEnd());
     for (int r = 0; r < D->nranks; ++r) {
         if (roff[r + 1] - roff[r] <= 0) continue;
         Box4 b;
         for (int d = 0; d < 4; ++d) { b.lo[d] = rb[r * 8 + 2 * d] - dlo[d]; b.n[d] = rb[r * 8 + 2 * d + 1] - rb[r * 8 + 2 * d] + 1; }
-        SLLB_CUDA(launch_unpack4d(dst->d, dn, b, D->recvbuf.p + roff[r], 0));
+        SLLB_CUDA(launch_unpack4d(dst->d, dn, b, D->recvbuf.p + roff[r], g_stream));
     }
     return SLLB_OK;
 }
@@ -462,6 +462,10 @@ int sllb_dist4d_remap(sllb_dist4d_t D, int direction) {
 /* 2D2V: sim_bsl_vp_2d2v_cart_poisson_serial                                                    */
 /* simulations/parallel/bsl_vp_2d2v_cart_poisson_serial/sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:650-1364 */
 /* ------------------------------------------------------------------------------------------ */
+// 1: on one GPU the last stage of the density reductions (sum of the per-chunk / per-CTA partial sums) is folded into the
+// first kernel of the direct Poisson solve instead of running as a kernel of its own (SLLB_FOLD_SUMS)
+static int g_fold_sums = [] { const char *e = getenv("SLLB_FOLD_SUMS"); return (e && e[0] == '1') ? 1 : 0; }();
+static int g_cuda_graphs = 1;   // sllb_set_cuda_graphs: replay one recorded time step as a CUDA graph (1D1V and 2D2V loops)
 struct sllb_sim4d {
     sllb_sim4d_params_t p;
     sllb_comm *comm = nullptr;
@@ -488,12 +492,30 @@ struct sllb_sim4d {
     // 3: the ranks' partial densities sit in the slots of the exchange buffer (summed inside the Poisson solve)
     int rho_state = 0;
     bool eloc_valid = false; // E1loc / E2loc were filled by the last field solve (tile extraction fused into it)
+    // 4: the per-CTA partial densities of the T-stage plane kernel are still unsummed (single GPU: the Poisson solve sums them)
+    const double *rho_parts = nullptr; int rho_nparts = 0;
+    DevBuf vtab[2];          // velocities of my x3 / x4 indices in the x-sequential layout (constant: no launch per stage)
+    DevBuf nrj_rows;         // per-row parts of the field energy written by the direct Poisson solve
+    bool nrj_rows_valid = false;
     double nrj = 0.0;
     int istep = 0;
     int layout = 0;    // which copy of f is current: 0 x-sequential, 1 v-sequential
     // per-step diagnostics on the device (sllb_diag.cu): second-moment weights of the two velocity axes per layout,
     // the per-line moments the last x4 pass of a step leaves behind, the four global moments, the field energy, the rows
     DevBuf w2dev[2], dl1, dl2, dkin, dscratch, m4, nrjd, rows_dev;
+    // one time step recorded as a CUDA graph (single GPU; the step is ~20 kernels, several of them a few microseconds
+    // long: on grids that fit in L2 the gaps between launches are a fifth of the step).  Two variants: with / without the
+    // diagnostics row.  A recording is replayed only from the same entry state it was recorded from.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        int entry_rho_state = -1, entry_layout = -1; bool entry_line_diag = false;
+        int exit_rho_state = 0, exit_layout = 0; bool exit_line_diag = false, exit_eloc = false;
+        long long launches = 0;
+    } graph[2];
+    cudaStream_t gstream = nullptr;
+    int eager_steps = 0;          // steps run with plain launches since f was last touched from outside: a step is recorded
+                                  // only after two of them, when every scratch buffer of the steady state exists
+    DevBuf dstep;                 // device-side counters read by the row kernel: [0] row index in this run, [1] time step
     bool want_line_diag = false;  // set by the time loop for the last stage of a step when diagnostics are on
     bool line_diag_valid = false; // dl1/dl2/dkin/linesum describe the current f
     PhaseTimer timer;
@@ -541,27 +563,33 @@ static int sim4d_fields(sllb_sim4d *S) {
     const double scale = S->delta[2] * S->delta[3];
     const long long tile = (long long)Fv->ext[0] * Fv->ext[1];
     const bool xchg = P > 1 && D->p2p && D->flag_barrier;   // density exchange by peer stores + flag barrier
-    const double *rho_in = S->rho_full.p;   // what the Poisson solve reads
+    const double *rho_in = S->rho_full.p;   // what the Poisson solve reads: in_scale * sum of nslots arrays n12 apart
     int nslots = 1;
+    double in_scale = 1.0;
+    const bool direct = S->poisson->direct && g_poisson_direct;
     if (S->rho_state == 3) {
         // every rank's partial sum over ITS planes sits in slot [rank] of my exchange buffer (T stage plane kernel)
         rho_in = D->xbuf.p; nslots = P;
+    } else if (S->rho_state == 4) {
+        // the plane kernel's per-CTA partial sums, unscaled: summed (in order) and scaled inside the Poisson solve
+        rho_in = S->rho_parts; nslots = S->rho_nparts; in_scale = scale;
     } else if (S->rho_state == 1) {
         // rho_full was accumulated by the plane kernel during the T stage (and all-reduced over the ranks)
+    } else if (P == 1 && direct && g_fold_sums) {
+        // one GPU: only the first stage of the velocity reduction runs as a kernel; its per-chunk partial sums are folded
+        // (in order) into the first kernel of the Poisson solve
+        const double *src = Fv->d;
+        long long nv = (long long)Fv->ext[2] * Fv->ext[3];
+        if (S->rho_state == 2) { src = S->linesum.p; nv = Fv->ext[2]; }   // sum over x4 came out of the last x4 pass
+        SLLB_TRY(Fv->red_scratch.ensure(reduce_scratch_doubles(tile, nv)));
+        SLLB_CUDA(launch_reduce_velocity_partials(src, tile, nv, Fv->red_scratch.p, &nslots, g_stream));
+        rho_in = Fv->red_scratch.p; in_scale = scale;
     } else {
-        double *rho_local = (P == 1) ? S->rho_full.p : S->rho_tile.p;
-        if (S->rho_state == 2) {
-            // sum over x4 came out of the last x4 pass; finish the sum over x3 (K3 on a [x1 x2][x3] array)
-            SLLB_TRY(Fv->red_scratch.ensure(reduce_scratch_doubles(tile, Fv->ext[2])));
-            SLLB_CUDA(launch_reduce_velocity(S->linesum.p, tile, Fv->ext[2], scale, rho_local, Fv->red_scratch.p, 0));
-        } else {
-            SLLB_TRY(sllb_reduce_velocity(Fv, 2, scale, rho_local));
-        }
         if (P > 1 && xchg) {
             // my tile goes straight into slot 8 of every rank's exchange buffer; the flag barrier completes the gather
             PeerX px;
             for (int r = 0; r < 8; ++r) px.p[r] = r < P ? D->peer_x[r] : nullptr;
-            k_bcast_tile<<<(unsigned)((tile + 255) / 256), 256, 0, 0>>>(S->rho_tile.p, Fv->ext[0], Fv->ext[1], S->bv[0], S->bv[2], N1,
+            k_bcast_tile<<<(unsigned)((tile + 255) / 256), 256, 0, g_stream>>>(S->rho_tile.p, Fv->ext[0], Fv->ext[1], S->bv[0], S->bv[2], N1,
                                                                         px, 8 * n12, P);
             count_launch();
             SLLB_CUDA(cudaGetLastError());
@@ -575,29 +603,33 @@ static int sim4d_fields(sllb_sim4d *S) {
                 const int *bb = &D->boxes[1][r * 8];
                 b.lo[0] = bb[0]; b.n[0] = bb[1] - bb[0] + 1; b.lo[1] = bb[2]; b.n[1] = bb[3] - bb[2] + 1;
                 b.lo[2] = b.lo[3] = 0; b.n[2] = b.n[3] = 1;
-                SLLB_CUDA(launch_unpack4d(S->rho_full.p, ext, b, S->rho_gather.p + (long long)r * tile, 0));
+                SLLB_CUDA(launch_unpack4d(S->rho_full.p, ext, b, S->rho_gather.p + (long long)r * tile, g_stream));
             }
         }
     }
     S->rho_state = 0;
     S->eloc_valid = false;
-    if (S->poisson->direct && g_poisson_direct) {
-        // three kernels: sum of the slots fused into the first, extraction of my E tiles fused into the last
+    S->nrj_rows_valid = false;
+    if (direct) {
+        // three kernels: sum of the slots fused into the first; extraction of my E tiles and the per-row parts of the
+        // field energy fused into the last
         const int tbox[4] = {S->bv[0], Fv->ext[0], S->bv[2], Fv->ext[1]};
-        SLLB_CUDA(poisson2d_direct_solve(S->poisson->direct, rho_in, nslots, n12, 1.0, rho_in != S->rho_full.p ? S->rho_full.p : nullptr,
-                                         0, nullptr, S->E1.p, S->E2.p, nullptr, P > 1 ? S->E1loc.p : nullptr,
-                                         P > 1 ? S->E2loc.p : nullptr, P > 1 ? tbox : nullptr, 0));
+        SLLB_TRY(S->nrj_rows.ensure((size_t)N2));
+        SLLB_CUDA(poisson2d_direct_solve(S->poisson->direct, rho_in, nslots, n12, in_scale, rho_in != S->rho_full.p ? S->rho_full.p : nullptr,
+                                         0, nullptr, S->E1.p, S->E2.p, S->nrj_rows.p, P > 1 ? S->E1loc.p : nullptr,
+                                         P > 1 ? S->E2loc.p : nullptr, P > 1 ? tbox : nullptr, g_stream));
         S->eloc_valid = P > 1;
+        S->nrj_rows_valid = true;
     } else {
-        if (nslots > 1) SLLB_CUDA(launch_sum_partials(rho_in, n12, nslots, 1.0, S->rho_full.p, 0));
+        if (nslots > 1) SLLB_CUDA(launch_sum_partials(rho_in, n12, nslots, in_scale, S->rho_full.p, g_stream));
         else if (rho_in != S->rho_full.p)
-            SLLB_CUDA(cudaMemcpyAsync(S->rho_full.p, rho_in, (size_t)n12 * sizeof(double), cudaMemcpyDeviceToDevice, 0));
+            SLLB_CUDA(cudaMemcpyAsync(S->rho_full.p, rho_in, (size_t)n12 * sizeof(double), cudaMemcpyDeviceToDevice, g_stream));
         SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho_full.p, nullptr, S->E1.p, S->E2.p, nullptr));
     }
     if (S->dim_split_V == 2) {
         // field_x{1,2}(:,:,2) = E of the Poisson problem with jacobian_E as right-hand side (:1113-1126)
         SLLB_CUDA(launch_jacobian2d(S->E1.p, S->E2.p, N1, N2, S->stencil_r, S->stencil_s, S->fdw.p,
-                                    4.0 / (S->delta[0] * S->delta[1]), S->jacE.p, 0));
+                                    4.0 / (S->delta[0] * S->delta[1]), S->jacE.p, g_stream));
         SLLB_TRY(sllb_poisson_solve(S->poisson, S->jacE.p, nullptr, S->K1.p, S->K2.p, nullptr));
     }
     return SLLB_OK;
@@ -619,7 +651,7 @@ static int sim4d_jac_diag(sllb_sim4d *S) {
     const size_t n12 = (size_t)N1 * N2;
     if (S->dim_split_V != 2)
         SLLB_CUDA(launch_jacobian2d(S->E1.p, S->E2.p, N1, N2, S->stencil_r, S->stencil_s, S->fdw.p,
-                                    4.0 / (S->delta[0] * S->delta[1]), S->jacE.p, 0));
+                                    4.0 / (S->delta[0] * S->delta[1]), S->jacE.p, g_stream));
     std::vector<double> j(n12);
     SLLB_CUDA(cudaMemcpy(j.data(), S->jacE.p, n12 * 8, cudaMemcpyDeviceToHost));
     double m = 0;
@@ -676,22 +708,32 @@ static int sim4d_diag_device(sllb_sim4d *S, double *d_row6) {
     const sllb_sim4d_params_t &p = S->p;
     SLLB_TRY(S->m4.ensure(4));
     SLLB_TRY(S->nrjd.ensure(1));
-    SLLB_CUDA(launch_dup_energy2d(S->E1.p, S->E2.p, p.nc[0], p.nc[1], S->delta[0] * S->delta[1], 1, S->nrjd.p, 0));
+    // field energy: the per-row parts the direct Poisson solve left behind, or one single-block reduction
+    const double *nrj_parts = S->nrjd.p;
+    int nn = 1;
+    double nrj_scale = 1.0;
+    if (S->nrj_rows_valid) { nrj_parts = S->nrj_rows.p; nn = p.nc[1]; nrj_scale = S->delta[0] * S->delta[1]; }
+    else SLLB_CUDA(launch_dup_energy2d(S->E1.p, S->E2.p, p.nc[0], p.nc[1], S->delta[0] * S->delta[1], 1, S->nrjd.p, g_stream));
     const double *w3 = S->w2dev[S->layout].p, *w4 = w3 + F->ext[2];
+    const double *m4p = S->m4.p;
+    int nb = 1;
     if (S->line_diag_valid && S->layout == 1) {
         SLLB_TRY(S->dscratch.ensure(moments_from_lines_scratch()));
-        SLLB_CUDA(launch_moments_from_lines(S->linesum.p, S->dl1.p, S->dl2.p, S->dkin.p, (long long)F->ext[0] * F->ext[1],
-                                            F->ext[2], w3, S->dscratch.p, S->m4.p, 0));
+        SLLB_CUDA(launch_moments_from_lines_partials(S->linesum.p, S->dl1.p, S->dl2.p, S->dkin.p, (long long)F->ext[0] * F->ext[1],
+                                                     F->ext[2], w3, S->dscratch.p, &nb, g_stream));
+        m4p = S->dscratch.p;
     } else {
         const long long nx = (long long)F->ext[0] * F->ext[1], nv = (long long)F->ext[2] * F->ext[3];
         SLLB_TRY(F->rows.ensure((size_t)nv * 3));
-        SLLB_CUDA(launch_row_sums(F->d, nx, nv, F->rows.p, 0));
-        SLLB_CUDA(launch_moments_from_rows(F->rows.p, F->ext[2], F->ext[3], w3, w4, S->m4.p, 0));
+        SLLB_CUDA(launch_row_sums(F->d, nx, nv, F->rows.p, g_stream));
+        SLLB_CUDA(launch_moments_from_rows(F->rows.p, F->ext[2], F->ext[3], w3, w4, S->m4.p, g_stream));
     }
     // several ranks: the row holds MY part of the four integrals (time and field energy on rank 0 only); the rows of the
-    // whole run are summed over the ranks by ONE all-reduce after the loop instead of one per step
-    SLLB_CUDA(launch_sim4d_row(S->m4.p, S->nrjd.p, S->istep * p.dt, S->delta[0] * S->delta[1] * S->delta[2] * S->delta[3],
-                               S->D->rank == 0 ? 1 : 0, d_row6, 0));
+    // whole run are summed over the ranks by ONE all-reduce after the loop instead of one per step.
+    // d_row6 == nullptr: the time loop's rows -- slot and time come from the device-side counters (graph replays)
+    SLLB_CUDA(launch_sim4d_row(m4p, nb, nrj_parts, nn, nrj_scale, S->istep * p.dt, p.dt,
+                               S->delta[0] * S->delta[1] * S->delta[2] * S->delta[3], S->D->rank == 0 ? 1 : 0, d_row6,
+                               d_row6 ? nullptr : S->rows_dev.p, d_row6 ? nullptr : S->dstep.p, g_stream));
     return SLLB_OK;
 }
 
@@ -704,11 +746,11 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     // cubic splines: both passes and the charge density in one sweep (K1c); on several GPUs the same kernel also
     // stores into the v-sequential layout of the owning ranks when the next stage is a V stage (`fuse`)
     if (S->m[0] == SLLB_METHOD_SPLINE && S->m[1] == SLLB_METHOD_SPLINE && S->o[0] == 4 && S->o[1] == 4 && g_plane_kernel) {
+        // displacement = -v * step * dt / delta_x with the velocity tables of my x3 / x4 indices (built once)
         DispDesc d0, d1;
-        SLLB_TRY(Fx->disp_scratch2.ensure((size_t)Fx->ext[3]));
-        SLLB_TRY(make_affine_disp(Fx, 0, 2, p.xmin[2] + S->bx[4] * S->delta[2], S->delta[2], -step * p.dt / S->delta[0], &d0));
-        SLLB_CUDA(launch_affine(Fx->disp_scratch2.p, Fx->ext[3], p.xmin[3] + S->bx[6] * S->delta[3], S->delta[3], 0));
-        d1.v = Fx->disp_scratch2.p; d1.scale = -step * p.dt / S->delta[1];
+        d0.v = S->vtab[0].p; d0.scale = -step * p.dt / S->delta[0];
+        d0.odiv = Fx->ext[1]; d0.omod = Fx->ext[2]; d0.ostr = 1; d0.idiv = d0.imod = 1; d0.istr = 0;
+        d1.v = S->vtab[1].p; d1.scale = -step * p.dt / S->delta[1];
         d1.odiv = Fx->ext[2]; d1.omod = Fx->ext[3]; d1.ostr = 1; d1.idiv = d1.imod = 1; d1.istr = 0;
         RemapDst rd;
         if (fuse) dist4d_remap_dst(S->D, 0, 1, &rd);
@@ -718,13 +760,17 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
         const bool xchg = D->nranks > 1 && D->p2p && D->flag_barrier;
         // several ranks: my partial density (the sum over MY planes) goes to slot [rank] of the exchange buffers
         double *rho_dst = xchg ? D->xbuf.p + (long long)D->rank * n12 : S->rho_full.p;
-        int rc = advect_plane_dev(Fx, d0, d1, S->delta[2] * S->delta[3], rho_dst, fuse ? &rd : nullptr);
+        // one GPU with the direct Poisson solve: the per-CTA partial densities stay unsummed, the solve folds them
+        const bool leave_parts = D->nranks == 1 && S->poisson->direct && g_poisson_direct && g_fold_sums;
+        int rc = advect_plane_dev(Fx, d0, d1, S->delta[2] * S->delta[3], rho_dst, fuse ? &rd : nullptr,
+                                  leave_parts ? &S->rho_parts : nullptr, leave_parts ? &S->rho_nparts : nullptr);
+        if (rc == SLLB_OK && leave_parts) { S->rho_state = 4; return SLLB_OK; }
         if (rc == SLLB_OK) {
             if (fuse) S->timer.mark(6);
             if (xchg) {
                 PeerX px;
                 for (int r = 0; r < 8; ++r) px.p[r] = r < D->nranks ? D->peer_x[r] : nullptr;
-                k_bcast_slot<<<(unsigned)((n12 + 255) / 256), 256, 0, 0>>>(rho_dst, n12, px, (long long)D->rank * n12, D->nranks, D->rank);
+                k_bcast_slot<<<(unsigned)((n12 + 255) / 256), 256, 0, g_stream>>>(rho_dst, n12, px, (long long)D->rank * n12, D->nranks, D->rank);
                 count_launch();
                 SLLB_CUDA(cudaGetLastError());
                 // ONE barrier covers both the remap stores of the plane kernel and the density slots
@@ -761,8 +807,8 @@ static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
     if (S->dim_split_V == 2) {
         // alpha = field(:,:,1) step(k+1) + field(:,:,2) step(k+2) (:1137-1141,1153-1157): one combined field, unit step
         const long long n12 = (long long)p.nc[0] * p.nc[1];
-        SLLB_CUDA(launch_lincomb2(S->E1.p, S->K1.p, step, step2, n12, S->C1.p, 0));
-        SLLB_CUDA(launch_lincomb2(S->E2.p, S->K2.p, step, step2, n12, S->C2.p, 0));
+        SLLB_CUDA(launch_lincomb2(S->E1.p, S->K1.p, step, step2, n12, S->C1.p, g_stream));
+        SLLB_CUDA(launch_lincomb2(S->E2.p, S->K2.p, step, step2, n12, S->C2.p, g_stream));
         e1 = S->C1.p; e2 = S->C2.p;
         step = 1.0;
     }
@@ -773,8 +819,8 @@ static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
         Box4 b;
         b.lo[0] = S->bv[0]; b.n[0] = S->bv[1] - S->bv[0] + 1; b.lo[1] = S->bv[2]; b.n[1] = S->bv[3] - S->bv[2] + 1;
         b.lo[2] = b.lo[3] = 0; b.n[2] = b.n[3] = 1;
-        SLLB_CUDA(launch_pack4d(e1, ext, b, S->E1loc.p, 0));
-        SLLB_CUDA(launch_pack4d(e2, ext, b, S->E2loc.p, 0));
+        SLLB_CUDA(launch_pack4d(e1, ext, b, S->E1loc.p, g_stream));
+        SLLB_CUDA(launch_pack4d(e2, ext, b, S->E2loc.p, g_stream));
         e1 = S->E1loc.p; e2 = S->E2loc.p;
     }
     // out(v) = in(v - E*step*dt)  (:1137-1166), displacement computed from E inside the kernel (K5)
@@ -840,6 +886,11 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
     sllb_dist4d_box(S->D, 0, S->bx);
     sllb_dist4d_box(S->D, 1, S->bv);
     rc = sim4d_w2_tables(S);
+    for (int a = 0; a < 2 && !rc; ++a) {
+        const int n = S->D->F[0]->ext[2 + a];
+        rc = S->vtab[a].ensure((size_t)n);
+        if (!rc) rc = check_cuda(launch_affine(S->vtab[a].p, n, p->xmin[2 + a] + S->bx[4 + 2 * a] * S->delta[2 + a], S->delta[2 + a], g_stream), "k_affine");
+    }
     if (rc) { sllb_sim4d_destroy(S); return rc; }
     const size_t n12 = (size_t)p->nc[0] * p->nc[1];
     sllb_field *Fv = S->D->F[1];
@@ -882,6 +933,8 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
 }
 int sllb_sim4d_destroy(sllb_sim4d_t S) {
     if (!S) return SLLB_OK;
+    for (auto &g : S->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (S->gstream) cudaStreamDestroy(S->gstream);
     if (S->s_up) cudaStreamDestroy(S->s_up);
     if (S->s_down) cudaStreamDestroy(S->s_down);
     sllb_poisson_destroy(S->poisson);
@@ -893,6 +946,7 @@ int sllb_sim4d_field(sllb_sim4d_t S, sllb_field_t *F) {
     if (!S || !F) return fail(SLLB_ERR_INVALID, "sim4d_field: null");
     S->rho_state = 0; // the caller may overwrite f through the handle
     S->line_diag_valid = false;
+    S->eager_steps = 0;
     SLLB_TRY(sim4d_to_layout(S, 0));
     *F = S->D->F[0];
     return SLLB_OK;
@@ -948,7 +1002,7 @@ int sllb_sim4d_checksum(sllb_sim4d_t S, double out[2]) {
     const int lo[4] = {b[0], b[2], b[4], b[6]};
     SLLB_TRY(S->dscratch.ensure(moments_from_lines_scratch()));
     SLLB_TRY(S->m4.ensure(4));
-    SLLB_CUDA(launch_checksum4d(F->d, F->ext, lo, S->dscratch.p, S->m4.p, 0));
+    SLLB_CUDA(launch_checksum4d(F->d, F->ext, lo, S->dscratch.p, S->m4.p, g_stream));
     if (S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->m4.p, 2));
     SLLB_CUDA(cudaMemcpy(out, S->m4.p, 2 * sizeof(double), cudaMemcpyDeviceToHost));
     return SLLB_OK;
@@ -1016,50 +1070,102 @@ int sllb_sim4d_thdiag(sllb_sim4d_t S, double *row13) {
     row13[10] = mass0; row13[11] = mass0; row13[12] = l20;
     return SLLB_OK;
 }
-int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows) {
-    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim4d_run: bad arguments");
-    const sllb_sim4d_params_t &p = S->p;
-    // splitting schedule: sll_m_time_splitting_coeff.F90:157-594 (sllb_splitting_coeff), loop :1030-1180
+// one time step: the stages of the splitting scheme + the diagnostics row (all launches go to g_stream)
+static int sim4d_one_step(sllb_sim4d *S, bool with_diagnostics, bool last_step, bool can_fuse) {
     const double *steps = S->steps;
     const int nsub = S->nb_split_step, dimV = S->dim_split_V;
     const bool beginT = S->begin_T;
-    (void)p;
+    int isub = 0; bool T = beginT;
+    for (int ss = 0; ss < nsub; ++ss) {
+        // the stage after this one (possibly the first stage of the next step) is of the other kind
+        // <=> f is needed in the other layout next: fuse the remap into this stage's last pass
+        const bool last_stage = (last_step && ss == nsub - 1);
+        const bool nextT = (ss == nsub - 1) ? beginT : !T;
+        const bool fuse = can_fuse && !last_stage && (nextT != T);
+        S->want_line_diag = with_diagnostics && ss == nsub - 1;
+        if (T) {
+            isub += 1;
+            SLLB_TRY(sim4d_to_layout(S, 0));
+            S->timer.mark(2);
+            SLLB_TRY(sim4d_T(S, steps[isub - 1], fuse));
+            S->timer.mark(0);
+        } else {
+            SLLB_TRY(sim4d_to_layout(S, 1));
+            S->timer.mark(2);
+            SLLB_TRY(sim4d_fields(S));
+            S->timer.mark(1);
+            SLLB_TRY(sim4d_V(S, steps[isub], dimV == 2 ? steps[isub + 1] : 0.0, fuse));
+            S->timer.mark(0);
+            isub += dimV;
+        }
+        T = !T;
+    }
+    S->want_line_diag = false;
+    if (with_diagnostics) {
+        SLLB_TRY(sim4d_diag_device(S, nullptr));
+        S->timer.mark(3);
+    }
+    return SLLB_OK;
+}
+int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *rows) {
+    if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim4d_run: bad arguments");
     S->timer.begin(g_phase_timers != 0);
     S->timer.mark(-1);
     const bool can_fuse = S->D->p2p && g_fused_remap && S->D->nranks > 1;
-    if (with_diagnostics && nsteps > 0) SLLB_TRY(S->rows_dev.ensure((size_t)6 * nsteps));
+    const bool diag = with_diagnostics != 0;
+    if (diag && nsteps > 0) SLLB_TRY(S->rows_dev.ensure((size_t)6 * nsteps));
+    SLLB_TRY(S->dstep.ensure(2));
+    {
+        const double init[2] = {0.0, (double)S->istep};
+        SLLB_CUDA(cudaMemcpy(S->dstep.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
+    // graphs: one GPU, no phase timers (their events would be recorded into the graph)
+    const bool graphs = g_cuda_graphs && S->D->nranks == 1 && !S->timer.on;
+    sllb_sim4d::StepGraph &G = S->graph[diag ? 1 : 0];
+    bool on_gstream = false;   // replays run on their own stream: the default stream must be idle when they start
     for (int it = 0; it < nsteps; ++it) {
-        int isub = 0; bool T = beginT;
-        for (int ss = 0; ss < nsub; ++ss) {
-            // the stage after this one (possibly the first stage of the next step) is of the other kind
-            // <=> f is needed in the other layout next: fuse the remap into this stage's last pass
-            const bool last_stage = (it == nsteps - 1 && ss == nsub - 1);
-            const bool nextT = (ss == nsub - 1) ? beginT : !T;
-            const bool fuse = can_fuse && !last_stage && (nextT != T);
-            S->want_line_diag = with_diagnostics && ss == nsub - 1;
-            if (T) {
-                isub += 1;
-                SLLB_TRY(sim4d_to_layout(S, 0));
-                S->timer.mark(2);
-                SLLB_TRY(sim4d_T(S, steps[isub - 1], fuse));
-                S->timer.mark(0);
-            } else {
-                SLLB_TRY(sim4d_to_layout(S, 1));
-                S->timer.mark(2);
-                SLLB_TRY(sim4d_fields(S));
-                S->timer.mark(1);
-                SLLB_TRY(sim4d_V(S, steps[isub], dimV == 2 ? steps[isub + 1] : 0.0, fuse));
-                S->timer.mark(0);
-                isub += dimV;
+        const bool matches = G.exec && G.entry_rho_state == S->rho_state && G.entry_layout == S->layout &&
+                             G.entry_line_diag == S->line_diag_valid;
+        if (graphs && !matches && S->eager_steps >= 2 && !G.exec) {
+            // every buffer the steady-state step needs exists after two plain steps (no allocation may happen while
+            // recording): record the next one (it is executed by the launch below, not while recording)
+            if (!S->gstream) SLLB_CUDA(cudaStreamCreateWithFlags(&S->gstream, cudaStreamNonBlocking));
+            SLLB_CUDA(cudaDeviceSynchronize());
+            cudaGraph_t graph = nullptr;
+            const long long l0 = launch_count();
+            G.entry_rho_state = S->rho_state; G.entry_layout = S->layout; G.entry_line_diag = S->line_diag_valid;
+            const int keep_rho = S->rho_state, keep_layout = S->layout; const bool keep_ld = S->line_diag_valid, keep_el = S->eloc_valid;
+            g_stream = S->gstream;
+            cudaError_t ce = cudaStreamBeginCapture(S->gstream, cudaStreamCaptureModeThreadLocal);
+            int rc = ce == cudaSuccess ? sim4d_one_step(S, diag, false, can_fuse) : SLLB_ERR_CUDA;
+            cudaError_t ee = cudaStreamEndCapture(S->gstream, &graph);
+            g_stream = 0;
+            G.launches = launch_count() - l0;
+            count_launches(-G.launches); // recorded, not executed
+            G.exit_rho_state = S->rho_state; G.exit_layout = S->layout; G.exit_line_diag = S->line_diag_valid; G.exit_eloc = S->eloc_valid;
+            S->rho_state = keep_rho; S->layout = keep_layout; S->line_diag_valid = keep_ld; S->eloc_valid = keep_el;
+            if (rc == SLLB_OK && ee == cudaSuccess && graph) ee = cudaGraphInstantiate(&G.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != SLLB_OK || ce != cudaSuccess || ee != cudaSuccess) { // fall back to plain launches, loudly recorded
+                cudaGetLastError();
+                G.exec = nullptr;
+                g_cuda_graphs = 0;
+                set_error("sim4d_run: CUDA graph capture failed, continuing with stream launches");
             }
-            T = !T;
+        }
+        const bool replay = graphs && G.exec && G.entry_rho_state == S->rho_state && G.entry_layout == S->layout &&
+                            G.entry_line_diag == S->line_diag_valid;
+        if (replay) {
+            if (!on_gstream) { SLLB_CUDA(cudaDeviceSynchronize()); on_gstream = true; }
+            SLLB_CUDA(cudaGraphLaunch(G.exec, S->gstream));
+            count_launches(G.launches);
+            S->rho_state = G.exit_rho_state; S->layout = G.exit_layout; S->line_diag_valid = G.exit_line_diag; S->eloc_valid = G.exit_eloc;
+        } else {
+            if (on_gstream) { SLLB_CUDA(cudaStreamSynchronize(S->gstream)); on_gstream = false; }
+            SLLB_TRY(sim4d_one_step(S, diag, it == nsteps - 1, can_fuse));
+            S->eager_steps += 1;
         }
         S->istep += 1;
-        S->want_line_diag = false;
-        if (with_diagnostics) {
-            SLLB_TRY(sim4d_diag_device(S, S->rows_dev.p + 6 * it));
-            S->timer.mark(3);
-        }
     }
     SLLB_CUDA(cudaDeviceSynchronize());
     if (S->D->nranks > 1 && S->D->flag_barrier) {
@@ -1067,8 +1173,8 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
         SLLB_CUDA(cudaMemcpy(&err, S->D->errflag.p, sizeof(double), cudaMemcpyDeviceToHost));
         if (err != 0.0) return fail(SLLB_ERR_CUDA, "sim4d_run: a rank did not reach the flag barrier within the time-out");
     }
-    if (with_diagnostics && nsteps > 0 && S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rows_dev.p, (int64_t)6 * nsteps));
-    if (with_diagnostics && nsteps > 0) {
+    if (diag && nsteps > 0 && S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rows_dev.p, (int64_t)6 * nsteps));
+    if (diag && nsteps > 0) {
         std::vector<double> h((size_t)6 * nsteps);
         SLLB_CUDA(cudaMemcpy(h.data(), S->rows_dev.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
         S->nrj = h[6 * (size_t)(nsteps - 1) + 1];
@@ -1109,6 +1215,11 @@ int sllb_sim4d_phase_ms(sllb_sim4d_t S, double out[4]) {
 struct sllb_sim2d {
     int nc[2]; double xmin[2], xmax[2], delta[2];
     int init; double kmode, eps, dt; int method, order;
+    int m[2], o[2];                       // advector_x1 / advector_x2 of the namelist (method, order per axis)
+    double steps[SLLB_SPLIT_MAX_STEPS];   // split_step of sll_t_splitting_coeff (dim_split_V = 1 cases)
+    int nsub = 3; bool beginT = false;
+    double time_init = 0.0;
+    DevBuf modes_part, modes_out;
     sllb_field *F = nullptr;
     sllb_poisson *poisson = nullptr;
     DevBuf rho, E;
@@ -1119,7 +1230,6 @@ struct sllb_sim2d {
     cudaGraphExec_t gexec = nullptr;
     long long glaunches = 0;   // kernels in the recorded step (launch bookkeeping of the replays)
 };
-static int g_cuda_graphs = 1;
 __global__ void k_init2d(double *f, int n0, int n1, double x0min, double x1min, double d0, double d1, int init,
                          double kmode, double eps) {
     const long long ntot = (long long)n0 * n1;
@@ -1127,8 +1237,11 @@ __global__ void k_init2d(double *f, int n0, int n1, double x0min, double x1min, 
         const int i = (int)(t % n0), j = (int)(t / n0);
         const double x = x0min + i * d0, v = x1min + j * d1;
         const double fac = 1.0 / sqrt(2.0 * 3.14159265358979323846);
-        f[t] = init == 0 ? fac * (1.0 + eps * cos(kmode * x)) * exp(-0.5 * v * v)
-                         : fac * (1.0 + eps * cos(kmode * x)) * v * v * exp(-0.5 * v * v);
+        // sll_f_landau_initializer_2d, sll_f_two_stream_instability_initializer_2d, sll_f_bump_on_tail_initializer_2d
+        // (sll_m_common_array_initializers.F90:507-595)
+        if (init == 0) f[t] = fac * (1.0 + eps * cos(kmode * x)) * exp(-0.5 * v * v);
+        else if (init == 1) f[t] = fac * (1.0 + eps * cos(kmode * x)) * v * v * exp(-0.5 * v * v);
+        else f[t] = fac * (1.0 + eps * cos(kmode * x)) * (0.9 * exp(-0.5 * v * v) + 0.2 * exp(-0.5 * ((v - 4.5) * (v - 4.5)) / (0.5 * 0.5)));
     }
 }
 static int sim2d_field(sllb_sim2d *S) {
@@ -1147,6 +1260,9 @@ int sllb_sim2d_create(int nc_x1, int nc_x2, double x1_min, double x1_max, double
     S->nc[0] = nc_x1; S->nc[1] = nc_x2; S->xmin[0] = x1_min; S->xmax[0] = x1_max; S->xmin[1] = x2_min; S->xmax[1] = x2_max;
     S->delta[0] = (x1_max - x1_min) / nc_x1; S->delta[1] = (x2_max - x2_min) / nc_x2;
     S->init = init; S->kmode = kmode; S->eps = eps; S->dt = dt; S->method = method; S->order = order;
+    if (init < 0 || init > 2) { delete S; return fail(SLLB_ERR_UNSUPPORTED, "sim2d_create: initial function 0 Landau, 1 two-stream, 2 bump-on-tail"); }
+    S->m[0] = S->m[1] = method; S->o[0] = S->o[1] = order;
+    S->steps[0] = 0.5; S->steps[1] = 1.0; S->steps[2] = 0.5;   // SLL_STRANG_VTV
     int rc = field_alloc(2, S->nc, &S->F);
     if (!rc) rc = sllb_poisson1d_create(nc_x1, x1_min, x1_max, &S->poisson);
     if (!rc) rc = S->rho.ensure(nc_x1);
@@ -1176,7 +1292,7 @@ int sllb_sim2d_field(sllb_sim2d_t S, sllb_field_t *F) {
 }
 int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
     if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim2d_run: bad arguments");
-    const double steps[3] = {0.5, 1.0, 0.5};
+    const double *steps = S->steps;
     // velocity weights for the moments: trapezoid over duplicated end points (see sim4d diagnostics)
     std::vector<double> w1(S->nc[1]), w2(S->nc[1]);
     for (int j = 0; j < S->nc[1]; ++j) {
@@ -1188,14 +1304,14 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
     std::vector<double> hE(S->nc[0]);
     if (S->gexec) SLLB_CUDA(cudaDeviceSynchronize()); // the replays run on their own stream: nothing of the caller's may be in flight
     auto one_step = [&]() -> int {
-        bool T = false;
-        for (int ss = 0; ss < 3; ++ss) {
+        bool T = S->beginT;
+        for (int ss = 0; ss < S->nsub; ++ss) {
             if (T) { // out(x) = in(x - v*step*dt)  (:1570-1585)
-                SLLB_TRY(sllb_advect_axis_affine(S->F, 0, S->method, S->order, 1, S->xmin[1], S->delta[1],
+                SLLB_TRY(sllb_advect_axis_affine(S->F, 0, S->m[0], S->o[0], 1, S->xmin[1], S->delta[1],
                                                  -steps[ss] * S->dt / S->delta[0]));
                 SLLB_TRY(sim2d_field(S));
             } else { // alpha = -E*step, out(v) = in(v + E*step*dt)  (:1656-1686)
-                SLLB_TRY(sllb_advect_axis_field(S->F, 1, S->method, S->order, S->E.p, 1, steps[ss] * S->dt / S->delta[1]));
+                SLLB_TRY(sllb_advect_axis_field(S->F, 1, S->m[1], S->o[1], S->E.p, 1, steps[ss] * S->dt / S->delta[1]));
             }
             T = !T;
         }
@@ -1242,11 +1358,121 @@ int sllb_sim2d_run(sllb_sim2d_t S, int nsteps, double *rows) {
             epot = 0.5 * epot * S->delta[0];
             const double dv = S->delta[1], dx = S->delta[0];
             double *r = rows + 8 * it;
-            r[0] = S->istep * S->dt; r[1] = m[0] * dv * dx; r[2] = m[1] * dv * dx; r[3] = m[3] * dv * dx;
+            r[0] = S->time_init + S->istep * S->dt; r[1] = m[0] * dv * dx; r[2] = m[1] * dv * dx; r[3] = m[3] * dv * dx;
             r[4] = m[2] * dv * dx; r[5] = 0.5 * m[4] * dv * dx; r[6] = epot; r[7] = r[5] + r[6];
         }
     }
     SLLB_CUDA(cudaDeviceSynchronize());
+    return SLLB_OK;
+}
+static void sim2d_drop_graph(sllb_sim2d *S) {
+    if (S->gexec) { cudaDeviceSynchronize(); cudaGraphExecDestroy(S->gexec); S->gexec = nullptr; }
+}
+/* split_case of the namelist (sll_m_sim_bsl_vp_1d1v_cart.F90:816-846): the 1D1V loop walks split_step(1..nb_split_step)
+ * alternating T and V (:1462-1696), so the schemes whose V stage takes two coefficients (the *VP* cases) do not apply */
+int sllb_sim2d_set_splitting(sllb_sim2d_t S, int split_case) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim2d_set_splitting: null");
+    double st[SLLB_SPLIT_MAX_STEPS];
+    int nsub = 0, bt = 0, dimv = 1;
+    SLLB_TRY(sllb_splitting_coeff(split_case, S->dt, st, nullptr, &nsub, &bt, &dimv));
+    if (dimv != 1) return fail(SLLB_ERR_UNSUPPORTED, "sim2d_set_splitting: splitting schemes with dim_split_V = 2 belong to the 2D2V simulation");
+    sim2d_drop_graph(S);
+    memcpy(S->steps, st, sizeof(st));
+    S->nsub = nsub; S->beginT = bt != 0;
+    return SLLB_OK;
+}
+int sllb_sim2d_set_advectors(sllb_sim2d_t S, int method_x1, int order_x1, int method_x2, int order_x2) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim2d_set_advectors: null");
+    sim2d_drop_graph(S);
+    S->m[0] = method_x1; S->o[0] = order_x1; S->m[1] = method_x2; S->o[1] = order_x2;
+    return SLLB_OK;
+}
+/* lim = {x1_min, x1_max, x2_min, x2_max} */
+int sllb_sim2d_geometry(sllb_sim2d_t S, double lim[4]) {
+    if (!S || !lim) return fail(SLLB_ERR_INVALID, "sim2d_geometry: null");
+    lim[0] = S->xmin[0]; lim[1] = S->xmax[0]; lim[2] = S->xmin[1]; lim[3] = S->xmax[1];
+    return SLLB_OK;
+}
+int sllb_sim2d_set_time(sllb_sim2d_t S, double time_init) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim2d_set_time: null");
+    S->time_init = time_init - S->istep * S->dt;
+    return SLLB_OK;
+}
+/* rho and E of the current state (N1 periodic cells each; NULL = skip) */
+int sllb_sim2d_fields_host(sllb_sim2d_t S, double *rho, double *efield) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim2d_fields_host: null");
+    SLLB_CUDA(cudaDeviceSynchronize());
+    if (rho) SLLB_CUDA(cudaMemcpy(rho, S->rho.p, (size_t)S->nc[0] * sizeof(double), cudaMemcpyDeviceToHost));
+    if (efield) SLLB_CUDA(cudaMemcpy(efield, S->E.p, (size_t)S->nc[0] * sizeof(double), cudaMemcpyDeviceToHost));
+    return SLLB_OK;
+}
+/* One row of the reference's thdiag.dat (:1703-1801): time, mass, l1norm, momentum, l2norm, kinetic_energy,
+ * potential_energy, their sum, then Re/Im of rho^_k for k = 0..nb_mode and f_hat_x2(k) = sum_v w_v |f^_k(v)|^2 for
+ * k = 0..nb_mode, with the normalised transform (1/N) sum_j u_j e^{-2 pi i j k / N}: 8 + 3 (nb_mode + 1) numbers. */
+int sllb_sim2d_thdiag(sllb_sim2d_t S, int nb_mode, double *row) {
+    if (!S || !row || nb_mode < 0) return fail(SLLB_ERR_INVALID, "sim2d_thdiag: bad arguments (nb_mode >= 0, :811-814)");
+    const int N1 = S->nc[0], N2 = S->nc[1], nm = nb_mode + 1;
+    SLLB_CUDA(cudaDeviceSynchronize());
+    std::vector<double> w1(N2), w2(N2);
+    for (int j = 0; j < N2; ++j) { const double v = S->xmin[1] + j * S->delta[1]; w1[j] = v; w2[j] = v * v; }
+    w1[0] = 0.5 * (S->xmin[1] + S->xmax[1]);
+    w2[0] = 0.5 * (S->xmin[1] * S->xmin[1] + S->xmax[1] * S->xmax[1]);
+    double m[5];
+    SLLB_TRY(moments_local(S->F, 1, w1.data(), w2.data(), m));
+    std::vector<double> hE(N1), hr(N1);
+    SLLB_TRY(sllb_sim2d_fields_host(S, hr.data(), hE.data()));
+    double epot = 0;
+    for (int i = 0; i < N1; ++i) epot += hE[i] * hE[i];
+    epot = 0.5 * epot * S->delta[0];
+    const double dv = S->delta[1], dx = S->delta[0];
+    row[0] = S->time_init + S->istep * S->dt; row[1] = m[0] * dv * dx; row[2] = m[1] * dv * dx; row[3] = m[3] * dv * dx;
+    row[4] = m[2] * dv * dx; row[5] = 0.5 * m[4] * dv * dx; row[6] = epot; row[7] = row[5] + row[6];
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < nm; ++k) {
+        double re = 0, im = 0;
+        for (int j = 0; j < N1; ++j) {
+            const double a = 2.0 * pi * (double)(((long long)j * k) % N1) / (double)N1;
+            re += hr[j] * cos(a); im -= hr[j] * sin(a);
+        }
+        // sll_f_fft_get_mode_r2c_1d: purely real at k = 0 and k = N/2 (interfaces/fft/sll_m_fft_fftw3.F90:320-323)
+        if (k % N1 == 0 || 2 * (k % N1) == N1) im = 0.0;
+        row[8 + 2 * k] = re / N1; row[9 + 2 * k] = im / N1;
+    }
+    SLLB_TRY(S->modes_part.ensure((size_t)N2 * nm));
+    SLLB_TRY(S->modes_out.ensure((size_t)nm));
+    SLLB_CUDA(launch_row_modes(S->F->d, N1, N2, nm, dv, S->modes_part.p, S->modes_out.p, g_stream));
+    SLLB_CUDA(cudaMemcpy(row + 8 + 2 * nm, S->modes_out.p, (size_t)nm * sizeof(double), cudaMemcpyDeviceToHost));
+    return SLLB_OK;
+}
+/* <restart_file>_proc_0000.rst of the reference (:1281-1307 read, :1762-1770 write): a raw stream of the time followed by
+ * f_x1 with the duplicated end points, (N1+1) x (N2+1) doubles, column-major */
+int sllb_sim2d_write_restart(sllb_sim2d_t S, const char *path) {
+    if (!S || !path) return fail(SLLB_ERR_INVALID, "sim2d_write_restart: null");
+    const int N1 = S->nc[0], N2 = S->nc[1];
+    std::vector<double> f((size_t)(N1 + 1) * (N2 + 1));
+    const int dup[2] = {1, 1};
+    SLLB_TRY(sllb_field_download(S->F, f.data(), dup));
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(SLLB_ERR_INVALID, std::string("sim2d_write_restart: cannot create ") + path);
+    const double t = S->time_init + S->istep * S->dt;
+    const bool ok = fwrite(&t, sizeof(double), 1, fp) == 1 && fwrite(f.data(), sizeof(double), f.size(), fp) == f.size();
+    fclose(fp);
+    return ok ? SLLB_OK : fail(SLLB_ERR_INVALID, "sim2d_write_restart: short write");
+}
+int sllb_sim2d_read_restart(sllb_sim2d_t S, const char *path, double *time) {
+    if (!S || !path) return fail(SLLB_ERR_INVALID, "sim2d_read_restart: null");
+    const int N1 = S->nc[0], N2 = S->nc[1];
+    std::vector<double> f((size_t)(N1 + 1) * (N2 + 1));
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(SLLB_ERR_INVALID, std::string("#file ") + path + " does not exist");
+    double t = 0.0;
+    const bool ok = fread(&t, sizeof(double), 1, fp) == 1 && fread(f.data(), sizeof(double), f.size(), fp) == f.size();
+    fclose(fp);
+    if (!ok) return fail(SLLB_ERR_INVALID, std::string("sim2d_read_restart: ") + path + " is shorter than 1 + (N1+1)(N2+1) doubles");
+    const int dup[2] = {1, 1};
+    SLLB_TRY(sllb_field_upload(S->F, f.data(), dup));
+    if (time) *time = t;
+    SLLB_TRY(sim2d_field(S));   // E of the restored state
     return SLLB_OK;
 }
 /* 1 (default): sllb_sim2d_run replays one recorded time step as a CUDA graph; 0: one launch per kernel */

@@ -193,6 +193,18 @@ def test_fortran_g20_12_formatter():
         assert len(sb.format_g20_12(x)) == 20
 
 
+def test_fortran_g25_15_formatter():
+    """the '(8g25.15)' / '(1g25.15)' cells of the 1D1V thdiag.dat (sll_m_sim_bsl_vp_1d1v_cart.F90:1778-1801)"""
+    assert sb.format_g(0.1, 25, 15) == "    0.100000000000000    "
+    assert sb.format_g(12.5663706012, 25, 15) == "     12.5663706012000    "
+    assert sb.format_g(-57.4593058704, 25, 15) == "    -57.4593058704000    "
+    assert sb.format_g(0.124099195637E-04, 25, 15) == "    0.124099195637000E-04"
+    assert sb.format_g(0.0, 25, 15) == "     0.00000000000000    "
+    for x in (1.0, 136.685004002, -3.3e-9, 7.25e17, 0.999999999999999999):
+        c = sb.format_g(x, 25, 15)
+        assert len(c) == 25 and abs(float(c) / x - 1) < 1e-14
+
+
 def test_namelist_front_end_host_logic(tmp_path):
     """sllb_sim4d_create_from_namelist: parsing, defaults and the reference's error messages happen on the host, before a
     device is needed (sll_m_sim_bsl_vp_2d2v_cart_poisson_serial.F90:300-624)"""

@@ -258,3 +258,16 @@ def test_periodic_interp_order_of_accuracy():
     f = np.asfortranarray(u.reshape(1, N, 1).copy())
     b = orc.advect_axis(f, 1, "spline", 4, np.array([-0.3]), (1, 1, 0, 1, 1, 0))[0, :, 0]
     assert np.abs(a - b).max() < 1e-13
+
+
+def test_poisson_2d_periodic_par_known_answer():
+    """sll_s_poisson_2d_periodic_par_solve (Delta phi = rho): the reference's own test (test_poisson_2d_periodic_par.F90:
+    phi = cos x sin y, rho = -2 phi on [0, 2 pi]^2, average error <= 1e-6; 512^2 there, 64^2 here: spectral, same error)."""
+    n = 64
+    L = 2 * np.pi
+    x = np.arange(n + 1) * L / n
+    phi_an = np.asfortranarray(np.cos(x)[:, None] * np.sin(x)[None, :])
+    phi = orc.poisson_2d_par(-2.0 * phi_an, n, n, L, L)
+    assert np.abs(phi - phi_an)[:-1, :-1].sum() / (n * n) < 1e-6
+    assert np.abs(phi - phi_an).max() < 1e-14
+    assert np.array_equal(phi[-1, :], phi[0, :]) and np.array_equal(phi[:, -1], phi[:, 0])
