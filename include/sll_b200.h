@@ -428,6 +428,10 @@ int sllb_sim4d_fields_host(sllb_sim4d_t S, double *rho, double *e1, double *e2);
 /* (sum w f, sum w f^2) over the GLOBAL field with a weight that depends on the global index of every point: equal (to
  * rounding) on any number of ranks, sensitive to misplaced elements (cross-rank exactness signal of bench.py) */
 int sllb_sim4d_checksum(sllb_sim4d_t S, double out[2]);
+/* several GPUs: 1 = the V stage that ends with a remap is cut into chunks of the local (x1,x2) tile, the HBM-bound x3 pass
+ * of chunk c+1 running under the NVLink-bound x4 + remap pass of chunk c (two streams); 0 (default) = two whole passes:
+ * measured slower on 2 GPUs (2.80-2.89 vs 2.76 ms per 128^4 step), kept as an opt-in.  Bit-identical values.  on = 2..8 also sets the number of chunks (default 4). */
+int sllb_set_v_overlap(int on);
 /* phase timing is opt-in: 1 = sllb_sim4d_run records one CUDA event per phase (pooled, reused), 0 (default) = none */
 int sllb_set_phase_timers(int on);
 

@@ -124,6 +124,10 @@ def set_remap_rotation(on):
     _ck(lib().sllb_set_remap_rotation(C.c_int(1 if on else 0)))
 
 
+def set_v_overlap(on):
+    _ck(lib().sllb_set_v_overlap(C.c_int(int(on))))
+
+
 def set_poisson_direct(on):
     """2D Poisson on small grids: 1 = three dense-DFT kernels (default), 0 = cuFFT"""
     _ck(lib().sllb_set_poisson_direct(C.c_int(1 if on else 0)))

@@ -174,12 +174,12 @@ int field_wrap(int ndim, const int *ext, double *d, sllb_field **F) {
 }
 
 int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap,
-                    double *linesum, const LineDiag *diag) {
+                    double *linesum, const LineDiag *diag, const LineSub *sub) {
     if (!F || axis < 0 || axis >= F->ndim) return fail(SLLB_ERR_INVALID, "advect_axis: bad field/axis");
     long long inner = 1, outer = 1;
     for (int d = 0; d < axis; ++d) inner *= F->ext[d];
     for (int d = axis + 1; d < F->ndim; ++d) outer *= F->ext[d];
-    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, g_stream, remap, linesum, diag);
+    cudaError_t e = launch_advect(F->d, outer, F->ext[axis], inner, method, order, dd, g_staging, g_stream, remap, linesum, diag, sub);
     if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "advect_axis: line sums are produced by the chunked strided spline kernel only"); }
     if (e == cudaErrorInvalidValue) {
         cudaGetLastError();

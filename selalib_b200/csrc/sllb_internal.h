@@ -109,7 +109,7 @@ int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<
                      std::vector<void *> &opened, bool *ok);
 // internal (device-pointer) entry points used by the simulations
 int advect_axis_dev(sllb_field *F, int axis, int method, int order, const DispDesc &dd, const RemapDst *remap = nullptr,
-                    double *linesum = nullptr, const LineDiag *diag = nullptr);
+                    double *linesum = nullptr, const LineDiag *diag = nullptr, const LineSub *sub = nullptr);
 // partials_out != NULL: the per-CTA partial densities are left unsummed ([nparts][n1*n2], unscaled) for the caller
 int advect_plane_dev(sllb_field *F, const DispDesc &dd0, const DispDesc &dd1, double rho_scale, double *d_rho,
                      const RemapDst *remap = nullptr, const double **partials_out = nullptr, int *nparts_out = nullptr);

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
                                                                   const int use_tma, const long long nlines,
                                                                   double *__restrict__ linesum,
                                                                   const __grid_constant__ RemapDst rd,
-                                                                  const LineDiag dg) {
+                                                                  const LineDiag dg, const LineSub sub) {
     constexpr int BW = 32;
     constexpr int NPART = DIAG ? 4 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -405,9 +405,14 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     const int tid = threadIdx.x, lane = tid & 31, chunk = tid >> 5;
     unsigned bid = blockIdx.x;
     if constexpr (REMAP) { bid += (unsigned)rd.block_rot; if (bid >= gridDim.x) bid -= gridDim.x; }
-    const long long l = (long long)bid * BW + lane;
+    long long l = (long long)bid * BW + lane;
     const bool active = l < nlines;
-    const long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    long long o = active ? l / inner : 0, in = active ? l - o * inner : 0;
+    if (sub.icount > 0 && active) {   // the l-th line of a subset (see LineSub); l becomes the line's number in the whole pass
+        const long long q = l / sub.icount, r = l - q * sub.icount;
+        o = (long long)sub.o_mul * q; in = sub.i0 + r + sub.in_pitch * q;
+        l = o * inner + in;
+    }
     double *base = f + o * (long long)N * inner + in;
     const int C = N / P, k0 = chunk * C, k1 = k0 + C;
 
@@ -1206,7 +1211,13 @@ static int remap_block_rotation(const RemapDst &rd, long long nblk) {
 template <int P>
 static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
                                          int staging, cudaStream_t st, const RemapDst &rd, double *linesum,
-                                         const LineDiag *diag) {
+                                         const LineDiag *diag, const LineSub *subp) {
+    LineSub sub = {0, 0, 0, 0, 0};
+    if (subp && subp->icount > 0) {
+        if (subp->icount % 32 != 0 || subp->i0 % 32 != 0 || subp->nlines % 32 != 0) return cudaErrorInvalidValue;
+        sub = *subp;
+        nlines = sub.nlines;
+    }
     const bool with_diag = diag != nullptr && linesum != nullptr && !rd.on && P >= 4;
     if (diag != nullptr && !with_diag) return cudaErrorNotSupported;
     LineDiag dg = {nullptr, nullptr, nullptr, nullptr};
@@ -1222,19 +1233,19 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
         if (e != cudaSuccess) return e;
         RemapDst rr = rd;
         rr.block_rot = remap_block_rotation(rd, nblk);
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg);
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);
     } else if (with_diag) {
         if constexpr (P >= 4) {
             auto kern = k_spline_strided_split<P, false, true>;
             e = set_smem(kern, smem);
             if (e != cudaSuccess) return e;
-            kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg);
+            kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
         }
     } else {
         auto kern = k_spline_strided_split<P, false>;
         e = set_smem(kern, smem);
         if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg);
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
     }
     COUNT_LAUNCH();
     return cudaGetLastError();
@@ -1414,7 +1425,7 @@ cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts,
 
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
                           const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap, double *linesum,
-                          const LineDiag *diag) {
+                          const LineDiag *diag, const LineSub *sub) {
     if (n < 8 || outer < 1 || inner < 1) return cudaErrorInvalidValue;
     RemapDst rd;
     if (remap && remap->on) {
@@ -1428,6 +1439,10 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
     if (e != cudaSuccess) return e;
     const long long nlines = outer * inner;
     if (nlines > 0x7fffffffLL * 8) return cudaErrorInvalidValue;
+    // line subsets: chunked strided spline kernel only
+    if (sub && sub->icount > 0 && !(method == METHOD_SPLINE && order == 4 && inner > 1 && (size_t)n * 32 * 8 + 128 + 8 * 32 * 8 <= SMEM_MAX &&
+                                    ((n % 4 == 0 && n / 4 >= 8) || (n % 2 == 0 && n / 2 >= 8))))
+        return cudaErrorNotSupported;
     if (method == METHOD_SPLINE && (order == 6 || order == 8)) {
         // quintic / septic periodic splines (sll_p_spline of order 6 / 8): thread per line on the strided tiles, for the
         // contiguous axis too (there the rows of the tile are gathered element by element)
@@ -1458,11 +1473,11 @@ cudaError_t launch_advect(double *f, long long outer, int n, long long inner, in
         if ((size_t)n * 32 * 8 + 128 + 8 * 32 * 8 <= SMEM_MAX) {
             int P = g_spline_split;
             if (P < 0) P = (n % 4 == 0 && n / 4 >= 32) ? 4 : ((n % 2 == 0 && n / 2 >= 32) ? 2 : 1);
-            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag);
-            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag);
-            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag);
+            if (P == 4 && n % 4 == 0 && n / 4 >= 8) return launch_spline_split_t<4>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag, sub);
+            if (P == 2 && n % 2 == 0 && n / 2 >= 8) return launch_spline_split_t<2>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag, sub);
+            if (P == 8 && n % 8 == 0 && n / 8 >= 8) return launch_spline_split_t<8>(f, nlines, n, inner, dd, staging, st, rd, linesum, diag, sub);
         }
-        if (linesum || diag) return cudaErrorNotSupported; // line sums come from the chunked kernel only
+        if (linesum || diag || (sub && sub->icount > 0)) return cudaErrorNotSupported; // line sums / subsets: chunked kernel only
         return launch_strided<0, 0>(f, nlines, n, inner, dd, staging, st, rd);
     }
     if (linesum || diag) return cudaErrorNotSupported;

@@ -32,9 +32,13 @@ struct RemapDst {
 // Per-line moments of the advected line next to its sum (time-loop diagnostics fused into the last pass of a step):
 // l1[line] = sum |out|, l2[line] = sum out^2, kin[line] = sum_i w2[i] out(i) with w2 indexed by the OUTPUT point.
 struct LineDiag { double *l1, *l2, *kin; const double *w2; };
+// A subset of the lines of a pass (chunked V stage: the x3 pass of one chunk of (x1,x2) overlaps the x4 + remap pass of
+// the previous one).  The n-th line of the subset is (o, in) = (o_mul * q, i0 + r + in_pitch * q), q = n / icount,
+// r = n % icount; icount = 0: all lines.  i0 and icount multiples of 32 keep the 256-byte TMA rows.
+struct LineSub { long long icount, i0, in_pitch, nlines; int o_mul; };
 cudaError_t launch_advect(double *f, long long outer, int n, long long inner, int method, int order,
                           const DispDesc &dd, int staging, cudaStream_t st, const RemapDst *remap = nullptr,
-                          double *linesum = nullptr, const LineDiag *diag = nullptr);
+                          double *linesum = nullptr, const LineDiag *diag = nullptr, const LineSub *sub = nullptr);
 // linesum (strided spline passes only, else cudaErrorNotSupported): linesum[line] = sum of the advected line;
 // diag needs linesum
 

@@ -204,6 +204,9 @@ struct sllb_dist4d {
     unsigned long long epoch = 0;
     bool flag_barrier = false;
     long long n12 = 0;
+    // chunked V stage: x3 pass of chunk c+1 (s_local, high priority) under the x4 + remap pass of chunk c (s_remap)
+    cudaStream_t s_local = nullptr, s_remap = nullptr;
+    cudaEvent_t ev_chunk[8] = {};
 };
 
 int g_fused_remap = 1; // 1: advect + remap in one kernel over peer memory when possible, 0: pack + NCCL + unpack
@@ -401,6 +404,10 @@ int sllb_dist4d_advect_remap(sllb_dist4d_t D, int from, int axis, int method, in
 }
 int sllb_dist4d_destroy(sllb_dist4d_t D) {
     if (!D) return SLLB_OK;
+    if (D->s_local) {
+        cudaStreamDestroy(D->s_local); cudaStreamDestroy(D->s_remap);
+        for (cudaEvent_t e : D->ev_chunk) if (e) cudaEventDestroy(e);
+    }
     for (void *ptr : D->ipc_opened) cudaIpcCloseMemHandle(ptr);
     sllb_field_destroy(D->F[1]);
     sllb_field_destroy(D->F[0]);
@@ -585,6 +592,14 @@ static int sim4d_fields(sllb_sim4d *S) {
         SLLB_CUDA(launch_reduce_velocity_partials(src, tile, nv, Fv->red_scratch.p, &nslots, g_stream));
         rho_in = Fv->red_scratch.p; in_scale = scale;
     } else {
+        double *rho_local = (P == 1) ? S->rho_full.p : S->rho_tile.p;
+        if (S->rho_state == 2) {
+            // sum over x4 came out of the last x4 pass; finish the sum over x3 (K3 on a [x1 x2][x3] array)
+            SLLB_TRY(Fv->red_scratch.ensure(reduce_scratch_doubles(tile, Fv->ext[2])));
+            SLLB_CUDA(launch_reduce_velocity(S->linesum.p, tile, Fv->ext[2], scale, rho_local, Fv->red_scratch.p, g_stream));
+        } else {
+            SLLB_TRY(sllb_reduce_velocity(Fv, 2, scale, rho_local));
+        }
         if (P > 1 && xchg) {
             // my tile goes straight into slot 8 of every rank's exchange buffer; the flag barrier completes the gather
             PeerX px;
@@ -799,6 +814,60 @@ static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
     }
     return SLLB_OK;
 }
+// Chunked V stage on several GPUs.  The x4 + remap pass is bound by NVLink (its stores go to the peers), the x3 pass by
+// HBM: the (x1,x2) tile of this rank is cut into chunks, the x3 pass of chunk c+1 runs on a high-priority stream while the
+// x4 + remap pass of chunk c runs on a second one.  The two streams are ordinary (blocking) streams: what was launched
+// before on the default stream (the field solve) precedes them, the flag barrier launched after them waits for both.
+// Same kernels, same arithmetic per line: values are bit-identical to the two whole passes.
+// SLLB_ERR_UNSUPPORTED (nothing launched) when the shape does not fit; the caller then runs the whole passes.
+static int g_v_chunks = [] { const char *e = getenv("SLLB_V_CHUNKS"); const int v = e ? atoi(e) : 4; return v >= 2 && v <= 8 ? v : 4; }();
+static int g_v_overlap = [] { const char *e = getenv("SLLB_V_OVERLAP"); return (e && e[0] == '1') ? 1 : 0; }();
+static int sim4d_V_chunked(sllb_sim4d *S, const double *e1, const double *e2, double step) {
+    sllb_dist4d *D = S->D;
+    sllb_field *Fv = D->F[1];
+    const sllb_sim4d_params_t &p = S->p;
+    if (!(S->m[2] == SLLB_METHOD_SPLINE && S->o[2] == 4 && S->m[3] == SLLB_METHOD_SPLINE && S->o[3] == 4)) return SLLB_ERR_UNSUPPORTED;
+    if (S->timer.on) return SLLB_ERR_UNSUPPORTED;   // the phase timers time whole passes on the default stream
+    const long long n12l = (long long)Fv->ext[0] * Fv->ext[1];
+    int nch = g_v_chunks;
+    while (nch > 1 && (n12l % (32LL * nch) != 0)) --nch;
+    if (nch < 2) return SLLB_ERR_UNSUPPORTED;
+    for (int a = 2; a < 4; ++a) {   // the conditions under which launch_advect takes the chunked strided kernel
+        const int n = Fv->ext[a];
+        if (n % 2 != 0 || n / 2 < 32 || (size_t)n * 32 * 8 + 128 + 8 * 32 * 8 > 227 * 1024 || g_spline_split >= 0) return SLLB_ERR_UNSUPPORTED;
+    }
+    if (!D->s_local) {
+        int lo = 0, hi = 0;
+        SLLB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_local, cudaStreamDefault, hi));
+        SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_remap, cudaStreamDefault, lo));
+        for (cudaEvent_t &e : D->ev_chunk) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    DispDesc d3, d4;
+    SLLB_TRY(make_field_disp(Fv, 2, e1, 2, -step * p.dt / S->delta[2], &d3));
+    SLLB_TRY(make_field_disp(Fv, 3, e2, 2, -step * p.dt / S->delta[3], &d4));
+    RemapDst rd;
+    dist4d_remap_dst(D, 1, 3, &rd);
+    const long long cnt = n12l / nch;
+    const cudaStream_t keep = g_stream;
+    int rc = SLLB_OK;
+    for (int c = 0; c < nch && !rc; ++c) {
+        // x3 pass (outer = x4 planes, inner = the (x1,x2) tile): lines (x4 = q, in = i0 + r)
+        LineSub s3 = {cnt, c * cnt, 0, cnt * Fv->ext[3], 1};
+        g_stream = D->s_local;
+        rc = advect_axis_dev(Fv, 2, S->m[2], S->o[2], d3, nullptr, nullptr, nullptr, &s3);
+        if (!rc) rc = check_cuda(cudaEventRecord(D->ev_chunk[c], D->s_local), "event record");
+        if (!rc) rc = check_cuda(cudaStreamWaitEvent(D->s_remap, D->ev_chunk[c], 0), "stream wait");
+        // x4 + remap pass (outer = 1, inner = tile * N3): lines in = i0 + r + n12l * x3
+        LineSub s4 = {cnt, c * cnt, n12l, cnt * Fv->ext[2], 0};
+        g_stream = D->s_remap;
+        if (!rc) rc = advect_axis_dev(Fv, 3, S->m[3], S->o[3], d4, &rd, nullptr, nullptr, &s4);
+    }
+    g_stream = keep;
+    if (rc) return fail(SLLB_ERR_CUDA, "sim4d: chunked V stage failed after its first launch: " + std::string(sllb_last_error()));
+    SLLB_TRY(dist4d_barrier(D));
+    return SLLB_OK;
+}
 static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
     sllb_field *Fv = S->D->F[1];
     S->line_diag_valid = false;
@@ -824,10 +893,15 @@ static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
         e1 = S->E1loc.p; e2 = S->E2loc.p;
     }
     // out(v) = in(v - E*step*dt)  (:1137-1166), displacement computed from E inside the kernel (K5)
+    S->rho_state = 0;
+    if (fuse && g_v_overlap) {
+        const int rcc = sim4d_V_chunked(S, e1, e2, step);
+        if (rcc == SLLB_OK) { S->layout = 0; return SLLB_OK; }
+        if (rcc != SLLB_ERR_UNSUPPORTED) return rcc;
+    }
     SLLB_TRY(sllb_advect_axis_field(Fv, 2, S->m[2], S->o[2], e1, 2, -step * p.dt / S->delta[2]));
     DispDesc dd;
     SLLB_TRY(make_field_disp(Fv, 3, e2, 2, -step * p.dt / S->delta[3], &dd));
-    S->rho_state = 0;
     if (fuse) {
         SLLB_TRY(dist4d_advect_remap_dev(S->D, 1, 3, S->m[3], S->o[3], dd, &S->timer));
         S->layout = 0;
@@ -1181,6 +1255,15 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
         if (rows) memcpy(rows, h.data(), h.size() * sizeof(double));
     }
     S->timer.collect(S->phase_ms);
+    return SLLB_OK;
+}
+/* 1: on several GPUs the V stage that ends with a remap runs chunked, the x3 pass of one chunk under the NVLink-bound
+ * x4 + remap pass of the previous one; 0 (default): two whole passes.  Same values.  Measured on 2 GPUs (128^4): 2.76 ms per
+ * step whole, 2.80 / 2.86 / 2.89 ms with 2 / 4 / 8 chunks -- the two kernels compete for the same SM slots and the remap
+ * pass loses more store bandwidth than the x3 pass hides (profiles/r02_v_overlap_n2_s10.json), hence opt-in. */
+int sllb_set_v_overlap(int on) {
+    g_v_overlap = on ? 1 : 0;
+    if (on >= 2 && on <= 8) g_v_chunks = on;   // 2..8: that many chunks
     return SLLB_OK;
 }
 /* 1: sllb_sim4d_run records a CUDA event per phase (sllb_sim4d_phase_ms*); 0 (default): no events on the hot path */

@@ -211,6 +211,28 @@ def main():
     res["sim4d_fused_equals_nccl_path"] = bool(np.array_equal(rq, rp) and np.array_equal(fq, fp))
     ok = ok and res["sim4d_fused_equals_nccl_path"]
 
+    # chunked V stage (x3 pass of one chunk under the x4 + remap pass of the previous one) == two whole passes; and a
+    # larger grid over more steps against the single-GPU run, with the position-weighted checksum
+    a5 = ([32, 32, 64, 64], [0, 0, -6, -6], [4 * np.pi, 4 * np.pi, 6, 6], 0.5, 0.5, 1e-3, 0.1)
+    outs = {}
+    for ov in (True, False):
+        sb.set_v_overlap(ov)
+        SV = sb.Sim4d(*a5, comm=comm)
+        rv = SV.run(4)
+        outs[ov] = (rv, SV.field().download(), SV.checksum())
+        SV.destroy()
+    sb.set_v_overlap(True)
+    res["sim4d_chunked_v_stage_equals_whole_passes"] = bool(np.array_equal(outs[True][0], outs[False][0]) and
+                                                            np.array_equal(outs[True][1], outs[False][1]))
+    ok = ok and res["sim4d_chunked_v_stage_equals_whole_passes"]
+    S1 = sb.Sim4d(*a5)
+    r1 = S1.run(4)
+    c1 = S1.checksum()
+    S1.destroy()
+    res["sim4d_32x32x64x64_rows_rel_vs_1gpu"] = float(np.abs(outs[True][0] / r1 - 1).max())
+    res["sim4d_32x32x64x64_checksum_rel_vs_1gpu"] = float(np.abs(outs[True][2] / c1 - 1).max())
+    ok = ok and res["sim4d_32x32x64x64_rows_rel_vs_1gpu"] < 1e-9 and res["sim4d_32x32x64x64_checksum_rel_vs_1gpu"] < 1e-12
+
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     res["ok"] = bool(flag.item())

@@ -126,11 +126,14 @@ def test_run_namelist_files_and_restart(sb, orc, tmp_path):
     th2 = read_thdiag(b / "thdiag.dat", ncol)
     assert th2.shape == (10, ncol)
     assert np.abs(th2[:, 0] - th[10:, 0]).max() < 1e-12
-    # the eight integrals column by column; the mode columns (many of them rounding noise) against the largest mode
+    # The restarted run recomputes E from the stored f (like the reference, :1365-1384) while the uninterrupted one still
+    # holds the E of its last T stage; the V stage conserves rho only to rounding, and rho = 1 - int f cancels three
+    # digits, so the two E differ by ~1e-13 relative.  The eight integrals column by column (the field energy sees that
+    # difference directly), the mode columns (many of them rounding noise) against the largest mode.
     scale = np.abs(th[10:, :8]).max(axis=0)
     scale[3] = scale[1]                                     # momentum ~ 0: measured against the mass
-    assert (np.abs(th2[:, :8] - th[10:, :8]) / scale).max() < 1e-13
-    assert np.abs(th2[:, 8:] - th[10:, 8:]).max() < 1e-13 * np.abs(th[10:, 8:]).max()
+    assert (np.abs(th2[:, :8] - th[10:, :8]) / scale).max() < 1e-11
+    assert np.abs(th2[:, 8:] - th[10:, 8:]).max() < 1e-11 * np.abs(th[10:, 8:]).max()
 
 
 def test_namelist_knobs_and_refusals(sb, tmp_path):
