@@ -517,15 +517,16 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
             part[(3 * P + chunk) * 32 + lane] = tk;
         }
         __syncthreads();
-        if (chunk < NPART && active) { // warp m folds moment m of the block's 32 lines over the P chunks
-            const double *pm = part + (size_t)chunk * P * 32;
-            double t = pm[lane];
+        if (active)
+            for (int m = chunk; m < NPART; m += P) { // warp `chunk` folds moments chunk, chunk + P, ... of the block's 32 lines
+                const double *pm = part + (size_t)m * P * 32;
+                double t = pm[lane];
 #pragma unroll
-            for (int c = 1; c < P; ++c) t += pm[c * 32 + lane];
-            double *dst = linesum;
-            if constexpr (DIAG) dst = (chunk == 0) ? linesum : (chunk == 1 ? dg.l1 : (chunk == 2 ? dg.l2 : dg.kin));
-            dst[l] = t;
-        }
+                for (int c = 1; c < P; ++c) t += pm[c * 32 + lane];
+                double *dst = linesum;
+                if constexpr (DIAG) dst = (m == 0) ? linesum : (m == 1 ? dg.l1 : (m == 2 ? dg.l2 : dg.kin));
+                dst[l] = t;
+            }
     }
 }
 
@@ -1218,7 +1219,7 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
         sub = *subp;
         nlines = sub.nlines;
     }
-    const bool with_diag = diag != nullptr && linesum != nullptr && !rd.on && P >= 4;
+    const bool with_diag = diag != nullptr && linesum != nullptr && !rd.on;
     if (diag != nullptr && !with_diag) return cudaErrorNotSupported;
     LineDiag dg = {nullptr, nullptr, nullptr, nullptr};
     if (with_diag) dg = *diag;
@@ -1235,12 +1236,10 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
         rr.block_rot = remap_block_rotation(rd, nblk);
         kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);
     } else if (with_diag) {
-        if constexpr (P >= 4) {
-            auto kern = k_spline_strided_split<P, false, true>;
-            e = set_smem(kern, smem);
-            if (e != cudaSuccess) return e;
-            kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
-        }
+        auto kern = k_spline_strided_split<P, false, true>;
+        e = set_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
     } else {
         auto kern = k_spline_strided_split<P, false>;
         e = set_smem(kern, smem);
@@ -1415,10 +1414,10 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
     return cudaGetLastError();
 }
 __global__ void k_reduce_stage2(const double *__restrict__ partial, long long nx, int nchunks, double scale,
-                                double *__restrict__ rho);
+                                double *__restrict__ rho);   // defined with K3 below
 // rho[x] = scale * sum_b partial[b][x]
 cudaError_t launch_sum_partials(const double *partial, long long nx, int nparts, double scale, double *rho, cudaStream_t st) {
-    k_reduce_stage2<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(partial, nx, nparts, scale, rho);
+    k_reduce_stage2<<<(unsigned)((nx + 31) / 32), 256, 0, st>>>(partial, nx, nparts, scale, rho);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
@@ -1585,16 +1584,32 @@ __global__ void __launch_bounds__(128) k_reduce_stage1(const double *__restrict_
     for (; v < v1; ++v) a0 += __ldcs(f + x + nx * v);
     partial[(long long)c * nx + x] = (a0 + a1) + (a2 + a3);
 }
-__global__ void k_reduce_stage2(const double *__restrict__ partial, long long nx, int nchunks, double scale,
-                                double *__restrict__ rho) {
-    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= nx) return;
-    double a = 0;
-    for (int c = 0; c < nchunks; ++c) a += partial[(long long)c * nx + x];
-    rho[x] = a * scale;
+// rho[x] = scale * sum_c partial[c][x].  Block = 32 consecutive x (one 256-byte row per part) times 8 groups of parts:
+// thread (x, g) adds the parts c = g, g + 8, ... in order, the eight group sums are then added in order -- a fixed
+// summation tree, eight times the parallelism of one thread per x (the plane kernel leaves up to 592 parts behind).
+__global__ void __launch_bounds__(256) k_reduce_stage2(const double *__restrict__ partial, long long nx, int nchunks, double scale,
+                                                       double *__restrict__ rho) {
+    __shared__ double sh[8][33];
+    const int xl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const long long x = (long long)blockIdx.x * 32 + xl;
+    double a0 = 0, a1 = 0;
+    if (x < nx) {
+        int c = g;
+        for (; c + 8 < nchunks; c += 16) {   // two independent chains per thread: loads of both are in flight together
+            a0 += partial[(long long)c * nx + x];
+            a1 += partial[(long long)(c + 8) * nx + x];
+        }
+        if (c < nchunks) a0 += partial[(long long)c * nx + x];
+    }
+    sh[g][xl] = a0 + a1;
+    __syncthreads();
+    if (g == 0 && x < nx) {
+        double a = sh[0][xl];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) a += sh[k][xl];
+        rho[x] = a * scale;
+    }
 }
-// first stage only: scratch[c][x] = sum over the c-th chunk of v; returns the number of chunks (the consumer sums them:
-// the direct Poisson solve folds that sum into its first kernel)
 cudaError_t launch_reduce_velocity_partials(const double *f, long long nx, long long nv, double *scratch, int *nchunks_out,
                                             cudaStream_t st) {
     int nchunks = (int)(nv < RED_CHUNKS ? nv : RED_CHUNKS);
@@ -1610,7 +1625,7 @@ cudaError_t launch_reduce_velocity(const double *f, long long nx, long long nv, 
     dim3 grid((unsigned)((nx + 127) / 128), nchunks);
     k_reduce_stage1<<<grid, 128, 0, st>>>(f, nx, nv, nchunks, scratch);
     COUNT_LAUNCH();
-    k_reduce_stage2<<<(unsigned)((nx + 255) / 256), 256, 0, st>>>(scratch, nx, nchunks, scale, rho);
+    k_reduce_stage2<<<(unsigned)((nx + 31) / 32), 256, 0, st>>>(scratch, nx, nchunks, scale, rho);
     COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -516,6 +516,7 @@ struct sllb_sim4d {
     struct StepGraph {
         cudaGraphExec_t exec = nullptr;
         int entry_rho_state = -1, entry_layout = -1; bool entry_line_diag = false;
+        const double *fd = nullptr;   // the array of f the recording works on (ensemble streaming rotates three of them)
         int exit_rho_state = 0, exit_layout = 0; bool exit_line_diag = false, exit_eloc = false;
         long long launches = 0;
     } graph[2];
@@ -1056,6 +1057,8 @@ int sllb_sim4d_stream_step(sllb_sim4d_t S, const double *host_next_in, double *h
     int rc = SLLB_OK;
     if (step_now) {
         S->rho_state = 0; S->layout = 0; // a fresh, independent state: fields are recomputed from this f
+        S->line_diag_valid = false;
+        S->eager_steps = 0;              // every call works on another of the three arrays: nothing to record
         rc = sllb_sim4d_run(S, 1, 0, nullptr);
     }
     SLLB_CUDA(cudaStreamSynchronize(S->s_up));
@@ -1198,7 +1201,7 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
     sllb_sim4d::StepGraph &G = S->graph[diag ? 1 : 0];
     bool on_gstream = false;   // replays run on their own stream: the default stream must be idle when they start
     for (int it = 0; it < nsteps; ++it) {
-        const bool matches = G.exec && G.entry_rho_state == S->rho_state && G.entry_layout == S->layout &&
+        const bool matches = G.exec && G.fd == S->D->F[0]->d && G.entry_rho_state == S->rho_state && G.entry_layout == S->layout &&
                              G.entry_line_diag == S->line_diag_valid;
         if (graphs && !matches && S->eager_steps >= 2 && !G.exec) {
             // every buffer the steady-state step needs exists after two plain steps (no allocation may happen while
@@ -1208,6 +1211,7 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
             cudaGraph_t graph = nullptr;
             const long long l0 = launch_count();
             G.entry_rho_state = S->rho_state; G.entry_layout = S->layout; G.entry_line_diag = S->line_diag_valid;
+            G.fd = S->D->F[0]->d;
             const int keep_rho = S->rho_state, keep_layout = S->layout; const bool keep_ld = S->line_diag_valid, keep_el = S->eloc_valid;
             g_stream = S->gstream;
             cudaError_t ce = cudaStreamBeginCapture(S->gstream, cudaStreamCaptureModeThreadLocal);
@@ -1227,8 +1231,8 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
                 set_error("sim4d_run: CUDA graph capture failed, continuing with stream launches");
             }
         }
-        const bool replay = graphs && G.exec && G.entry_rho_state == S->rho_state && G.entry_layout == S->layout &&
-                            G.entry_line_diag == S->line_diag_valid;
+        const bool replay = graphs && G.exec && G.fd == S->D->F[0]->d && G.entry_rho_state == S->rho_state &&
+                            G.entry_layout == S->layout && G.entry_line_diag == S->line_diag_valid;
         if (replay) {
             if (!on_gstream) { SLLB_CUDA(cudaDeviceSynchronize()); on_gstream = true; }
             SLLB_CUDA(cudaGraphLaunch(G.exec, S->gstream));

@@ -146,7 +146,7 @@ def test_namelist_knobs_and_refusals(sb, tmp_path):
     rows = S.run(2)
     assert np.isfinite(rows).all() and abs(rows[-1, 1] / rows[0, 1] - 1) < 1e-10     # mass conserved
     S.destroy()
-    for old, new in (('"SLL_STRANG_VTV"', '"SLL_ORDER6VP_VTV"'), ('"SLL_CARTESIAN_MESH"', '"SLL_TWO_GRID_MESH"'),
+    for old, new in (('"SLL_STRANG_VTV"', '"SLL_ORDER6VPnew1_VTV"'), ('"SLL_CARTESIAN_MESH"', '"SLL_TWO_GRID_MESH"'),
                      ('"SLL_NO_DRIVE"', '"SLL_KEEN_DRIVE"'), ('"SLL_LANDAU"', '"SLL_BEAM"')):
         p.write_text(txt.replace(old, new))
         with pytest.raises(sb.SllbError):
