@@ -232,7 +232,9 @@ def c5_block(sb, torch, dist, comm, rank, world, peak):
         S1 = sb.Sim6d(*args6, time_in_phase=False)
         r1 = S1.run(warmup + steps)
         S1.destroy()
-        scale = np.maximum(np.abs(r1).max(axis=0), 1e-300)
+        # the 14 columns of the reference's .dat file; the ones that are rounding noise around zero (momenta, ...) are
+        # measured against the largest column instead of against themselves
+        scale = np.maximum(np.abs(r1).max(axis=0), 1e-12 * np.abs(r1).max())
         rows_vs_1gpu = float((np.abs(rows - r1) / scale).max())
     barrier()
     hw = 3

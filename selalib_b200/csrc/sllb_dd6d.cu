@@ -36,6 +36,11 @@ struct sllb_dd6d {
     size_t pcap = 0;                      // capacity of each in doubles
     std::vector<void *> peers, ipc_opened;
     DevBuf flag;
+    // barrier through flags in peer-mapped memory instead of an all-reduce (one launch of a few microseconds)
+    DevBuf sigbuf, errflag;
+    unsigned long long *peer_sig[8] = {};
+    unsigned long long epoch = 0;
+    bool flag_barrier = false;
     int parity = 0;
     double exch_ms = 0.0;      // device time of the last halo exchange (pack + send/recv)
     // pipelined split-axis pass: the lines are cut into chunks, the exchange of chunk c+1 (peer stores + barrier, on
@@ -65,6 +70,16 @@ void cart_coords(const int procs[6], int rank, int c[6]) {
 long long outer_of(const sllb_dd6d *D, int axis) { long long o = 1; for (int d = axis + 1; d < 6; ++d) o *= D->nw[d]; return o; }
 long long inner_of(const sllb_dd6d *D, int axis) { long long i = 1; for (int d = 0; d < axis; ++d) i *= D->nw[d]; return i; }
 } // namespace
+
+// cross-rank barrier after peer stores: flags in peer-mapped memory, or the all-reduce it replaces
+static int dd6d_barrier(sllb_dd6d *D, cudaStream_t st) {
+    if (D->flag_barrier) {
+        D->epoch += 1;
+        return check_cuda(launch_flag_barrier(D->peer_sig, D->nranks, D->rank, D->epoch, D->errflag.p, st), "k_flag_barrier");
+    }
+    SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, st));
+    return SLLB_OK;
+}
 
 extern "C" {
 
@@ -126,12 +141,28 @@ int sllb_dd6d_create(sllb_comm_t c, const int global[6], const int procs_in[6], 
                 size_t bcap = 0; // one value per line of the longest split axis
                 for (int d = 1; d < 6; ++d)
                     if (D->procs[d] > 1 && (size_t)(D->F->total / D->nw[d]) > bcap) bcap = (size_t)(D->F->total / D->nw[d]);
-                void *mine[8];
+                void *mine[9];
                 for (int k = 0; k < 4 && !rc; ++k) { rc = D->pbuf[k].ensure(cap); mine[k] = D->pbuf[k].p; }
                 for (int k = 4; k < 8 && !rc; ++k) { rc = D->pbuf[k].ensure(bcap); mine[k] = D->pbuf[k].p; }
                 if (!rc) rc = D->flag.ensure(2);
+                if (!rc) rc = D->sigbuf.ensure(16);
+                if (!rc) rc = D->errflag.ensure(1);
+                if (!rc) rc = check_cuda(cudaMemset(D->sigbuf.p, 0, 16 * sizeof(double)), "memset");
+                if (!rc) rc = check_cuda(cudaMemset(D->errflag.p, 0, sizeof(double)), "memset");
+                mine[8] = D->sigbuf.p;
                 bool ok = false;
-                if (!rc) rc = peer_map_buffers(D->comm, mine, 8, D->peers, D->ipc_opened, &ok);
+                std::vector<void *> all;
+                if (!rc) rc = peer_map_buffers(D->comm, mine, 9, all, D->ipc_opened, &ok);
+                if (!rc && ok) {
+                    // the halo / boundary-sum buffers keep their [rank][8] indexing; the ninth buffer is the flag array
+                    D->peers.assign((size_t)D->nranks * 8, nullptr);
+                    for (int r = 0; r < D->nranks; ++r) {
+                        for (int k = 0; k < 8; ++k) D->peers[(size_t)r * 8 + k] = all[(size_t)r * 9 + k];
+                        D->peer_sig[r] = static_cast<unsigned long long *>(all[(size_t)r * 9 + 8]);
+                    }
+                    const char *eb = getenv("SLLB_FLAG_BARRIER");
+                    D->flag_barrier = !(eb && eb[0] == '0');
+                }
                 D->p2p = ok;
                 D->pcap = cap;
                 D->bcap = bcap;
@@ -224,7 +255,7 @@ int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) 
         double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + par * 2 + 0]);
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, dst_r, 0));
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, dst_l, 0));
-        SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, 0));
+        SLLB_TRY(dd6d_barrier(D, 0));
         D->cur_l = D->pbuf[par * 2 + 0].p; D->cur_r = D->pbuf[par * 2 + 1].p;
         D->parity ^= 1;
     } else {
@@ -339,7 +370,7 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
     for (size_t c = 0; c < boxes.size(); ++c) {
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, h, dst_r, D->s_comm, &boxes[c], pack_blocks));
         SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - h, h, dst_l, D->s_comm, &boxes[c], pack_blocks));
-        SLLB_NCCL(ncclAllReduce(D->flag.p, D->flag.p, 1, ncclDouble, ncclSum, D->comm->comm, D->s_comm));
+        SLLB_TRY(dd6d_barrier(D, D->s_comm));
         SLLB_CUDA(cudaEventRecord(D->ev_chunk[c], D->s_comm));
     }
     SLLB_CUDA(cudaEventRecord(D->ev_comm1, D->s_comm));
@@ -711,6 +742,11 @@ int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
         } else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
     }
     SLLB_CUDA(cudaDeviceSynchronize());
+    if (S->D->flag_barrier) {
+        double err = 0.0;
+        SLLB_CUDA(cudaMemcpy(&err, S->D->errflag.p, sizeof(double), cudaMemcpyDeviceToHost));
+        if (err != 0.0) return fail(SLLB_ERR_CUDA, "sim6d_run: a rank did not reach the flag barrier within the time-out");
+    }
     return SLLB_OK;
 }
 int sllb_sim6d_halo_ms(sllb_sim6d_t S, double *ms, int reset) {

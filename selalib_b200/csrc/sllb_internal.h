@@ -104,6 +104,10 @@ void poisson2d_direct_destroy(Poisson2dDirect *P);
 cudaError_t poisson2d_direct_solve(Poisson2dDirect *P, const double *rho, int nslots, long long slot_stride, double scale,
                                    double *rho_sum, int mode, double *phi, double *e1, double *e2, double *nrj_rows,
                                    double *tile_e1, double *tile_e2, const int tile_box[4], cudaStream_t st);
+// cross-rank barrier through 64-bit flags in peer-mapped memory (sllb_sims.cu): sig[q] = rank q's flag array (8 slots,
+// slot r = last epoch rank r published); epochs grow by one per barrier; *err is raised when a peer never arrives
+cudaError_t launch_flag_barrier(unsigned long long *const sig[8], int nranks, int rank, unsigned long long epoch, double *err,
+                                cudaStream_t st);
 extern int g_poisson_direct;   // 1 (default): 2D solves on small grids take the direct path; 0: always cuFFT
 int peer_map_buffers(sllb_comm *comm, void *const *mine, int count, std::vector<void *> &peers,
                      std::vector<void *> &opened, bool *ok);

@@ -84,7 +84,11 @@ int create_from_namelist(const char *filename, sllb_sim2d_t *S, Sim2dNml *out) {
     if (out->nb_mode < 0) return fail(SLLB_ERR_INVALID, "#bad value of nb_mode; #should be >=0");
     if (out->freq_diag < 1 || out->freq_diag_time < 1 || out->freq_diag_restart < 1) return fail(SLLB_ERR_INVALID, "#freq_diag* must be >= 1");
     int split = 0;
-    const std::string sc = get_str(nml, "time_iterations", "split_case", "SLL_STRANG_VTV");
+    std::string sc = get_str(nml, "time_iterations", "split_case", "SLL_STRANG_VTV");
+    // this simulation spells them SLL_ORDER6VPNEW_TVT / SLL_ORDER6VPNEW1_VTV / SLL_ORDER6VPNEW2_VTV (:840-845), the 2D2V one
+    // (whose table the library holds) SLL_ORDER6VPnew...
+    const size_t pos = sc.find("VPNEW");
+    if (pos != std::string::npos) sc.replace(pos, 5, "VPnew");
     if (sllb_splitting_case_from_name(sc.c_str(), &split)) return fail(SLLB_ERR_INVALID, "#split_case not defined");
     // &advector (:548-556,866-925)
     int mm[2], oo[2];

@@ -270,6 +270,16 @@ __global__ void __launch_bounds__(32) k_flag_barrier(const PeerSig sig, const in
     }
     __syncthreads();
 }
+namespace sllb {
+cudaError_t launch_flag_barrier(unsigned long long *const sig[8], int nranks, int rank, unsigned long long epoch, double *err,
+                                cudaStream_t st) {
+    PeerSig s;
+    for (int r = 0; r < 8; ++r) s.p[r] = r < nranks ? sig[r] : nullptr;
+    k_flag_barrier<<<1, 32, 0, st>>>(s, nranks, rank, epoch, err);
+    count_launch();
+    return cudaGetLastError();
+}
+} // namespace sllb
 // all ranks call this at the same point of their streams
 static int dist4d_barrier(sllb_dist4d *D) {
     if (D->nranks < 2) return SLLB_OK;
@@ -1190,7 +1200,13 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
     S->timer.mark(-1);
     const bool can_fuse = S->D->p2p && g_fused_remap && S->D->nranks > 1;
     const bool diag = with_diagnostics != 0;
-    if (diag && nsteps > 0) SLLB_TRY(S->rows_dev.ensure((size_t)6 * nsteps));
+    if (diag && nsteps > 0) {
+        // the recorded steps carry the address of the row buffer: if it has to grow, the recordings go
+        const double *before = S->rows_dev.p;
+        SLLB_TRY(S->rows_dev.ensure((size_t)6 * (nsteps > 4096 ? nsteps : 4096)));
+        if (before && before != S->rows_dev.p)
+            for (auto &g : S->graph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    }
     SLLB_TRY(S->dstep.ensure(2));
     {
         const double init[2] = {0.0, (double)S->istep};

@@ -139,14 +139,14 @@ def test_run_namelist_files_and_restart(sb, orc, tmp_path):
 def test_namelist_knobs_and_refusals(sb, tmp_path):
     p = tmp_path / "k.nml"
     txt = NML.format(restart="no_restart_file", from_restart=".false.", nit=2)
-    p.write_text(txt.replace('"SLL_STRANG_VTV"', '"SLL_TRIPLE_JUMP_TVT"').replace('advector_x2 = "SLL_SPLINES"', 'advector_x2 = "SLL_LAGRANGE"')
+    p.write_text(txt.replace('"SLL_STRANG_VTV"', '"SLL_ORDER6VPNEW1_VTV"').replace('advector_x2 = "SLL_SPLINES"', 'advector_x2 = "SLL_LAGRANGE"')
                  .replace("order_x2 = 4", "order_x2 = 6").replace('"SLL_LANDAU"', '"SLL_BUMP_ON_TAIL"'))
     S, nit, fdt, nbm = sb.Sim2d.from_namelist(str(p))
     assert (nit, fdt, nbm) == (2, 1, 3)
     rows = S.run(2)
     assert np.isfinite(rows).all() and abs(rows[-1, 1] / rows[0, 1] - 1) < 1e-10     # mass conserved
     S.destroy()
-    for old, new in (('"SLL_STRANG_VTV"', '"SLL_ORDER6VPnew1_VTV"'), ('"SLL_CARTESIAN_MESH"', '"SLL_TWO_GRID_MESH"'),
+    for old, new in (('"SLL_STRANG_VTV"', '"SLL_ORDER6VPOT_VTV"'), ('"SLL_CARTESIAN_MESH"', '"SLL_TWO_GRID_MESH"'),
                      ('"SLL_NO_DRIVE"', '"SLL_KEEN_DRIVE"'), ('"SLL_LANDAU"', '"SLL_BEAM"')):
         p.write_text(txt.replace(old, new))
         with pytest.raises(sb.SllbError):
