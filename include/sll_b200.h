@@ -383,6 +383,13 @@ typedef struct {
     /* advector_x1..x4 / order_x1..x4 of the namelist (:556-624): per-axis method and order; order_axis[d] = 0 means
      * "use method / order above" */
     int method_axis[4], order_axis[4];
+    /* 0 (default): f lives on the periodic cells (N points per direction).  1: additionally carry the duplicated v_max
+     * planes the reference's (N+1)-point arrays hold: a T stage moves them with +v_max while the v_min planes (the same
+     * periodic cell) move with -v_max (:1037-1064), both enter the trapezoid rho with weight 1/2
+     * (sll_m_reduction.F90:229-272), the next V stage overwrites them with the v_min planes again.  That end-plane term is
+     * the whole difference between the two modes (~1e-9 .. 1e-6 of the field energy); with 1 the traces follow the
+     * reference to rounding.  One GPU, splitting schemes whose step ends with a V stage. */
+    int dup_velocity_planes;
 } sllb_sim4d_params_t;
 int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm /* NULL = single GPU */, sllb_sim4d_t *S);
 int sllb_sim4d_destroy(sllb_sim4d_t S);

@@ -37,7 +37,7 @@ class Sim4dParams(C.Structure):
     _fields_ = [("nc", C.c_int * 4), ("xmin", C.c_double * 4), ("xmax", C.c_double * 4),
                 ("kx1", C.c_double), ("kx2", C.c_double), ("eps", C.c_double), ("dt", C.c_double),
                 ("split", C.c_int), ("method", C.c_int), ("order", C.c_int), ("stencil_r", C.c_int), ("stencil_s", C.c_int),
-                ("method_axis", C.c_int * 4), ("order_axis", C.c_int * 4)]
+                ("method_axis", C.c_int * 4), ("order_axis", C.c_int * 4), ("dup_velocity_planes", C.c_int)]
 
 
 class Sim6dParams(C.Structure):
@@ -520,10 +520,12 @@ def format_g(x, w, d):
 
 
 class Sim4d:
-    def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None, stencil=(0, 0)):
+    def __init__(self, nc, xmin, xmax, kx1, kx2, eps, dt, split=0, method=METHOD_SPLINE, order=4, comm=None, stencil=(0, 0),
+                 dup_velocity_planes=False):
         if isinstance(split, str):
             split = splitting_case(split)
         p = Sim4dParams()
+        p.dup_velocity_planes = 1 if dup_velocity_planes else 0
         p.nc[:] = nc; p.xmin[:] = xmin; p.xmax[:] = xmax
         p.kx1, p.kx2, p.eps, p.dt = kx1, kx2, eps, dt
         p.split, p.method, p.order = split, method, order

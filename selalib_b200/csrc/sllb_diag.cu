@@ -124,6 +124,50 @@ cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// dup_velocity_planes mode of the 2D2V loop: the N4 + N3 + 1 side planes (x3 = N3 with x4 < N4, x4 = N4 with x3 < N3, the
+// corner) that the reference's (N+1)-point arrays carry next to the periodic cells.
+// ------------------------------------------------------------------------------------------------
+// side[m] <- the cell plane it duplicates: (0, m) for m < n4, (m - n4, 0) for n4 <= m < n4 + n3, (0, 0) for the corner
+__global__ void __launch_bounds__(256) k_dup_fill(const double *__restrict__ f, const long long n12, const int n3, const int n4,
+                                                  double *__restrict__ side) {
+    const long long ntot = n12 * (n3 + n4 + 1);
+    for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < ntot; t += (long long)gridDim.x * 256) {
+        const long long m = t / n12, x = t - m * n12;
+        long long plane = 0;
+        if (m < n4) plane = (long long)n3 * m;
+        else if (m < n4 + n3) plane = m - n4;
+        side[t] = f[plane * n12 + x];
+    }
+}
+cudaError_t launch_dup_fill(const double *f, long long n12, int n3, int n4, double *side, cudaStream_t st) {
+    k_dup_fill<<<148 * 4, 256, 0, st>>>(f, n12, n3, n4, side);
+    count_launch();
+    return cudaGetLastError();
+}
+// rho(x) += scale * [ sum_m cd(m) side[m](x) - 1/2 sum_{i4} c(i4) f(x,0,i4) ... ], i.e. the trapezoid rule over the
+// (N3+1)(N4+1) nodes written as the plain sum over the cells plus a correction: the cells of the x3 = 0 and x4 = 0 planes
+// lose half their weight (the corner cell three quarters), the side planes come in with weight 1/2 (the corner 1/4).
+__global__ void __launch_bounds__(128) k_dup_rho_corr(const double *__restrict__ f, const double *__restrict__ side, const long long n12,
+                                                      const int n3, const int n4, const double scale, double *__restrict__ rho) {
+    const long long x = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (x >= n12) return;
+    double a = 0.0;
+    for (int m = 0; m < n4; ++m)       // x3 = N3 side (weight 1/2, 1/4 at x4 = 0) against the x3 = 0 cells they duplicate
+        a += (m == 0 ? 0.25 : 0.5) * (side[(long long)m * n12 + x] - f[(long long)n3 * m * n12 + x]);
+    for (int i3 = 0; i3 < n3; ++i3)    // x4 = N4 side against the x4 = 0 cells
+        a += (i3 == 0 ? 0.25 : 0.5) * (side[(long long)(n4 + i3) * n12 + x] - f[(long long)i3 * n12 + x]);
+    // corner node (N3, N4): weight 1/4; the cell (0,0) keeps 1/4 of its weight: 1 - 1/4 (above, twice) - 1/4 here
+    a += 0.25 * (side[(long long)(n3 + n4) * n12 + x] - f[x]);
+    rho[x] += scale * a;
+}
+cudaError_t launch_dup_rho_corr(const double *f, const double *side, long long n12, int n3, int n4, double scale, double *rho,
+                                cudaStream_t st) {
+    k_dup_rho_corr<<<(unsigned)((n12 + 127) / 128), 128, 0, st>>>(f, side, n12, n3, n4, scale, rho);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // position-weighted checksums of a local box of the 4D field: out2 = (sum w f, sum w f^2) with a weight that depends on the
 // GLOBAL index of the point, w = 1 + ((3 g0 + 5 g1 + 7 g2 + 11 g3) mod 64) / 64, so that any misplaced element shows
 __global__ void __launch_bounds__(RT) k_checksum4d1(const double *__restrict__ f, const int n0, const int n1, const int n2,

@@ -141,6 +141,10 @@ size_t moments_from_lines_scratch();
 // nrj = scale * sum over the (n1+1)(n2+1) nodes including the periodic duplicates of a^2 + (squared ? b^2 : 2 b)
 cudaError_t launch_dup_energy2d(const double *a, const double *b, int n1, int n2, double scale, int squared, double *out1,
                                 cudaStream_t st);
+// dup_velocity_planes mode: side planes <- the cell planes they duplicate; rho += scale * (trapezoid - plain sum)
+cudaError_t launch_dup_fill(const double *f, long long n12, int n3, int n4, double *side, cudaStream_t st);
+cudaError_t launch_dup_rho_corr(const double *f, const double *side, long long n12, int n3, int n4, double scale, double *rho,
+                                cudaStream_t st);
 // (sum w f, sum w f^2), w from the global index of every point; scratch: moments_from_lines_scratch() doubles
 cudaError_t launch_checksum4d(const double *f, const int ext[4], const int lo[4], double *scratch, double *out2, cudaStream_t st);
 // out[k] = w * sum_v |f^_k(v)|^2, k < nmodes (f is [nv][n1], x fastest); part: scratch of nv * nmodes doubles

@@ -15,6 +15,7 @@
 #include "sllb_device.cuh"
 #include "sllb_lagrange.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace sllb {
@@ -875,7 +876,7 @@ template <bool RHO, bool REMAP>
 __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1, const int N2,
                                                            const long long nplanes, const DispDesc dd1,
                                                            const DispDesc dd2, double *__restrict__ rho_partial,
-                                                           const __grid_constant__ RemapDst rd) {
+                                                           const __grid_constant__ RemapDst rd, const int l2_prefetch) {
     constexpr int C = SLLB_PR_C;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -902,6 +903,10 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
     }
     for (; pl < nplanes; pl += gridDim.x) {
         double *gp = f + pl * (long long)npl;
+        // The shared plane is busy until pass B has taken it into registers, so the bulk copy of the next plane can
+        // only be issued halfway through this iteration: during pass A nothing of this CTA is in flight from HBM.
+        // Asking for the next plane in L2 now keeps the DRAM reads going through pass A; the bulk copy then hits L2.
+        if (l2_prefetch && tid == 0 && pl + gridDim.x < nplanes) bulk_prefetch_l2(f + (pl + gridDim.x) * (long long)npl, (uint32_t)(npl * 8));
         const double d1 = disp_of(dd1, pl * N2, 0); // constant over the plane (checked by the launcher)
         const double d2 = disp_of(dd2, pl, 0);
         const double fl1 = floor(d1), fl2 = floor(d2);
@@ -1342,6 +1347,11 @@ static cudaError_t launch_spline_contig_split_t(double *f, long long nlines, int
 
 // K1c launcher.  Returns cudaErrorNotSupported when the plane does not fit the kernel's assumptions (the
 // caller then runs the two passes separately).
+// L2 prefetch of the next plane (cp.async.bulk.prefetch.L2, SASS UBLKPF) at the top of every iteration of the plane
+// kernel.  Measured on 128^4 (profiles/r02_plane_ab_s18.log): without the fused charge density 0.851 -> 0.788 ms, with it
+// 0.998 -> 1.059 ms (the per-CTA partial densities and the prefetched planes compete for L2).  1 (default): only the
+// variant without the charge density prefetches; 2: both; 0: neither.
+int g_plane_l2_prefetch = [] { const char *e = getenv("SLLB_PLANE_L2_PREFETCH"); return e ? atoi(e) : 1; }();
 int g_plane_ept = 0; // tuning knob: 0 auto (register-resident variant), 16 or 32: in-place variant with that many points per thread
 static int plane_ept(int n1, int n2, bool rho) {
     if (g_plane_ept == 16 && !rho) return 16;
@@ -1391,7 +1401,7 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
     do {                                                                                     \
         e = set_smem(KERN, smem);                                                            \
         if (e != cudaSuccess) return e;                                                      \
-        KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial, rd);    \
+        KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial, rd, (g_plane_l2_prefetch >= 2 || (g_plane_l2_prefetch == 1 && !rho)) ? 1 : 0);    \
     } while (0)
 #define SLLB_PLANE_LAUNCH(KERN)                                                              \
     do {                                                                                     \

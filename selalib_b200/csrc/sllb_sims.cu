@@ -511,6 +511,10 @@ struct sllb_sim4d {
     bool eloc_valid = false; // E1loc / E2loc were filled by the last field solve (tile extraction fused into it)
     // 4: the per-CTA partial densities of the T-stage plane kernel are still unsummed (single GPU: the Poisson solve sums them)
     const double *rho_parts = nullptr; int rho_nparts = 0;
+    // dup_velocity_planes: the N4 + N3 + 1 side planes of the reference's (N+1)-point velocity axes, their velocities
+    sllb_field *Fdup = nullptr;
+    DevBuf vdup[2];
+    bool dup_valid = false;  // the side planes differ from the cells they duplicate (a T stage has moved them apart)
     DevBuf vtab[2];          // velocities of my x3 / x4 indices in the x-sequential layout (constant: no launch per stage)
     DevBuf nrj_rows;         // per-row parts of the field energy written by the direct Poisson solve
     bool nrj_rows_valid = false;
@@ -632,6 +636,11 @@ static int sim4d_fields(sllb_sim4d *S) {
                 SLLB_CUDA(launch_unpack4d(S->rho_full.p, ext, b, S->rho_gather.p + (long long)r * tile, g_stream));
             }
         }
+    }
+    if (S->Fdup && S->dup_valid) {
+        // trapezoid rule over the (N3+1)(N4+1) nodes = plain sum over the cells + the end-plane correction
+        if (rho_in != S->rho_full.p || nslots != 1) return fail(SLLB_ERR_UNSUPPORTED, "sim4d: dup_velocity_planes needs the summed density (SLLB_FOLD_SUMS=0)");
+        SLLB_CUDA(launch_dup_rho_corr(Fv->d, S->Fdup->d, n12, Fv->ext[2], Fv->ext[3], scale, S->rho_full.p, g_stream));
     }
     S->rho_state = 0;
     S->eloc_valid = false;
@@ -763,8 +772,30 @@ static int sim4d_diag_device(sllb_sim4d *S, double *d_row6) {
     return SLLB_OK;
 }
 
+// dup_velocity_planes: the side planes take part in a T stage with THEIR velocities (x3 = N3 / x4 = N4 sit at +v_max, the
+// cells they duplicate at v_min = -v_max: :1037-1064 loops over all N+1 points of the velocity axes)
+static int sim4d_T_side_planes(sllb_sim4d *S, double step) {
+    sllb_field *Fx = S->D->F[0], *G = S->Fdup;
+    const sllb_sim4d_params_t &p = S->p;
+    const int M = G->ext[2];
+    if (!S->dup_valid) SLLB_CUDA(launch_dup_fill(Fx->d, (long long)Fx->ext[0] * Fx->ext[1], Fx->ext[2], Fx->ext[3], G->d, g_stream));
+    DispDesc d0, d1;
+    d0.v = S->vdup[0].p; d0.scale = -step * p.dt / S->delta[0];
+    d0.odiv = G->ext[1]; d0.omod = M; d0.ostr = 1; d0.idiv = d0.imod = 1; d0.istr = 0;
+    d1.v = S->vdup[1].p; d1.scale = -step * p.dt / S->delta[1];
+    d1.odiv = 1; d1.omod = M; d1.ostr = 1; d1.idiv = d1.imod = 1; d1.istr = 0;
+    SLLB_TRY(advect_axis_dev(G, 0, S->m[0], S->o[0], d0));
+    SLLB_TRY(advect_axis_dev(G, 1, S->m[1], S->o[1], d1));
+    S->dup_valid = true;
+    return SLLB_OK;
+}
+static int sim4d_T_cells(sllb_sim4d *S, double step, bool fuse);
 // `fuse`: the stage's last pass writes straight into the other layout (advect + remap in one kernel)
 static int sim4d_T(sllb_sim4d *S, double step, bool fuse) {
+    if (S->Fdup) SLLB_TRY(sim4d_T_side_planes(S, step));   // before the cells move: a fresh copy is taken from them
+    return sim4d_T_cells(S, step, fuse);
+}
+static int sim4d_T_cells(sllb_sim4d *S, double step, bool fuse) {
     sllb_field *Fx = S->D->F[0];
     const sllb_sim4d_params_t &p = S->p;
     S->rho_state = 0;
@@ -882,6 +913,7 @@ static int sim4d_V_chunked(sllb_sim4d *S, const double *e1, const double *e2, do
 static int sim4d_V(sllb_sim4d *S, double step, double step2, bool fuse) {
     sllb_field *Fv = S->D->F[1];
     S->line_diag_valid = false;
+    S->dup_valid = false;   // out(N+1) = out(1): every V pass rewrites the duplicated planes from the cells
     const sllb_sim4d_params_t &p = S->p;
     const double *e1 = S->E1.p, *e2 = S->E2.p;
     if (S->dim_split_V == 2) {
@@ -976,6 +1008,27 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
         rc = S->vtab[a].ensure((size_t)n);
         if (!rc) rc = check_cuda(launch_affine(S->vtab[a].p, n, p->xmin[2 + a] + S->bx[4 + 2 * a] * S->delta[2 + a], S->delta[2 + a], g_stream), "k_affine");
     }
+    if (!rc && p->dup_velocity_planes) {
+        // a step must end with a V stage (it re-synchronises the duplicated planes before the diagnostics are taken)
+        const bool ends_with_T = (S->begin_T && S->nb_split_step % 2 == 1) || (!S->begin_T && S->nb_split_step % 2 == 0);
+        if (S->D->nranks != 1) rc = fail(SLLB_ERR_UNSUPPORTED, "sim4d_create: dup_velocity_planes is a single-GPU mode");
+        else if (ends_with_T) rc = fail(SLLB_ERR_UNSUPPORTED, "sim4d_create: dup_velocity_planes needs a splitting scheme whose step ends with a V stage");
+        if (!rc) {
+            const int n3 = p->nc[2], n4 = p->nc[3], M = n3 + n4 + 1;
+            const int ext3[3] = {p->nc[0], p->nc[1], M};
+            rc = field_alloc(3, ext3, &S->Fdup);
+            std::vector<double> v3(M), v4(M);
+            for (int m = 0; m < M; ++m) {
+                // side plane m: (x3 = N3, x4 = m) | (x3 = m - N4, x4 = N4) | the corner; the duplicated node sits at v_max
+                v3[m] = (m < n4 || m == n3 + n4) ? p->xmax[2] : p->xmin[2] + (m - n4) * S->delta[2];
+                v4[m] = (m < n4) ? p->xmin[3] + m * S->delta[3] : p->xmax[3];
+            }
+            for (int a = 0; a < 2 && !rc; ++a) {
+                rc = S->vdup[a].ensure((size_t)M);
+                if (!rc) rc = check_cuda(cudaMemcpy(S->vdup[a].p, a == 0 ? v3.data() : v4.data(), sizeof(double) * M, cudaMemcpyHostToDevice), "dup velocities");
+            }
+        }
+    }
     if (rc) { sllb_sim4d_destroy(S); return rc; }
     const size_t n12 = (size_t)p->nc[0] * p->nc[1];
     sllb_field *Fv = S->D->F[1];
@@ -1018,6 +1071,7 @@ int sllb_sim4d_create(const sllb_sim4d_params_t *p, sllb_comm_t comm, sllb_sim4d
 }
 int sllb_sim4d_destroy(sllb_sim4d_t S) {
     if (!S) return SLLB_OK;
+    sllb_field_destroy(S->Fdup);
     for (auto &g : S->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (S->gstream) cudaStreamDestroy(S->gstream);
     if (S->s_up) cudaStreamDestroy(S->s_up);
@@ -1218,7 +1272,7 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
     bool on_gstream = false;   // replays run on their own stream: the default stream must be idle when they start
     for (int it = 0; it < nsteps; ++it) {
         const bool matches = G.exec && G.fd == S->D->F[0]->d && G.entry_rho_state == S->rho_state && G.entry_layout == S->layout &&
-                             G.entry_line_diag == S->line_diag_valid;
+                             G.entry_line_diag == S->line_diag_valid && !S->dup_valid;
         if (graphs && !matches && S->eager_steps >= 2 && !G.exec) {
             // every buffer the steady-state step needs exists after two plain steps (no allocation may happen while
             // recording): record the next one (it is executed by the launch below, not while recording)
@@ -1248,7 +1302,7 @@ int sllb_sim4d_run(sllb_sim4d_t S, int nsteps, int with_diagnostics, double *row
             }
         }
         const bool replay = graphs && G.exec && G.fd == S->D->F[0]->d && G.entry_rho_state == S->rho_state &&
-                            G.entry_layout == S->layout && G.entry_line_diag == S->line_diag_valid;
+                            G.entry_layout == S->layout && G.entry_line_diag == S->line_diag_valid && !S->dup_valid;
         if (replay) {
             if (!on_gstream) { SLLB_CUDA(cudaDeviceSynchronize()); on_gstream = true; }
             SLLB_CUDA(cudaGraphLaunch(G.exec, S->gstream));

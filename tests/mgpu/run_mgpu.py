@@ -115,6 +115,11 @@ def main():
             ref = R.field(1 - src).download()
             R.field(1 - src).upload(np.zeros_like(ref))
             R.field(src).upload(np.asfortranarray(glob4[sl4]))
+            # the fused pass stores into the OTHER ranks' destination arrays: nobody may start before everybody has
+            # finished zeroing its own (a race of this script, not of the library: the time loops separate the two with
+            # the barrier of the previous stage)
+            sb.synchronize()
+            dist.barrier()
             R.advect_remap(src, axis, method, order, disp.data_ptr(), 0.7, dsel)
             sb.synchronize()
             fused_ok = fused_ok and np.array_equal(R.field(1 - src).download(), ref)
@@ -236,7 +241,13 @@ def main():
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     res["ok"] = bool(flag.item())
+    # every rank's verdict: rank 0 prints its own numbers plus, for the other ranks, whatever differs from "all fine"
+    res["rank_ok"] = bool(ok)
+    allres = [None] * world
+    dist.all_gather_object(allres, res)
     if rank == 0:
+        res["ranks_failing"] = {str(r): {k: v for k, v in a.items() if (isinstance(v, bool) and not v) or (isinstance(v, float) and v > 1e-9)}
+                                for r, a in enumerate(allres) if not a["rank_ok"]}
         print(json.dumps(res), flush=True)
     comm.destroy()
     dist.destroy_process_group()

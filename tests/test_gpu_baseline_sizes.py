@@ -132,3 +132,28 @@ def test_c5_block_x_pass_and_halo_v_pass(sb, orc):
     e_v = relerr(D.field().download(), ref2)
     D.destroy()
     assert e_v < TOL, e_v
+
+
+@pytest.mark.parametrize("nc,nsteps,split", [([16, 16, 32, 32], 10, 0), ([64, 64, 64, 64], 3, 0), ([16, 16, 32, 32], 4, "SLL_ORDER6VPnew1_VTV")])
+def test_dup_velocity_planes_mode_follows_the_reference(sb, orc, nc, nsteps, split):
+    """opt-in dup_velocity_planes: the duplicated v_max planes are carried like the reference's (N+1)-point arrays do
+    (moved with +v_max in the T stage, half weight in the trapezoid rho, rewritten by the next V stage): field energy and
+    f then follow the REFERENCE-mode oracle to rounding -- the 1e-9 .. 1e-6 end-plane term of the default mode is gone."""
+    S = sb.Sim4d(nc, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, split=split, dup_velocity_planes=True)
+    rows = S.run(nsteps)
+    f = S.field().download()
+    S.destroy()
+    orows, of = orc.sim4d(nc, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, nsteps, split=split, method=0, want_f=True)
+    assert relerr(f, of[:-1, :-1, :-1, :-1]) < 1e-11
+    err = np.abs(rows[:, 1:] / orows[1:, 1:] - 1).max(axis=0)
+    assert err.max() < 1e-10, err
+    # and the default mode differs from the reference by more than that (else this test shows nothing)
+    S = sb.Sim4d(nc, XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, split=split)
+    r0 = S.run(nsteps)
+    S.destroy()
+    assert np.abs(r0[:, 1] / orows[1:, 1] - 1).max() > 10 * err[0]
+
+
+def test_dup_velocity_planes_refusals(sb):
+    with pytest.raises(sb.SllbError):
+        sb.Sim4d([16, 16, 32, 32], XMIN, XMAX, 0.5, 0.5, 1e-3, 0.1, split=1, dup_velocity_planes=True)   # Strang TVT ends with T
