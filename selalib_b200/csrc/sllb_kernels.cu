@@ -872,7 +872,11 @@ __device__ __forceinline__ void chunk_solve(double (&g)[SLLB_PR_C], double *exch
     }
 }
 
-template <bool RHO, bool REMAP>
+// TACC (with RHO): the 32 charge-density accumulators of every thread live in tensor memory (warp w: lanes of quadrant
+// w mod 4, columns 64 (w / 4) .. + 63) instead of 12 registers + 20 shared-memory slots: no register spills, 80 KB of shared
+// memory and 40 shared-memory accesses per thread and plane less; the TMEM loads of a group of 8 are in flight while the 8
+// values are evaluated.
+template <bool RHO, bool REMAP, bool TACC = false>
 __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1, const int N2,
                                                            const long long nplanes, const DispDesc dd1,
                                                            const DispDesc dd2, double *__restrict__ rho_partial,
@@ -888,11 +892,29 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
     const int PA = N1 / C, PB = N2 / C;
     const int rowA = (w / PA) * 32 + lane, chA = w % PA; // pass A: row = x2 index, chunk along x1
     const int colB = (w / PB) * 32 + lane, chB = w % PB; // pass B: column = x1 index, chunk along x2
-    double acc[SLLB_PR_ACCR];
+    double acc[(RHO && TACC) ? 1 : SLLB_PR_ACCR];
 #pragma unroll
-    for (int j = 0; j < SLLB_PR_ACCR; ++j) acc[j] = 0.0;
-    if (RHO)
+    for (int j = 0; j < ((RHO && TACC) ? 1 : SLLB_PR_ACCR); ++j) acc[j] = 0.0;
+    if (RHO && !TACC)
         for (int j = 0; j < C - SLLB_PR_ACCR; ++j) accs[(size_t)j * T + tid] = 0.0;
+    uint32_t tbase = 0, tcols = 0, talloc = 0;
+    if constexpr (RHO && TACC) {
+        uint32_t *tslot = reinterpret_cast<uint32_t *>(smem_raw + 64);
+        tcols = 64u * (uint32_t)((T / 32 + 3) / 4);
+        tcols = tcols <= 64 ? 64 : (tcols <= 128 ? 128 : 256);
+        if (w == 0) tmem_alloc(tslot, tcols);
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        talloc = *tslot;
+        tbase = talloc + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)((w >> 2) * 64);
+        uint32_t z[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) z[k] = 0u;
+#pragma unroll
+        for (int jb = 0; jb < C; jb += 8) tmem_st16(tbase + 2 * jb, z);
+        tmem_wait_st();
+    }
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
     uint32_t phase = 0;
@@ -982,22 +1004,53 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
                 om.seek(chB * C);
             }
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                const double b1 = (j + 1 < C) ? g[j + 1] : n0;
-                const double b2 = (j + 2 < C) ? g[j + 2] : ((j + 2 == C) ? n0 : n1);
-                const double b3 = (j + 3 < C) ? g[j + 3] : ((j + 3 == C) ? n0 : ((j + 3 == C + 1) ? n1 : n2));
-                const double v = fma(w3, b3, fma(w2, b2, fma(w1, b1, w0 * g[j])));
-                if constexpr (REMAP) { st_stream(om.p, v); om.next(); }
-                else st_stream(out + (size_t)j * N1, v);
-                if constexpr (RHO) {
-                    if (j < SLLB_PR_ACCR) acc[j] += v;
-                    else accs[(size_t)(j - SLLB_PR_ACCR) * T + tid] += v;
+            for (int jb = 0; jb < C; jb += 4) {
+                uint32_t r[8];
+                if constexpr (RHO && TACC) tmem_ld8(tbase + 2 * jb, r);   // in flight while the 4 values are evaluated
+                double vv[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = jb + jj;
+                    const double b1 = (j + 1 < C) ? g[j + 1] : n0;
+                    const double b2 = (j + 2 < C) ? g[j + 2] : ((j + 2 == C) ? n0 : n1);
+                    const double b3 = (j + 3 < C) ? g[j + 3] : ((j + 3 == C) ? n0 : ((j + 3 == C + 1) ? n1 : n2));
+                    const double v = fma(w3, b3, fma(w2, b2, fma(w1, b1, w0 * g[j])));
+                    vv[jj] = v;
+                    if constexpr (REMAP) { st_stream(om.p, v); om.next(); }
+                    else st_stream(out + (size_t)j * N1, v);
+                    if constexpr (RHO && !TACC) {
+                        if (j < SLLB_PR_ACCR) acc[j] += v;
+                        else accs[(size_t)(j - SLLB_PR_ACCR) * T + tid] += v;
+                    }
+                }
+                if constexpr (RHO && TACC) {
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const double a = __hiloint2double((int)r[2 * jj + 1], (int)r[2 * jj]) + vv[jj];
+                        r[2 * jj] = (uint32_t)__double2loint(a); r[2 * jj + 1] = (uint32_t)__double2hiint(a);
+                    }
+                    tmem_st8(tbase + 2 * jb, r);
                 }
             }
+            if constexpr (RHO && TACC) tmem_wait_st();   // the next plane loads these columns again
         }
         __syncthreads(); // exchange arrays are reused by the next plane
     }
-    if constexpr (RHO) {
+    if constexpr (RHO && TACC) {
+        double *rp = rho_partial + (long long)blockIdx.x * npl + (size_t)(chB * C) * N1 + colB;
+#pragma unroll
+        for (int jb = 0; jb < C; jb += 8) {
+            uint32_t r[16];
+            tmem_ld16(tbase + 2 * jb, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) rp[(size_t)(jb + jj) * N1] = __hiloint2double((int)r[2 * jj + 1], (int)r[2 * jj]);
+        }
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (w == 0) tmem_dealloc(talloc, tcols);
+    } else if constexpr (RHO) {
         double *rp = rho_partial + (long long)blockIdx.x * npl + (size_t)(chB * C) * N1 + colB;
 #pragma unroll
         for (int j = 0; j < C; ++j) rp[(size_t)j * N1] = (j < SLLB_PR_ACCR) ? acc[j] : accs[(size_t)(j - SLLB_PR_ACCR) * T + tid];
@@ -1357,10 +1410,14 @@ static int plane_ept(int n1, int n2, bool rho) {
     if (g_plane_ept == 16 && !rho) return 16;
     return 32;
 }
+// 1: the charge-density accumulators of the plane kernel live in tensor memory (SLLB_PLANE_TMEM), 0 (default): 12 registers +
+// 20 shared-memory slots per thread.  Measured on 128^4 (profiles/r02_plane_ab_s19_tmem.log): 1.027 vs 0.975 ms -- TMEM reads
+// run at 64 B/clk/SM, half the shared-memory rate, and the accumulate is a read-modify-write; kept as an opt-in variant.
+int g_plane_tmem = [] { const char *e = getenv("SLLB_PLANE_TMEM"); return e ? atoi(e) : 0; }();
 static size_t plane_smem(int n1, int n2, bool rho) {
     const size_t T = (size_t)n1 * n2 / SLLB_PR_C;
     if (g_plane_ept != 0) return 128 + (size_t)n1 * n2 * 8;
-    return 128 + (size_t)n1 * n2 * 8 + 4 * T * 8 + (rho ? (SLLB_PR_C - SLLB_PR_ACCR) * T * 8 : 0);
+    return 128 + (size_t)n1 * n2 * 8 + 4 * T * 8 + ((rho && !g_plane_tmem) ? (SLLB_PR_C - SLLB_PR_ACCR) * T * 8 : 0);
 }
 int plane_grid(int n1, int n2, long long nplanes) {
     const size_t smem = plane_smem(n1, n2, true);
@@ -1411,10 +1468,12 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
     } while (0)
     if (g_plane_ept == 0) {
         if (rd.on) {
-            if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true>));
+            if (rho && g_plane_tmem) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, true>));
+            else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true>));
             else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, true>));
         } else {
-            if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false>));
+            if (rho && g_plane_tmem) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, true>));
+            else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false>));
             else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, false>));
         }
     } else if (rho) SLLB_PLANE_LAUNCH((k_spline_plane<32, true>));
