@@ -528,12 +528,14 @@ class Sim4d:
         p.dup_velocity_planes = 1 if dup_velocity_planes else 0
         p.nc[:] = nc; p.xmin[:] = xmin; p.xmax[:] = xmax
         p.kx1, p.kx2, p.eps, p.dt = kx1, kx2, eps, dt
-        p.split, p.method, p.order = split, method, order
+        p.split = split
         p.stencil_r, p.stencil_s = stencil
         if isinstance(method, (tuple, list)):      # per-axis advectors (advector_x1..x4 / order_x1..x4)
             orders = order if isinstance(order, (tuple, list)) else [order] * 4
             p.method_axis[:] = list(method); p.order_axis[:] = list(orders)
             p.method, p.order = method[0], orders[0]
+        else:
+            p.method, p.order = method, order
         self.h = vp()
         self.nc = tuple(int(c) for c in nc)
         _ck(lib().sllb_sim4d_create(C.byref(p), comm.h if comm is not None else None, C.byref(self.h)))

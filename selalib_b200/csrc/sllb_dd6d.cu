@@ -71,6 +71,40 @@ long long outer_of(const sllb_dd6d *D, int axis) { long long o = 1; for (int d =
 long long inner_of(const sllb_dd6d *D, int axis) { long long i = 1; for (int d = 0; d < axis; ++d) i *= D->nw[d]; return i; }
 } // namespace
 
+// Edge planes j0 .. j0+hw-1 of `axis` (lines of the sub-box `box`, all lines when NULL) into a halo buffer laid out
+// [outer][hw][inner], possibly in a peer's memory.  Default: the COPY ENGINES (cudaMemcpy2DAsync, device to device over
+// NVLink): no SM is spent on the transfer, so the stencil kernel of the previous chunk keeps the whole GPU, and the DMA
+// path moves 750+ GB/s where the capped pack kernel running beside the stencil kernel reached ~510.  SLLB_HALO_DMA=0: the
+// pack kernel (K7).
+static int g_halo_dma = [] { const char *e = getenv("SLLB_HALO_DMA"); return (e && e[0] == '0') ? 0 : 1; }();
+static int halo_copy(sllb_dd6d *D, int axis, int j0, int hw, double *dst, cudaStream_t st, const LineBox *box, int max_blocks) {
+    if (hw <= 0) return SLLB_OK;
+    const int n = D->nw[axis];
+    long long outer = 1, inner = 1;
+    for (int d = axis + 1; d < 6; ++d) outer *= D->nw[d];
+    for (int d = 0; d < axis; ++d) inner *= D->nw[d];
+    LineBox b;
+    if (box) b = *box;
+    else { b.o0 = 0; b.ocount = outer; b.i0 = 0; b.icount = inner; }
+    const bool whole_rows = (b.i0 == 0 && b.icount == inner);
+    if (!g_halo_dma || (!whole_rows && b.ocount != 1)) {
+        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, j0, hw, dst, st, box, max_blocks));
+        return SLLB_OK;
+    }
+    const double *src = D->F->d;
+    if (whole_rows) {
+        // per o one contiguous block of hw * inner doubles: rows of a 2D copy
+        SLLB_CUDA(cudaMemcpy2DAsync(dst + (size_t)b.o0 * hw * inner, (size_t)hw * inner * sizeof(double),
+                                    src + ((size_t)b.o0 * n + j0) * inner, (size_t)n * inner * sizeof(double),
+                                    (size_t)hw * inner * sizeof(double), (size_t)b.ocount, cudaMemcpyDeviceToDevice, st));
+    } else {
+        // one o, a range of `in`: the hw planes are the rows
+        SLLB_CUDA(cudaMemcpy2DAsync(dst + (size_t)b.o0 * hw * inner + b.i0, (size_t)inner * sizeof(double),
+                                    src + ((size_t)b.o0 * n + j0) * inner + b.i0, (size_t)inner * sizeof(double),
+                                    (size_t)b.icount * sizeof(double), (size_t)hw, cudaMemcpyDeviceToDevice, st));
+    }
+    return SLLB_OK;
+}
 // cross-rank barrier after peer stores: flags in peer-mapped memory, or the all-reduce it replaces
 static int dd6d_barrier(sllb_dd6d *D, cudaStream_t st) {
     if (D->flag_barrier) {
@@ -253,8 +287,8 @@ int sllb_dd6d_halo_exchange(sllb_dd6d_t D, int axis, int hw_left, int hw_right) 
         const int par = D->parity;
         double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 8 + par * 2 + 1]);
         double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + par * 2 + 0]);
-        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, hw_right, dst_r, 0));
-        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - hw_left, hw_left, dst_l, 0));
+        SLLB_TRY(halo_copy(D, axis, 0, hw_right, dst_r, 0, nullptr, 0));
+        SLLB_TRY(halo_copy(D, axis, n - hw_left, hw_left, dst_l, 0, nullptr, 0));
         SLLB_TRY(dd6d_barrier(D, 0));
         D->cur_l = D->pbuf[par * 2 + 0].p; D->cur_r = D->pbuf[par * 2 + 1].p;
         D->parity ^= 1;
@@ -368,8 +402,8 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
     SLLB_CUDA(cudaStreamWaitEvent(D->s_comp, D->ev_start, 0));
     SLLB_CUDA(cudaEventRecord(D->ev_comm0, D->s_comm));
     for (size_t c = 0; c < boxes.size(); ++c) {
-        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, 0, h, dst_r, D->s_comm, &boxes[c], pack_blocks));
-        SLLB_CUDA(launch_halo_pack(D->F->d, outer, n, inner, n - h, h, dst_l, D->s_comm, &boxes[c], pack_blocks));
+        SLLB_TRY(halo_copy(D, axis, 0, h, dst_r, D->s_comm, &boxes[c], pack_blocks));
+        SLLB_TRY(halo_copy(D, axis, n - h, h, dst_l, D->s_comm, &boxes[c], pack_blocks));
         SLLB_TRY(dd6d_barrier(D, D->s_comm));
         SLLB_CUDA(cudaEventRecord(D->ev_chunk[c], D->s_comm));
     }
