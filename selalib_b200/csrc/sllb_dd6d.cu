@@ -48,6 +48,7 @@ struct sllb_dd6d {
     cudaStream_t s_comm = nullptr, s_comp = nullptr;
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_comm0 = nullptr, ev_comm1 = nullptr, ev_chunk[16] = {};
     bool exch_pending = false; // exch_ms of the last pipelined pass still to be read from ev_comm0/1
+    int pre_axis = -1, pre_h = 0, pre_chunks = 0;   // a pipelined exchange issued ahead of its pass (dd6d_halo_prefetch)
     cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr; // around the last plain exchange (read lazily by sllb_dd6d_exchange_ms)
     bool xch_pending = false;
 };
@@ -370,36 +371,40 @@ extern "C" int sllb_dd6d_chunk_boxes(long long outer, long long inner, int nchun
     *nboxes = (int)b.size();
     return SLLB_OK;
 }
-/* Split-axis pass with the exchange pipelined against the stencil: chunk c of the lines is exchanged (edge planes stored
- * straight into the neighbours' halo buffers, all-reduce as barrier) on the communication stream while the halo-cells
- * kernel works on chunk c-1 on the compute stream.  Same kernels, same values as exchange-then-advect. */
-static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const DispDesc &dd, int nchunks) {
-    const int h = (stencil - 1) / 2, n = D->nw[axis];
+static int dd6d_pipeline_setup(sllb_dd6d *D) {
+    if (D->s_comm) return SLLB_OK;
+    // the stencil kernel fills every SM up to the resident-block limit with its one-warp blocks; the communication
+    // stream gets the higher priority so that the few pack blocks of the next chunk are placed as soon as slots free up
+    int prio_lo = 0, prio_hi = 0;
+    SLLB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_comm, cudaStreamNonBlocking, prio_hi));
+    SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_comp, cudaStreamNonBlocking, prio_lo));
+    SLLB_CUDA(cudaEventCreateWithFlags(&D->ev_start, cudaEventDisableTiming));
+    SLLB_CUDA(cudaEventCreateWithFlags(&D->ev_end, cudaEventDisableTiming));
+    SLLB_CUDA(cudaEventCreate(&D->ev_comm0));
+    SLLB_CUDA(cudaEventCreate(&D->ev_comm1));
+    for (cudaEvent_t &e : D->ev_chunk) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return SLLB_OK;
+}
+// The exchange half of a pipelined split-axis pass: chunk by chunk, the edge planes go into the neighbours' halo buffers and a
+// barrier follows, all on the communication stream, which starts after what has been launched on the default stream so
+// far.  Event c fires when the halo of chunk c is complete on every rank.  The halo planes depend on f only (not on the
+// displacement), so this half may be issued EARLY: sllb_sim6d_run starts the exchange of the first split velocity axis
+// right after the x passes, and it runs under the charge density / Poisson / diagnostics work that separates the x passes
+// from the v passes (dd6d_halo_prefetch); the pass itself then finds its halo already on its way.
+static int dd6d_pipeline_exchange(sllb_dd6d *D, int axis, int h, int nchunks) {
+    const int n = D->nw[axis];
     const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
-    if (!D->s_comm) {
-        // the stencil kernel fills every SM up to the resident-block limit with its one-warp blocks; the communication
-        // stream gets the higher priority so that the few pack blocks of the next chunk are placed as soon as slots free up
-        int prio_lo = 0, prio_hi = 0;
-        SLLB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_comm, cudaStreamNonBlocking, prio_hi));
-        SLLB_CUDA(cudaStreamCreateWithPriority(&D->s_comp, cudaStreamNonBlocking, prio_lo));
-        SLLB_CUDA(cudaEventCreateWithFlags(&D->ev_start, cudaEventDisableTiming));
-        SLLB_CUDA(cudaEventCreateWithFlags(&D->ev_end, cudaEventDisableTiming));
-        SLLB_CUDA(cudaEventCreate(&D->ev_comm0));
-        SLLB_CUDA(cudaEventCreate(&D->ev_comm1));
-        for (cudaEvent_t &e : D->ev_chunk) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    SLLB_TRY(dd6d_pipeline_setup(D));
     const std::vector<LineBox> boxes = chunk_boxes(outer, inner, nchunks);
-    // two pack blocks per SM: enough stores in flight for NVLink, and the stencil kernel of the previous chunk keeps most of
-    // every SM
+    // two pack blocks per SM (pack-kernel route): enough stores in flight for NVLink, and the stencil kernel of the
+    // previous chunk keeps most of every SM
     static const int pack_blocks = [] { const char *e = getenv("SLLB_PACK_BLOCKS"); return (e && atoi(e) > 0) ? atoi(e) : 148 * 2; }();
     const int par = D->parity;
     double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 8 + par * 2 + 1]);
     double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + par * 2 + 0]);
-    D->cur_l = D->pbuf[par * 2 + 0].p; D->cur_r = D->pbuf[par * 2 + 1].p;
     SLLB_CUDA(cudaEventRecord(D->ev_start, 0));
     SLLB_CUDA(cudaStreamWaitEvent(D->s_comm, D->ev_start, 0));
-    SLLB_CUDA(cudaStreamWaitEvent(D->s_comp, D->ev_start, 0));
     SLLB_CUDA(cudaEventRecord(D->ev_comm0, D->s_comm));
     for (size_t c = 0; c < boxes.size(); ++c) {
         SLLB_TRY(halo_copy(D, axis, 0, h, dst_r, D->s_comm, &boxes[c], pack_blocks));
@@ -408,6 +413,24 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
         SLLB_CUDA(cudaEventRecord(D->ev_chunk[c], D->s_comm));
     }
     SLLB_CUDA(cudaEventRecord(D->ev_comm1, D->s_comm));
+    D->pre_axis = axis; D->pre_h = h; D->pre_chunks = nchunks;
+    return SLLB_OK;
+}
+/* Split-axis pass with the exchange pipelined against the stencil: chunk c of the lines is exchanged (edge planes stored
+ * straight into the neighbours' halo buffers, barrier) on the communication stream while the halo-cells kernel works on
+ * chunk c-1 on the compute stream.  Same kernels, same values as exchange-then-advect. */
+static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const DispDesc &dd, int nchunks) {
+    const int h = (stencil - 1) / 2, n = D->nw[axis];
+    const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
+    // the exchange half: already under way if it was prefetched for exactly this pass
+    if (!(D->pre_axis == axis && D->pre_h == h && D->pre_chunks == nchunks)) SLLB_TRY(dd6d_pipeline_exchange(D, axis, h, nchunks));
+    D->pre_axis = -1;
+    const std::vector<LineBox> boxes = chunk_boxes(outer, inner, nchunks);
+    const int par = D->parity;
+    D->cur_l = D->pbuf[par * 2 + 0].p; D->cur_r = D->pbuf[par * 2 + 1].p;
+    // the stencil half starts after everything launched on the default stream so far (the displacement field)
+    SLLB_CUDA(cudaEventRecord(D->ev_end, 0));
+    SLLB_CUDA(cudaStreamWaitEvent(D->s_comp, D->ev_end, 0));
     for (size_t c = 0; c < boxes.size(); ++c) {
         SLLB_CUDA(cudaStreamWaitEvent(D->s_comp, D->ev_chunk[c], 0));
         cudaError_t e = launch_lagrange_halo(D->F->d, D->cur_l, D->cur_r, outer, n, inner, stencil, dd, g_staging, D->s_comp, &boxes[c]);
@@ -422,6 +445,21 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
     D->xch_pending = false;
     return SLLB_OK;
 }
+// conditions under which sllb_dd6d_advect_axis takes the pipelined route (device-resident displacement assumed)
+static bool dd6d_pipelined_ok(sllb_dd6d *D, int axis, int h) {
+    if (g_halo_chunks < 0) { const char *e = getenv("SLLB_HALO_CHUNKS"); g_halo_chunks = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 4; }
+    if (axis < 1 || axis > 5 || D->procs[axis] < 2) return false;
+    const size_t cl = (size_t)(outer_of(D, axis) * h * inner_of(D, axis));
+    return D->p2p && g_halo_p2p && cl <= D->pcap && g_halo_chunks > 1 && h <= D->nw[axis];
+}
+static int g_halo_prefetch = [] { const char *e = getenv("SLLB_HALO_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
+// Start the halo exchange of a coming fixed-stencil pass along `axis` now (f is final for it, its displacement is not
+// known yet).  No-op when the pass would not be pipelined.
+static int dd6d_halo_prefetch(sllb_dd6d *D, int axis, int stencil) {
+    const int h = (stencil - 1) / 2;
+    if (!g_halo_prefetch || stencil < 3 || stencil > 11 || stencil % 2 == 0 || !dd6d_pipelined_ok(D, axis, h)) return SLLB_OK;
+    return dd6d_pipeline_exchange(D, axis, h, g_halo_chunks);
+}
 extern "C" {
 /* halo exchange + sll_s_advection_6d_lagrange_dd_slim_advect_eta{axis+1}: fixed odd stencil, in place.
  * procs(axis) == 1 uses the periodic kernel directly (same arithmetic as the reference's local periodic
@@ -434,18 +472,14 @@ int sllb_dd6d_advect_axis(sllb_dd6d_t D, int axis, int stencil, const sllb_disp_
     if (axis == 0) return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: a split contiguous axis (eta1) is not implemented "
                                                      "(sll_f_set_process_grid splits eta1 only from 64 ranks on)");
     const int h = (stencil - 1) / 2;
-    if (g_halo_chunks < 0) { const char *e = getenv("SLLB_HALO_CHUNKS"); g_halo_chunks = (e && atoi(e) >= 1 && atoi(e) <= 16) ? atoi(e) : 4; }
-    {
-        const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
-        const size_t cl = (size_t)(outer * h * inner);
-        if (D->p2p && g_halo_p2p && D->procs[axis] > 1 && cl <= D->pcap && g_halo_chunks > 1 && disp->values_on_device && h <= D->nw[axis]) {
-            DispDesc ddp;
-            ddp.v = disp->values; ddp.scale = disp->scale;
-            ddp.odiv = disp->odiv > 0 ? disp->odiv : 1; ddp.omod = disp->omod > 0 ? disp->omod : 1; ddp.ostr = disp->ostr;
-            ddp.idiv = disp->idiv > 0 ? disp->idiv : 1; ddp.imod = disp->imod > 0 ? disp->imod : 1; ddp.istr = disp->istr;
-            return dd6d_advect_axis_pipelined(D, axis, stencil, ddp, g_halo_chunks);
-        }
+    if (disp->values_on_device && dd6d_pipelined_ok(D, axis, h)) {
+        DispDesc ddp;
+        ddp.v = disp->values; ddp.scale = disp->scale;
+        ddp.odiv = disp->odiv > 0 ? disp->odiv : 1; ddp.omod = disp->omod > 0 ? disp->omod : 1; ddp.ostr = disp->ostr;
+        ddp.idiv = disp->idiv > 0 ? disp->idiv : 1; ddp.imod = disp->imod > 0 ? disp->imod : 1; ddp.istr = disp->istr;
+        return dd6d_advect_axis_pipelined(D, axis, stencil, ddp, g_halo_chunks);
     }
+    if (D->pre_axis >= 0) return fail(SLLB_ERR_INVALID, "dd6d_advect_axis: a prefetched halo exchange is pending for another pass");
     D->exch_pending = false;
     SLLB_TRY(sllb_dd6d_halo_exchange(D, axis, h, h));
     DispDesc dd;
@@ -767,6 +801,8 @@ int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
     }
     for (int it = 1; it <= nsteps; ++it) {
         SLLB_TRY(sllb_sim6d_advect_x(S));
+        // f is final for the first v pass: its halo leaves now, under the field solve and the diagnostics
+        if (S->p.advector != SLLB_ADVECTOR_SPLINE) SLLB_TRY(dd6d_halo_prefetch(S->D, 3, S->p.stencil_v));
         SLLB_TRY(sllb_sim6d_fields(S));
         S->itime += 1;
         if (rows) SLLB_TRY(sllb_sim6d_diagnostics(S, (double)S->itime * S->p.delta_t, rows + 14 * (row++)));
