@@ -221,8 +221,15 @@ def c5_block(sb, torch, dist, comm, rank, world, peak):
     v1.record()
     barrier()
     v_ms = maxr(v0.elapsed_time(v1)) / (3 * reps)
+    # exchange time per split pass: opt-in (one host synchronisation per pass), measured in a loop of its own
+    sb.dd6d_set_exchange_timing(True)
+    S.halo_ms()
+    for _ in range(reps):
+        S.advect_v(0.01)
     nsplit = sum(1 for p in lay["procs"][3:] if p > 1)
     halo_ms = maxr(S.halo_ms()) / max(1, nsplit * reps)
+    sb.dd6d_set_exchange_timing(False)
+    barrier()
     S.destroy()
     local_pts = float(np.prod(lay["nw"]))
     npts = float(n) ** 6

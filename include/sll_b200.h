@@ -515,6 +515,9 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt);
 int sllb_sim6d_fields(sllb_sim6d_t S);                                   /* rho, Poisson, E */
 int sllb_sim6d_diagnostics(sllb_sim6d_t S, double time, double *row14);  /* one row of <prefix>.dat */
 int sllb_sim6d_halo_ms(sllb_sim6d_t S, double *ms, int reset);           /* accumulated halo-exchange device time */
+/* the accumulation above costs one host synchronisation per split pass (and keeps the exchange of the next pass from being
+ * issued early), so it is opt-in: 1 = time every exchange, 0 (default) = none */
+int sllb_dd6d_set_exchange_timing(int on);
 int sllb_sim6d_destroy(sllb_sim6d_t S);
 
 #ifdef __cplusplus

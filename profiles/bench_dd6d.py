@@ -85,6 +85,7 @@ def main():
     barrier()
     x_ms = maxr(x0.elapsed_time(x1)) / (3 * reps)
     v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sb.dd6d_set_exchange_timing(True)   # opt-in: one host synchronisation per split pass
     S.halo_ms()
     v0.record()
     for _ in range(reps):

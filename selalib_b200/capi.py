@@ -124,6 +124,10 @@ def set_remap_rotation(on):
     _ck(lib().sllb_set_remap_rotation(C.c_int(1 if on else 0)))
 
 
+def dd6d_set_exchange_timing(on):
+    _ck(lib().sllb_dd6d_set_exchange_timing(C.c_int(1 if on else 0)))
+
+
 def set_v_overlap(on):
     _ck(lib().sllb_set_v_overlap(C.c_int(int(on))))
 

@@ -49,6 +49,8 @@ struct sllb_dd6d {
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_comm0 = nullptr, ev_comm1 = nullptr, ev_chunk[16] = {};
     bool exch_pending = false; // exch_ms of the last pipelined pass still to be read from ev_comm0/1
     int pre_axis = -1, pre_h = 0, pre_chunks = 0;   // a pipelined exchange issued ahead of its pass (dd6d_halo_prefetch)
+    cudaEvent_t ev_sten[16] = {};                   // stencil kernel of chunk c of the last pipelined pass has finished
+    int sten_axis = -1, sten_chunks = 0;            // ... which pass that was
     cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr; // around the last plain exchange (read lazily by sllb_dd6d_exchange_ms)
     bool xch_pending = false;
 };
@@ -232,6 +234,7 @@ int sllb_dd6d_destroy(sllb_dd6d_t D) {
         cudaStreamDestroy(D->s_comm); cudaStreamDestroy(D->s_comp);
         cudaEventDestroy(D->ev_start); cudaEventDestroy(D->ev_end); cudaEventDestroy(D->ev_comm0); cudaEventDestroy(D->ev_comm1);
         for (cudaEvent_t e : D->ev_chunk) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : D->ev_sten) if (e) cudaEventDestroy(e);
     }
     if (D->ev_x0) { cudaEventDestroy(D->ev_x0); cudaEventDestroy(D->ev_x1); }
     for (void *ptr : D->ipc_opened) cudaIpcCloseMemHandle(ptr);
@@ -384,6 +387,7 @@ static int dd6d_pipeline_setup(sllb_dd6d *D) {
     SLLB_CUDA(cudaEventCreate(&D->ev_comm0));
     SLLB_CUDA(cudaEventCreate(&D->ev_comm1));
     for (cudaEvent_t &e : D->ev_chunk) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : D->ev_sten) SLLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return SLLB_OK;
 }
 // The exchange half of a pipelined split-axis pass: chunk by chunk, the edge planes go into the neighbours' halo buffers and a
@@ -392,7 +396,10 @@ static int dd6d_pipeline_setup(sllb_dd6d *D) {
 // displacement), so this half may be issued EARLY: sllb_sim6d_run starts the exchange of the first split velocity axis
 // right after the x passes, and it runs under the charge density / Poisson / diagnostics work that separates the x passes
 // from the v passes (dd6d_halo_prefetch); the pass itself then finds its halo already on its way.
-static int dd6d_pipeline_exchange(sllb_dd6d *D, int axis, int h, int nchunks) {
+// chain_after_axis >= 0: chunk c of this exchange waits only for the stencil kernel of chunk c of the pipelined pass along
+// that axis (both passes cut the SAME slowest axis into the same ranges, so the edge planes of chunk c are final as soon
+// as that kernel is) instead of for the whole previous pass.
+static int dd6d_pipeline_exchange(sllb_dd6d *D, int axis, int h, int nchunks, int chain_after_axis = -1) {
     const int n = D->nw[axis];
     const long long outer = outer_of(D, axis), inner = inner_of(D, axis);
     SLLB_TRY(dd6d_pipeline_setup(D));
@@ -403,10 +410,14 @@ static int dd6d_pipeline_exchange(sllb_dd6d *D, int axis, int h, int nchunks) {
     const int par = D->parity;
     double *dst_r = static_cast<double *>(D->peers[(size_t)D->left[axis] * 8 + par * 2 + 1]);
     double *dst_l = static_cast<double *>(D->peers[(size_t)D->right[axis] * 8 + par * 2 + 0]);
-    SLLB_CUDA(cudaEventRecord(D->ev_start, 0));
-    SLLB_CUDA(cudaStreamWaitEvent(D->s_comm, D->ev_start, 0));
+    const bool chained = chain_after_axis >= 0 && D->sten_axis == chain_after_axis && D->sten_chunks == (int)boxes.size();
+    if (!chained) {
+        SLLB_CUDA(cudaEventRecord(D->ev_start, 0));
+        SLLB_CUDA(cudaStreamWaitEvent(D->s_comm, D->ev_start, 0));
+    }
     SLLB_CUDA(cudaEventRecord(D->ev_comm0, D->s_comm));
     for (size_t c = 0; c < boxes.size(); ++c) {
+        if (chained) SLLB_CUDA(cudaStreamWaitEvent(D->s_comm, D->ev_sten[c], 0));
         SLLB_TRY(halo_copy(D, axis, 0, h, dst_r, D->s_comm, &boxes[c], pack_blocks));
         SLLB_TRY(halo_copy(D, axis, n - h, h, dst_l, D->s_comm, &boxes[c], pack_blocks));
         SLLB_TRY(dd6d_barrier(D, D->s_comm));
@@ -436,7 +447,9 @@ static int dd6d_advect_axis_pipelined(sllb_dd6d *D, int axis, int stencil, const
         cudaError_t e = launch_lagrange_halo(D->F->d, D->cur_l, D->cur_r, outer, n, inner, stencil, dd, g_staging, D->s_comp, &boxes[c]);
         if (e == cudaErrorInvalidValue) { cudaGetLastError(); return fail(SLLB_ERR_UNSUPPORTED, "dd6d_advect_axis: stencil / block size not implemented"); }
         SLLB_TRY(check_cuda(e, "k_lagrange_halo launch"));
+        SLLB_CUDA(cudaEventRecord(D->ev_sten[c], D->s_comp));
     }
+    D->sten_axis = axis; D->sten_chunks = (int)boxes.size();
     SLLB_CUDA(cudaEventRecord(D->ev_end, D->s_comp));
     SLLB_CUDA(cudaStreamWaitEvent(0, D->ev_end, 0));
     D->parity ^= 1;
@@ -452,6 +465,9 @@ static bool dd6d_pipelined_ok(sllb_dd6d *D, int axis, int h) {
     const size_t cl = (size_t)(outer_of(D, axis) * h * inner_of(D, axis));
     return D->p2p && g_halo_p2p && cl <= D->pcap && g_halo_chunks > 1 && h <= D->nw[axis];
 }
+// 1: sllb_sim6d_advect_v reads the exchange time of every split pass (sllb_sim6d_halo_ms) -- a host synchronisation per
+// pass, which also keeps the next exchange from being issued early; 0 (default): no timing, no synchronisation
+static int g_exchange_timing = 0;
 static int g_halo_prefetch = [] { const char *e = getenv("SLLB_HALO_PREFETCH"); return (e && e[0] == '0') ? 0 : 1; }();
 // Start the halo exchange of a coming fixed-stencil pass along `axis` now (f is final for it, its displacement is not
 // known yet).  No-op when the pass would not be pipelined.
@@ -459,6 +475,16 @@ static int dd6d_halo_prefetch(sllb_dd6d *D, int axis, int stencil) {
     const int h = (stencil - 1) / 2;
     if (!g_halo_prefetch || stencil < 3 || stencil > 11 || stencil % 2 == 0 || !dd6d_pipelined_ok(D, axis, h)) return SLLB_OK;
     return dd6d_pipeline_exchange(D, axis, h, g_halo_chunks);
+}
+// The exchange of the pass along `axis`, chunk by chunk behind the stencil kernels of the pipelined pass along `prev` that
+// has just been issued: legal when both passes cut the slowest axis (eta6) into the same ranges -- both have at least
+// `chunks` outer indices and eta6 divides evenly -- and `prev` is not the slowest axis itself.
+static int dd6d_halo_prefetch_chained(sllb_dd6d *D, int axis, int prev, int stencil) {
+    const int h = (stencil - 1) / 2;
+    if (!g_halo_prefetch || stencil < 3 || stencil > 11 || stencil % 2 == 0 || !dd6d_pipelined_ok(D, axis, h)) return SLLB_OK;
+    if (D->sten_axis != prev || prev >= axis || axis >= 5 || D->sten_chunks != g_halo_chunks) return SLLB_OK;
+    if (outer_of(D, prev) < g_halo_chunks || outer_of(D, axis) < g_halo_chunks || D->nw[5] % g_halo_chunks != 0) return SLLB_OK;
+    return dd6d_pipeline_exchange(D, axis, h, g_halo_chunks, prev);
 }
 extern "C" {
 /* halo exchange + sll_s_advection_6d_lagrange_dd_slim_advect_eta{axis+1}: fixed odd stencil, in place.
@@ -771,9 +797,20 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
         ds.odiv = ds.omod = 1; ds.ostr = 0; ds.idiv = 1; ds.imod = nx3; ds.istr = 1;
         // splines: halo of one plane on both sides, shifts 0 and -1 (:1082-1087); else fixed Lagrange
         if (S->p.advector == SLLB_ADVECTOR_SPLINE) SLLB_TRY(sllb_dd6d_advect_axis_spline(S->D, 3 + d, &ds, nullptr, 1, 1));
-        else SLLB_TRY(sllb_dd6d_advect_axis(S->D, 3 + d, S->p.stencil_v, &ds));
-        if (S->D->procs[3 + d] > 1) { double ms = 0; SLLB_TRY(sllb_dd6d_exchange_ms(S->D, &ms)); S->halo_ms += ms; }
+        else {
+            S->D->sten_axis = -1;
+            SLLB_TRY(sllb_dd6d_advect_axis(S->D, 3 + d, S->p.stencil_v, &ds));
+            if (g_exchange_timing && S->D->procs[3 + d] > 1) { double ms = 0; SLLB_TRY(sllb_dd6d_exchange_ms(S->D, &ms)); S->halo_ms += ms; }
+            // the halo of the next v pass follows this pass chunk by chunk instead of waiting for all of it
+            if (d < 2 && S->D->sten_axis == 3 + d) SLLB_TRY(dd6d_halo_prefetch_chained(S->D, 4 + d, 3 + d, S->p.stencil_v));
+            continue;
+        }
+        if (g_exchange_timing && S->D->procs[3 + d] > 1) { double ms = 0; SLLB_TRY(sllb_dd6d_exchange_ms(S->D, &ms)); S->halo_ms += ms; }
     }
+    return SLLB_OK;
+}
+int sllb_dd6d_set_exchange_timing(int on) {
+    g_exchange_timing = on ? 1 : 0;
     return SLLB_OK;
 }
 /* Rows sllb_sim6d_run(S, nsteps, rows) will write: the first call on a handle also writes the t = 0 row. */

@@ -180,6 +180,25 @@ def main():
         res["sim6d_first_v_axis_split_f_vs_1gpu"] = float(np.abs(fp - f1[slb]).max() / np.abs(f1).max())
         ok = ok and res["sim6d_first_v_axis_split_rows_vs_1gpu"] < 1e-12 and res["sim6d_first_v_axis_split_f_vs_1gpu"] < 1e-12
 
+    # 3a'. two consecutive split velocity axes (eta4, eta5): the exchange of the second follows the stencil kernels of the first
+    #      chunk by chunk (dd6d_halo_prefetch_chained)
+    if world == 4:
+        n6 = [8, 8, 8, 16, 16, 16]
+        args = (n6, 6.0, [12.5663706144] * 3, 7, 7, 0.01, 0.01, [0.5] * 3)
+        S1 = sb.Sim6d(*args)
+        r1 = S1.run(3)
+        f1 = S1.field().download()
+        S1.destroy()
+        SP = sb.Sim6d(*args, comm=comm, process_grid=[1, 1, 1, 2, 2, 1])
+        rp = SP.run(3)
+        lay = SP.layout()
+        fp = SP.field().download()
+        SP.destroy()
+        slb = tuple(slice(lay["mn"][d], lay["mn"][d] + lay["nw"][d]) for d in range(6))
+        res["sim6d_chained_exchange_rows_vs_1gpu"] = float(np.abs(rp - r1).max())
+        res["sim6d_chained_exchange_f_vs_1gpu"] = float(np.abs(fp - f1[slb]).max() / np.abs(f1).max())
+        ok = ok and res["sim6d_chained_exchange_rows_vs_1gpu"] < 1e-12 and res["sim6d_chained_exchange_f_vs_1gpu"] < 1e-12
+
     # 3b. local splines (sll_t_advection_6d_spline_dd_slim): the P-rank result depends on the decomposition through the
     #     15-term boundary series; it must match the oracle's emulation of exactly this process grid to 1e-12, through
     #     peer stores and through ncclSend/ncclRecv
