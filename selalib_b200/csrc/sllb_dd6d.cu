@@ -596,6 +596,9 @@ struct sllb_sim6d {
     sllb_field *F = nullptr;
     sllb_poisson *poisson = nullptr;
     DevBuf rho, phi, ex, ey, ez, small;
+    DevBuf wt6, mom_part, mom9;   // fused density + moments sweep (sllb_diag.cu): weights per local velocity index, partials
+    bool mom_valid = false;       // mom9 holds the nine moments of the current f
+    bool want_moments = false;    // the time loop writes diagnostics rows: sllb_sim6d_fields takes the fused sweep
     bool started = false;
     bool half_kick_pending = false; // the previous sllb_sim6d_run ended with the closing half kick of time_in_phase
     int itime = 0;
@@ -628,6 +631,31 @@ extern "C" {
  * then Poisson and E (sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:605-616) */
 int sllb_sim6d_fields(sllb_sim6d_t S) {
     if (!S) return fail(SLLB_ERR_INVALID, "sim6d_fields: null");
+    S->mom_valid = false;
+    if (S->want_moments) {
+        // one sweep over f gives the density partials AND the nine velocity moments of the diagnostics row
+        sllb_field *F = S->F;
+        const long long nx = (long long)F->ext[0] * F->ext[1] * F->ext[2], nv = (long long)F->ext[3] * F->ext[4] * F->ext[5];
+        if (!S->wt6.p) {
+            std::vector<double> w((size_t)nv * 6);
+            for (long long v = 0; v < nv; ++v) {
+                const int idx[3] = {(int)(v % F->ext[3]), (int)((v / F->ext[3]) % F->ext[4]), (int)(v / ((long long)F->ext[3] * F->ext[4]))};
+                for (int a = 0; a < 3; ++a) {
+                    const double vel = S->emin[3 + a] + S->de[3 + a] * (double)(idx[a] + S->D->mn[3 + a]);
+                    w[(size_t)v * 6 + a] = vel; w[(size_t)v * 6 + 3 + a] = vel * vel;
+                }
+            }
+            SLLB_TRY(S->wt6.ensure(w.size()));
+            SLLB_CUDA(cudaMemcpy(S->wt6.p, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice));
+            SLLB_TRY(S->mom_part.ensure(reduce_moments6d_scratch(nx, nv)));
+            SLLB_TRY(S->mom9.ensure(9));
+        }
+        SLLB_TRY(F->red_scratch.ensure((size_t)nx * reduce_moments6d_chunks(nv)));
+        int nparts = 0;
+        SLLB_CUDA(launch_reduce_moments6d(F->d, nx, nv, S->wt6.p, F->red_scratch.p, &nparts, S->mom_part.p, S->mom9.p, g_stream));
+        SLLB_CUDA(launch_sum_partials(F->red_scratch.p, nx, nparts, -(S->de[3] * S->de[4] * S->de[5]), S->rho.p, g_stream));
+        S->mom_valid = true;
+    } else
     SLLB_TRY(sllb_reduce_velocity(S->F, 3, -(S->de[3] * S->de[4] * S->de[5]), S->rho.p));
     if (S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho.p, (int64_t)S->p.n[0] * S->p.n[1] * S->p.n[2]));
     SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p));
@@ -649,7 +677,8 @@ int sllb_sim6d_diagnostics(sllb_sim6d_t S, double time, double *row14) {
             w1.push_back(v); w2.push_back(v * v);
         }
     double m[9];
-    SLLB_TRY(moments_local(S->F, 3, w1.data(), w2.data(), m));
+    if (S->mom_valid) SLLB_CUDA(cudaMemcpy(m, S->mom9.p, sizeof(m), cudaMemcpyDeviceToHost));   // came out of the density sweep
+    else SLLB_TRY(moments_local(S->F, 3, w1.data(), w2.data(), m));
     if (S->D->nranks > 1) {
         SLLB_CUDA(cudaMemcpy(S->small.p + 5, m, sizeof(m), cudaMemcpyHostToDevice));
         SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->small.p + 5, 9));
@@ -827,6 +856,7 @@ int sllb_sim6d_run_rows(sllb_sim6d_t S, int nsteps, int *nrows) {
 int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
     if (!S || nsteps < 0) return fail(SLLB_ERR_INVALID, "sim6d_run: bad arguments");
     int row = 0;
+    S->want_moments = rows != nullptr;   // the field solve of every step is followed by a diagnostics row
     if (!S->started) {
         if (rows) SLLB_TRY(sllb_sim6d_diagnostics(S, 0.0, rows));
         row = 1;
@@ -847,7 +877,9 @@ int sllb_sim6d_run(sllb_sim6d_t S, int nsteps, double *rows) {
             SLLB_TRY(sllb_sim6d_advect_v(S, 0.5 * S->p.delta_t));
             S->half_kick_pending = true;
         } else SLLB_TRY(sllb_sim6d_advect_v(S, S->p.delta_t));
+        S->mom_valid = false;
     }
+    S->want_moments = false;
     SLLB_CUDA(cudaDeviceSynchronize());
     if (S->D->flag_barrier) {
         double err = 0.0;

@@ -125,6 +125,106 @@ cudaError_t launch_absmax(const double *a, long long n, double *out1, cudaStream
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3D3V: the charge density and the nine velocity moments of the diagnostics row in ONE sweep over f.
+// f is [nv][nx] (x fastest).  Block = 128 consecutive x, blockIdx.y = chunk of v: every thread adds f over the chunk's v
+// (first stage of the density reduction, K3) and, on the side, nine accumulators sum_v w_k(v) f(x,v) with
+// w = (1, |.|, (.)^2, v4, v5, v6, v4^2, v5^2, v6^2) (sll_s_time_history_diagnostics, sll_m_sim_6d_utilities.F90:249-644,
+// asks for exactly these integrals); the block folds them and leaves 9 numbers per block.  The reference sweeps f once
+// for rho and once more for the diagnostics; so did round 1 (k_reduce_stage1 + k_row_sums).
+// ------------------------------------------------------------------------------------------------
+#define SLLB_RM_XPT 4      // x values per thread: the six weights of a velocity index are read once per four elements
+#define SLLB_RM_VMAX 64    // most velocity indices a chunk may hold (weights staged in shared memory)
+__global__ void __launch_bounds__(128) k_reduce_moments6d(const double *__restrict__ f, const long long nx, const long long nv,
+                                                          const int nchunks, const double *__restrict__ wt /* [nv][6] */,
+                                                          double *__restrict__ partial, double *__restrict__ mom_part) {
+    __shared__ double wsh[SLLB_RM_VMAX * 6];
+    __shared__ double sh[9][4];
+    const long long x0 = (long long)blockIdx.x * (128 * SLLB_RM_XPT) + threadIdx.x;
+    const int c = blockIdx.y;
+    const long long v0 = nv * c / nchunks, v1 = nv * (c + 1) / nchunks;
+    for (int i = threadIdx.x; i < (int)(v1 - v0) * 6; i += 128) wsh[i] = wt[v0 * 6 + i];
+    __syncthreads();
+    double a[SLLB_RM_XPT], m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < SLLB_RM_XPT; ++j) a[j] = 0.0;
+    for (long long v = v0; v < v1; ++v) {
+        double t[SLLB_RM_XPT];
+#pragma unroll
+        for (int j = 0; j < SLLB_RM_XPT; ++j) {
+            const long long x = x0 + 128 * j;
+            t[j] = x < nx ? __ldcs(f + x + nx * v) : 0.0;
+        }
+        const double *w = wsh + 6 * (v - v0);
+        double s1 = 0.0, sa = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < SLLB_RM_XPT; ++j) { a[j] += t[j]; s1 += t[j]; sa += fabs(t[j]); s2 = fma(t[j], t[j], s2); }
+        m[1] += sa; m[2] += s2;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) m[3 + k] = fma(w[k], s1, m[3 + k]);   // the weights multiply the sum over this thread's x
+    }
+#pragma unroll
+    for (int j = 0; j < SLLB_RM_XPT; ++j) {
+        const long long x = x0 + 128 * j;
+        if (x < nx) partial[(long long)c * nx + x] = a[j];
+        m[0] += a[j];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[k] += __shfl_xor_sync(0xffffffffu, m[k], o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 9; ++k) sh[k][threadIdx.x >> 5] = m[k];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        const int k = threadIdx.x;
+        mom_part[((long long)c * gridDim.x + blockIdx.x) * 9 + k] = (sh[k][0] + sh[k][1]) + (sh[k][2] + sh[k][3]);
+    }
+}
+__global__ void __launch_bounds__(RT) k_moments6d_finish(const double *__restrict__ mom_part, const long long nblocks,
+                                                         double *__restrict__ out9) {
+    __shared__ double sh[9][32];
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long b = threadIdx.x; b < nblocks; b += RT)
+        for (int k = 0; k < 9; ++k) v[k] += mom_part[b * 9 + k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 9; ++k) sh[k][threadIdx.x >> 5] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 9) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += sh[threadIdx.x][i];
+        out9[threadIdx.x] = t;
+    }
+}
+static int rm_chunks(long long nv) {
+    long long ch = nv < 128 ? nv : 128;
+    while ((nv + ch - 1) / ch > SLLB_RM_VMAX) ch *= 2;   // at most SLLB_RM_VMAX velocity indices per chunk
+    return (int)ch;
+}
+int reduce_moments6d_chunks(long long nv) { return rm_chunks(nv); }
+size_t reduce_moments6d_scratch(long long nx, long long nv) {
+    return (size_t)(((nx + 128 * SLLB_RM_XPT - 1) / (128 * SLLB_RM_XPT)) * rm_chunks(nv) * 9);
+}
+// partial: reduce_scratch_doubles(nx, nv) doubles (the density partials, to be folded by launch_sum_partials with *nchunks
+// parts); mom_part: reduce_moments6d_scratch doubles; out9: the nine moments
+cudaError_t launch_reduce_moments6d(const double *f, long long nx, long long nv, const double *wt, double *partial, int *nchunks_out,
+                                    double *mom_part, double *out9, cudaStream_t st) {
+    const int nchunks = rm_chunks(nv);
+    dim3 grid((unsigned)((nx + 128 * SLLB_RM_XPT - 1) / (128 * SLLB_RM_XPT)), nchunks);
+    k_reduce_moments6d<<<grid, 128, 0, st>>>(f, nx, nv, nchunks, wt, partial, mom_part);
+    count_launch();
+    k_moments6d_finish<<<1, RT, 0, st>>>(mom_part, (long long)grid.x * grid.y, out9);
+    count_launch();
+    *nchunks_out = nchunks;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // dup_velocity_planes mode of the 2D2V loop: the N4 + N3 + 1 side planes (x3 = N3 with x4 < N4, x4 = N4 with x3 < N3, the
 // corner) that the reference's (N+1)-point arrays carry next to the periodic cells.
 // ------------------------------------------------------------------------------------------------

@@ -141,6 +141,12 @@ size_t moments_from_lines_scratch();
 // nrj = scale * sum over the (n1+1)(n2+1) nodes including the periodic duplicates of a^2 + (squared ? b^2 : 2 b)
 cudaError_t launch_dup_energy2d(const double *a, const double *b, int n1, int n2, double scale, int squared, double *out1,
                                 cudaStream_t st);
+// 3D3V: density partials + the nine velocity moments of the diagnostics row in one sweep over f ([nv][nx]); wt = [nv][6]
+// weights (v4, v5, v6, v4^2, v5^2, v6^2 of every local velocity index)
+size_t reduce_moments6d_scratch(long long nx, long long nv);
+int reduce_moments6d_chunks(long long nv);   // the density partials are [chunks][nx]
+cudaError_t launch_reduce_moments6d(const double *f, long long nx, long long nv, const double *wt, double *partial, int *nchunks_out,
+                                    double *mom_part, double *out9, cudaStream_t st);
 // dup_velocity_planes mode: side planes <- the cell planes they duplicate; rho += scale * (trapezoid - plain sum)
 cudaError_t launch_dup_fill(const double *f, long long n12, int n3, int n4, double *side, cudaStream_t st);
 cudaError_t launch_dup_rho_corr(const double *f, const double *side, long long n12, int n3, int n4, double scale, double *rho,
