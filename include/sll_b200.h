@@ -518,6 +518,15 @@ int sllb_sim6d_halo_ms(sllb_sim6d_t S, double *ms, int reset);           /* accu
 /* the accumulation above costs one host synchronisation per split pass (and keeps the exchange of the next pass from being
  * issued early), so it is opt-in: 1 = time every exchange, 0 (default) = none */
 int sllb_dd6d_set_exchange_timing(int on);
+/* sll_t_clocks of the 6D simulation (sll_m_sim_6d_utilities.F90:132-140,765-826; labels of
+ * sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:684-957): wall-clock seconds under P, PC, PF, D, X, X1..X3, V, X4..X6, H4..H6;
+ * sllb_sim6d_write_clocks writes them like sll_s_finalize_clocks does ("sll_clocks.txt" when path is NULL).  Opt-in:
+ * every phase boundary waits for the default stream. */
+int sllb_sim6d_set_clocks(sllb_sim6d_t S, int on);
+int sllb_sim6d_write_clocks(sllb_sim6d_t S, const char *path);
+/* hosts with their own time loop: between sllb_sim6d_advect_x and sllb_sim6d_fields -- the halo of the first split
+ * velocity axis leaves now and travels under the field solve (sllb_sim6d_run does this itself) */
+int sllb_sim6d_prefetch_v_halo(sllb_sim6d_t S);
 int sllb_sim6d_destroy(sllb_sim6d_t S);
 
 #ifdef __cplusplus

@@ -785,6 +785,13 @@ class Sim6d:
         _ck(lib().sllb_dd6d_layout(d, *arrs))
         return dict(zip(("procs", "coords", "mn", "nw", "left", "right"), [tuple(a[:]) for a in arrs]))
 
+    def set_clocks(self, on=True):
+        """the reference's stopwatch table (labels P, PC, PF, D, X, X1..X3, V, X4..X6, H4..H6)"""
+        _ck(lib().sllb_sim6d_set_clocks(self.h, C.c_int(1 if on else 0)))
+
+    def write_clocks(self, path):
+        _ck(lib().sllb_sim6d_write_clocks(self.h, path.encode()))
+
     def advect_x(self):
         _ck(lib().sllb_sim6d_advect_x(self.h))
 

@@ -52,6 +52,7 @@ struct Compat6d {
     std::vector<double> mirror;  // host mirror of the local block handed out by get_distribution
     bool mirror_out = false;     // the caller may have written into the mirror
     int rank = 0;
+    bool clocks = false;         // SLLB_CLOCKS=1: the reference's stopwatch table, written to sll_clocks.txt by run
 };
 
 sllb_comm *g_compat_comm = nullptr;
@@ -145,6 +146,11 @@ void sim_bsl_vp_3d3v_cart_dd_slim_init(void **sim, const char *filename) {
     c->nml_dir = slash == std::string::npos ? "." : fn.substr(0, slash);
     c->rank = g_compat_comm ? g_compat_comm->rank : 0;
     CK(sllb_sim6d_create_dist(&c->p, g_compat_comm, pg, &c->S), fun);
+    {
+        const char *e = getenv("SLLB_CLOCKS");
+        c->clocks = e && e[0] == '1';
+        if (c->clocks) CK(sllb_sim6d_set_clocks(c->S, 1), fun);
+    }
     sllb_dd6d_t D = nullptr;
     CK(sllb_sim6d_decomposition(c->S, &D), fun);
     CK(sllb_dd6d_layout(D, nullptr, nullptr, c->mn, c->nw, nullptr, nullptr), fun);
@@ -171,6 +177,7 @@ void sim_bsl_vp_3d3v_cart_dd_slim_run(void **sim) {
     int itime;
     for (itime = c->first_time_step; itime <= last; ++itime) {
         CK(sllb_sim6d_advect_x(c->S), fun);
+        CK(sllb_sim6d_prefetch_v_halo(c->S), fun);
         CK(sllb_sim6d_fields(c->S), fun);
         if (itime % c->n_diagnostics == 0) {
             double row[14];
@@ -186,6 +193,8 @@ void sim_bsl_vp_3d3v_cart_dd_slim_run(void **sim) {
     c->first_time_step = itime;
     c->ctest = false; // like the interface's run (:101)
     CK(sllb_synchronize(), fun);
+    // sll_s_finalize_clocks (:760): rank 0 leaves sll_clocks.txt behind when the stopwatches were on (SLLB_CLOCKS=1)
+    if (c->rank == 0 && c->clocks) CK(sllb_sim6d_write_clocks(c->S, "sll_clocks.txt"), fun);
     if (c->rank == 0) printf(" Leaving main loop.\n");
 }
 

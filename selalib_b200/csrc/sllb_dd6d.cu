@@ -599,6 +599,11 @@ struct sllb_sim6d {
     DevBuf wt6, mom_part, mom9;   // fused density + moments sweep (sllb_diag.cu): weights per local velocity index, partials
     bool mom_valid = false;       // mom9 holds the nine moments of the current f
     bool want_moments = false;    // the time loop writes diagnostics rows: sllb_sim6d_fields takes the fused sweep
+    // sll_t_clocks of the reference (sll_m_sim_6d_utilities.F90:132-140,765-826): wall-clock seconds per labelled phase,
+    // slot [first char - '/'][second char - '/'] ('/' = one-character label).  Opt-in: every phase boundary waits for the
+    // default stream.
+    bool clocks_on = false;
+    double clocks[44][44] = {};
     bool started = false;
     bool half_kick_pending = false; // the previous sllb_sim6d_run ended with the closing half kick of time_in_phase
     int itime = 0;
@@ -629,8 +634,31 @@ extern "C" {
 
 /* rho = -dV_v sum f (sll_m_sim_6d_utilities.F90:203-245), summed over the velocity communicator (:195),
  * then Poisson and E (sll_m_sim_bsl_vp_3d3v_cart_dd_slim.F90:605-616) */
+} // extern "C"
+#include <chrono>
+namespace {
+// a running phase of the reference's stopwatch table; stop() waits for the default stream first so that the interval
+// covers the device work issued inside it
+struct Clock6d {
+    sllb_sim6d *S; const char *label; std::chrono::steady_clock::time_point t0;
+    Clock6d(sllb_sim6d *s, const char *l) : S(s), label(l) {
+        if (S->clocks_on) { cudaStreamSynchronize(0); t0 = std::chrono::steady_clock::now(); }
+    }
+    void stop() {
+        if (!S->clocks_on || !label) return;
+        cudaStreamSynchronize(0);
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const int i = label[0] - '/', j = label[1] ? label[1] - '/' : 0;
+        if (i >= 0 && i < 44 && j >= 0 && j < 44) S->clocks[i][j] += dt;
+        label = nullptr;
+    }
+    ~Clock6d() { stop(); }
+};
+} // namespace
+extern "C" {
 int sllb_sim6d_fields(sllb_sim6d_t S) {
     if (!S) return fail(SLLB_ERR_INVALID, "sim6d_fields: null");
+    Clock6d ck_p(S, "P"), ck_pc(S, "PC");
     S->mom_valid = false;
     if (S->want_moments) {
         // one sweep over f gives the density partials AND the nine velocity moments of the diagnostics row
@@ -658,12 +686,37 @@ int sllb_sim6d_fields(sllb_sim6d_t S) {
     } else
     SLLB_TRY(sllb_reduce_velocity(S->F, 3, -(S->de[3] * S->de[4] * S->de[5]), S->rho.p));
     if (S->D->nranks > 1) SLLB_TRY(sllb_comm_allreduce_sum(S->comm, S->rho.p, (int64_t)S->p.n[0] * S->p.n[1] * S->p.n[2]));
+    ck_pc.stop();
+    Clock6d ck_pf(S, "PF");
     SLLB_TRY(sllb_poisson_solve(S->poisson, S->rho.p, S->phi.p, S->ex.p, S->ey.p, S->ez.p));
+    return SLLB_OK;
+}
+/* sll_t_clocks: 1 = accumulate wall-clock seconds under the reference's labels (P, PC, PF: charge density + Poisson; D:
+ * diagnostics; X, X1..X3: x advections; V, X4..X6, H4..H6: v advections and their halo exchanges), 0 (default) = off */
+int sllb_sim6d_set_clocks(sllb_sim6d_t S, int on) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_set_clocks: null");
+    S->clocks_on = on != 0;
+    g_exchange_timing = on != 0;
+    return SLLB_OK;
+}
+/* sll_s_finalize_clocks (:775-796): one line per label with a positive time, in the order of the table */
+int sllb_sim6d_write_clocks(sllb_sim6d_t S, const char *path) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_write_clocks: null");
+    FILE *fp = fopen(path ? path : "sll_clocks.txt", "w");
+    if (!fp) return fail(SLLB_ERR_INVALID, "sim6d_write_clocks: cannot create the file");
+    for (int i = 0; i < 44; ++i)
+        for (int j = 0; j < 44; ++j)
+            if (S->clocks[i][j] > 0.0) {
+                char label[3] = {(char)('/' + i), j == 0 ? '\0' : (char)('/' + j), '\0'};
+                fprintf(fp, " %s  %.16G     \n", label, S->clocks[i][j]);   // list-directed: blank, label, blanks, real
+            }
+    fclose(fp);
     return SLLB_OK;
 }
 /* sll_s_time_history_diagnostics (sll_m_sim_6d_utilities.F90:249-644): time + 13 numbers */
 int sllb_sim6d_diagnostics(sllb_sim6d_t S, double time, double *row14) {
     if (!S || !row14) return fail(SLLB_ERR_INVALID, "sim6d_diagnostics: null");
+    Clock6d ck_d(S, "D");
     const int *n = S->p.n;
     const double Lx = S->emax[0] - S->emin[0], Ly = S->emax[1] - S->emin[1], Lz = S->emax[2] - S->emin[2];
     const double vol_x = Lx * Ly * Lz;
@@ -777,6 +830,8 @@ int sllb_sim6d_decomposition(sllb_sim6d_t S, sllb_dd6d_t *D) {
 /* advect_x (:817-865): eta1..3 with disp_eta = -v*dt/dx (:590-592); x is not split, local periodic wrap */
 int sllb_sim6d_advect_x(sllb_sim6d_t S) {
     if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_x: null");
+    Clock6d ck_x(S, "X");
+    static const char *const xl[3] = {"X1", "X2", "X3"};
     if (S->p.advector != SLLB_ADVECTOR_FIXED) {
         // fadvect_eta1..3 (:866-880): the displacement array of the conjugate velocity axis, block by block in the
         // reference, line by line here (the block only fixes the integer part, carried by the shift table)
@@ -787,6 +842,7 @@ int sllb_sim6d_advect_x(sllb_sim6d_t S) {
             long long stride = 1;
             for (int a = d + 1; a < d + 3; ++a) stride *= S->D->nw[a];
             ds.odiv = stride; ds.omod = S->D->nw[d + 3]; ds.ostr = 1; ds.idiv = 1; ds.imod = 1; ds.istr = 0;
+            Clock6d ck_a(S, xl[d]);
             if (S->p.advector == SLLB_ADVECTOR_SPLINE) SLLB_TRY(sllb_dd6d_advect_axis_spline(S->D, d, &ds, S->shift_x[d].data(), S->hw_x[d][0], S->hw_x[d][1]));
             else SLLB_TRY(sllb_advect_axis(S->F, d, SLLB_METHOD_LAGRANGE_CENTERED, S->p.stencil_x, &ds));
         }
@@ -809,9 +865,11 @@ int sllb_sim6d_advect_x(sllb_sim6d_t S) {
         if (rc == SLLB_OK) first = 2;
         else if (rc != SLLB_ERR_UNSUPPORTED) return rc;
     }
-    for (int d = first; d < 3; ++d)
+    for (int d = first; d < 3; ++d) {
+        Clock6d ck_a(S, xl[d]);
         SLLB_TRY(sllb_advect_axis_affine(S->F, d, SLLB_METHOD_LAGRANGE_FIXED, S->p.stencil_x, d + 3,
                                          S->emin[d + 3] + S->D->mn[d + 3] * S->de[d + 3], S->de[d + 3], -S->p.delta_t / S->de[d]));
+    }
     return SLLB_OK;
 }
 /* advect_v (:889-958): per axis halo exchange, then eta4..6 with displacement E*dt/dv as a 3D field */
@@ -819,7 +877,15 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
     if (!S) return fail(SLLB_ERR_INVALID, "sim6d_advect_v: null");
     const double *E[3] = {S->ex.p, S->ey.p, S->ez.p};
     const long long nx3 = (long long)S->p.n[0] * S->p.n[1] * S->p.n[2];
+    Clock6d ck_v(S, "V");
+    static const char *const vl[3] = {"X4", "X5", "X6"};
     for (int d = 0; d < 3; ++d) {
+        Clock6d ck_a(S, vl[d]);
+        const double halo_before = S->halo_ms;
+        struct HaloClock {   // H4..H6: the exchange part of this pass, from the device-side exchange timer
+            sllb_sim6d *S; int d; double before;
+            ~HaloClock() { if (S->clocks_on) S->clocks['H' - '/']['4' + d - '/'] += (S->halo_ms - before) * 1e-3; }
+        } hck{S, d, halo_before};
         sllb_disp_t ds;
         memset(&ds, 0, sizeof(ds));
         ds.values = E[d]; ds.nvalues = nx3; ds.values_on_device = 1; ds.scale = dt / S->de[3 + d];
@@ -837,6 +903,13 @@ int sllb_sim6d_advect_v(sllb_sim6d_t S, double dt) {
         if (g_exchange_timing && S->D->procs[3 + d] > 1) { double ms = 0; SLLB_TRY(sllb_dd6d_exchange_ms(S->D, &ms)); S->halo_ms += ms; }
     }
     return SLLB_OK;
+}
+/* For hosts that keep their own time loop: call between sllb_sim6d_advect_x and sllb_sim6d_fields.  f is final for the
+ * first v pass then, so the halo exchange of the first split velocity axis starts now and runs under the field solve. */
+int sllb_sim6d_prefetch_v_halo(sllb_sim6d_t S) {
+    if (!S) return fail(SLLB_ERR_INVALID, "sim6d_prefetch_v_halo: null");
+    if (S->p.advector == SLLB_ADVECTOR_SPLINE) return SLLB_OK;
+    return dd6d_halo_prefetch(S->D, 3, S->p.stencil_v);
 }
 int sllb_dd6d_set_exchange_timing(int on) {
     g_exchange_timing = on ? 1 : 0;

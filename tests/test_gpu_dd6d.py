@@ -147,6 +147,30 @@ def test_sim6d_run_in_two_calls_equals_one_call(sb, in_phase):
         assert np.array_equal(r2, r1) and np.array_equal(f2, f1)
 
 
+def test_sim6d_clocks_file(sb, tmp_path):
+    """sll_clocks.txt (sll_s_finalize_clocks, sll_m_sim_6d_utilities.F90:775-796): the labels the reference's time loop
+    uses, wall-clock seconds, only the ones that ran; and the stopwatches do not change the results"""
+    args = ([8, 8, 8, 16, 16, 16], 6.0, [12.5663706144] * 3, 5, 5, 0.01, 0.01, [0.5] * 3)
+    S0 = sb.Sim6d(*args)
+    r0 = S0.run(2)
+    S0.destroy()
+    S = sb.Sim6d(*args)
+    S.set_clocks(True)
+    r = S.run(2)
+    path = str(tmp_path / "sll_clocks.txt")
+    S.write_clocks(path)
+    S.destroy()
+    assert np.array_equal(r, r0)
+    got = {}
+    for line in open(path):
+        label, val = line.split()
+        got[label] = float(val)
+    assert set(got) == {"D", "P", "PC", "PF", "V", "X", "X1", "X2", "X3", "X4", "X5", "X6"}      # one GPU: no H4..H6
+    assert all(v > 0 for v in got.values())
+    assert got["X"] >= got["X1"] + got["X2"] + got["X3"] - 1e-9 and got["P"] >= got["PC"] + got["PF"] - 1e-9
+    assert list(got) == sorted(got)                       # table order = ASCII order of the labels
+
+
 def test_cpp_interface_of_the_reference_simulation(sb, tmp_path):
     """Our restatement of simulations/parallel/bsl_vp_3d3v_cart_dd/test_cpp_interface.cpp: a C++ host drives the
     simulation through the reference's own C symbols (namelist in, <prefix>.dat out) and the result is checked
