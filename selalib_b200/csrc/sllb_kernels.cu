@@ -876,7 +876,16 @@ __device__ __forceinline__ void chunk_solve(double (&g)[SLLB_PR_C], double *exch
 // w mod 4, columns 64 (w / 4) .. + 63) instead of 12 registers + 20 shared-memory slots: no register spills, 80 KB of shared
 // memory and 40 shared-memory accesses per thread and plane less; the TMEM loads of a group of 8 are in flight while the 8
 // values are evaluated.
-template <bool RHO, bool REMAP, bool TACC = false>
+// WPA = M > 0 (N1 = 32 M): pass A is WARP-COOPERATIVE and reads its rows straight from global memory -- a warp owns a row,
+// lane l holds the M consecutive points M l .. M l + M - 1 (two 16-byte loads per lane, 1 KB per warp: coalesced), the two
+// first-order recurrences run as M - 1 local steps plus a log-step shuffle scan of the lane-end values (ratio (-q)^M; 8 lanes
+// x 4 points = the 27-term reach of the reference's series and more), the four-point evaluation takes its three outside
+// coefficients from the neighbouring lanes, and the results are scattered to their final x1 positions in the shared plane
+// with an XOR swizzle (p ^ ((p >> 4) & 3)) that keeps both this stride-M scatter and pass B's column reads free of bank
+// conflicts.  No bulk copy, no mbarrier, no block-wide barrier and no exchange array in pass A: the warps of a CTA drift
+// apart and overlap their global loads with each other's arithmetic; the next row is in flight while the current one is
+// solved.  Pass B is unchanged.
+template <bool RHO, bool REMAP, bool TACC = false, int WPA = 0>
 __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1, const int N2,
                                                            const long long nplanes, const DispDesc dd1,
                                                            const DispDesc dd2, double *__restrict__ rho_partial,
@@ -919,7 +928,7 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
     __syncthreads();
     uint32_t phase = 0;
     long long pl = blockIdx.x;
-    if (tid == 0 && pl < nplanes) {
+    if (WPA == 0 && tid == 0 && pl < nplanes) {
         mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
         bulk_g2s(s, f + pl * (long long)npl, (uint32_t)(npl * 8), bar);
     }
@@ -933,6 +942,77 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
         const double d2 = disp_of(dd2, pl, 0);
         const double fl1 = floor(d1), fl2 = floor(d2);
         double g[C];
+        if constexpr (WPA > 0) {
+            // ---- pass A, warp-cooperative: rows straight from global memory ----
+            constexpr int M = WPA;
+            constexpr double q = 0.26794919243112270647;
+            const int nwarps = T >> 5;
+            double qm[M];                       // (-q)^(j+1)
+            qm[0] = -q;
+#pragma unroll
+            for (int j = 1; j < M; ++j) qm[j] = -q * qm[j - 1];
+            const double dxa = d1 - fl1, cdxa = 1.0 - dxa, s6a = 1.60769515458673623883 * (1.0 / 6.0);
+            const double wa0 = cdxa * cdxa * cdxa * s6a;
+            const double wa1 = (1.0 + 3.0 * cdxa + 3.0 * cdxa * cdxa - 3.0 * cdxa * cdxa * cdxa) * s6a;
+            const double wa2 = (1.0 + 3.0 * dxa + 3.0 * dxa * dxa - 3.0 * dxa * dxa * dxa) * s6a;
+            const double wa3 = dxa * dxa * dxa * s6a;
+            int p0 = (int)(((long long)M * lane - (long long)fl1) % N1);   // output position of this lane's first cell
+            if (p0 < 0) p0 += N1;
+            const double2 *src = reinterpret_cast<const double2 *>(gp + (size_t)M * lane);
+            double a[M], nx[M];
+            if (w < N2) {
+#pragma unroll
+                for (int j = 0; j < M; j += 2) { const double2 t = __ldcs(src + ((size_t)w * N1 + j) / 2); nx[j] = t.x; nx[j + 1] = t.y; }
+            }
+            for (int r = w; r < N2; r += nwarps) {
+#pragma unroll
+                for (int j = 0; j < M; ++j) a[j] = nx[j];
+                if (r + nwarps < N2) {          // the next row of this warp is in flight while this one is solved
+#pragma unroll
+                    for (int j = 0; j < M; j += 2) { const double2 t = __ldcs(src + ((size_t)(r + nwarps) * N1 + j) / 2); nx[j] = t.x; nx[j + 1] = t.y; }
+                }
+                // forward recurrence e_i = f_i - q e_{i-1}: local steps from zero, scan of the lane-end values, carry-in
+#pragma unroll
+                for (int j = 1; j < M; ++j) a[j] = fma(-q, a[j - 1], a[j]);
+                double Tn = a[M - 1], mult = qm[M - 1];
+#pragma unroll
+                for (int sft = 1; sft * M < 32; sft <<= 1) {
+                    Tn = fma(mult, __shfl_sync(0xffffffffu, Tn, (lane - sft) & 31), Tn);
+                    mult *= mult;
+                }
+                const double Tp = __shfl_sync(0xffffffffu, Tn, (lane - 1) & 31);
+#pragma unroll
+                for (int j = 0; j < M; ++j) a[j] = fma(qm[j], Tp, a[j]);
+                // backward recurrence g_i = e_i - q g_{i+1}, mirrored
+#pragma unroll
+                for (int j = M - 2; j >= 0; --j) a[j] = fma(-q, a[j + 1], a[j]);
+                double Un = a[0];
+                mult = qm[M - 1];
+#pragma unroll
+                for (int sft = 1; sft * M < 32; sft <<= 1) {
+                    Un = fma(mult, __shfl_sync(0xffffffffu, Un, (lane + sft) & 31), Un);
+                    mult *= mult;
+                }
+                const double Ux = __shfl_sync(0xffffffffu, Un, (lane + 1) & 31);
+#pragma unroll
+                for (int j = 0; j < M; ++j) a[j] = fma(qm[M - 1 - j], Ux, a[j]);
+                // cell c = M lane + j: w0 g[c-1] + w1 g[c] + w2 g[c+1] + w3 g[c+2], stored at position (c - dcell) mod N1
+                double e[M + 3];
+                e[0] = __shfl_sync(0xffffffffu, a[M - 1], (lane - 1) & 31);
+#pragma unroll
+                for (int j = 0; j < M; ++j) e[j + 1] = a[j];
+                e[M + 1] = __shfl_sync(0xffffffffu, a[0], (lane + 1) & 31);
+                e[M + 2] = __shfl_sync(0xffffffffu, a[1], (lane + 1) & 31);
+                double *row = s + (size_t)r * N1;
+                int p = p0;
+#pragma unroll
+                for (int j = 0; j < M; ++j) {
+                    row[p ^ ((p >> 4) & 3)] = fma(wa3, e[j + 3], fma(wa2, e[j + 2], fma(wa1, e[j + 1], wa0 * e[j])));
+                    p = (p == N1 - 1) ? 0 : p + 1;
+                }
+            }
+            __syncthreads();
+        } else {
         // ---- pass A: rows ----
         int k0 = chA * C + (lane & 15);        // skewed chunk start: conflict-free banks with pitch N1
         if (k0 >= N1) k0 -= N1;
@@ -954,11 +1034,12 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
             for (int j = 0; j < C; ++j) { row[i1] = g[j]; i1 = (i1 == N1 - 1) ? 0 : i1 + 1; }
         }
         __syncthreads();
+        }
         // ---- pass B: columns; the chunk grid is shifted so that this thread's cells are points 32*chB + j ----
         {
             int k = (int)(((long long)chB * C - 1 + (long long)fl2) % N2);
             if (k < 0) k += N2;
-            const double *col = s + colB;
+            const double *col = s + (WPA > 0 ? (colB ^ ((colB >> 4) & 3)) : colB);
 #pragma unroll
             for (int j = 0; j < C; ++j) { g[j] = col[(size_t)k * N1]; k = (k == N2 - 1) ? 0 : k + 1; }
         }
@@ -970,7 +1051,7 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
             exch[chB * N1 + colB] = g[C - 1];
             __syncthreads();
             const long long nxt = pl + gridDim.x;
-            if (tid == 0 && nxt < nplanes) { // the plane is dead in shared memory: fetch the next one
+            if (WPA == 0 && tid == 0 && nxt < nplanes) { // the plane is dead in shared memory: fetch the next one
                 mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
                 bulk_g2s(s, f + nxt * (long long)npl, (uint32_t)(npl * 8), bar);
             }
