@@ -405,13 +405,19 @@ def run_ours(args, rank, world, local_rank):
     t_dom = sum(strided) / len(strided)
     peak, peak_src = measured_peak()
     achieved = 16.0 * local_pts / (t_dom * 1e-3) / 1e9
-    traffic, traffic_src = None, None
+    traffic, traffic_src, plane_traffic = None, None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic = tj["kernels"]["k_spline_strided_split<4, 0>"]["dram_bytes_per_launch"] * local_pts / float(128) ** 4
+            # the plain variant of the strided spline pass: P = 4, no remap stores, no line diagnostics (all-zero trailing
+            # template arguments; the list grew from <4, 0> to <4, 0, 0> in round 2)
+            names = [k for k in tj["kernels"] if k.startswith("k_spline_strided_split<4") and
+                     all(t.strip() == "0" for t in k[k.index("<") + 1:k.rindex(">")].split(",")[1:])]
+            traffic = tj["kernels"][names[0]]["dram_bytes_per_launch"] * local_pts / float(128) ** 4
             traffic_src = tj.get("source")
+            t_plane = [k for k in tj["kernels"] if k.startswith("k_spline_plane_r<1")]
+            plane_traffic = tj["kernels"][t_plane[0]]["dram_bytes_per_launch"] * local_pts / float(128) ** 4 if t_plane else None
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": f"k_spline_strided_split<4>: {timed_on}",
@@ -424,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
                     "kernel": "k_spline_plane_r<rho> (x1 pass + x2 pass + charge density in one sweep) + the sum of its per-CTA partial densities", "ms_per_launch": plane_ms,
                     "algorithmic_bytes_per_launch": 32.0 * local_pts, "achieved_gbs_at_16B_per_point_per_pass": 32.0 * local_pts / (plane_ms * 1e-3) / 1e9,
                     "hbm_bytes_moved_per_launch": 16.0 * local_pts, "hbm_gbs": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9,
-                    "frac_of_measured_hbm": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9 / peak},
+                    "frac_of_measured_hbm": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9 / peak, "traffic": plane_traffic},
                 "whole_step_frac_of_aggregate_hbm_roofline": 16.0 * value / 1e9 / (peak * world),
                 "timing": f"CUDA events on the launch stream, {reps} launches after 3 warm-ups, field {ext} "
                           f"({local_pts * 8 / 1e9:.2f} GB > L2)"}
