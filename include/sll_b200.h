@@ -171,6 +171,11 @@ int sllb_advect_plane(sllb_field_t F, int method, int order, const sllb_disp_t *
                       double rho_scale, double *d_rho);
 /* tuning knob: on = 0 disables K1c inside the simulations; points_per_thread 0 (auto), 16 or 32 */
 int sllb_set_plane_kernel(int on, int points_per_thread);
+/* tuning knob of the register-resident plane kernel: tmem_accumulators = 1 / 0: the 32 charge-density accumulators of a
+ * thread in tensor memory / in 12 registers + 20 shared-memory slots, -1 (default): tensor memory where the extents are
+ * compile-time constants; const_extents = 1 (default): 128 x 128 and 64 x 64 planes run instantiations with compile-time
+ * extents (no register spills, wraps as masks), 0: the run-time-extent kernel for every shape.  Same results either way. */
+int sllb_set_plane_variant(int tmem_accumulators, int const_extents);
 /* tuning knob: 0 = auto, 1 = TMA bulk staging, 2 = cp.async staging (strided kernels) */
 int sllb_set_staging(int mode);
 /* tuning knob: chunks per line of the strided spline kernel: -1 = auto, 1, 2, 4, 8 */

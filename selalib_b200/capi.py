@@ -116,6 +116,10 @@ def set_plane_kernel(on, points_per_thread=0):
     _ck(lib().sllb_set_plane_kernel(C.c_int(1 if on else 0), C.c_int(points_per_thread)))
 
 
+def set_plane_variant(tmem_accumulators=-1, const_extents=1):
+    _ck(lib().sllb_set_plane_variant(C.c_int(tmem_accumulators), C.c_int(const_extents)))
+
+
 def set_fused_remap(on):
     _ck(lib().sllb_set_fused_remap(C.c_int(1 if on else 0)))
 

@@ -297,6 +297,14 @@ int sllb_set_plane_kernel(int on, int points_per_thread) {
     return SLLB_OK;
 }
 
+int sllb_set_plane_variant(int tmem_accumulators, int const_extents) {
+    if (tmem_accumulators < -1 || tmem_accumulators > 1 || const_extents < 0 || const_extents > 1)
+        return fail(SLLB_ERR_INVALID, "set_plane_variant: tmem_accumulators in {-1, 0, 1}, const_extents in {0, 1}");
+    g_plane_tmem = tmem_accumulators;
+    g_plane_const_dims = const_extents;
+    return SLLB_OK;
+}
+
 int sllb_set_remap_rotation(int on) {
     g_remap_rotation = on ? 1 : 0;
     return SLLB_OK;

@@ -416,6 +416,13 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     }
     double *base = f + o * (long long)N * inner + in;
     const int C = N / P, k0 = chunk * C, k1 = k0 + C;
+    // DIAG: the kinetic-energy weights of the axis sit in the (until the end unused) chunk-sum area when they fit
+    // (N <= 128 P): one shared-memory read per point -- a broadcast where neighbouring lines share the cell shift --
+    // instead of a global load
+    const bool w2_shared = DIAG && N <= NPART * P * 32;
+    if constexpr (DIAG)
+        if (w2_shared)
+            for (int j = tid; j < N; j += 32 * P) part[j] = __ldg(dg.w2 + j);
 
     if (use_tma) {
         if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -496,13 +503,14 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
             double *p = base + (long long)iout0 * inner;
             double *const ptop = base + (long long)(N - 1) * inner;
             int iout = iout0;
+            const double *wk = w2_shared ? part : dg.w2;
 #pragma unroll 8
             for (int k = k1 - 1; k >= k0; --k) {
                 const double a0 = fma(-q, a1, sc[k * BW]);
                 const double val = fma(w3, a3, fma(w2, a2, fma(w1, a1, w0 * a0))); // cell k+1
                 st_stream(p, val);
                 total += val;
-                if constexpr (DIAG) { t1 += fabs(val); t2 = fma(val, val, t2); tk = fma(__ldg(dg.w2 + iout), val, tk); }
+                if constexpr (DIAG) { t1 += fabs(val); t2 = fma(val, val, t2); tk = fma(wk[iout], val, tk); }
                 p = (iout == 0) ? ptop : p - inner;
                 iout = (iout == 0) ? N - 1 : iout - 1;
                 a3 = a2; a2 = a1; a1 = a0;
@@ -511,6 +519,7 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     }
     // optional: sum of every advected line (charge-density reduction fused into the pass, see K3b)
     if (linesum != nullptr) {
+        if constexpr (DIAG) __syncthreads();   // the weights in `part` are dead only when every warp has left its loop
         part[chunk * 32 + lane] = total;
         if constexpr (DIAG) {
             part[(P + chunk) * 32 + lane] = t1;
@@ -876,17 +885,15 @@ __device__ __forceinline__ void chunk_solve(double (&g)[SLLB_PR_C], double *exch
 // w mod 4, columns 64 (w / 4) .. + 63) instead of 12 registers + 20 shared-memory slots: no register spills, 80 KB of shared
 // memory and 40 shared-memory accesses per thread and plane less; the TMEM loads of a group of 8 are in flight while the 8
 // values are evaluated.
-// WPA = M > 0 (N1 = 32 M): pass A is WARP-COOPERATIVE and reads its rows straight from global memory -- a warp owns a row,
-// lane l holds the M consecutive points M l .. M l + M - 1 (two 16-byte loads per lane, 1 KB per warp: coalesced), the two
-// first-order recurrences run as M - 1 local steps plus a log-step shuffle scan of the lane-end values (ratio (-q)^M; 8 lanes
-// x 4 points = the 27-term reach of the reference's series and more), the four-point evaluation takes its three outside
-// coefficients from the neighbouring lanes, and the results are scattered to their final x1 positions in the shared plane
-// with an XOR swizzle (p ^ ((p >> 4) & 3)) that keeps both this stride-M scatter and pass B's column reads free of bank
-// conflicts.  No bulk copy, no mbarrier, no block-wide barrier and no exchange array in pass A: the warps of a CTA drift
-// apart and overlap their global loads with each other's arithmetic; the next row is in flight while the current one is
-// solved.  Pass B is unchanged.
-template <bool RHO, bool REMAP, bool TACC = false, int WPA = 0>
-__global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1, const int N2,
+// NC > 0: square planes of NC x NC points with NC a power of two known at compile time (128^4, 64^4: the BASELINE sizes) --
+// the periodic wraps become masks, the chunk and row arithmetic constants, the strides immediates.
+template <int NC>
+__device__ __forceinline__ int wrap_next(const int k, const int n) {
+    if constexpr (NC > 0) return (k + 1) & (NC - 1);
+    else return (k == n - 1) ? 0 : k + 1;
+}
+template <bool RHO, bool REMAP, bool TACC = false, int NC = 0>
+__global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ f, const int N1r, const int N2r,
                                                            const long long nplanes, const DispDesc dd1,
                                                            const DispDesc dd2, double *__restrict__ rho_partial,
                                                            const __grid_constant__ RemapDst rd, const int l2_prefetch) {
@@ -894,7 +901,9 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *s = reinterpret_cast<double *>(smem_raw + 128);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, T = blockDim.x;
+    static_assert(NC == 0 || ((NC & (NC - 1)) == 0 && NC >= 32 && NC * NC / SLLB_PR_C <= 512), "square power-of-two planes");
+    const int N1 = NC > 0 ? NC : N1r, N2 = NC > 0 ? NC : N2r;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, T = NC > 0 ? NC * NC / SLLB_PR_C : (int)blockDim.x;
     const int npl = N1 * N2;
     double *exch = s + npl;                    // 4 * T doubles
     double *accs = exch + 4 * (size_t)T;       // RHO: (C - ACCR) * T doubles
@@ -928,7 +937,7 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
     __syncthreads();
     uint32_t phase = 0;
     long long pl = blockIdx.x;
-    if (WPA == 0 && tid == 0 && pl < nplanes) {
+    if (tid == 0 && pl < nplanes) {
         mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
         bulk_g2s(s, f + pl * (long long)npl, (uint32_t)(npl * 8), bar);
     }
@@ -942,77 +951,6 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
         const double d2 = disp_of(dd2, pl, 0);
         const double fl1 = floor(d1), fl2 = floor(d2);
         double g[C];
-        if constexpr (WPA > 0) {
-            // ---- pass A, warp-cooperative: rows straight from global memory ----
-            constexpr int M = WPA;
-            constexpr double q = 0.26794919243112270647;
-            const int nwarps = T >> 5;
-            double qm[M];                       // (-q)^(j+1)
-            qm[0] = -q;
-#pragma unroll
-            for (int j = 1; j < M; ++j) qm[j] = -q * qm[j - 1];
-            const double dxa = d1 - fl1, cdxa = 1.0 - dxa, s6a = 1.60769515458673623883 * (1.0 / 6.0);
-            const double wa0 = cdxa * cdxa * cdxa * s6a;
-            const double wa1 = (1.0 + 3.0 * cdxa + 3.0 * cdxa * cdxa - 3.0 * cdxa * cdxa * cdxa) * s6a;
-            const double wa2 = (1.0 + 3.0 * dxa + 3.0 * dxa * dxa - 3.0 * dxa * dxa * dxa) * s6a;
-            const double wa3 = dxa * dxa * dxa * s6a;
-            int p0 = (int)(((long long)M * lane - (long long)fl1) % N1);   // output position of this lane's first cell
-            if (p0 < 0) p0 += N1;
-            const double2 *src = reinterpret_cast<const double2 *>(gp + (size_t)M * lane);
-            double a[M], nx[M];
-            if (w < N2) {
-#pragma unroll
-                for (int j = 0; j < M; j += 2) { const double2 t = __ldcs(src + ((size_t)w * N1 + j) / 2); nx[j] = t.x; nx[j + 1] = t.y; }
-            }
-            for (int r = w; r < N2; r += nwarps) {
-#pragma unroll
-                for (int j = 0; j < M; ++j) a[j] = nx[j];
-                if (r + nwarps < N2) {          // the next row of this warp is in flight while this one is solved
-#pragma unroll
-                    for (int j = 0; j < M; j += 2) { const double2 t = __ldcs(src + ((size_t)(r + nwarps) * N1 + j) / 2); nx[j] = t.x; nx[j + 1] = t.y; }
-                }
-                // forward recurrence e_i = f_i - q e_{i-1}: local steps from zero, scan of the lane-end values, carry-in
-#pragma unroll
-                for (int j = 1; j < M; ++j) a[j] = fma(-q, a[j - 1], a[j]);
-                double Tn = a[M - 1], mult = qm[M - 1];
-#pragma unroll
-                for (int sft = 1; sft * M < 32; sft <<= 1) {
-                    Tn = fma(mult, __shfl_sync(0xffffffffu, Tn, (lane - sft) & 31), Tn);
-                    mult *= mult;
-                }
-                const double Tp = __shfl_sync(0xffffffffu, Tn, (lane - 1) & 31);
-#pragma unroll
-                for (int j = 0; j < M; ++j) a[j] = fma(qm[j], Tp, a[j]);
-                // backward recurrence g_i = e_i - q g_{i+1}, mirrored
-#pragma unroll
-                for (int j = M - 2; j >= 0; --j) a[j] = fma(-q, a[j + 1], a[j]);
-                double Un = a[0];
-                mult = qm[M - 1];
-#pragma unroll
-                for (int sft = 1; sft * M < 32; sft <<= 1) {
-                    Un = fma(mult, __shfl_sync(0xffffffffu, Un, (lane + sft) & 31), Un);
-                    mult *= mult;
-                }
-                const double Ux = __shfl_sync(0xffffffffu, Un, (lane + 1) & 31);
-#pragma unroll
-                for (int j = 0; j < M; ++j) a[j] = fma(qm[M - 1 - j], Ux, a[j]);
-                // cell c = M lane + j: w0 g[c-1] + w1 g[c] + w2 g[c+1] + w3 g[c+2], stored at position (c - dcell) mod N1
-                double e[M + 3];
-                e[0] = __shfl_sync(0xffffffffu, a[M - 1], (lane - 1) & 31);
-#pragma unroll
-                for (int j = 0; j < M; ++j) e[j + 1] = a[j];
-                e[M + 1] = __shfl_sync(0xffffffffu, a[0], (lane + 1) & 31);
-                e[M + 2] = __shfl_sync(0xffffffffu, a[1], (lane + 1) & 31);
-                double *row = s + (size_t)r * N1;
-                int p = p0;
-#pragma unroll
-                for (int j = 0; j < M; ++j) {
-                    row[p ^ ((p >> 4) & 3)] = fma(wa3, e[j + 3], fma(wa2, e[j + 2], fma(wa1, e[j + 1], wa0 * e[j])));
-                    p = (p == N1 - 1) ? 0 : p + 1;
-                }
-            }
-            __syncthreads();
-        } else {
         // ---- pass A: rows ----
         int k0 = chA * C + (lane & 15);        // skewed chunk start: conflict-free banks with pitch N1
         if (k0 >= N1) k0 -= N1;
@@ -1022,7 +960,7 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
             const double *row = s + (size_t)rowA * N1;
             int k = k0;
 #pragma unroll
-            for (int j = 0; j < C; ++j) { g[j] = row[k]; k = (k == N1 - 1) ? 0 : k + 1; }
+            for (int j = 0; j < C; ++j) { g[j] = row[k]; k = wrap_next<NC>(k, N1); }
         }
         chunk_solve(g, exch, rowA, N2, chA, PA, d1 - fl1);
         {
@@ -1031,17 +969,16 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
             int i1 = (int)(((long long)k0 + 1 - (long long)fl1) % N1);
             if (i1 < 0) i1 += N1;
 #pragma unroll
-            for (int j = 0; j < C; ++j) { row[i1] = g[j]; i1 = (i1 == N1 - 1) ? 0 : i1 + 1; }
+            for (int j = 0; j < C; ++j) { row[i1] = g[j]; i1 = wrap_next<NC>(i1, N1); }
         }
         __syncthreads();
-        }
         // ---- pass B: columns; the chunk grid is shifted so that this thread's cells are points 32*chB + j ----
         {
             int k = (int)(((long long)chB * C - 1 + (long long)fl2) % N2);
             if (k < 0) k += N2;
-            const double *col = s + (WPA > 0 ? (colB ^ ((colB >> 4) & 3)) : colB);
+            const double *col = s + colB;
 #pragma unroll
-            for (int j = 0; j < C; ++j) { g[j] = col[(size_t)k * N1]; k = (k == N2 - 1) ? 0 : k + 1; }
+            for (int j = 0; j < C; ++j) { g[j] = col[(size_t)k * N1]; k = wrap_next<NC>(k, N2); }
         }
         // (the first barrier inside chunk_solve also says: every thread has read the plane)
         {
@@ -1051,7 +988,7 @@ __global__ void __launch_bounds__(512, 1) k_spline_plane_r(double *__restrict__ 
             exch[chB * N1 + colB] = g[C - 1];
             __syncthreads();
             const long long nxt = pl + gridDim.x;
-            if (WPA == 0 && tid == 0 && nxt < nplanes) { // the plane is dead in shared memory: fetch the next one
+            if (tid == 0 && nxt < nplanes) { // the plane is dead in shared memory: fetch the next one
                 mbar_arrive_expect_tx(bar, (uint32_t)(npl * 8));
                 bulk_g2s(s, f + nxt * (long long)npl, (uint32_t)(npl * 8), bar);
             }
@@ -1483,22 +1420,35 @@ static cudaError_t launch_spline_contig_split_t(double *f, long long nlines, int
 // caller then runs the two passes separately).
 // L2 prefetch of the next plane (cp.async.bulk.prefetch.L2, SASS UBLKPF) at the top of every iteration of the plane
 // kernel.  Measured on 128^4 (profiles/r02_plane_ab_s18.log): without the fused charge density 0.851 -> 0.788 ms, with it
-// 0.998 -> 1.059 ms (the per-CTA partial densities and the prefetched planes compete for L2).  1 (default): only the
-// variant without the charge density prefetches; 2: both; 0: neither.
+// 0.998 -> 1.059 ms for the generic-extent kernel; the compile-time-extent instantiations (no spills any more) gain in both
+// forms (profiles/r02_plane_const_ab.log: 0.712 -> 0.694 and 0.803 -> 0.777 ms).  1 (default): the variant without the
+// charge density and the compile-time-extent instantiations prefetch; 2: all; 0: none.
 int g_plane_l2_prefetch = [] { const char *e = getenv("SLLB_PLANE_L2_PREFETCH"); return e ? atoi(e) : 1; }();
 int g_plane_ept = 0; // tuning knob: 0 auto (register-resident variant), 16 or 32: in-place variant with that many points per thread
 static int plane_ept(int n1, int n2, bool rho) {
     if (g_plane_ept == 16 && !rho) return 16;
     return 32;
 }
-// 1: the charge-density accumulators of the plane kernel live in tensor memory (SLLB_PLANE_TMEM), 0 (default): 12 registers +
-// 20 shared-memory slots per thread.  Measured on 128^4 (profiles/r02_plane_ab_s19_tmem.log): 1.027 vs 0.975 ms -- TMEM reads
-// run at 64 B/clk/SM, half the shared-memory rate, and the accumulate is a read-modify-write; kept as an opt-in variant.
-int g_plane_tmem = [] { const char *e = getenv("SLLB_PLANE_TMEM"); return e ? atoi(e) : 0; }();
+// The charge-density accumulators of the plane kernel: 12 registers + 20 shared-memory slots per thread, or all 32 in tensor
+// memory (tcgen05.alloc / ld / st used as a scratchpad).  With run-time extents the TMEM form is the slower one (1.027 vs
+// 0.975 ms on 128^4, profiles/r02_plane_ab_s19_tmem.log: the kernel spills either way); with compile-time extents neither
+// form spills and TMEM wins clearly: 0.663 vs 0.777 ms (profiles/r02_plane_const_ab2.log), faster than the kernel without
+// the fused density.  SLLB_PLANE_TMEM: 1 / 0 force, unset = TMEM for the 128 x 128 compile-time-extent instantiation only.
+int g_plane_tmem = [] { const char *e = getenv("SLLB_PLANE_TMEM"); return e ? atoi(e) : -1; }();
+// 1: square 128 x 128 / 64 x 64 planes run the instantiation with compile-time extents (SLLB_PLANE_CONST_DIMS=0: the generic one)
+int g_plane_const_dims = [] { const char *e = getenv("SLLB_PLANE_CONST_DIMS"); return e ? atoi(e) : 1; }();
+static int plane_const_extent(int n1, int n2) {
+    return (g_plane_const_dims && g_plane_ept == 0 && n1 == n2 && (n1 == 128 || n1 == 64)) ? n1 : 0;
+}
+static bool plane_tmem(int n1, int n2, bool rho) {
+    if (!rho || g_plane_ept != 0) return false;
+    if (g_plane_tmem >= 0) return g_plane_tmem != 0;
+    return plane_const_extent(n1, n2) == 128;   // 64 x 64 (128 threads, 4 CTAs per SM): 0.069 vs 0.064 ms on 64^4, stays off
+}
 static size_t plane_smem(int n1, int n2, bool rho) {
     const size_t T = (size_t)n1 * n2 / SLLB_PR_C;
     if (g_plane_ept != 0) return 128 + (size_t)n1 * n2 * 8;
-    return 128 + (size_t)n1 * n2 * 8 + 4 * T * 8 + ((rho && !g_plane_tmem) ? (SLLB_PR_C - SLLB_PR_ACCR) * T * 8 : 0);
+    return 128 + (size_t)n1 * n2 * 8 + 4 * T * 8 + ((rho && !plane_tmem(n1, n2, rho)) ? (SLLB_PR_C - SLLB_PR_ACCR) * T * 8 : 0);
 }
 int plane_grid(int n1, int n2, long long nplanes) {
     const size_t smem = plane_smem(n1, n2, true);
@@ -1539,7 +1489,7 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
     do {                                                                                     \
         e = set_smem(KERN, smem);                                                            \
         if (e != cudaSuccess) return e;                                                      \
-        KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial, rd, (g_plane_l2_prefetch >= 2 || (g_plane_l2_prefetch == 1 && !rho)) ? 1 : 0);    \
+        KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial, rd, (g_plane_l2_prefetch >= 2 || (g_plane_l2_prefetch == 1 && (!rho || nc == 128 || nc == 64))) ? 1 : 0);    \
     } while (0)
 #define SLLB_PLANE_LAUNCH(KERN)                                                              \
     do {                                                                                     \
@@ -1547,13 +1497,21 @@ cudaError_t launch_spline_plane(double *f, int n1, int n2, long long nplanes, co
         if (e != cudaSuccess) return e;                                                      \
         KERN<<<grid, threads, smem, st>>>(f, n1, n2, nplanes, dd1, dd2, rho_partial);        \
     } while (0)
-    if (g_plane_ept == 0) {
+    const int nc = plane_const_extent(n1, n2);
+    const bool tm = plane_tmem(n1, n2, rho);
+    if (nc == 128) {
+        if (rd.on) { if (tm) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, true, 128>)); else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, false, 128>)); else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, true, false, 128>)); }
+        else { if (tm) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, true, 128>)); else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, false, 128>)); else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, false, false, 128>)); }
+    } else if (nc == 64) {
+        if (rd.on) { if (tm) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, true, 64>)); else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, false, 64>)); else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, true, false, 64>)); }
+        else { if (tm) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, true, 64>)); else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, false, 64>)); else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, false, false, 64>)); }
+    } else if (g_plane_ept == 0) {
         if (rd.on) {
-            if (rho && g_plane_tmem) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, true>));
+            if (tm) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true, true>));
             else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, true>));
             else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, true>));
         } else {
-            if (rho && g_plane_tmem) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, true>));
+            if (tm) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false, true>));
             else if (rho) SLLB_PLANE_LAUNCH_R((k_spline_plane_r<true, false>));
             else SLLB_PLANE_LAUNCH_R((k_spline_plane_r<false, false>));
         }

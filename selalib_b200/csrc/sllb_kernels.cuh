@@ -118,6 +118,8 @@ cudaError_t launch_pack4d(const double *src, const int ext[4], Box4 box, double 
 cudaError_t launch_unpack4d(double *dst, const int ext[4], Box4 box, const double *buf, cudaStream_t st);
 
 extern int g_plane_ept;    // plane kernel: 0 auto, 16 or 32 points per thread
+extern int g_plane_tmem;   // plane kernel, charge-density accumulators in tensor memory: -1 auto, 0, 1
+extern int g_plane_const_dims; // plane kernel: instantiations with compile-time extents for 128 x 128 / 64 x 64 planes
 extern int g_remap_rotation; // fused remap: rank-dependent start tile
 extern int g_spline_split; // -1 auto, else lines are cut into this many chunks (1,2,4,8)
 long long launch_count();

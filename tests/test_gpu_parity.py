@@ -341,6 +341,37 @@ def test_advect_plane_kernel(sb, orc, shape, ept):
     F.destroy()
 
 
+@pytest.mark.parametrize("shape", [(128, 128, 19, 17), (64, 64, 41, 23)])
+@pytest.mark.parametrize("tmem,const_extents", [(-1, 1), (0, 1), (1, 1), (0, 0), (1, 0)])
+def test_advect_plane_kernel_variants_many_planes(sb, orc, shape, tmem, const_extents):
+    """K1c with more planes than CTAs (every CTA accumulates its charge density over several planes): the instantiations
+    with compile-time extents and the run-time-extent kernel, accumulators in tensor memory and in registers + shared
+    memory, all against two oracle passes + a plain sum."""
+    rng = np.random.default_rng(SEED + 700 + sum(shape))
+    f0 = np.asfortranarray(rng.standard_normal(shape))
+    n3, n4 = shape[2], shape[3]
+    v3 = rng.uniform(-70, 70, n3)
+    v4 = rng.uniform(-70, 70, n4)
+    d0 = (shape[1], n3, 1, 1, 1, 0)
+    d1 = (n3, n4, 1, 1, 1, 0)
+    ref = orc.advect_axis(f0.copy(order="F"), 0, "spline", 4, v3 * 0.9, d0)
+    ref = orc.advect_axis(ref, 1, "spline", 4, v4 * 1.1, d1)
+    rho_ref = 0.25 * ref.reshape(shape[0], shape[1], -1).sum(axis=2)
+    F = sb.Field(shape)
+    sb.set_plane_variant(tmem, const_extents)
+    try:
+        F.upload(f0)
+        rho = F.advect_plane(v3, d0, 0.9, v4, d1, 1.1, rho_scale=0.25)
+        assert relerr(F.download(), ref) < TOL
+        assert np.abs(rho - rho_ref).max() < 1e-12 * np.abs(ref).max() * (n3 * n4)
+        F.upload(f0)
+        assert F.advect_plane(v3, d0, 0.9, v4, d1, 1.1) is None
+        assert relerr(F.download(), ref) < TOL
+    finally:
+        sb.set_plane_variant(-1, 1)
+    F.destroy()
+
+
 def test_advect_plane_kernel_unsupported(sb):
     F = sb.Field((48, 40, 4))
     with pytest.raises(sb.SllbError) as ei:
