@@ -390,13 +390,17 @@ __global__ void __launch_bounds__(1024) k_lagrange_strided_split(double *__restr
 // tile is C instead of N steps and P times more warps are resident to hide latency.
 // Chunk [k0,k1) computes g[k] for k = k1+2 .. k0 and emits cells k0+1 .. k1 (mod N).
 // ------------------------------------------------------------------------------------------------
-template <int P, bool REMAP, bool DIAG = false>
-__global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restrict__ f, const int N,
+// NC > 0: line length known at compile time and a power of two (128, 64: the BASELINE sizes) -- wraps become masks and
+// the chunk loops have constant trip counts; matters for the DIAG variant, whose extra arithmetic makes it issue-bound.
+template <int P, bool REMAP, bool DIAG = false, int NC = 0>
+__global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restrict__ f, const int Nr,
                                                                   const long long inner, const DispDesc dd,
                                                                   const int use_tma, const long long nlines,
                                                                   double *__restrict__ linesum,
                                                                   const __grid_constant__ RemapDst rd,
                                                                   const LineDiag dg, const LineSub sub) {
+    static_assert(NC == 0 || ((NC & (NC - 1)) == 0 && NC % P == 0), "power-of-two line length");
+    const int N = NC > 0 ? NC : Nr;
     constexpr int BW = 32;
     constexpr int NPART = DIAG ? 4 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -442,11 +446,11 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
     // forward start value from pristine f: e[k0] = f[k0] + sum_i (-q)^{i+1} f[k0-1-i]
     double e = sc[k0 * BW];
     {
-        int idx = (k0 == 0) ? N - 1 : k0 - 1;
+        int idx = NC > 0 ? ((k0 - 1) & (NC - 1)) : ((k0 == 0) ? N - 1 : k0 - 1);
 #pragma unroll
         for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
             e = fma(c_pw[i], sc[idx * BW], e);
-            idx = (idx == 0) ? N - 1 : idx - 1;
+            idx = NC > 0 ? ((idx - 1) & (NC - 1)) : ((idx == 0) ? N - 1 : idx - 1);
         }
     }
     __syncthreads(); // every chunk has read its warm-up inputs before anybody overwrites f with e
@@ -476,17 +480,17 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
         int i0 = k1;     if (i0 >= N) i0 -= N;
         double g = sc[i2 * BW];
         {
-            int idx = (i2 == N - 1) ? 0 : i2 + 1;
+            int idx = NC > 0 ? ((i2 + 1) & (NC - 1)) : ((i2 == N - 1) ? 0 : i2 + 1);
 #pragma unroll
             for (int i = 0; i < SLLB_NUM_TERMS; ++i) {
                 g = fma(c_pw[i], sc[idx * BW], g);
-                idx = (idx == N - 1) ? 0 : idx + 1;
+                idx = NC > 0 ? ((idx + 1) & (NC - 1)) : ((idx == N - 1) ? 0 : idx + 1);
             }
         }
         double a3 = g;                                  // g[k1+2]
         double a2 = fma(-q, a3, sc[i1 * BW]);           // g[k1+1]
         double a1 = fma(-q, a2, sc[i0 * BW]);           // g[k1]
-        const int iout0 = ((k1 - dcell) % N + N) % N;   // output index of cell k1 (mod N)
+        const int iout0 = NC > 0 ? ((k1 - dcell) & (NC - 1)) : ((k1 - dcell) % N + N) % N;   // output index of cell k1 (mod N)
         if constexpr (REMAP) {
             OutMap om = make_outmap(rd, o, in, N, inner);
             om.seek(iout0);
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(32 * P) k_spline_strided_split(double *__restr
                 total += val;
                 if constexpr (DIAG) { t1 += fabs(val); t2 = fma(val, val, t2); tk = fma(wk[iout], val, tk); }
                 p = (iout == 0) ? ptop : p - inner;
-                iout = (iout == 0) ? N - 1 : iout - 1;
+                iout = NC > 0 ? ((iout - 1) & (NC - 1)) : ((iout == 0) ? N - 1 : iout - 1);
                 a3 = a2; a2 = a1; a1 = a0;
             }
         }
@@ -1285,6 +1289,10 @@ static int remap_block_rotation(const RemapDst &rd, long long nblk) {
     if (tp <= 1 || nblk % tp != 0) return 0;
     return (int)((rd.rank % tp) * (nblk / tp));
 }
+// strided spline pass, instantiations with a compile-time line length (N = 32 P: 128 with P = 4, 64 with P = 2; 28 % fewer
+// instructions): 0 none, 1 the variant with the fused diagnostics, 2 (default) the plain variant too (SLLB_SPLIT_CONST_LEN).
+// 128^4 step 3.54 / 3.48 / 3.43 ms, 64^4 step 0.313 / 0.307 / 0.301 ms (profiles/r02_split_const_ab.log).
+int g_split_const_len = [] { const char *e = getenv("SLLB_SPLIT_CONST_LEN"); return e ? atoi(e) : 2; }();
 template <int P>
 static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, long long inner, const DispDesc &dd,
                                          int staging, cudaStream_t st, const RemapDst &rd, double *linesum,
@@ -1311,8 +1319,18 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
         RemapDst rr = rd;
         rr.block_rot = remap_block_rotation(rd, nblk);
         kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);
+    } else if (with_diag && g_split_const_len && N == 32 * P && (P == 4 || P == 2)) {
+        auto kern = k_spline_strided_split<P, false, true, 32 * P>;
+        e = set_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
     } else if (with_diag) {
         auto kern = k_spline_strided_split<P, false, true>;
+        e = set_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
+    } else if (g_split_const_len >= 2 && N == 32 * P && (P == 4 || P == 2)) {
+        auto kern = k_spline_strided_split<P, false, false, 32 * P>;
         e = set_smem(kern, smem);
         if (e != cudaSuccess) return e;
         kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
