@@ -410,10 +410,10 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            # the plain variant of the strided spline pass: P = 4, no remap stores, no line diagnostics (all-zero trailing
-            # template arguments; the list grew from <4, 0> to <4, 0, 0> in round 2)
+            # the plain variant of the strided spline pass: <P = 4, REMAP = 0, DIAG = 0[, compile-time line length]>
             names = [k for k in tj["kernels"] if k.startswith("k_spline_strided_split<4") and
-                     all(t.strip() == "0" for t in k[k.index("<") + 1:k.rindex(">")].split(",")[1:])]
+                     all(t.strip() == "0" for t in k[k.index("<") + 1:k.rindex(">")].split(",")[1:3])]
+            names.sort(key=lambda k: -tj["kernels"][k]["launches"])
             traffic = tj["kernels"][names[0]]["dram_bytes_per_launch"] * local_pts / float(128) ** 4
             traffic_src = tj.get("source")
             t_plane = [k for k in tj["kernels"] if k.startswith("k_spline_plane_r<1")]
@@ -431,7 +431,10 @@ def run_ours(args, rank, world, local_rank):
                     "algorithmic_bytes_per_launch": 32.0 * local_pts, "achieved_gbs_at_16B_per_point_per_pass": 32.0 * local_pts / (plane_ms * 1e-3) / 1e9,
                     "hbm_bytes_moved_per_launch": 16.0 * local_pts, "hbm_gbs": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9,
                     "frac_of_measured_hbm": 16.0 * local_pts / (plane_ms * 1e-3) / 1e9 / peak, "traffic": plane_traffic},
+                # 6 passes at 16 B per point over the step time (above 1 on one GPU: the T stage moves f once for two passes),
+                # and the same with the 5 sweeps over f a step really makes on one GPU (x1+x2 fused, x3, x4, x3, x4)
                 "whole_step_frac_of_aggregate_hbm_roofline": 16.0 * value / 1e9 / (peak * world),
+                "whole_step_frac_of_hbm_roofline_5_sweeps": (16.0 * value * 5.0 / 6.0 / 1e9 / peak) if world == 1 else None,
                 "timing": f"CUDA events on the launch stream, {reps} launches after 3 warm-ups, field {ext} "
                           f"({local_pts * 8 / 1e9:.2f} GB > L2)"}
 

@@ -1312,7 +1312,14 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + 31) / 32;
     cudaError_t e;
-    if (rd.on) {
+    if (rd.on && g_split_const_len >= 2 && N == 32 * P && (P == 4 || P == 2)) {
+        auto kern = k_spline_strided_split<P, true, false, 32 * P>;
+        e = set_smem(kern, smem);
+        if (e != cudaSuccess) return e;
+        RemapDst rr = rd;
+        rr.block_rot = remap_block_rotation(rd, nblk);
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);
+    } else if (rd.on) {
         auto kern = k_spline_strided_split<P, true>;
         e = set_smem(kern, smem);
         if (e != cudaSuccess) return e;
