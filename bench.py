@@ -330,6 +330,7 @@ def run_ours(args, rank, world, local_rank):
              "l2": float(rows_t[-1, 5]), "checksum_wf": float(csum[0]), "checksum_wf2": float(csum[1]),
              "what": "after the timed region; checksum = sum w f and sum w f^2 with w a function of the GLOBAL index of every point"}
     # the same region without the diagnostics rows, and the per-phase breakdown (pooled CUDA events, opt-in)
+    S.run(min(args.warmup, 3), diagnostics=False)   # its own recorded step is captured here, not inside the region
     barrier()
     e0.record()
     S.run(args.steps, diagnostics=False)
