@@ -1275,7 +1275,7 @@ static cudaError_t launch_strided_t(double *f, long long nlines, int N, long lon
     return cudaGetLastError();
 }
 
-int g_spline_split = -1; // -1 auto, else forced P in {1,2,4}
+int g_spline_split = [] { const char *e = getenv("SLLB_SPLINE_SPLIT"); return e ? atoi(e) : -1; }(); // -1 auto, else forced P in {1,2,4,8}
 int g_remap_rotation = 1; // fused remap: 1 = ranks start their sweep at different destination ranks
 // A fused pass walks its tiles with the slowest non-advected axis outermost.  When the destination layout splits
 // that axis, every rank would store to the same group of receivers at the same time (all senders into
@@ -1312,41 +1312,31 @@ static cudaError_t launch_spline_split_t(double *f, long long nlines, int N, lon
     int use_tma = (staging == STAGING_CPASYNC) ? 0 : (tma_ok ? 1 : 0);
     long long nblk = (nlines + 31) / 32;
     cudaError_t e;
-    if (rd.on && g_split_const_len >= 2 && N == 32 * P && (P == 4 || P == 2)) {
-        auto kern = k_spline_strided_split<P, true, false, 32 * P>;
-        e = set_smem(kern, smem);
-        if (e != cudaSuccess) return e;
-        RemapDst rr = rd;
-        rr.block_rot = remap_block_rotation(rd, nblk);
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);
-    } else if (rd.on) {
-        auto kern = k_spline_strided_split<P, true>;
-        e = set_smem(kern, smem);
-        if (e != cudaSuccess) return e;
-        RemapDst rr = rd;
-        rr.block_rot = remap_block_rotation(rd, nblk);
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);
-    } else if (with_diag && g_split_const_len && N == 32 * P && (P == 4 || P == 2)) {
-        auto kern = k_spline_strided_split<P, false, true, 32 * P>;
-        e = set_smem(kern, smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
+    RemapDst rr = rd;
+    if (rd.on) rr.block_rot = remap_block_rotation(rd, nblk);
+#define SLLB_SPLIT_LAUNCH(...)                                                                                  \
+    do {                                                                                                        \
+        auto kern = k_spline_strided_split<__VA_ARGS__>;                                                        \
+        e = set_smem(kern, smem);                                                                               \
+        if (e != cudaSuccess) return e;                                                                         \
+        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rr, dg, sub);     \
+    } while (0)
+    // compile-time line length: 128 or 64 points, at least 16 per chunk
+    const int nc = ((N == 128 || N == 64) && N / P >= 16 && g_split_const_len >= (with_diag ? 1 : 2)) ? N : 0;
+    if (rd.on) {
+        if (nc == 128) SLLB_SPLIT_LAUNCH(P, true, false, 128);
+        else if (nc == 64) SLLB_SPLIT_LAUNCH(P, true, false, 64);
+        else SLLB_SPLIT_LAUNCH(P, true);
     } else if (with_diag) {
-        auto kern = k_spline_strided_split<P, false, true>;
-        e = set_smem(kern, smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
-    } else if (g_split_const_len >= 2 && N == 32 * P && (P == 4 || P == 2)) {
-        auto kern = k_spline_strided_split<P, false, false, 32 * P>;
-        e = set_smem(kern, smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
+        if (nc == 128) SLLB_SPLIT_LAUNCH(P, false, true, 128);
+        else if (nc == 64) SLLB_SPLIT_LAUNCH(P, false, true, 64);
+        else SLLB_SPLIT_LAUNCH(P, false, true);
     } else {
-        auto kern = k_spline_strided_split<P, false>;
-        e = set_smem(kern, smem);
-        if (e != cudaSuccess) return e;
-        kern<<<(unsigned)nblk, 32 * P, smem, st>>>(f, N, inner, dd, use_tma, nlines, linesum, rd, dg, sub);
+        if (nc == 128) SLLB_SPLIT_LAUNCH(P, false, false, 128);
+        else if (nc == 64) SLLB_SPLIT_LAUNCH(P, false, false, 64);
+        else SLLB_SPLIT_LAUNCH(P, false);
     }
+#undef SLLB_SPLIT_LAUNCH
     COUNT_LAUNCH();
     return cudaGetLastError();
 }
