@@ -284,6 +284,18 @@ def test_new_entry_points_fail_loudly_without_a_device():
         assert e.value.code == sb.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
 
 
+def test_tuning_setters_reject_values_outside_their_range():
+    """the kernel-variant switches validate their arguments on the host (no device needed) and keep the defaults"""
+    for bad in ((2, 1), (-2, 1), (0, 2), (0, -1)):
+        with pytest.raises(sb.SllbError) as e:
+            sb.set_plane_variant(*bad)
+        assert e.value.code == sb.ERR_INVALID
+    with pytest.raises(sb.SllbError):
+        sb.set_plane_kernel(True, 8)
+    sb.set_plane_variant(-1, 1)     # the defaults: accepted
+    sb.set_plane_kernel(True, 0)
+
+
 def _build_c_driver(tmp_path):
     import subprocess
     libdir = os.path.join(ROOT, "selalib_b200", "lib")
