@@ -92,6 +92,8 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 // streaming store: written once, not re-read by this pass
 __device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+// two consecutive doubles, p 16-byte aligned
+__device__ __forceinline__ void st_stream2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
 
 __device__ __forceinline__ double disp_of(const DispDesc &d, long long o, long long in) {
     return d.scale * d.v[((o / d.odiv) % d.omod) * d.ostr + ((in / d.idiv) % d.imod) * d.istr];
