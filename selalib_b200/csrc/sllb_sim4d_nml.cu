@@ -36,7 +36,7 @@ int sllb_format_g(double x, int w, int d, char *buf) {
             snprintf(f, sizeof(f), d - s == 0 ? "%.*f." : "%.*f", d - s, x); // F16.0 keeps the decimal point
             snprintf(body, sizeof(body), "%*s    ", w - 4, f);
         } else {
-            char digits[32];
+            char digits[64];   // d <= 53 significant digits (w <= 60)
             int nd = 0;
             for (const char *c = e; c < ep; ++c) if (*c >= '0' && *c <= '9') digits[nd++] = *c;
             digits[nd] = 0;
